@@ -1,0 +1,209 @@
+/*
+ * isg.h — C ABI of libisg.so: the B200 (sm_100a) decode hot path of
+ * aspirantll/instance-segmentation (utils/decode.py, utils/kmeans.py, utils/nms.py).
+ *
+ * The reference has no FFI: its boundary is a set of Python module functions
+ * (SURVEY.md §8b).  Each entry point below names the reference function
+ * (file:line, relative to the reference tree) whose arithmetic it replaces.
+ *
+ * Conventions (every function):
+ *   - all pointers are DEVICE pointers unless the parameter is documented as
+ *     "host"; the caller owns every buffer (inputs, outputs, workspace);
+ *   - nothing is allocated, no global mutable state, nothing throws;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); functions
+ *     do not synchronise unless documented ("blocking");
+ *   - return value: 0 = ok, < 0 = ISG_E* (bad argument etc.), > 0 = cudaError_t;
+ *   - image planes are row-major fp32; "plane stride"/"image stride" are in
+ *     elements; rows are contiguous (stride W).
+ *   - coordinates: pixel = (y, x) = (row, col) as in the reference's
+ *     kp_mask.nonzero() (utils/decode.py:312); boxes are (x1, y1, x2, y2).
+ */
+#ifndef ISG_H_
+#define ISG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISG_ABI_VERSION 1
+
+#define ISG_OK            0
+#define ISG_EINVAL       (-1)  /* bad argument (null pointer, negative extent, k > H*W ...) */
+#define ISG_EWORKSPACE   (-2)  /* workspace too small or misaligned */
+#define ISG_EUNSUPPORTED (-3)  /* size outside the supported range (see each function) */
+#define ISG_ENOTCONVERGED (-4) /* isg_kmeans hit max_iter */
+
+typedef void* isg_stream_t;    /* cudaStream_t */
+
+/* words per seed record (32 B): {y0,y1,x0,x1 : int32 inclusive in-box bounds; cy,cx : fp32 grid
+ * coordinate of the truncated box centre; 2 words padding} */
+#define ISG_SEED_WORDS 8
+/* words per ghost-filter record (16 B): {xlo,xhi,ylo,yhi : fp32, strict bounds} */
+#define ISG_GHOST_WORDS 4
+/* words per instance-statistics record: {count, ymin, xmin, ymax, xmax : int32} */
+#define ISG_STAT_WORDS 5
+
+/* NMS conventions */
+#define ISG_NMS_PLUS1_LE 0  /* utils/nms.py:19,31-36: areas and overlaps use +1, survivor iff IoU <= thr (fp32 thr) */
+#define ISG_NMS_TV_GT    1  /* torchvision batched_nms as called at utils/decode.py:400: no +1, suppress iff IoU > thr, class aware */
+#define ISG_NMS_MAX_BOXES 16384
+
+/* k-means metrics (utils/kmeans.py:34-39) */
+#define ISG_KMEANS_EUCLIDEAN 0
+#define ISG_KMEANS_COSINE    1
+
+int         isg_abi_version(void);
+const char* isg_strerror(int code);
+/* host query: 1 if `device` is a compute-capability 10.x part this library was built for, else 0 */
+int         isg_device_supported(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 — boundary-keypoint selection.  Replaces select_points (utils/decode.py:71-85) and
+ * nms_hm (utils/decode.py:42-48).
+ *   sel(p)  = kp[p] is among the k largest values of the image            (topk, :81)
+ *   v(p)    = sel(p) ? kp[p] : 0                                          (mat*mask, :84)
+ *   keep(p) = sel(p) && v(p) == max over the 3x3 window clipped to the image of v   (:45-47,85)
+ * With ties at the k-th value every tied pixel is selected (torch.topk's choice is unspecified).
+ * ------------------------------------------------------------------------------------------ */
+size_t isg_topk_workspace_bytes(int B);
+/* k-th largest value per image as an order-preserving uint32 key (see isg_float_key in DESIGN.md).
+ * kp: [B] images of H*W fp32, image b at kp + b*img_stride.  k in [0, H*W]; k > H*W -> ISG_EINVAL
+ * (the reference's topk raises).  k == 0 selects nothing (key = 0xFFFFFFFF). */
+int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t img_stride, int k,
+                       uint32_t* thr_key /*[B]*/, void* ws, size_t ws_bytes, isg_stream_t stream);
+/* keep mask from a threshold.  keepbits: [B,H,ceil(W/32)] uint32, bit i of word w = pixel x = 32w+i.
+ * mask_u8 (nullable): [B,H,W] uint8 0/1, the tensor select_points returns. */
+int isg_keep_points(const float* kp, int B, int H, int W, int64_t img_stride, const uint32_t* thr_key,
+                    uint32_t* keepbits, uint8_t* mask_u8, isg_stream_t stream);
+/* isg_topk_threshold + isg_keep_points; workspace = isg_topk_workspace_bytes(B) + 4*B bytes */
+size_t isg_select_points_workspace_bytes(int B);
+int isg_select_points(const float* kp, int B, int H, int W, int64_t img_stride, int k,
+                      uint32_t* keepbits, uint8_t* mask_u8, void* ws, size_t ws_bytes, isg_stream_t stream);
+/* nms_hm (utils/decode.py:42-48): keep[p] = heat[p] == max over kernel x kernel window (stride 1,
+ * -inf padding).  heat: [planes,H,W]; kernel odd, 1..15. */
+int isg_nms_hm(const float* heat, int planes, int H, int W, int kernel, uint8_t* keep, isg_stream_t stream);
+/* kp_mask.nonzero() (utils/decode.py:312): row-major (y,x) int32 pairs of the set bits.
+ * idx: [B,cap,2]; count: [B] = number of set bits (may exceed cap; only the first cap are written). */
+int isg_compact_points(const uint32_t* keepbits, int B, int H, int W, int cap,
+                       int32_t* idx, int32_t* count, isg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Seeds.  Replaces decode_single's box -> centre/size arithmetic (utils/decode.py:428-432) and the
+ * seed tensors of group_kp (:316-322) plus the per-instance ghost-filter bounds (:339-352).
+ * rois: [B,Nmax,4] fp32 (x1,y1,x2,y2); n_seeds: [B] int32 (<= Nmax).
+ * ys: [H], xs: [W] fp32 coordinate tables (utils/utils.py:453-458 sliced as at utils/decode.py:304).
+ * ghost_k = fp32(0.5 + wh_delta); scale = compute_scale() (utils/decode.py:34-35, 1 by default).
+ * seeds: [B,Nmax,ISG_SEED_WORDS] 32-bit words; ghost: [B,Nmax,ISG_GHOST_WORDS] fp32.
+ * ------------------------------------------------------------------------------------------ */
+int isg_build_seeds(const float* rois, const int32_t* n_seeds, int B, int Nmax,
+                    const float* ys, const float* xs, int H, int W, float ghost_k, float scale,
+                    uint32_t* seeds, float* ghost, isg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1+K3 — embedding + Gaussian membership + assignment.  Replaces group_kp's arithmetic core
+ * (utils/decode.py:303-328) and the per-instance ghost filter / pixel count (:337-356).
+ *   e = tanh(ae[0:2]) + grid ; s = exp(ae[2:4])           (per PIXEL)       (:305,315)
+ *   P[m,j] = exp(-((e_y-c_jy)^2*s_y + (e_x-c_jx)^2*s_x)) * inbox[m,j]       (:325-327, no FMA)
+ *   score, label = max_j P (first index on ties; all-zero row -> label 0)   (:328)
+ * ae: image b at ae + b*img_stride, plane c at + c*plane_stride (4 planes).  The input is NOT
+ * modified (the reference overwrites ae[0:2] in place, utils/decode.py:305; no caller reads it).
+ * flag[m] = 1 iff the pixel passes its instance's strict ghost filter (:351-353).
+ * stats (nullable): [B,Nmax,ISG_STAT_WORDS] int32, must be pre-initialised by isg_stats_init;
+ * receives count / bbox of the flagged pixels of each instance.
+ * ------------------------------------------------------------------------------------------ */
+int isg_stats_init(int32_t* stats, int B, int Nmax, isg_stream_t stream);
+/* sparse (reference-faithful): only the compacted keep pixels.  idx [B,cap,2], count [B] from
+ * isg_compact_points.  label [B,cap] int32, score [B,cap] fp32, flag [B,cap] uint8. */
+int isg_assign_sparse(const float* ae, int64_t img_stride, int64_t plane_stride,
+                      const int32_t* idx, const int32_t* count, int cap,
+                      const uint32_t* seeds, const float* ghost, const int32_t* n_seeds, int B, int Nmax,
+                      int H, int W, const float* ys, const float* xs,
+                      int32_t* label, float* score, uint8_t* flag, int32_t* stats, isg_stream_t stream);
+/* dense fused: every pixel.  Reads kp (+1-pixel halo) and the 4 ae planes once, applies the
+ * top-k threshold and the 3x3 peak test, assigns every pixel, writes label_map [B,H,W] int32,
+ * keepbits [B,H,ceil(W/32)], optional score_map [B,H,W] fp32 (nullable), and accumulates stats
+ * for the keep pixels.  label_map[keep] equals isg_assign_sparse's label (rows are independent). */
+int isg_assign_dense(const float* kp, int64_t kp_img_stride,
+                     const float* ae, int64_t ae_img_stride, int64_t ae_plane_stride,
+                     const uint32_t* thr_key,
+                     const uint32_t* seeds, const float* ghost, const int32_t* n_seeds, int B, int Nmax,
+                     int H, int W, const float* ys, const float* xs,
+                     int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats,
+                     isg_stream_t stream);
+/* dense mode: labels / scores / ghost flags of the compacted keep pixels read back from the maps.
+ * score_map nullable (then score is not written). */
+int isg_gather_labels(const int32_t* label_map, const float* score_map, const int32_t* idx,
+                      const int32_t* count, int cap, const float* ghost, int B, int Nmax, int H, int W,
+                      int32_t* label, float* score, uint8_t* flag, isg_stream_t stream);
+/* per-instance point sets (utils/decode.py:342-353): the flagged pixels of instance i, in row-major
+ * order, as fp32 (x,y) pairs (detransform_pixel's flip, utils/tranform.py:157-159).
+ * offsets: [B,Nmax+1] int32 exclusive prefix of the per-instance counts; points: [B,cap,2] fp32. */
+int isg_group_points(const int32_t* idx, const int32_t* label, const uint8_t* flag, const int32_t* count,
+                     int cap, const int32_t* n_seeds, int B, int Nmax,
+                     int32_t* offsets, float* points, isg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Box head front-end.  Replaces BBoxTransform (utils/utils.py:318-346), ClipBoxes (:349-363) and
+ * the score/threshold/class selection of decode_boxes (utils/decode.py:381-399).
+ * anchors: [A,4] (y1,x1,y2,x2); regression: [B,A,4] (dy,dx,dh,dw); classification: [B,A,C].
+ * Candidates (score > thr, fp32 compare) are appended in unspecified order; isg_box_nms orders
+ * them by (score desc, anchor index asc).  cand_*: [B,cap,...]; cand_anchor: [B,cap] int32;
+ * cand_count: [B] (true count, may exceed cap; only cap are stored).  cand_count must be zeroed.
+ * ------------------------------------------------------------------------------------------ */
+int isg_decode_boxes(const float* anchors, const float* regression, const float* classification,
+                     int B, int A, int C, int H, int W, float thr, int cap,
+                     float* cand_boxes, float* cand_scores, int32_t* cand_cls, int32_t* cand_anchor,
+                     int32_t* cand_count, isg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5 — greedy box NMS.  Replaces py_cpu_nms (utils/nms.py:11-39; ISG_NMS_PLUS1_LE) and
+ * torchvision.ops.batched_nms as called at utils/decode.py:400 (ISG_NMS_TV_GT).
+ * boxes [B,cap,4] (x1,y1,x2,y2), scores [B,cap], cls [B,cap] int32 (nullable = class agnostic),
+ * tiebreak [B,cap] int32 (nullable: candidate index is used; on equal scores the LARGER tiebreak
+ * value is visited first for PLUS1_LE and the SMALLER first for TV_GT), count [B] device int32
+ * (clamped to cap).  cap <= ISG_NMS_MAX_BOXES.
+ * keep [B,cap] int32: candidate indices in pick order; n_keep [B].
+ * ------------------------------------------------------------------------------------------ */
+size_t isg_box_nms_workspace_bytes(int B, int cap);
+int isg_box_nms(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
+                const int32_t* count, int B, int cap, double thr, int convention,
+                int32_t* keep, int32_t* n_keep, void* ws, size_t ws_bytes, isg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6 — bit-packed mask-IoU NMS.  IoU = (|A&B|+1)/(|A|B|+1) in fp64 (utils/image.py:188-191) inside
+ * the greedy loop of utils/nms.py:23-37 (survivor iff IoU <= thr), class aware (cls nullable).
+ * masks: [n,H,Wwords] uint32 (bit i of word w = pixel x = 32w+i; padding bits must be 0).
+ * bboxes (nullable): [n,4] int32 (x0,y0,x1,y1) inclusive pixel bounds that contain every set bit of
+ * the mask — used only to skip empty regions.
+ * ------------------------------------------------------------------------------------------ */
+size_t isg_mask_nms_workspace_bytes(int n);
+int isg_mask_nms(const uint32_t* masks, int n, int H, int Wwords, const int32_t* bboxes,
+                 const float* scores, const int32_t* cls, double thr,
+                 int32_t* keep, int32_t* n_keep, void* ws, size_t ws_bytes, isg_stream_t stream);
+/* pairwise mask statistics for n_pairs (a,b) index pairs: inter/union popcounts (int64 [n_pairs,2]).
+ * Backs compute_iou_for_mask / is_cover (utils/image.py:188-191,205-207). */
+int isg_mask_pair_counts(const uint32_t* masks, int n, int H, int Wwords, const int32_t* pairs, int n_pairs,
+                         int64_t* inter_union, isg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4 — seeded k-means with per-cluster allowed distance.  Replaces kmeans / pairwise_distance /
+ * pairwise_cosine (utils/kmeans.py:16-130).  BLOCKING: iterates until center_shift^2 < tol
+ * (utils/kmeans.py:90) or max_iter, synchronising `stream` to read the convergence flag.
+ * X [M,D] fp32, centers [N,D] fp32 in/out, allow [N] fp32, labels [M] int32 out (N = outlier),
+ * iters_host: host int* (nullable).  D <= 16.
+ * ------------------------------------------------------------------------------------------ */
+size_t isg_kmeans_workspace_bytes(int M, int N, int D);
+int isg_kmeans(const float* X, int M, int D, float* centers, const float* allow, int N,
+               float tol, int metric, int max_iter, int32_t* labels, int* iters_host,
+               void* ws, size_t ws_bytes, isg_stream_t stream);
+/* pairwise_distance (:96-109) / pairwise_cosine (:112-130): out [M,N] fp32 */
+int isg_pairwise(const float* X, int M, const float* Y, int N, int D, int metric, float* out,
+                 isg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISG_H_ */

@@ -1,0 +1,537 @@
+// K1 + K3 — embedding, Gaussian membership, assignment, per-instance statistics and grouping.
+// Reference: group_kp (utils/decode.py:303-356) and decode_single (utils/decode.py:428-432).
+//
+// Parity-critical arithmetic uses __f*_rn intrinsics so that nvcc never contracts it into FMAs:
+// torch evaluates  (e - c)^2 * sigma  and the 2-term sum with separate roundings (:326-327).
+#include "keep.cuh"
+
+namespace isg {
+
+struct __align__(16) SeedRec {   // ISG_SEED_WORDS = 8
+  int y0, y1, x0, x1;            // inclusive in-box pixel bounds (empty: y0 > y1)
+  float cy, cx;                  // grid coordinate of the truncated centre (utils/decode.py:317)
+  int id;                        // seed index (used by the per-tile compacted copy)
+  int pad;
+};
+static_assert(sizeof(SeedRec) == ISG_SEED_WORDS * 4, "seed record layout");
+
+__device__ __forceinline__ int clamp_to_int(float v) {
+  v = fminf(fmaxf(v, -1073741824.0f), 1073741824.0f);
+  return (int)v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// seeds: one thread per (image, box)
+// ---------------------------------------------------------------------------------------------
+__global__ void build_seeds_kernel(const float* __restrict__ rois, const int32_t* __restrict__ n_seeds,
+                                   int Nmax, const float* __restrict__ ys, const float* __restrict__ xs,
+                                   int H, int W, float ghost_k, float scale, SeedRec* __restrict__ seeds,
+                                   float4* __restrict__ ghost) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Nmax) return;
+  SeedRec s;
+  s.y0 = 1; s.y1 = 0; s.x0 = 1; s.x1 = 0; s.cy = 0.f; s.cx = 0.f; s.id = j; s.pad = 0;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j < n_seeds[b]) {
+    const float4 r = reinterpret_cast<const float4*>(rois)[(size_t)b * Nmax + j];  // x1,y1,x2,y2
+    // decode_single: lt = (y1,x1), rb = (y2,x2); centre = (lt+rb)/2; wh = rb-lt   (:428-432)
+    const float cy = __fmul_rn(__fadd_rn(r.y, r.w), 0.5f), cx = __fmul_rn(__fadd_rn(r.x, r.z), 0.5f);
+    const float hy = __fsub_rn(r.w, r.y), wx = __fsub_rn(r.z, r.x);
+    // group_kp: lt = c - wh/2, rb = c + wh/2 ; inbox = (p - lt >= 0) & (rb - p >= 0)   (:321-325)
+    const float lty = __fsub_rn(cy, __fmul_rn(hy, 0.5f)), ltx = __fsub_rn(cx, __fmul_rn(wx, 0.5f));
+    const float rby = __fadd_rn(cy, __fmul_rn(hy, 0.5f)), rbx = __fadd_rn(cx, __fmul_rn(wx, 0.5f));
+    // p is an integer-valued float, so  p - lt >= 0  <=>  p >= ceil(lt)  and  rb - p >= 0  <=>  p <= floor(rb)
+    const bool finite = (lty == lty) && (ltx == ltx) && (rby == rby) && (rbx == rbx);
+    if (finite) {
+      s.y0 = clamp_to_int(ceilf(lty)); s.y1 = clamp_to_int(floorf(rby));
+      s.x0 = clamp_to_int(ceilf(ltx)); s.x1 = clamp_to_int(floorf(rbx));
+    }
+    // seed coordinate = grid value at the truncated centre (:316-317); clamped into the image
+    int iy = clamp_to_int(cy), ix = clamp_to_int(cx);
+    iy = min(max(iy, 0), H - 1); ix = min(max(ix, 0), W - 1);
+    s.cy = ys[iy]; s.cx = xs[ix];
+    // ghost filter bounds (:339-352): x -/+ (0.5+wh_delta)*w, y -/+ (0.5+wh_delta)*h, fp32
+    const float w = __fmul_rn(wx, scale), h = __fmul_rn(hy, scale);
+    g.x = __fsub_rn(cx, __fmul_rn(ghost_k, w)); g.y = __fadd_rn(cx, __fmul_rn(ghost_k, w));
+    g.z = __fsub_rn(cy, __fmul_rn(ghost_k, h)); g.w = __fadd_rn(cy, __fmul_rn(ghost_k, h));
+  }
+  seeds[(size_t)b * Nmax + j] = s;
+  ghost[(size_t)b * Nmax + j] = g;
+}
+
+__global__ void stats_init_kernel(int32_t* stats, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t* s = stats + (size_t)i * ISG_STAT_WORDS;
+  s[0] = 0; s[1] = 0x7fffffff; s[2] = 0x7fffffff; s[3] = -1; s[4] = -1;
+}
+
+__device__ __forceinline__ bool ghost_pass(const float4 g, int y, int x) {
+  const float fx = (float)x, fy = (float)y;
+  return (g.x < fx) && (fx < g.y) && (g.z < fy) && (fy < g.w);   // strict (:351-352)
+}
+__device__ __forceinline__ void stats_add(int32_t* stats, int y, int x) {
+  atomicAdd(stats + 0, 1);
+  atomicMin(stats + 1, y); atomicMin(stats + 2, x);
+  atomicMax(stats + 3, y); atomicMax(stats + 4, x);
+}
+
+// membership of one pixel against one seed centre; returns P = exp(-q)
+__device__ __forceinline__ float membership(float ey, float ex, float sy, float sx, float cy, float cx) {
+  const float dy = __fsub_rn(ey, cy), dx = __fsub_rn(ex, cx);
+  const float qy = __fmul_rn(__fmul_rn(dy, dy), sy);
+  const float qx = __fmul_rn(__fmul_rn(dx, dx), sx);
+  return expf(-__fadd_rn(qy, qx));
+}
+
+// ---------------------------------------------------------------------------------------------
+// sparse: one thread per compacted keep pixel, all seeds of the image staged in shared memory
+// ---------------------------------------------------------------------------------------------
+constexpr int kSparseThreads = 256;
+
+__global__ void __launch_bounds__(kSparseThreads)
+assign_sparse_kernel(const float* __restrict__ ae, int64_t img_stride, int64_t plane_stride,
+                     const int32_t* __restrict__ idx, const int32_t* __restrict__ count, int cap,
+                     const SeedRec* __restrict__ seeds, const float4* __restrict__ ghost,
+                     const int32_t* __restrict__ n_seeds, int Nmax, int W,
+                     const float* __restrict__ ys, const float* __restrict__ xs,
+                     int32_t* __restrict__ label, float* __restrict__ score, uint8_t* __restrict__ flag,
+                     int32_t* __restrict__ stats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SeedRec* s_seed = reinterpret_cast<SeedRec*>(smem_raw);
+  __shared__ __align__(8) uint64_t bar;
+  const int b = blockIdx.y;
+  const int M = min(count[b], cap);
+  if ((int)(blockIdx.x * kSparseThreads) >= M) return;
+  const int n = min(n_seeds[b], Nmax);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  if (n > 0) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar, (uint32_t)(n * sizeof(SeedRec)));
+      bulk_g2s(s_seed, seeds + (size_t)b * Nmax, (uint32_t)(n * sizeof(SeedRec)), &bar);
+    }
+  }
+  const int m = blockIdx.x * kSparseThreads + threadIdx.x;
+  int y = 0, x = 0;
+  float ey = 0.f, ex = 0.f, sy = 0.f, sx = 0.f;
+  if (m < M) {
+    y = idx[((size_t)b * cap + m) * 2];
+    x = idx[((size_t)b * cap + m) * 2 + 1];
+    const float* p = ae + (int64_t)b * img_stride + (int64_t)y * W + x;
+    const float a0 = __ldg(p), a1 = __ldg(p + plane_stride), a2 = __ldg(p + 2 * plane_stride),
+                a3 = __ldg(p + 3 * plane_stride);
+    ey = __fadd_rn(tanhf(a0), ys[y]); ex = __fadd_rn(tanhf(a1), xs[x]);   // :305
+    sy = expf(a2); sx = expf(a3);                                         // :315
+  }
+  if (n > 0) mbar_wait(&bar, 0);
+  if (m >= M) return;
+  float best = 0.0f;
+  int lab = 0;
+  for (int j = 0; j < n; ++j) {
+    const SeedRec s = s_seed[j];
+    if (y >= s.y0 && y <= s.y1 && x >= s.x0 && x <= s.x1) {
+      const float P = membership(ey, ex, sy, sx, s.cy, s.cx);
+      if (P > best) { best = P; lab = j; }   // strict: first index wins ties (:328)
+    }
+  }
+  const size_t o = (size_t)b * cap + m;
+  label[o] = lab;
+  if (score) score[o] = best;
+  bool f = false;
+  if (n > 0) {
+    f = ghost_pass(ghost[(size_t)b * Nmax + lab], y, x);
+    if (f && stats) stats_add(stats + ((size_t)b * Nmax + lab) * ISG_STAT_WORDS, y, x);
+  }
+  if (flag) flag[o] = f ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense fused kernel: tile = 128 px x (8 warps * RW rows); lane owns 4 consecutive pixels of a row
+// ---------------------------------------------------------------------------------------------
+constexpr int kDenseWarps = 8;
+
+template <int RW, bool VEC, bool SCORE>
+__global__ void __launch_bounds__(32 * kDenseWarps)
+assign_dense_kernel(const float* __restrict__ kp, int64_t kp_img_stride,
+                    const float* __restrict__ ae, int64_t ae_img_stride, int64_t ae_plane_stride,
+                    const uint32_t* __restrict__ thr_key,
+                    const SeedRec* __restrict__ seeds, const float4* __restrict__ ghost,
+                    const int32_t* __restrict__ n_seeds, int Nmax, int H, int W, int Wwords,
+                    const float* __restrict__ ys, const float* __restrict__ xs,
+                    int32_t* __restrict__ label_map, float* __restrict__ score_map,
+                    uint32_t* __restrict__ keepbits, int32_t* __restrict__ stats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SeedRec* s_all = reinterpret_cast<SeedRec*>(smem_raw);   // [Nmax] whole table (bulk copy target)
+  SeedRec* s_hit = s_all + Nmax;                           // [Nmax] seeds intersecting this tile
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_wcnt[kDenseWarps];
+
+  const int b = blockIdx.z;
+  const int lane = threadIdx.x, warp = threadIdx.y, tid = warp * 32 + lane;
+  const int n = min(n_seeds[b], Nmax);
+  const int tile_x0 = blockIdx.x * 128, tile_y0 = blockIdx.y * (kDenseWarps * RW);
+  const int tile_x1 = min(tile_x0 + 127, W - 1), tile_y1 = min(tile_y0 + kDenseWarps * RW - 1, H - 1);
+
+  // (1) seed table -> shared memory through the TMA unit (1-D bulk copy), asynchronously
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  if (tid == 0 && n > 0) {
+    mbar_expect_tx(&bar, (uint32_t)(n * sizeof(SeedRec)));
+    bulk_g2s(s_all, seeds + (size_t)b * Nmax, (uint32_t)(n * sizeof(SeedRec)), &bar);
+  }
+
+  // (2) issue every pixel load of this thread (ae: 4 planes x RW rows; streamed, read once)
+  const int x0 = tile_x0 + lane * 4;
+  const int ybeg = tile_y0 + warp * RW;
+  const float* aeb = ae + (int64_t)b * ae_img_stride;
+  float a[RW][4][4];   // [row][plane][px]
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const int y = ybeg + r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float* p = aeb + c * ae_plane_stride + (int64_t)y * W + x0;
+      if (VEC && y < H && x0 + 3 < W) {
+        const float4 v = ldg_stream4(p);
+        a[r][c][0] = v.x; a[r][c][1] = v.y; a[r][c][2] = v.z; a[r][c][3] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[r][c][i] = (y < H && x0 + i < W) ? ldg_stream1(p + i) : 0.0f;
+      }
+    }
+  }
+
+  // (3) keep bits from kp (threshold + 3x3 peak); hides the ae latency
+  const int thr = skey_from_ukey(thr_key[b]);
+  const float* kpb = kp + (int64_t)b * kp_img_stride;
+  uint32_t nib[RW];
+  {
+    float raw_up[4], raw_mid[4], raw_dn[4];
+    Row6 up = load_vrow<VEC>(kpb, ybeg - 1, x0, H, W, thr, lane, raw_up);
+    Row6 mid = load_vrow<VEC>(kpb, ybeg, x0, H, W, thr, lane, raw_mid);
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      Row6 dn = load_vrow<VEC>(kpb, ybeg + r + 1, x0, H, W, thr, lane, raw_dn);
+      nib[r] = (ybeg + r < H) ? keep_nibble(up, mid, dn, raw_mid, x0, W, thr) : 0u;
+      const uint32_t word = nibbles_to_word(nib[r], lane);
+      if ((lane & 7) == 0 && x0 < W && ybeg + r < H)
+        keepbits[((size_t)b * H + ybeg + r) * Wwords + (x0 >> 5)] = word;
+      up = mid; mid = dn;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) raw_mid[i] = raw_dn[i];
+    }
+  }
+
+  // (4) cull the seed table against this tile, preserving seed order (first-index rule)
+  int T = 0;
+  if (n > 0) {
+    mbar_wait(&bar, 0);
+    for (int j0 = 0; j0 < n; j0 += 32 * kDenseWarps) {
+      const int j = j0 + tid;
+      bool hit = false;
+      SeedRec s;
+      if (j < n) {
+        s = s_all[j];
+        hit = s.y0 <= tile_y1 && s.y1 >= tile_y0 && s.x0 <= tile_x1 && s.x1 >= tile_x0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) s_wcnt[warp] = __popc(bal);
+      __syncthreads();
+      int pre = T, tot = 0;
+#pragma unroll
+      for (int w = 0; w < kDenseWarps; ++w) {
+        const int c = s_wcnt[w];
+        if (w < warp) pre += c;
+        tot += c;
+      }
+      if (hit) { s.id = j; s_hit[pre + __popc(bal & ((1u << lane) - 1u))] = s; }
+      T += tot;
+      __syncthreads();
+    }
+  }
+
+  // (5) embedding (per pixel) : e = tanh(ae01) + grid, s = exp(ae23)      (:305,315)
+  float xs4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xs4[i] = (x0 + i < W) ? __ldg(xs + x0 + i) : 0.0f;
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const float yv = (ybeg + r < H) ? __ldg(ys + ybeg + r) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[r][0][i] = __fadd_rn(tanhf(a[r][0][i]), yv);
+      a[r][1][i] = __fadd_rn(tanhf(a[r][1][i]), xs4[i]);
+      a[r][2][i] = expf(a[r][2][i]);
+      a[r][3][i] = expf(a[r][3][i]);
+    }
+  }
+
+  // (6) membership against the culled seeds, ascending seed index
+  float best[RW][4];
+  int lab[RW][4];
+#pragma unroll
+  for (int r = 0; r < RW; ++r)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { best[r][i] = 0.0f; lab[r][i] = 0; }
+
+  for (int t = 0; t < T; ++t) {
+    const int4 bx = *reinterpret_cast<const int4*>(&s_hit[t]);          // y0,y1,x0,x1 (broadcast)
+    if (bx.x > ybeg + RW - 1 || bx.y < ybeg) continue;                   // warp-uniform row cull
+    if (bx.z > x0 + 3 || bx.w < x0) continue;                            // lane column cull
+    const float4 cc = *reinterpret_cast<const float4*>(&s_hit[t].cy);   // cy,cx,id,pad
+    const int id = __float_as_int(cc.z);
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      const int y = ybeg + r;
+      if (y < bx.x || y > bx.y) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = x0 + i;
+        if (x >= bx.z && x <= bx.w) {
+          const float P = membership(a[r][0][i], a[r][1][i], a[r][2][i], a[r][3][i], cc.x, cc.y);
+          if (P > best[r][i]) { best[r][i] = P; lab[r][i] = id; }
+        }
+      }
+    }
+  }
+
+  // (7) stores + statistics of the keep pixels
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const int y = ybeg + r;
+    if (y >= H) break;
+    int32_t* lrow = label_map + ((size_t)b * H + y) * W + x0;
+    if (VEC && x0 + 3 < W) {
+      stg_stream4(lrow, lab[r][0], lab[r][1], lab[r][2], lab[r][3]);
+      if (SCORE) stg_stream4f(score_map + ((size_t)b * H + y) * W + x0, best[r][0], best[r][1], best[r][2], best[r][3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (x0 + i < W) {
+          lrow[i] = lab[r][i];
+          if (SCORE) score_map[((size_t)b * H + y) * W + x0 + i] = best[r][i];
+        }
+    }
+    if (nib[r] && stats && n > 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if ((nib[r] >> i) & 1u) {
+          const int l = lab[r][i];
+          if (ghost_pass(ghost[(size_t)b * Nmax + l], y, x0 + i))
+            stats_add(stats + ((size_t)b * Nmax + l) * ISG_STAT_WORDS, y, x0 + i);
+        }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense mode: read labels / scores of the compacted keep pixels back from the maps
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_labels_kernel(const int32_t* __restrict__ label_map, const float* __restrict__ score_map,
+                                     const int32_t* __restrict__ idx, const int32_t* __restrict__ count, int cap,
+                                     const float4* __restrict__ ghost, int Nmax, int H, int W,
+                                     int32_t* __restrict__ label, float* __restrict__ score,
+                                     uint8_t* __restrict__ flag) {
+  const int b = blockIdx.y;
+  const int M = min(count[b], cap);
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const size_t o = (size_t)b * cap + m;
+  const int y = idx[o * 2], x = idx[o * 2 + 1];
+  const size_t p = ((size_t)b * H + y) * W + x;
+  const int l = label_map[p];
+  label[o] = l;
+  if (score && score_map) score[o] = score_map[p];
+  if (flag) flag[o] = (Nmax > 0 && l >= 0 && l < Nmax && ghost_pass(ghost[(size_t)b * Nmax + l], y, x)) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grouping: one warp per instance scans the image's label list and compacts its flagged pixels in
+// row-major order (deterministic, no atomics).
+// ---------------------------------------------------------------------------------------------
+constexpr int kGroupWarps = 8;
+
+__global__ void __launch_bounds__(32 * kGroupWarps)
+group_count_kernel(const int32_t* __restrict__ label, const uint8_t* __restrict__ flag,
+                   const int32_t* __restrict__ count, int cap, const int32_t* __restrict__ n_seeds, int Nmax,
+                   int32_t* __restrict__ offsets) {
+  // offsets[b][i+1] = number of flagged pixels of instance i (scanned in place by group_scan_kernel)
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * kGroupWarps + threadIdx.y;
+  if (i >= Nmax) return;
+  const int lane = threadIdx.x;
+  const int M = min(count[b], cap);
+  int c = 0;
+  if (i < n_seeds[b]) {
+    const int32_t* lb = label + (size_t)b * cap;
+    const uint8_t* fb = flag + (size_t)b * cap;
+    for (int m = lane; m < M; m += 32) c += (lb[m] == i && fb[m]) ? 1 : 0;
+    c = warp_sum(c);
+  }
+  if (lane == 0) offsets[(size_t)b * (Nmax + 1) + i + 1] = c;
+}
+
+__global__ void group_scan_kernel(int32_t* __restrict__ offsets, int Nmax) {
+  // one warp per image: in-place exclusive scan of offsets[b][1..Nmax]
+  const int b = blockIdx.x, lane = threadIdx.x;
+  int32_t* o = offsets + (size_t)b * (Nmax + 1);
+  int carry = 0;
+  if (lane == 0) o[0] = 0;
+  for (int base = 0; base < Nmax; base += 32) {
+    const int i = base + lane;
+    const int v = i < Nmax ? o[i + 1] : 0;
+    int s = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, s, d);
+      if (lane >= d) s += u;
+    }
+    if (i < Nmax) o[i + 1] = carry + s;
+    carry += __shfl_sync(0xffffffffu, s, 31);
+  }
+}
+
+__global__ void __launch_bounds__(32 * kGroupWarps)
+group_scatter_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ label,
+                     const uint8_t* __restrict__ flag, const int32_t* __restrict__ count, int cap,
+                     const int32_t* __restrict__ n_seeds, int Nmax, const int32_t* __restrict__ offsets,
+                     float* __restrict__ points) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * kGroupWarps + threadIdx.y;
+  if (i >= Nmax || i >= n_seeds[b]) return;
+  const int lane = threadIdx.x;
+  const int M = min(count[b], cap);
+  const int32_t* lb = label + (size_t)b * cap;
+  const uint8_t* fb = flag + (size_t)b * cap;
+  const int32_t* ib = idx + (size_t)b * cap * 2;
+  float2* out = reinterpret_cast<float2*>(points) + (size_t)b * cap;
+  int off = offsets[(size_t)b * (Nmax + 1) + i];
+  for (int m0 = 0; m0 < M; m0 += 32) {
+    const int m = m0 + lane;
+    const bool hit = m < M && lb[m] == i && fb[m];
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int y = ib[2 * m], x = ib[2 * m + 1];
+      out[off + __popc(bal & ((1u << lane) - 1u))] = make_float2((float)x, (float)y);   // (x,y) flip
+    }
+    off += __popc(bal);
+  }
+}
+
+}  // namespace isg
+
+using namespace isg;
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" int isg_build_seeds(const float* rois, const int32_t* n_seeds, int B, int Nmax, const float* ys,
+                               const float* xs, int H, int W, float ghost_k, float scale, uint32_t* seeds,
+                               float* ghost, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!rois || !n_seeds || !ys || !xs || !seeds || !ghost || B <= 0 || Nmax <= 0 || H <= 0 || W <= 0) return ISG_EINVAL;
+  if (!aligned16(rois) || !aligned16(seeds) || !aligned16(ghost) || B > 65535) return ISG_EINVAL;
+  dim3 grid(cdiv(Nmax, 128), B);
+  build_seeds_kernel<<<grid, 128, 0, stream>>>(rois, n_seeds, Nmax, ys, xs, H, W, ghost_k, scale,
+                                               reinterpret_cast<SeedRec*>(seeds), reinterpret_cast<float4*>(ghost));
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" int isg_stats_init(int32_t* stats, int B, int Nmax, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!stats || B <= 0 || Nmax <= 0) return ISG_EINVAL;
+  const int n = B * Nmax;
+  stats_init_kernel<<<cdiv(n, 256), 256, 0, stream>>>(stats, n);
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" int isg_assign_sparse(const float* ae, int64_t img_stride, int64_t plane_stride, const int32_t* idx,
+                                 const int32_t* count, int cap, const uint32_t* seeds, const float* ghost,
+                                 const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys,
+                                 const float* xs, int32_t* label, float* score, uint8_t* flag, int32_t* stats,
+                                 isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!ae || !idx || !count || !seeds || !ghost || !n_seeds || !ys || !xs || !label) return ISG_EINVAL;
+  if (B <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || cap <= 0 || B > 65535) return ISG_EINVAL;
+  if (!aligned16(seeds) || !aligned16(ghost)) return ISG_EINVAL;
+  const size_t smem = (size_t)Nmax * sizeof(SeedRec);
+  if (smem > 200 * 1024) return ISG_EUNSUPPORTED;
+  ISG_CUDA(cudaFuncSetAttribute(assign_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(cap, kSparseThreads), B);
+  assign_sparse_kernel<<<grid, kSparseThreads, smem, stream>>>(
+      ae, img_stride, plane_stride, idx, count, cap, reinterpret_cast<const SeedRec*>(seeds),
+      reinterpret_cast<const float4*>(ghost), n_seeds, Nmax, W, ys, xs, label, score, flag, stats);
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+template <int RW>
+static int launch_dense(const float* kp, int64_t kp_img_stride, const float* ae, int64_t ae_img_stride,
+                        int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds, const float* ghost,
+                        const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys, const float* xs,
+                        int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats, bool vec,
+                        cudaStream_t stream) {
+  const size_t smem = (size_t)Nmax * sizeof(SeedRec) * 2;
+  dim3 block(32, kDenseWarps), grid(cdiv(W, 128), cdiv(H, kDenseWarps * RW), B);
+  const int Wwords = cdiv(W, 32);
+#define ISG_DENSE_LAUNCH(VEC_, SCORE_)                                                                          \
+  do {                                                                                                          \
+    ISG_CUDA(cudaFuncSetAttribute(assign_dense_kernel<RW, VEC_, SCORE_>,                                        \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+    assign_dense_kernel<RW, VEC_, SCORE_><<<grid, block, smem, stream>>>(                                       \
+        kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, reinterpret_cast<const SeedRec*>(seeds), \
+        reinterpret_cast<const float4*>(ghost), n_seeds, Nmax, H, W, Wwords, ys, xs, label_map, score_map,      \
+        keepbits, stats);                                                                                       \
+  } while (0)
+  if (vec) { if (score_map) ISG_DENSE_LAUNCH(true, true); else ISG_DENSE_LAUNCH(true, false); }
+  else     { if (score_map) ISG_DENSE_LAUNCH(false, true); else ISG_DENSE_LAUNCH(false, false); }
+#undef ISG_DENSE_LAUNCH
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" int isg_assign_dense(const float* kp, int64_t kp_img_stride, const float* ae, int64_t ae_img_stride,
+                                int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds,
+                                const float* ghost, const int32_t* n_seeds, int B, int Nmax, int H, int W,
+                                const float* ys, const float* xs, int32_t* label_map, float* score_map,
+                                uint32_t* keepbits, int32_t* stats, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!kp || !ae || !thr_key || !seeds || !ghost || !n_seeds || !ys || !xs || !label_map || !keepbits) return ISG_EINVAL;
+  if (B <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
+  if (kp_img_stride < (int64_t)H * W || ae_plane_stride < (int64_t)H * W) return ISG_EINVAL;
+  if (!aligned16(seeds) || !aligned16(ghost)) return ISG_EINVAL;
+  if ((size_t)Nmax * sizeof(SeedRec) * 2 > 200 * 1024) return ISG_EUNSUPPORTED;
+  const bool vec = (W % 4 == 0) && (kp_img_stride % 4 == 0) && (ae_img_stride % 4 == 0) && (ae_plane_stride % 4 == 0) &&
+                   aligned16(kp) && aligned16(ae) && aligned16(label_map) && (!score_map || aligned16(score_map));
+  return launch_dense<4>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
+                         Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, vec, stream);
+}
+
+extern "C" int isg_gather_labels(const int32_t* label_map, const float* score_map, const int32_t* idx,
+                                 const int32_t* count, int cap, const float* ghost, int B, int Nmax, int H, int W,
+                                 int32_t* label, float* score, uint8_t* flag, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!label_map || !idx || !count || !ghost || !label || B <= 0 || cap <= 0 || H <= 0 || W <= 0 || Nmax <= 0) return ISG_EINVAL;
+  dim3 grid(cdiv(cap, 256), B);
+  gather_labels_kernel<<<grid, 256, 0, stream>>>(label_map, score_map, idx, count, cap,
+                                                 reinterpret_cast<const float4*>(ghost), Nmax, H, W, label, score, flag);
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" int isg_group_points(const int32_t* idx, const int32_t* label, const uint8_t* flag, const int32_t* count,
+                                int cap, const int32_t* n_seeds, int B, int Nmax, int32_t* offsets, float* points,
+                                isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!idx || !label || !flag || !count || !n_seeds || !offsets || !points) return ISG_EINVAL;
+  if (B <= 0 || Nmax <= 0 || cap <= 0 || B > 65535) return ISG_EINVAL;
+  dim3 block(32, kGroupWarps), grid(cdiv(Nmax, kGroupWarps), B);
+  group_count_kernel<<<grid, block, 0, stream>>>(label, flag, count, cap, n_seeds, Nmax, offsets);
+  group_scan_kernel<<<B, 32, 0, stream>>>(offsets, Nmax);
+  group_scatter_kernel<<<grid, block, 0, stream>>>(idx, label, flag, count, cap, n_seeds, Nmax, offsets, points);
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}

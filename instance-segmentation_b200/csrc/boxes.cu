@@ -1,0 +1,480 @@
+// Box head front-end, K5 greedy box NMS (bitmask matrix + chunked suppression scan) and K6
+// bit-packed mask-IoU NMS.
+// Reference: decode_boxes (utils/decode.py:377-419), BBoxTransform / ClipBoxes
+// (utils/utils.py:318-363), py_cpu_nms (utils/nms.py:11-39), torchvision batched_nms semantics at
+// utils/decode.py:400, mask IoU formula (utils/image.py:188-191).
+#include <algorithm>
+#include "common.cuh"
+
+namespace isg {
+
+// ---------------------------------------------------------------------------------------------
+// front-end: score = max_c cls, class = argmax_c (first index), threshold, box transform, clip
+// ---------------------------------------------------------------------------------------------
+constexpr int kFrontThreads = 256;
+
+__global__ void __launch_bounds__(kFrontThreads)
+decode_boxes_kernel(const float* __restrict__ anchors, const float* __restrict__ regression,
+                    const float* __restrict__ classification, int A, int C, float xmax_clip, float ymax_clip,
+                    float thr, int cap, float4* __restrict__ cand_boxes, float* __restrict__ cand_scores,
+                    int32_t* __restrict__ cand_cls, int32_t* __restrict__ cand_anchor,
+                    int32_t* __restrict__ cand_count, bool vec) {
+  const int b = blockIdx.y;
+  const int a = blockIdx.x * kFrontThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  float best = -INFINITY;
+  int cls = 0;
+  if (a < A) {
+    const float* p = classification + ((size_t)b * A + a) * C;
+    if (vec) {
+      for (int c = 0; c < C; c += 4) {
+        const float4 v = ldg_stream4(p + c);
+        if (v.x > best) { best = v.x; cls = c; }
+        if (v.y > best) { best = v.y; cls = c + 1; }
+        if (v.z > best) { best = v.z; cls = c + 2; }
+        if (v.w > best) { best = v.w; cls = c + 3; }
+      }
+    } else {
+      for (int c = 0; c < C; ++c) {
+        const float v = ldg_stream1(p + c);
+        if (v > best) { best = v; cls = c; }
+      }
+    }
+  }
+  const bool hit = (a < A) && (best > thr);                  // scores > threshold (utils/decode.py:384)
+  const unsigned bal = __ballot_sync(0xffffffffu, hit);
+  if (bal == 0) return;
+  int base = 0;
+  if (lane == __ffs(bal) - 1) base = atomicAdd(cand_count + b, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+  if (!hit) return;
+  const int pos = base + __popc(bal & ((1u << lane) - 1u));
+  if (pos >= cap) return;
+  // BBoxTransform (utils/utils.py:331-346); anchors (y1,x1,y2,x2), regression (dy,dx,dh,dw)
+  const float4 an = __ldg(reinterpret_cast<const float4*>(anchors) + a);
+  const float4 rg = __ldg(reinterpret_cast<const float4*>(regression) + (size_t)b * A + a);
+  const float yca = __fmul_rn(__fadd_rn(an.x, an.z), 0.5f), xca = __fmul_rn(__fadd_rn(an.y, an.w), 0.5f);
+  const float ha = __fsub_rn(an.z, an.x), wa = __fsub_rn(an.w, an.y);
+  const float w = __fmul_rn(expf(rg.w), wa), h = __fmul_rn(expf(rg.z), ha);
+  const float yc = __fadd_rn(__fmul_rn(rg.x, ha), yca), xc = __fadd_rn(__fmul_rn(rg.y, wa), xca);
+  float ymin = __fsub_rn(yc, __fmul_rn(h, 0.5f)), xmin = __fsub_rn(xc, __fmul_rn(w, 0.5f));
+  float ymax = __fadd_rn(yc, __fmul_rn(h, 0.5f)), xmax = __fadd_rn(xc, __fmul_rn(w, 0.5f));
+  // ClipBoxes (utils/utils.py:357-361)
+  xmin = fmaxf(xmin, 0.0f); ymin = fmaxf(ymin, 0.0f);
+  xmax = fminf(xmax, xmax_clip); ymax = fminf(ymax, ymax_clip);
+  const size_t o = (size_t)b * cap + pos;
+  cand_boxes[o] = make_float4(xmin, ymin, xmax, ymax);
+  cand_scores[o] = best;
+  cand_cls[o] = cls;
+  cand_anchor[o] = a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NMS step 1: order candidates by (score desc, tiebreak) — single-CTA bitonic sort in shared memory
+// ---------------------------------------------------------------------------------------------
+constexpr int kSortThreads = 1024;
+
+struct NmsWs {           // per-image views into the workspace
+  int32_t* order;        // [cap]   candidate index of rank r
+  float4* sbox;          // [cap]   boxes in rank order
+  int32_t* scls;         // [cap]
+  unsigned long long* mask;  // [cap][nw]
+};
+
+__host__ __device__ inline size_t nms_ws_per_image(int cap) {
+  const size_t nw = (size_t)(cap + 63) / 64;
+  size_t s = 0;
+  s += ((size_t)cap * 4 + 15) & ~(size_t)15;   // order
+  s += (size_t)cap * 16;                       // sbox
+  s += ((size_t)cap * 4 + 15) & ~(size_t)15;   // scls
+  s += (size_t)cap * nw * 8;                   // mask
+  return (s + 255) & ~(size_t)255;
+}
+__host__ __device__ inline NmsWs nms_ws_view(void* ws, int b, int cap) {
+  char* p = (char*)ws + (size_t)b * nms_ws_per_image(cap);
+  NmsWs v;
+  v.order = (int32_t*)p; p += ((size_t)cap * 4 + 15) & ~(size_t)15;
+  v.sbox = (float4*)p;   p += (size_t)cap * 16;
+  v.scls = (int32_t*)p;  p += ((size_t)cap * 4 + 15) & ~(size_t)15;
+  v.mask = (unsigned long long*)p;
+  return v;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+nms_sort_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int32_t* __restrict__ cls,
+                const int32_t* __restrict__ tiebreak, const int32_t* __restrict__ count, int cap, int P,
+                int convention, void* ws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);   // [P]
+  uint32_t* val = reinterpret_cast<uint32_t*>(key + P);                        // [P]
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int n = min(max(count[b], 0), cap);
+  int Pn = 1;
+  while (Pn < n) Pn <<= 1;   // <= P
+  for (int i = t; i < Pn; i += kSortThreads) {
+    unsigned long long k = 0ull;
+    if (i < n) {
+      const size_t o = (size_t)b * cap + i;
+      const uint32_t tb = tiebreak ? (uint32_t)tiebreak[o] : (uint32_t)i;
+      // descending sort on the 64-bit key: PLUS1_LE visits the larger tiebreak first (argsort()[::-1]
+      // of utils/nms.py:20 on small inputs), TV_GT the smaller (stable descending sort)
+      const uint32_t low = (convention == ISG_NMS_PLUS1_LE) ? tb : (0xffffffffu - tb);
+      k = ((unsigned long long)float_key(scores[o]) << 32) | low;
+    }
+    key[i] = k; val[i] = (uint32_t)i;
+  }
+  __syncthreads();
+  for (int size = 2; size <= Pn; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = t; i < (Pn >> 1); i += kSortThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);   // first half of each bitonic block descending
+        const unsigned long long a = key[lo], c = key[hi];
+        if ((a < c) == desc) {
+          key[lo] = c; key[hi] = a;
+          const uint32_t va = val[lo]; val[lo] = val[hi]; val[hi] = va;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  NmsWs v = nms_ws_view(ws, b, cap);
+  for (int r = t; r < n; r += kSortThreads) {
+    const int i = (int)val[r];
+    const size_t o = (size_t)b * cap + i;
+    v.order[r] = i;
+    v.sbox[r] = boxes[o];
+    v.scls[r] = cls ? cls[o] : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NMS step 2: suppression bitmask, 64 x 64 boxes per CTA, upper triangle only
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool suppresses_tv(const float4 a, const float4 c, double thr) {
+  // torchvision nms_kernel_impl: no +1, suppress iff ovr > thr (ovr fp32 promoted to double)
+  const float areaa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float areac = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
+  const float xx1 = fmaxf(a.x, c.x), yy1 = fmaxf(a.y, c.y), xx2 = fminf(a.z, c.z), yy2 = fminf(a.w, c.w);
+  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(areaa, areac), inter));
+  return (double)ovr > thr;
+}
+__device__ __forceinline__ bool suppresses_plus1(const float4 a, const float4 c, float thr) {
+  // utils/nms.py:19,26-36: +1 convention, survivor iff ovr <= thr (NaN is suppressed)
+  const float areaa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
+  const float areac = __fmul_rn(__fadd_rn(__fsub_rn(c.z, c.x), 1.0f), __fadd_rn(__fsub_rn(c.w, c.y), 1.0f));
+  const float xx1 = fmaxf(a.x, c.x), yy1 = fmaxf(a.y, c.y), xx2 = fminf(a.z, c.z), yy2 = fminf(a.w, c.w);
+  const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+  const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(areaa, areac), inter));
+  return !(ovr <= thr);
+}
+
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const int32_t* __restrict__ count, int cap, double thr, int convention, void* ws) {
+  const int rb = blockIdx.y, cb = blockIdx.x, b = blockIdx.z;
+  if (cb < rb) return;
+  const int n = min(max(count[b], 0), cap);
+  if (rb * 64 >= n || cb * 64 >= n) return;
+  const NmsWs v = nms_ws_view(ws, b, cap);
+  const int nw = (cap + 63) / 64;
+  __shared__ float4 cbox[64];
+  __shared__ int ccls[64];
+  const int t = threadIdx.x;
+  const int j = cb * 64 + t;
+  if (j < n) { cbox[t] = v.sbox[j]; ccls[t] = v.scls[j]; }
+  __syncthreads();
+  const int i = rb * 64 + t;
+  if (i >= n) return;
+  const float4 a = v.sbox[i];
+  const int ac = v.scls[i];
+  const int ncol = min(64, n - cb * 64);
+  unsigned long long bits = 0ull;
+  const float thr_f = (float)thr;
+  for (int c = (rb == cb ? t + 1 : 0); c < ncol; ++c) {
+    if (ccls[c] != ac) continue;   // class aware (batched_nms); class-agnostic callers pass cls = NULL -> all 0
+    const bool s = (convention == ISG_NMS_TV_GT) ? suppresses_tv(a, cbox[c], thr) : suppresses_plus1(a, cbox[c], thr_f);
+    if (s) bits |= 1ull << c;
+  }
+  v.mask[(size_t)i * nw + cb] = bits;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NMS step 3: greedy scan.  One CTA per image; 64-box chunks are resolved in order.  The
+// within-chunk dependency (64 sequential steps on one 64-bit word) runs in one thread on shared
+// memory; the cross-chunk propagation (OR of the kept rows into later words) is parallel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;   // >= nw for cap <= 16384
+
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_kernel(const int32_t* __restrict__ count, int cap, void* ws, int32_t* __restrict__ keep,
+                int32_t* __restrict__ n_keep) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int n = min(max(count[b], 0), cap);
+  const NmsWs v = nms_ws_view(ws, b, cap);
+  const int nw = (cap + 63) / 64;
+  const int nchunk = (n + 63) / 64;
+  __shared__ unsigned long long remv[kScanThreads];
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_kept;
+  remv[t] = 0ull;
+  int nk = 0;
+  int32_t* out = keep + (size_t)b * cap;
+  __syncthreads();
+  for (int c = 0; c < nchunk; ++c) {
+    const int base = c * 64;
+    const int m = min(64, n - base);
+    if (t < m) diag[t] = v.mask[(size_t)(base + t) * nw + c];
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long word = remv[c], kept = 0ull;
+      for (int q = 0; q < m; ++q) {
+        if (!((word >> q) & 1ull)) { kept |= 1ull << q; word |= diag[q]; }
+      }
+      s_kept = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = s_kept;
+    if (t < m && ((kept >> t) & 1ull))
+      out[nk + __popcll(kept & ((1ull << t) - 1ull))] = v.order[base + t];
+    nk += __popcll(kept);
+    // propagate the kept rows of this chunk to the later words
+    const int w = t;
+    if (w > c && w < nchunk) {
+      unsigned long long acc = 0ull, kk = kept;
+      while (kk) {
+        const int q = __ffsll((long long)kk) - 1;
+        kk &= kk - 1;
+        acc |= v.mask[(size_t)(base + q) * nw + w];
+      }
+      remv[w] |= acc;
+    }
+    __syncthreads();
+  }
+  if (t == 0) n_keep[b] = nk;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6 mask NMS
+// ---------------------------------------------------------------------------------------------
+struct MaskWs {
+  int32_t* order;            // [n]
+  int32_t* area;             // [n]
+  int4* bbox;                // [n] x0,y0,x1,y1 inclusive (tight), empty mask: x0 > x1
+  int32_t* scls;             // [n] (rank order)
+  int32_t* cnt;              // [1] = n (device copy for the shared scan kernel)
+  unsigned long long* mask;  // [n][nw]
+};
+// The sort/scan kernels are shared with box NMS, so the layout must start like NmsWs(cap = n).
+__host__ __device__ inline size_t mask_extra_bytes(int n) {
+  return (((size_t)n * 4 + 15) & ~(size_t)15) + (size_t)n * 16 + 256;
+}
+
+__global__ void __launch_bounds__(256)
+mask_area_kernel(const uint32_t* __restrict__ masks, int H, int Wwords, const int4* __restrict__ given,
+                 int32_t* __restrict__ area, int4* __restrict__ bbox) {
+  const int i = blockIdx.x, t = threadIdx.x;
+  const uint32_t* m = masks + (size_t)i * H * Wwords;
+  int y0 = 0, y1 = H - 1, w0 = 0, w1 = Wwords - 1;
+  if (given) {
+    const int4 g = given[i];
+    y0 = max(g.y, 0); y1 = min(g.w, H - 1); w0 = max(g.x >> 5, 0); w1 = min(g.z >> 5, Wwords - 1);
+  }
+  const int nwords = max(w1 - w0 + 1, 0), nrows = max(y1 - y0 + 1, 0);
+  int a = 0, bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -1, by1 = -1;
+  for (int e = t; e < nwords * nrows; e += 256) {
+    const int r = e / nwords, w = e - r * nwords;
+    const uint32_t v = __ldg(m + (size_t)(y0 + r) * Wwords + w0 + w);
+    if (v) {
+      a += __popc(v);
+      const int y = y0 + r, xb = (w0 + w) * 32;
+      by0 = min(by0, y); by1 = max(by1, y);
+      bx0 = min(bx0, xb + __ffs(v) - 1); bx1 = max(bx1, xb + 31 - __clz(v));
+    }
+  }
+  __shared__ int sa[8], s0[8], s1[8], s2[8], s3[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+    bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+  }
+  if ((t & 31) == 0) { sa[t >> 5] = a; s0[t >> 5] = bx0; s1[t >> 5] = by0; s2[t >> 5] = bx1; s3[t >> 5] = by1; }
+  __syncthreads();
+  if (t == 0) {
+    for (int w = 1; w < 8; ++w) {
+      a += sa[w]; bx0 = min(bx0, s0[w]); by0 = min(by0, s1[w]); bx1 = max(bx1, s2[w]); by1 = max(by1, s3[w]);
+    }
+    area[i] = a;
+    bbox[i] = make_int4(bx0, by0, bx1, by1);
+  }
+}
+
+// one warp per ordered pair (ri < rj in rank order)
+__global__ void __launch_bounds__(256)
+mask_pair_kernel(const uint32_t* __restrict__ masks, int n, int H, int Wwords, const int32_t* __restrict__ order,
+                 const int32_t* __restrict__ scls, const int32_t* __restrict__ area, const int4* __restrict__ bbox,
+                 double thr, unsigned long long* __restrict__ mask, int nw) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long npairs = (long long)n * n;
+  for (long long p = warp0; p < npairs; p += nwarps) {
+    const int ri = (int)(p / n), rj = (int)(p - (long long)ri * n);
+    if (rj <= ri) continue;
+    if (scls[ri] != scls[rj]) continue;
+    const int i = order[ri], j = order[rj];
+    const int4 bi = bbox[i], bj = bbox[j];
+    const int x0 = max(bi.x, bj.x), y0 = max(bi.y, bj.y), x1 = min(bi.z, bj.z), y1 = min(bi.w, bj.w);
+    long long inter = 0;
+    if (x0 <= x1 && y0 <= y1) {
+      const int w0 = x0 >> 5, wn = (x1 >> 5) - w0 + 1, nr = y1 - y0 + 1;
+      const uint32_t* mi = masks + (size_t)i * H * Wwords;
+      const uint32_t* mj = masks + (size_t)j * H * Wwords;
+      int c = 0;
+      for (int e = lane; e < wn * nr; e += 32) {
+        const int r = e / wn, w = e - r * wn;
+        const size_t o = (size_t)(y0 + r) * Wwords + w0 + w;
+        c += __popc(__ldg(mi + o) & __ldg(mj + o));
+      }
+      inter = warp_sum(c);
+    }
+    if (lane == 0) {
+      const long long uni = (long long)area[i] + (long long)area[j] - inter;
+      const double iou = (double)(inter + 1) / (double)(uni + 1);   // utils/image.py:188-191
+      if (!(iou <= thr)) atomicOr(&mask[(size_t)ri * nw + (rj >> 6)], 1ull << (rj & 63));
+    }
+  }
+}
+
+__global__ void mask_pair_counts_kernel(const uint32_t* __restrict__ masks, int H, int Wwords,
+                                        const int32_t* __restrict__ pairs, long long* __restrict__ out) {
+  const int p = blockIdx.x, t = threadIdx.x;
+  const uint32_t* ma = masks + (size_t)pairs[2 * p] * H * Wwords;
+  const uint32_t* mb = masks + (size_t)pairs[2 * p + 1] * H * Wwords;
+  long long in = 0, un = 0;
+  for (int e = t; e < H * Wwords; e += blockDim.x) {
+    const uint32_t a = __ldg(ma + e), c = __ldg(mb + e);
+    in += __popc(a & c); un += __popc(a | c);
+  }
+  __shared__ long long si[8], su[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { in += __shfl_xor_sync(0xffffffffu, in, o); un += __shfl_xor_sync(0xffffffffu, un, o); }
+  if ((t & 31) == 0) { si[t >> 5] = in; su[t >> 5] = un; }
+  __syncthreads();
+  if (t == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { in += si[w]; un += su[w]; }
+    out[2 * p] = in; out[2 * p + 1] = un;
+  }
+}
+
+__global__ void set_int_kernel(int32_t* p, int v) { *p = v; }
+
+}  // namespace isg
+
+using namespace isg;
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+static int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+extern "C" int isg_decode_boxes(const float* anchors, const float* regression, const float* classification, int B,
+                                int A, int C, int H, int W, float thr, int cap, float* cand_boxes,
+                                float* cand_scores, int32_t* cand_cls, int32_t* cand_anchor, int32_t* cand_count,
+                                isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!anchors || !regression || !classification || !cand_boxes || !cand_scores || !cand_cls || !cand_anchor || !cand_count)
+    return ISG_EINVAL;
+  if (B <= 0 || A <= 0 || C <= 0 || H <= 0 || W <= 0 || cap <= 0 || B > 65535) return ISG_EINVAL;
+  if (!aligned16(anchors) || !aligned16(regression) || !aligned16(cand_boxes)) return ISG_EINVAL;
+  const bool vec = (C % 4 == 0) && aligned16(classification);
+  dim3 grid(cdiv(A, kFrontThreads), B);
+  decode_boxes_kernel<<<grid, kFrontThreads, 0, stream>>>(anchors, regression, classification, A, C, (float)(W - 1),
+                                                          (float)(H - 1), thr, cap, reinterpret_cast<float4*>(cand_boxes),
+                                                          cand_scores, cand_cls, cand_anchor, cand_count, vec);
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" size_t isg_box_nms_workspace_bytes(int B, int cap) {
+  if (B <= 0 || cap <= 0) return 0;
+  return (size_t)B * nms_ws_per_image(cap);
+}
+
+static int run_nms_stages(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
+                          const int32_t* count, int B, int cap, double thr, int convention, int32_t* keep,
+                          int32_t* n_keep, void* ws, cudaStream_t stream, bool box_mask) {
+  const int P = next_pow2(cap);
+  const size_t smem = (size_t)P * 12;
+  ISG_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_sort_kernel<<<B, kSortThreads, smem, stream>>>(reinterpret_cast<const float4*>(boxes), scores, cls, tiebreak,
+                                                     count, cap, P, convention, ws);
+  if (box_mask) {
+    const int nw = cdiv(cap, 64);
+    dim3 grid(nw, nw, B);
+    nms_mask_kernel<<<grid, 64, 0, stream>>>(count, cap, thr, convention, ws);
+    nms_scan_kernel<<<B, kScanThreads, 0, stream>>>(count, cap, ws, keep, n_keep);
+  }
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" int isg_box_nms(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
+                           const int32_t* count, int B, int cap, double thr, int convention, int32_t* keep,
+                           int32_t* n_keep, void* ws, size_t ws_bytes, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!boxes || !scores || !count || !keep || !n_keep || B <= 0 || cap <= 0 || B > 65535) return ISG_EINVAL;
+  if (convention != ISG_NMS_PLUS1_LE && convention != ISG_NMS_TV_GT) return ISG_EINVAL;
+  if (cap > ISG_NMS_MAX_BOXES) return ISG_EUNSUPPORTED;
+  if (!aligned16(boxes)) return ISG_EINVAL;
+  if (!ws || ws_bytes < isg_box_nms_workspace_bytes(B, cap) || ((uintptr_t)ws & 255)) return ISG_EWORKSPACE;
+  return run_nms_stages(boxes, scores, cls, tiebreak, count, B, cap, thr, convention, keep, n_keep, ws, stream, true);
+}
+
+extern "C" size_t isg_mask_nms_workspace_bytes(int n) {
+  if (n <= 0) return 0;
+  return nms_ws_per_image(n) + mask_extra_bytes(n);
+}
+
+extern "C" int isg_mask_nms(const uint32_t* masks, int n, int H, int Wwords, const int32_t* bboxes,
+                            const float* scores, const int32_t* cls, double thr, int32_t* keep, int32_t* n_keep,
+                            void* ws, size_t ws_bytes, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!masks || !scores || !keep || !n_keep || n <= 0 || H <= 0 || Wwords <= 0) return ISG_EINVAL;
+  if (n > ISG_NMS_MAX_BOXES) return ISG_EUNSUPPORTED;
+  if (bboxes && !aligned16(bboxes)) return ISG_EINVAL;
+  if (!ws || ws_bytes < isg_mask_nms_workspace_bytes(n) || ((uintptr_t)ws & 255)) return ISG_EWORKSPACE;
+  // layout: [NmsWs(cap=n)] [area n*4 (16-aligned)] [bbox n*16] [cnt]
+  char* extra = (char*)ws + nms_ws_per_image(n);
+  int32_t* area = (int32_t*)extra;
+  int4* bbox = (int4*)(extra + (((size_t)n * 4 + 15) & ~(size_t)15));
+  int32_t* cnt = (int32_t*)((char*)bbox + (size_t)n * 16);
+  NmsWs v = nms_ws_view(ws, 0, n);
+  const int nw = cdiv(n, 64);
+  set_int_kernel<<<1, 1, 0, stream>>>(cnt, n);
+  mask_area_kernel<<<n, 256, 0, stream>>>(masks, H, Wwords, reinterpret_cast<const int4*>(bboxes), area, bbox);
+  // rank order by (score desc, larger index first on ties) — the greedy loop of utils/nms.py:20-37.
+  // sbox is not needed: boxes pointer is only dereferenced for sbox, so hand the sort a dummy view.
+  int rc = run_nms_stages(reinterpret_cast<const float*>(bbox), scores, cls, nullptr, cnt, 1, n, thr, ISG_NMS_PLUS1_LE,
+                          keep, n_keep, ws, stream, false);
+  if (rc) return rc;
+  ISG_CUDA(cudaMemsetAsync(v.mask, 0, (size_t)n * nw * 8, stream));
+  const long long pairs = (long long)n * n;
+  const int blocks = (int)std::min<long long>((pairs * 32 + 255) / 256, 148LL * 64);
+  mask_pair_kernel<<<blocks, 256, 0, stream>>>(masks, n, H, Wwords, v.order, v.scls, area, bbox, thr, v.mask, nw);
+  nms_scan_kernel<<<1, kScanThreads, 0, stream>>>(cnt, n, ws, keep, n_keep);
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" int isg_mask_pair_counts(const uint32_t* masks, int n, int H, int Wwords, const int32_t* pairs,
+                                    int n_pairs, int64_t* inter_union, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!masks || !pairs || !inter_union || n <= 0 || H <= 0 || Wwords <= 0 || n_pairs <= 0) return ISG_EINVAL;
+  mask_pair_counts_kernel<<<n_pairs, 256, 0, stream>>>(masks, H, Wwords, pairs, reinterpret_cast<long long*>(inter_union));
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
