@@ -93,12 +93,16 @@ int isg_compact_points(const uint32_t* keepbits, int B, int H, int W, int cap,
 /* ------------------------------------------------------------------------------------------
  * Seeds.  Replaces decode_single's box -> centre/size arithmetic (utils/decode.py:428-432) and the
  * seed tensors of group_kp (:316-322) plus the per-instance ghost-filter bounds (:339-352).
- * rois: [B,Nmax,4] fp32 (x1,y1,x2,y2); n_seeds: [B] int32 (<= Nmax).
+ * rois: [B,Nmax,4] fp32, layout ISG_BOX_XYXY (x1,y1,x2,y2: the dict decode_boxes returns) or
+ * ISG_BOX_CYCXHW (cy,cx,h,w: group_kp's center_indexes / center_whs arguments); n_seeds: [B] int32.
  * ys: [H], xs: [W] fp32 coordinate tables (utils/utils.py:453-458 sliced as at utils/decode.py:304).
- * ghost_k = fp32(0.5 + wh_delta); scale = compute_scale() (utils/decode.py:34-35, 1 by default).
+ * ghost_k = fp32(0.5 + wh_delta), or < 0 to disable the ghost filter (every pixel passes);
+ * scale = compute_scale() (utils/decode.py:34-35, 1 by default).
  * seeds: [B,Nmax,ISG_SEED_WORDS] 32-bit words; ghost: [B,Nmax,ISG_GHOST_WORDS] fp32.
  * ------------------------------------------------------------------------------------------ */
-int isg_build_seeds(const float* rois, const int32_t* n_seeds, int B, int Nmax,
+#define ISG_BOX_XYXY   0
+#define ISG_BOX_CYCXHW 1
+int isg_build_seeds(const float* rois, int layout, const int32_t* n_seeds, int B, int Nmax,
                     const float* ys, const float* xs, int H, int W, float ghost_k, float scale,
                     uint32_t* seeds, float* ghost, isg_stream_t stream);
 
@@ -151,7 +155,7 @@ int isg_group_points(const int32_t* idx, const int32_t* label, const uint8_t* fl
  * anchors: [A,4] (y1,x1,y2,x2); regression: [B,A,4] (dy,dx,dh,dw); classification: [B,A,C].
  * Candidates (score > thr, fp32 compare) are appended in unspecified order; isg_box_nms orders
  * them by (score desc, anchor index asc).  cand_*: [B,cap,...]; cand_anchor: [B,cap] int32;
- * cand_count: [B] (true count, may exceed cap; only cap are stored).  cand_count must be zeroed.
+ * cand_count: [B] (true count, may exceed cap; only cap are stored); zeroed by the call.
  * ------------------------------------------------------------------------------------------ */
 int isg_decode_boxes(const float* anchors, const float* regression, const float* classification,
                      int B, int A, int C, int H, int W, float thr, int cap,
@@ -172,6 +176,20 @@ int isg_box_nms(const float* boxes, const float* scores, const int32_t* cls, con
                 const int32_t* count, int B, int cap, double thr, int convention,
                 int32_t* keep, int32_t* n_keep, void* ws, size_t ws_bytes, isg_stream_t stream);
 
+/* BBoxTransform.forward for every anchor (utils/utils.py:318-346) -> boxes [B,A,4] (x1,y1,x2,y2); clip != 0
+ * also applies ClipBoxes (utils/utils.py:349-363) for an H x W image. */
+int isg_bbox_transform(const float* anchors, const float* regression, int B, int A, int clip, int H, int W,
+                       float* boxes, isg_stream_t stream);
+/* ClipBoxes.forward in place on n boxes (x1,y1,x2,y2) (utils/utils.py:357-361) */
+int isg_clip_boxes(float* boxes, int64_t n, int H, int W, isg_stream_t stream);
+
+/* kept candidates -> per-image detection tables in pick (= score descending) order, the dict that
+ * decode_boxes returns (utils/decode.py:402-411) kept on the device: rois [B,Nmax,4], scores [B,Nmax],
+ * cls [B,Nmax] int32, n_out [B] = min(n_keep, Nmax). */
+int isg_gather_kept(const float* cand_boxes, const float* cand_scores, const int32_t* cand_cls,
+                    const int32_t* keep, const int32_t* n_keep, int B, int cap, int Nmax,
+                    float* rois, float* scores, int32_t* cls, int32_t* n_out, isg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K6 — bit-packed mask-IoU NMS.  IoU = (|A&B|+1)/(|A|B|+1) in fp64 (utils/image.py:188-191) inside
  * the greedy loop of utils/nms.py:23-37 (survivor iff IoU <= thr), class aware (cls nullable).
@@ -183,6 +201,9 @@ size_t isg_mask_nms_workspace_bytes(int n);
 int isg_mask_nms(const uint32_t* masks, int n, int H, int Wwords, const int32_t* bboxes,
                  const float* scores, const int32_t* cls, double thr,
                  int32_t* keep, int32_t* n_keep, void* ws, size_t ws_bytes, isg_stream_t stream);
+/* dense masks [n,H,W] uint8 (non-zero = set; poly_to_mask output, utils/image.py:180-185) -> bit-packed
+ * [n,H,ceil(W/32)] uint32 */
+int isg_pack_masks(const uint8_t* dense, int n, int H, int W, uint32_t* bits, isg_stream_t stream);
 /* pairwise mask statistics for n_pairs (a,b) index pairs: inter/union popcounts (int64 [n_pairs,2]).
  * Backs compute_iou_for_mask / is_cover (utils/image.py:188-191,205-207). */
 int isg_mask_pair_counts(const uint32_t* masks, int n, int H, int Wwords, const int32_t* pairs, int n_pairs,

@@ -23,7 +23,7 @@ __device__ __forceinline__ int clamp_to_int(float v) {
 // ---------------------------------------------------------------------------------------------
 // seeds: one thread per (image, box)
 // ---------------------------------------------------------------------------------------------
-__global__ void build_seeds_kernel(const float* __restrict__ rois, const int32_t* __restrict__ n_seeds,
+__global__ void build_seeds_kernel(const float* __restrict__ rois, int layout, const int32_t* __restrict__ n_seeds,
                                    int Nmax, const float* __restrict__ ys, const float* __restrict__ xs,
                                    int H, int W, float ghost_k, float scale, SeedRec* __restrict__ seeds,
                                    float4* __restrict__ ghost) {
@@ -34,10 +34,15 @@ __global__ void build_seeds_kernel(const float* __restrict__ rois, const int32_t
   s.y0 = 1; s.y1 = 0; s.x0 = 1; s.x1 = 0; s.cy = 0.f; s.cx = 0.f; s.id = j; s.pad = 0;
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
   if (j < n_seeds[b]) {
-    const float4 r = reinterpret_cast<const float4*>(rois)[(size_t)b * Nmax + j];  // x1,y1,x2,y2
-    // decode_single: lt = (y1,x1), rb = (y2,x2); centre = (lt+rb)/2; wh = rb-lt   (:428-432)
-    const float cy = __fmul_rn(__fadd_rn(r.y, r.w), 0.5f), cx = __fmul_rn(__fadd_rn(r.x, r.z), 0.5f);
-    const float hy = __fsub_rn(r.w, r.y), wx = __fsub_rn(r.z, r.x);
+    const float4 r = reinterpret_cast<const float4*>(rois)[(size_t)b * Nmax + j];
+    float cy, cx, hy, wx;
+    if (layout == ISG_BOX_XYXY) {   // x1,y1,x2,y2
+      // decode_single: lt = (y1,x1), rb = (y2,x2); centre = (lt+rb)/2; wh = rb-lt   (:428-432)
+      cy = __fmul_rn(__fadd_rn(r.y, r.w), 0.5f); cx = __fmul_rn(__fadd_rn(r.x, r.z), 0.5f);
+      hy = __fsub_rn(r.w, r.y); wx = __fsub_rn(r.z, r.x);
+    } else {                        // cy,cx,h,w : group_kp's center_indexes / center_whs (:288)
+      cy = r.x; cx = r.y; hy = r.z; wx = r.w;
+    }
     // group_kp: lt = c - wh/2, rb = c + wh/2 ; inbox = (p - lt >= 0) & (rb - p >= 0)   (:321-325)
     const float lty = __fsub_rn(cy, __fmul_rn(hy, 0.5f)), ltx = __fsub_rn(cx, __fmul_rn(wx, 0.5f));
     const float rby = __fadd_rn(cy, __fmul_rn(hy, 0.5f)), rbx = __fadd_rn(cx, __fmul_rn(wx, 0.5f));
@@ -53,8 +58,12 @@ __global__ void build_seeds_kernel(const float* __restrict__ rois, const int32_t
     s.cy = ys[iy]; s.cx = xs[ix];
     // ghost filter bounds (:339-352): x -/+ (0.5+wh_delta)*w, y -/+ (0.5+wh_delta)*h, fp32
     const float w = __fmul_rn(wx, scale), h = __fmul_rn(hy, scale);
-    g.x = __fsub_rn(cx, __fmul_rn(ghost_k, w)); g.y = __fadd_rn(cx, __fmul_rn(ghost_k, w));
-    g.z = __fsub_rn(cy, __fmul_rn(ghost_k, h)); g.w = __fadd_rn(cy, __fmul_rn(ghost_k, h));
+    if (ghost_k < 0.0f) {   // ghost filter disabled: every pixel passes
+      g = make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY);
+    } else {
+      g.x = __fsub_rn(cx, __fmul_rn(ghost_k, w)); g.y = __fadd_rn(cx, __fmul_rn(ghost_k, w));
+      g.z = __fsub_rn(cy, __fmul_rn(ghost_k, h)); g.w = __fadd_rn(cy, __fmul_rn(ghost_k, h));
+    }
   }
   seeds[(size_t)b * Nmax + j] = s;
   ghost[(size_t)b * Nmax + j] = g;
@@ -426,14 +435,15 @@ using namespace isg;
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-extern "C" int isg_build_seeds(const float* rois, const int32_t* n_seeds, int B, int Nmax, const float* ys,
+extern "C" int isg_build_seeds(const float* rois, int layout, const int32_t* n_seeds, int B, int Nmax, const float* ys,
                                const float* xs, int H, int W, float ghost_k, float scale, uint32_t* seeds,
                                float* ghost, isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!rois || !n_seeds || !ys || !xs || !seeds || !ghost || B <= 0 || Nmax <= 0 || H <= 0 || W <= 0) return ISG_EINVAL;
   if (!aligned16(rois) || !aligned16(seeds) || !aligned16(ghost) || B > 65535) return ISG_EINVAL;
+  if (layout != ISG_BOX_XYXY && layout != ISG_BOX_CYCXHW) return ISG_EINVAL;
   dim3 grid(cdiv(Nmax, 128), B);
-  build_seeds_kernel<<<grid, 128, 0, stream>>>(rois, n_seeds, Nmax, ys, xs, H, W, ghost_k, scale,
+  build_seeds_kernel<<<grid, 128, 0, stream>>>(rois, layout, n_seeds, Nmax, ys, xs, H, W, ghost_k, scale,
                                                reinterpret_cast<SeedRec*>(seeds), reinterpret_cast<float4*>(ghost));
   ISG_LAUNCH_CHECK();
   return ISG_OK;

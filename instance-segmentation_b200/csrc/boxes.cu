@@ -374,6 +374,70 @@ __global__ void mask_pair_counts_kernel(const uint32_t* __restrict__ masks, int 
 
 __global__ void set_int_kernel(int32_t* p, int v) { *p = v; }
 
+// BBoxTransform for every anchor (utils/utils.py:318-346), optional ClipBoxes (:349-363)
+__global__ void bbox_transform_kernel(const float4* __restrict__ anchors, const float4* __restrict__ regression, int A,
+                                      int clip, float xmax_clip, float ymax_clip, float4* __restrict__ out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (a >= A) return;
+  const float4 an = __ldg(anchors + a);
+  const float4 rg = regression[(size_t)b * A + a];
+  const float yca = __fmul_rn(__fadd_rn(an.x, an.z), 0.5f), xca = __fmul_rn(__fadd_rn(an.y, an.w), 0.5f);
+  const float ha = __fsub_rn(an.z, an.x), wa = __fsub_rn(an.w, an.y);
+  const float w = __fmul_rn(expf(rg.w), wa), h = __fmul_rn(expf(rg.z), ha);
+  const float yc = __fadd_rn(__fmul_rn(rg.x, ha), yca), xc = __fadd_rn(__fmul_rn(rg.y, wa), xca);
+  float ymin = __fsub_rn(yc, __fmul_rn(h, 0.5f)), xmin = __fsub_rn(xc, __fmul_rn(w, 0.5f));
+  float ymax = __fadd_rn(yc, __fmul_rn(h, 0.5f)), xmax = __fadd_rn(xc, __fmul_rn(w, 0.5f));
+  if (clip) {
+    xmin = fmaxf(xmin, 0.0f); ymin = fmaxf(ymin, 0.0f);
+    xmax = fminf(xmax, xmax_clip); ymax = fminf(ymax, ymax_clip);
+  }
+  out[(size_t)b * A + a] = make_float4(xmin, ymin, xmax, ymax);
+}
+
+__global__ void clip_boxes_kernel(float4* __restrict__ boxes, long long n, float xmax_clip, float ymax_clip) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 v = boxes[i];
+  v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fminf(v.z, xmax_clip); v.w = fminf(v.w, ymax_clip);
+  boxes[i] = v;
+}
+
+// dense masks (one byte per pixel, non-zero = set) -> bit-packed words; one warp per output word group
+__global__ void pack_masks_kernel(const uint8_t* __restrict__ dense, long long rows, int W, int Wwords,
+                                  uint32_t* __restrict__ bits) {
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // global warp = (row, word)
+  const int lane = threadIdx.x & 31;
+  if (gw >= rows * Wwords) return;
+  const long long r = gw / Wwords;
+  const int w = (int)(gw - r * Wwords);
+  const int x = w * 32 + lane;
+  const bool on = (x < W) && dense[r * W + x] != 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, on);
+  if (lane == 0) bits[gw] = bal;
+}
+
+// kept candidates -> dense per-image detection tables in pick (= score descending) order
+__global__ void gather_kept_kernel(const float4* __restrict__ cand_boxes, const float* __restrict__ cand_scores,
+                                   const int32_t* __restrict__ cand_cls, const int32_t* __restrict__ keep,
+                                   const int32_t* __restrict__ n_keep, int cap, int Nmax, float4* __restrict__ rois,
+                                   float* __restrict__ scores, int32_t* __restrict__ cls, int32_t* __restrict__ n_out) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(n_keep[b], Nmax);
+  if (r == 0) n_out[b] = n;
+  if (r >= Nmax) return;
+  float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sc = 0.f;
+  int c = 0;
+  if (r < n) {
+    const size_t o = (size_t)b * cap + keep[(size_t)b * cap + r];
+    bx = cand_boxes[o]; sc = cand_scores[o]; c = cand_cls[o];
+  }
+  const size_t d = (size_t)b * Nmax + r;
+  rois[d] = bx; scores[d] = sc; cls[d] = c;
+}
+
 }  // namespace isg
 
 using namespace isg;
@@ -391,10 +455,58 @@ extern "C" int isg_decode_boxes(const float* anchors, const float* regression, c
   if (B <= 0 || A <= 0 || C <= 0 || H <= 0 || W <= 0 || cap <= 0 || B > 65535) return ISG_EINVAL;
   if (!aligned16(anchors) || !aligned16(regression) || !aligned16(cand_boxes)) return ISG_EINVAL;
   const bool vec = (C % 4 == 0) && aligned16(classification);
+  ISG_CUDA(cudaMemsetAsync(cand_count, 0, (size_t)B * sizeof(int32_t), stream));
   dim3 grid(cdiv(A, kFrontThreads), B);
   decode_boxes_kernel<<<grid, kFrontThreads, 0, stream>>>(anchors, regression, classification, A, C, (float)(W - 1),
                                                           (float)(H - 1), thr, cap, reinterpret_cast<float4*>(cand_boxes),
                                                           cand_scores, cand_cls, cand_anchor, cand_count, vec);
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" int isg_gather_kept(const float* cand_boxes, const float* cand_scores, const int32_t* cand_cls,
+                               const int32_t* keep, const int32_t* n_keep, int B, int cap, int Nmax, float* rois,
+                               float* scores, int32_t* cls, int32_t* n_out, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!cand_boxes || !cand_scores || !cand_cls || !keep || !n_keep || !rois || !scores || !cls || !n_out) return ISG_EINVAL;
+  if (B <= 0 || cap <= 0 || Nmax <= 0 || B > 65535) return ISG_EINVAL;
+  if (!aligned16(cand_boxes) || !aligned16(rois)) return ISG_EINVAL;
+  dim3 grid(cdiv(Nmax, 128), B);
+  gather_kept_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const float4*>(cand_boxes), cand_scores, cand_cls, keep,
+                                               n_keep, cap, Nmax, reinterpret_cast<float4*>(rois), scores, cls, n_out);
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" int isg_bbox_transform(const float* anchors, const float* regression, int B, int A, int clip, int H, int W,
+                                  float* boxes, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!anchors || !regression || !boxes || B <= 0 || A <= 0 || B > 65535) return ISG_EINVAL;
+  if (!aligned16(anchors) || !aligned16(regression) || !aligned16(boxes)) return ISG_EINVAL;
+  dim3 grid(cdiv(A, 256), B);
+  bbox_transform_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(anchors),
+                                                  reinterpret_cast<const float4*>(regression), A, clip, (float)(W - 1),
+                                                  (float)(H - 1), reinterpret_cast<float4*>(boxes));
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" int isg_clip_boxes(float* boxes, int64_t n, int H, int W, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!boxes || n <= 0 || !aligned16(boxes)) return ISG_EINVAL;
+  clip_boxes_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, stream>>>(reinterpret_cast<float4*>(boxes), n, (float)(W - 1),
+                                                                 (float)(H - 1));
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" int isg_pack_masks(const uint8_t* dense, int n, int H, int W, uint32_t* bits, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!dense || !bits || n <= 0 || H <= 0 || W <= 0) return ISG_EINVAL;
+  const int Wwords = cdiv(W, 32);
+  const long long rows = (long long)n * H;
+  const long long threads = rows * Wwords * 32;
+  pack_masks_kernel<<<(unsigned)cdiv64(threads, 256), 256, 0, stream>>>(dense, rows, W, Wwords, bits);
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }

@@ -1,0 +1,237 @@
+"""Batched device pipeline behind the drop-in modules.
+
+PyTorch is used for device memory, streams and host<->device copies only; every computation is a
+libisg.so kernel enqueued on torch's current stream.  A plan owns all outputs and workspaces for a
+fixed (batch, height, width, max seeds) shape so that a decode step allocates nothing and never
+synchronises with the host; results are read back once per batch.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call
+
+GRID_H, GRID_W = 1024, 2048   # utils/utils.py:453-458 of the reference
+
+
+def require_cuda(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("isg_b200 has no CPU path: pass a CUDA device (got %s)" % device)
+    if not torch.cuda.is_available():
+        raise RuntimeError("isg_b200 needs a CUDA device (B200, sm_100a); none is visible")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+_device_checked = set()
+
+
+def check_device(device: torch.device) -> None:
+    if device.index in _device_checked:
+        return
+    if not _lib.lib().isg_device_supported(device.index):
+        raise RuntimeError("libisg.so is built for sm_100a (B200) only; device %s is not supported" % device)
+    _device_checked.add(device.index)
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+_tables = {}
+
+
+def coordinate_tables(H: int, W: int, device: torch.device):
+    """ys [H], xs [W] on `device`, the slices of the reference grid used at utils/decode.py:304."""
+    if H > GRID_H or W > GRID_W:
+        raise RuntimeError("the reference coordinate grid is 1024x2048 (utils/utils.py:453-458); got %dx%d" % (H, W))
+    key = (H, W, device.index)
+    if key not in _tables:
+        ys = torch.linspace(0, 1, GRID_H)[:H].contiguous().to(device)
+        xs = torch.linspace(0, 2, GRID_W)[:W].contiguous().to(device)
+        _tables[key] = (ys, xs)
+    return _tables[key]
+
+
+def _rows_contiguous(t: torch.Tensor) -> bool:
+    return t.stride(-1) == 1 and t.stride(-2) == t.shape[-1]
+
+
+def as_f32_planes(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    """fp32 tensor on `device` whose last two dims are contiguous rows (copies only when needed)."""
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    if t.dtype != torch.float32:
+        t = t.float()
+    if not _rows_contiguous(t):
+        t = t.contiguous()
+    return t
+
+
+class DecodePlan:
+    """select -> assign (dense or sparse) -> compact -> group for a batch of B images of HxW."""
+
+    def __init__(self, B: int, H: int, W: int, max_seeds: int, kp_th: int, device, mode: str = "sparse",
+                 want_score: bool = True, wh_delta: float = 0.1, scale: float = 1.0):
+        if mode not in ("dense", "sparse"):
+            raise ValueError("mode must be 'dense' or 'sparse'")
+        self.device = require_cuda(device)
+        check_device(self.device)
+        self.B, self.H, self.W, self.N = int(B), int(H), int(W), max(int(max_seeds), 1)
+        self.kp_th = int(kp_th)
+        if self.kp_th > H * W:
+            raise RuntimeError("selected index k out of range")   # torch.topk, utils/decode.py:81
+        self.cap = max(min(self.kp_th, H * W), 1)
+        self.mode, self.want_score = mode, bool(want_score)
+        # wh_delta None disables the device ghost filter (non-identity val transforms filter on the host)
+        self.ghost_k = -1.0 if wh_delta is None else float(np.float32(0.5 + wh_delta))
+        self.scale = float(scale)
+        self.Ww = (W + 31) // 32
+        self.events = []
+        d, i32, f32 = self.device, torch.int32, torch.float32
+        B, N, cap = self.B, self.N, self.cap
+        self.ys, self.xs = coordinate_tables(H, W, d)
+        self.thr_key = torch.empty(B, dtype=i32, device=d)
+        self.keepbits = torch.empty((B, H, self.Ww), dtype=i32, device=d)
+        self.idx = torch.empty((B, cap, 2), dtype=i32, device=d)
+        self.count = torch.empty(B, dtype=i32, device=d)
+        self.label = torch.empty((B, cap), dtype=i32, device=d)
+        self.score = torch.empty((B, cap), dtype=f32, device=d) if want_score else None
+        self.flag = torch.empty((B, cap), dtype=torch.uint8, device=d)
+        self.stats = torch.empty((B, N, _lib.STAT_WORDS), dtype=i32, device=d)
+        self.seeds = torch.empty((B, N, _lib.SEED_WORDS), dtype=i32, device=d)
+        self.ghost = torch.empty((B, N, _lib.GHOST_WORDS), dtype=f32, device=d)
+        self.offsets = torch.empty((B, N + 1), dtype=i32, device=d)
+        self.points = torch.empty((B, cap, 2), dtype=f32, device=d)
+        self.ws_bytes = int(_lib.lib().isg_topk_workspace_bytes(B))
+        self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=d)
+        if mode == "dense":
+            self.label_map = torch.empty((B, H, W), dtype=i32, device=d)
+            self.score_map = torch.empty((B, H, W), dtype=f32, device=d) if want_score else None
+        else:
+            self.label_map = self.score_map = None
+
+    # ------------------------------------------------------------------------------------------
+    def run(self, kp: torch.Tensor, ae: torch.Tensor, rois: torch.Tensor, n_seeds: torch.Tensor,
+            layout: int = _lib.ISG_BOX_XYXY, time_main: bool = False) -> None:
+        """kp [B,1,H,W] or [B,H,W]; ae [B,4,H,W]; rois [B,N,4] fp32 ((x1,y1,x2,y2) or (cy,cx,h,w), see `layout`);
+        n_seeds [B] int32 — all on the plan's device.  Enqueues the kernels on the current stream and returns
+        without synchronising.  time_main=True brackets the assignment kernel with CUDA events on the launching
+        stream and appends the pair to self.events (bench.py's roofline measurement)."""
+        B, H, W, N, cap = self.B, self.H, self.W, self.N, self.cap
+        if kp.dim() == 4:
+            kp = kp[:, 0]
+        assert kp.shape == (B, H, W) and ae.shape == (B, 4, H, W), (kp.shape, ae.shape)
+        assert rois.shape == (B, N, 4) and rois.is_contiguous() and rois.dtype == torch.float32
+        assert n_seeds.shape == (B,) and n_seeds.dtype == torch.int32
+        assert kp.dtype == torch.float32 and ae.dtype == torch.float32 and _rows_contiguous(kp) and _rows_contiguous(ae)
+        s = stream_ptr(self.device)
+        kp_stride = kp.stride(0) if B > 1 else H * W
+        ae_img = ae.stride(0) if B > 1 else 4 * H * W
+        ae_plane = ae.stride(1)
+        call("isg_build_seeds", ptr(rois), layout, ptr(n_seeds), B, N, ptr(self.ys), ptr(self.xs), H, W, self.ghost_k,
+             self.scale, ptr(self.seeds), ptr(self.ghost), s)
+        call("isg_stats_init", ptr(self.stats), B, N, s)
+        call("isg_topk_threshold", ptr(kp), B, H, W, kp_stride, self.kp_th, ptr(self.thr_key), ptr(self.ws),
+             self.ws_bytes, s)
+        ev = None
+        if time_main:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        if self.mode == "dense":
+            if ev:
+                ev[0].record()
+            call("isg_assign_dense", ptr(kp), kp_stride, ptr(ae), ae_img, ae_plane, ptr(self.thr_key), ptr(self.seeds),
+                 ptr(self.ghost), ptr(n_seeds), B, N, H, W, ptr(self.ys), ptr(self.xs), ptr(self.label_map),
+                 ptr(self.score_map), ptr(self.keepbits), ptr(self.stats), s)
+            if ev:
+                ev[1].record()
+            call("isg_compact_points", ptr(self.keepbits), B, H, W, cap, ptr(self.idx), ptr(self.count), s)
+            call("isg_gather_labels", ptr(self.label_map), ptr(self.score_map), ptr(self.idx), ptr(self.count), cap,
+                 ptr(self.ghost), B, N, H, W, ptr(self.label), ptr(self.score), ptr(self.flag), s)
+        else:
+            call("isg_keep_points", ptr(kp), B, H, W, kp_stride, ptr(self.thr_key), ptr(self.keepbits), 0, s)
+            call("isg_compact_points", ptr(self.keepbits), B, H, W, cap, ptr(self.idx), ptr(self.count), s)
+            if ev:
+                ev[0].record()
+            call("isg_assign_sparse", ptr(ae), ae_img, ae_plane, ptr(self.idx), ptr(self.count), cap, ptr(self.seeds),
+                 ptr(self.ghost), ptr(n_seeds), B, N, H, W, ptr(self.ys), ptr(self.xs), ptr(self.label),
+                 ptr(self.score), ptr(self.flag), ptr(self.stats), s)
+            if ev:
+                ev[1].record()
+        call("isg_group_points", ptr(self.idx), ptr(self.label), ptr(self.flag), ptr(self.count), cap, ptr(n_seeds),
+             B, N, ptr(self.offsets), ptr(self.points), s)
+        if ev:
+            self.events.append(ev)
+
+
+class BoxPlan:
+    """decode_boxes on the device: front-end -> class-aware NMS -> per-image detection tables."""
+
+    def __init__(self, B: int, A: int, C: int, H: int, W: int, device, cap: int = 4096, max_keep: int = 1024):
+        self.device = require_cuda(device)
+        check_device(self.device)
+        self.B, self.A, self.C, self.H, self.W = int(B), int(A), int(C), int(H), int(W)
+        self.cap = int(min(cap, _lib.ISG_NMS_MAX_BOXES, A))
+        self.N = int(min(max_keep, self.cap))
+        d, i32, f32 = self.device, torch.int32, torch.float32
+        B, cap, N = self.B, self.cap, self.N
+        self.cand_boxes = torch.empty((B, cap, 4), dtype=f32, device=d)
+        self.cand_scores = torch.empty((B, cap), dtype=f32, device=d)
+        self.cand_cls = torch.empty((B, cap), dtype=i32, device=d)
+        self.cand_anchor = torch.empty((B, cap), dtype=i32, device=d)
+        self.cand_count = torch.empty(B, dtype=i32, device=d)
+        self.keep = torch.empty((B, cap), dtype=i32, device=d)
+        self.n_keep = torch.empty(B, dtype=i32, device=d)
+        self.rois = torch.empty((B, N, 4), dtype=f32, device=d)
+        self.scores = torch.empty((B, N), dtype=f32, device=d)
+        self.cls = torch.empty((B, N), dtype=i32, device=d)
+        self.n_seeds = torch.empty(B, dtype=i32, device=d)
+        self.ws_bytes = int(_lib.lib().isg_box_nms_workspace_bytes(B, cap))
+        self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=d)
+        self.ws_off = (-self.ws.data_ptr()) % 256
+
+    def run(self, anchors: torch.Tensor, regression: torch.Tensor, classification: torch.Tensor, cls_th: float,
+            iou_th: float) -> None:
+        B, A, C = self.B, self.A, self.C
+        assert anchors.numel() == A * 4 and regression.shape == (B, A, 4) and classification.shape == (B, A, C)
+        assert anchors.is_contiguous() and regression.is_contiguous() and classification.is_contiguous()
+        s = stream_ptr(self.device)
+        call("isg_decode_boxes", ptr(anchors), ptr(regression), ptr(classification), B, A, C, self.H, self.W,
+             float(np.float32(cls_th)), self.cap, ptr(self.cand_boxes), ptr(self.cand_scores), ptr(self.cand_cls),
+             ptr(self.cand_anchor), ptr(self.cand_count), s)
+        call("isg_box_nms", ptr(self.cand_boxes), ptr(self.cand_scores), ptr(self.cand_cls), ptr(self.cand_anchor),
+             ptr(self.cand_count), B, self.cap, float(iou_th), _lib.ISG_NMS_TV_GT, ptr(self.keep), ptr(self.n_keep),
+             self.ws.data_ptr() + self.ws_off, self.ws_bytes, s)
+        call("isg_gather_kept", ptr(self.cand_boxes), ptr(self.cand_scores), ptr(self.cand_cls), ptr(self.keep),
+             ptr(self.n_keep), B, self.cap, self.N, ptr(self.rois), ptr(self.scores), ptr(self.cls), ptr(self.n_seeds), s)
+
+
+_plans = {}
+
+
+def get_decode_plan(B, H, W, max_seeds, kp_th, device, mode, want_score=True, wh_delta=0.1, scale=1.0) -> DecodePlan:
+    device = require_cuda(device)
+    key = ("d", B, H, W, max_seeds, kp_th, device.index, mode, want_score, wh_delta, float(scale))
+    if key not in _plans:
+        if len(_plans) > 8:
+            _plans.clear()
+        _plans[key] = DecodePlan(B, H, W, max_seeds, kp_th, device, mode, want_score, wh_delta, scale)
+    return _plans[key]
+
+
+def get_box_plan(B, A, C, H, W, device, cap=4096, max_keep=1024) -> BoxPlan:
+    device = require_cuda(device)
+    key = ("b", B, A, C, H, W, device.index, cap, max_keep)
+    if key not in _plans:
+        if len(_plans) > 8:
+            _plans.clear()
+        _plans[key] = BoxPlan(B, A, C, H, W, device, cap, max_keep)
+    return _plans[key]

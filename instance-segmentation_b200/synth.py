@@ -259,3 +259,61 @@ def make_masks(seed: int, n: int, H: int, W: int, C: int = 80):
         boxes[i] = (x0, y0, x1, y1)
     scores = _distinct_float32(rs.uniform(0.05, 1.0, size=n).astype(np.float32))
     return masks, boxes, scores, cls
+
+
+# --------------------------------------------------------------------------------------------
+# full scene: image + a box head whose decoded, NMS-surviving boxes are the image's instances
+# --------------------------------------------------------------------------------------------
+def make_scene(seed: int, H: int, W: int, N: int, C: int = 8, anchors: np.ndarray | None = None, n_dup: int = 2,
+               cls_th: float = 0.3, iou_th: float = 0.2):
+    """Returns (Image, regression [A,4], classification [A,C], anchors [1,A,4]).
+
+    Every instance box of the image is produced by one anchor (regression = inverse BBoxTransform, score and
+    class of the instance); `n_dup` lower-scored, shifted duplicates per instance give the NMS real work.
+    Duplicates keep integer+0.5 centres and even sizes, and no candidate pair has an IoU within 1e-3 of
+    `iou_th`, so the kept set is stable against ulp-level differences in exp().
+    """
+    if anchors is None:
+        anchors = make_anchors(H, W)
+    img = make_image(seed, H, W, N, C)
+    rs = np.random.RandomState(seed + 7919)
+    A = anchors.shape[1]
+    an = anchors[0].astype(np.float64)
+    a_cy, a_cx = (an[:, 0] + an[:, 2]) / 2, (an[:, 1] + an[:, 3]) / 2
+    a_h, a_w = an[:, 2] - an[:, 0], an[:, 3] - an[:, 1]
+    regression = rs.normal(0.0, 0.1, size=(A, 4)).astype(np.float32)
+    classification = rs.uniform(0.0, 0.05, size=(A, C)).astype(np.float32)
+
+    cand = []   # (box xyxy float64, score, cls)
+    for j in range(len(img.rois)):
+        x1, y1, x2, y2 = img.rois[j].astype(np.float64)
+        cand.append(((x1, y1, x2, y2), float(img.scores[j]), int(img.class_ids[j])))
+        for d in range(n_dup):
+            dx, dy = int(rs.randint(-4, 5)), int(rs.randint(-4, 5))
+            gw, gh = 2 * int(rs.randint(-2, 3)), 2 * int(rs.randint(-2, 3))
+            bx = (x1 + dx - gw / 2, y1 + dy - gh / 2, x2 + dx + gw / 2, y2 + dy + gh / 2)
+            if bx[0] < 0 or bx[1] < 0 or bx[2] > W - 1 or bx[3] > H - 1 or bx[2] - bx[0] < 4 or bx[3] - bx[1] < 4:
+                continue
+            cand.append((bx, float(img.scores[j]) * float(rs.uniform(0.45, 0.95)), int(img.class_ids[j])))
+    boxes = np.array([c[0] for c in cand], dtype=np.float64)
+    scores = _distinct_float32(np.array([c[1] for c in cand], dtype=np.float32))
+    classes = np.array([c[2] for c in cand], dtype=np.int64)
+    ok = scores > cls_th + 1e-3
+    iou = _iou_matrix(boxes)
+    np.fill_diagonal(iou, 0.0)
+    near = np.abs(iou - iou_th) < 1e-3
+    for i in np.nonzero(near.any(axis=1))[0]:
+        if i >= len(img.rois) and ok[i] and (near[i] & ok).any():     # only ever drop duplicates
+            ok[i] = False
+    used = np.zeros(A, dtype=bool)
+    for i in np.nonzero(ok)[0]:
+        x1, y1, x2, y2 = boxes[i]
+        cy, cx, h, w = (y1 + y2) / 2, (x1 + x2) / 2, y2 - y1, x2 - x1
+        cost = np.abs(np.log(a_h / h)) + np.abs(np.log(a_w / w)) + (np.abs(a_cy - cy) / a_h + np.abs(a_cx - cx) / a_w)
+        cost[used] = np.inf
+        a = int(np.argmin(cost))
+        used[a] = True
+        regression[a] = np.array([(cy - a_cy[a]) / a_h[a], (cx - a_cx[a]) / a_w[a], np.log(h / a_h[a]), np.log(w / a_w[a])],
+                                 dtype=np.float32)
+        classification[a, classes[i]] = scores[i]
+    return img, regression, classification, anchors

@@ -1,0 +1,471 @@
+"""Drop-in for the reference's utils/decode.py: same function names, argument order and return structures,
+device work done by libisg.so (sm_100a CUDA) instead of torch/numpy ops.
+
+Differences that are deliberate:
+  * there is no CPU path: tensors are moved to the CUDA `device` argument; a CPU `device` raises;
+  * the network outputs are not modified (the reference overwrites hm_ae[0:2] in place at :305 and
+    clips the transformed anchors in place at utils/utils.py:357-361; no caller reads them afterwards);
+  * the batch is decoded in one set of launches instead of the serial multi_apply map (:458);
+  * drawing (decode_cfg.draw_flag) is a host-side debug aid and delegates to the reference's
+    utils.visualize when that module is importable, otherwise it is skipped with a warning.
+All file:line citations refer to the reference's utils/decode.py unless stated.
+"""
+from __future__ import annotations
+
+import math
+import os
+import warnings
+from typing import Iterable
+
+import numpy as np
+import torch
+
+from .. import _lib, engine
+from .._lib import call
+from ..engine import ptr, require_cuda, stream_ptr
+from . import image, parell_util
+from .kmeans import kmeans            # noqa: F401  (imported, never called — like the reference, :16)
+from .nms import py_cpu_nms
+from .utils import BBoxTransform, ClipBoxes, generate_coordinates   # noqa: F401
+
+base_dir = r""        # :28
+target_size = 1       # :29
+device = None         # set by test.py:134 / evaluate.py:40
+draw_flag = False     # set by evaluate.py:41 (the code reads decode_cfg.draw_flag, like the reference)
+
+# "dense": fused label map for every pixel (isg_assign_dense); "sparse": only the selected pixels, the
+# reference's own amount of work (isg_assign_sparse).  Both give identical detections.
+decode_mode = os.environ.get("ISG_DECODE_MODE", "sparse")
+
+_xym = None
+
+
+def __getattr__(name):
+    # `xym` (:31) is a 16 MiB CPU tensor the reference builds at import; built lazily here.
+    global _xym
+    if name == "xym":
+        if _xym is None:
+            _xym = generate_coordinates()
+        return _xym
+    raise AttributeError(name)
+
+
+def compute_scale(info):            # :34-35
+    return target_size
+
+
+def to_numpy(tensor):               # :38-39
+    return tensor.cpu().numpy()
+
+
+def _device_of(t: torch.Tensor, fallback=None) -> torch.device:
+    if t.is_cuda:
+        return t.device
+    if fallback is not None:
+        return require_cuda(fallback)
+    if device is not None:
+        return require_cuda(device)
+    raise RuntimeError("isg_b200 has no CPU path: pass CUDA tensors or set decode.device to a CUDA device")
+
+
+# ----------------------------------------------------------------------------------------------
+# K2
+# ----------------------------------------------------------------------------------------------
+def nms_hm(heat, kernel=3):
+    """:42-48 — uint8 mask of the pixels equal to their kernel x kernel maximum."""
+    dev = _device_of(heat)
+    h = engine.as_f32_planes(heat, dev)
+    if h.dim() < 2:
+        raise ValueError("heat must have at least 2 dims")
+    H, W = h.shape[-2], h.shape[-1]
+    h = h.contiguous()
+    planes = h.numel() // (H * W)
+    keep = torch.empty(h.shape, dtype=torch.uint8, device=dev)
+    call("isg_nms_hm", ptr(h), planes, H, W, int(kernel), ptr(keep), stream_ptr(dev))
+    return keep
+
+
+def select_points(mat, k):
+    """:71-85 — uint8 [H,W]: the k largest pixels that are 3x3 maxima of (mat where selected else 0)."""
+    dev = _device_of(mat)
+    m = engine.as_f32_planes(mat, dev)
+    H, W = m.shape
+    k = int(k)
+    if k > H * W:
+        raise RuntimeError("selected index k out of range")     # what torch.topk raises at :81
+    lib = _lib.lib()
+    ws_bytes = int(lib.isg_select_points_workspace_bytes(1))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    keepbits = torch.empty((H, (W + 31) // 32), dtype=torch.int32, device=dev)
+    mask = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    call("isg_select_points", ptr(m), 1, H, W, H * W, k, ptr(keepbits), ptr(mask), ptr(ws), ws_bytes, stream_ptr(dev))
+    return mask
+
+
+# ----------------------------------------------------------------------------------------------
+# a7 — polygon stage (host glue this round; SURVEY.md §8 f1 moves it to the GPU)
+# ----------------------------------------------------------------------------------------------
+def find_internal_point(kps, default):
+    """:51-68"""
+    import cv2
+    kps = np.array(kps)
+    if cv2.pointPolygonTest(kps, tuple(default), False) > 0:
+        return default
+    mean = kps.mean(axis=0).reshape(-1)
+    if cv2.pointPolygonTest(kps, tuple(mean), False) > 0:
+        return mean
+    n = kps.shape[0]
+    for i in range(n):
+        mids = (kps[i][None, :] + kps[1:]) / 2
+        for point in mids:
+            if cv2.pointPolygonTest(kps, tuple(point), False) > 0:
+                return point
+    return default
+
+
+def cartesian2polar(kps, center_loc):
+    """:88-113 — [K,2] float32 (theta in [0,2pi), distance); vectorised, same fp32 arithmetic."""
+    d = (np.asarray(kps) - center_loc).astype(np.float32)
+    dx, dy = d[:, 0], d[:, 1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        seta = np.arctan(dy / dx)
+        seta = np.where(dx < 0, seta + np.float32(np.pi), seta)
+        seta = np.where((dx > 0) & (dy < 0), seta + np.float32(2 * np.pi), seta)
+        seta = np.where((dx == 0) & (dy > 0), np.float32(np.pi / 2), seta)
+        seta = np.where((dx == 0) & (dy < 0), np.float32(3 * np.pi / 2), seta)
+        dist = np.sqrt(dx ** 2 + dy ** 2)
+    return np.stack((seta, dist), axis=1).astype(np.float32)
+
+
+def polar2cartesian(kps, center_loc):
+    """:116-128"""
+    ang, dist = kps[:, 0], kps[:, 1]
+    delta = np.hstack(((dist * np.cos(ang)).reshape(-1, 1), (dist * np.sin(ang)).reshape(-1, 1)))
+    return delta + center_loc
+
+
+def filter_ghost_polygons(polygons, center):
+    """:131-141 (unused by the decode; kept for API parity — expects shapely-like polygons)."""
+    import cv2
+    if not isinstance(polygons, Iterable):
+        polygons = [polygons]
+    max_area, max_poly = 0, None
+    for poly in polygons:
+        np_poly = np.array(poly.exterior.coords).astype(np.float32)
+        if poly.area > max_area and cv2.pointPolygonTest(np_poly, tuple(center), False) > 0:
+            max_area, max_poly = poly.area, np_poly
+    return max_poly
+
+
+def smooth_polygon(polar_pts, sorted_inds, k=360):
+    """:144-163 (unused by the decode; kept for API parity)."""
+    d_seta = 2 * np.pi / 12
+    selected, cur_ind, cur_dist, cur_bin = [], -1, -1, 0
+    for ind in sorted_inds:
+        index = math.floor(polar_pts[ind][0] / d_seta)
+        if index != cur_bin:
+            if cur_ind >= 0:
+                selected.append(cur_ind)
+            cur_ind, cur_dist, cur_bin = -1, -1, index
+        elif polar_pts[ind][1] > cur_dist:
+            cur_ind, cur_dist = ind, polar_pts[ind][1]
+    if cur_ind >= 0:
+        selected.append(cur_ind)
+    return selected
+
+
+def aug_group(pts, center_loc):
+    """:167-204 — order the points by polar angle about an internal point; None if degenerate."""
+    import cv2
+    center_loc = center_loc.reshape(-1)
+    internal_point = find_internal_point(pts, center_loc)
+    polar_pts = cartesian2polar(pts, internal_point)
+    sorted_inds = np.argsort(polar_pts[:, 0])
+    sorted_kp = pts[sorted_inds]
+    if image.poly_to_mask(sorted_kp).sum() == 0:
+        return None
+    if cv2.pointPolygonTest(sorted_kp, tuple(center_loc), False) > 0:
+        return sorted_kp
+    return None
+
+
+# ----------------------------------------------------------------------------------------------
+# drawing helpers (:207-251): debug output, delegated to the reference's utils.visualize if present
+# ----------------------------------------------------------------------------------------------
+_warned_draw = False
+
+
+def _visualize():
+    global _warned_draw
+    try:
+        from utils import visualize   # the reference's module, present when used as a drop-in
+        return visualize
+    except Exception:
+        if not _warned_draw:
+            warnings.warn("decode_cfg.draw_flag is set but the reference's utils.visualize is not importable; drawing skipped")
+            _warned_draw = True
+        return None
+
+
+def draw_kp(img, kps, transforms, kp_threshold, infos, keyword):
+    import cv2
+    vis = _visualize()
+    if vis is None or img is None:
+        return img
+    for kp in kps:
+        img = vis.visualize_kp(img, transforms.detransform_pixel(kp.astype(np.float32), infos))
+    cv2.imwrite(r'{}/{}_{}{}.png'.format(base_dir, os.path.basename(infos.img_path), keyword, kp_threshold), img)
+    return img
+
+
+def draw_kp_mask(kp_mask, transforms, kp_threshold, infos, keyword):
+    import cv2
+    cv2.imwrite(r'{}/mask_{}{}'.format(base_dir, keyword, os.path.basename(infos.img_path)), to_numpy(kp_mask) * 255)
+    draw_kp(cv2.imread(infos.img_path), to_numpy(kp_mask.nonzero()), transforms, kp_threshold, infos, keyword)
+
+
+def draw_box(box_sizes, centers, trans_info, transforms):
+    import cv2
+    vis = _visualize()
+    img = cv2.imread(trans_info.img_path)
+    if vis is None or img is None:
+        return
+    centers = [transforms.detransform_pixel(center, trans_info)[0] for center in centers]
+    box_sizes = [box_size[::-1] * compute_scale(trans_info) for box_size in box_sizes]
+    img = vis.visualize_box(img, centers, box_sizes, mask=True)
+    cv2.imwrite(r'{}/{}_{}.png'.format(base_dir, os.path.basename(trans_info.img_path), "box"), img)
+
+
+def draw_candid(kps, lt, rb, img, color):
+    import cv2
+    if img is None:
+        return img
+    cv2.rectangle(img, lt, rb, color)
+    return cv2.drawKeypoints(img, cv2.KeyPoint_convert(kps.reshape((-1, 1, 2))), None, color=color)
+
+
+# ----------------------------------------------------------------------------------------------
+# host side of group_kp: per-instance filter + polygons from the grouped device output
+# ----------------------------------------------------------------------------------------------
+def _identity_transform(transforms) -> bool:
+    """True when detransform_pixel is the plain (y,x)->(x,y) flip (utils/tranform.py:157-171 with the default
+    val_trans.trans_seq = [])."""
+    try:
+        return 'resize' not in transforms.configer.get('val_trans', 'trans_seq')
+    except Exception:
+        return getattr(transforms, "isg_identity", False)
+
+
+def _polygons_for_image(points, offsets, n, centres_yx, whs, center_cls, center_confs, transforms, info, decode_cfg,
+                        identity):
+    """:337-369 — `points` [*,2] fp32 (x,y) grouped by instance (ghost-filtered on the device when `identity`)."""
+    n_clss, n_confs, n_centers, kps = [], [], [], []
+    draw = bool(getattr(decode_cfg, "draw_flag", False))
+    img = None
+    if draw:
+        import cv2
+        img = cv2.imread(info.img_path)
+        color = [int(e) for e in np.random.randint(0, 257, 3)]
+    for i in range(n):
+        pts = points[offsets[i]:offsets[i + 1]]
+        center_loc = transforms.detransform_pixel(centres_yx[i], info)[0]
+        if not identity:
+            # non-identity val transform: the device grouped by label only; filter like :339-353 on the host
+            h, w = tuple(whs[i] * compute_scale(info))
+            true_pixels = transforms.detransform_pixel(pts[:, ::-1], info)
+            x, y = center_loc[0], center_loc[1]
+            x_mask = (x - (0.5 + decode_cfg.wh_delta) * w < true_pixels[:, 0]) * (true_pixels[:, 0] < x + (0.5 + decode_cfg.wh_delta) * w)
+            y_mask = (y - (0.5 + decode_cfg.wh_delta) * h < true_pixels[:, 1]) * (true_pixels[:, 1] < y + (0.5 + decode_cfg.wh_delta) * h)
+            pts = true_pixels[x_mask * y_mask]
+        if pts.shape[0] < decode_cfg.obj_pixel_th:                 # :355
+            continue
+        np_poly = aug_group(pts, center_loc)                        # :359
+        if np_poly is not None:
+            if draw and img is not None:
+                h, w = tuple(whs[i] * compute_scale(info))
+                x, y = center_loc[0], center_loc[1]
+                img = draw_candid(np_poly, (int(x - w / 2), int(y - h / 2)), (int(x + w / 2), int(y + h / 2)), img,
+                                  (color[0] * (i + 1) % 256, color[1] * (i + 1) % 256, color[2] * (i + 1) % 256))
+            kps.append(np_poly)
+            n_centers.append(center_loc)
+            n_clss.append(center_cls[i])
+            n_confs.append(center_confs[i])
+    if draw and img is not None:
+        import cv2
+        cv2.imwrite(r'{}/{}_{}.png'.format(base_dir, os.path.basename(info.img_path), "candid"), img)
+    return n_clss, n_confs, n_centers, kps
+
+
+def _run_plan(kp, ae, boxes_dev, n_dev, layout, decode_cfg, transforms, dev, max_seeds):
+    """Enqueue select/assign/group for a batch; returns (plan, identity)."""
+    B, H, W = kp.shape[0], kp.shape[-2], kp.shape[-1]
+    identity = _identity_transform(transforms)
+    plan = engine.get_decode_plan(B, H, W, max_seeds, int(decode_cfg.kp_th), dev, decode_mode, want_score=False,
+                                  wh_delta=float(decode_cfg.wh_delta) if identity else None,
+                                  scale=float(compute_scale(None)))
+    plan.run(kp, ae, boxes_dev, n_dev, layout)
+    return plan, identity
+
+
+def group_kp(hm_kp, hm_ae, transforms, center_whs, center_indexes, center_cls, center_confs, info, decode_cfg, device):
+    """:288-374 — group the boundary key points of ONE image around the detected box centres.
+    hm_kp [H,W], hm_ae [4,H,W]; center_indexes / center_whs: per-box (y,x) centres and (h,w) sizes."""
+    objs_num = len(center_indexes)
+    dev = _device_of(hm_kp, device)
+    kp = engine.as_f32_planes(hm_kp, dev)[None]
+    ae = engine.as_f32_planes(hm_ae, dev)[None]
+    if objs_num == 0:
+        return [], [], [], []
+    centres = np.vstack(center_indexes).astype(np.float32).reshape(-1, 2)
+    whs = np.vstack(center_whs).astype(np.float32).reshape(-1, 2)
+    boxes = torch.from_numpy(np.ascontiguousarray(np.concatenate([centres, whs], axis=1))[None]).to(dev)
+    n_dev = torch.tensor([objs_num], dtype=torch.int32, device=dev)
+    plan, identity = _run_plan(kp, ae, boxes, n_dev, _lib.ISG_BOX_CYCXHW, decode_cfg, transforms, dev, objs_num)
+    if decode_cfg.draw_flag:
+        mask = select_points(kp[0], decode_cfg.kp_th)
+        draw_kp_mask(mask, transforms, decode_cfg.kp_th, info, "bound")
+    count = int(plan.count[0].item())
+    if count == 0:                                                   # :300
+        return [], [], [], []
+    offsets = plan.offsets[0].cpu().numpy()
+    points = plan.points[0, :int(offsets[objs_num])].cpu().numpy()
+    return _polygons_for_image(points, offsets, objs_num, centres, whs, center_cls, center_confs, transforms, info,
+                               decode_cfg, identity)
+
+
+# ----------------------------------------------------------------------------------------------
+# a2 — box head
+# ----------------------------------------------------------------------------------------------
+_EMPTY = {'rois': np.array(()), 'class_ids': np.array(()), 'scores': np.array(())}
+
+
+def _decode_boxes_device(height, width, anchors, regression, classification, threshold, iou_threshold, dev,
+                         cap=4096, max_keep=1024):
+    """front-end + class-aware NMS on the device; returns the BoxPlan holding the detection tables."""
+    reg = engine.as_f32_planes(regression, dev).contiguous()
+    cls = engine.as_f32_planes(classification, dev).contiguous()
+    anc = engine.as_f32_planes(anchors, dev).contiguous()
+    B, A, C = cls.shape
+    while True:
+        plan = engine.get_box_plan(B, A, C, height, width, dev, cap, max_keep)
+        plan.run(anc, reg, cls, threshold, iou_threshold)
+        return plan
+
+
+def decode_boxes(x, anchors, regression, classification, threshold, iou_threshold):
+    """:377-419 — list (per image) of {'rois' f32 [n,4] (x1,y1,x2,y2), 'class_ids' i64 [n], 'scores' f32 [n]}
+    sorted by score descending; empty images give three empty arrays."""
+    dev = _device_of(classification)
+    height, width = x.shape[2], x.shape[3]
+    cap, max_keep = 4096, 1024
+    while True:
+        plan = _decode_boxes_device(height, width, anchors, regression, classification, threshold, iou_threshold, dev,
+                                    cap, max_keep)
+        n_cand = plan.cand_count.cpu().numpy()
+        n_keep = plan.n_keep.cpu().numpy()
+        if n_cand.max(initial=0) > plan.cap and plan.cap < min(_lib.ISG_NMS_MAX_BOXES, plan.A):
+            cap = min(cap * 4, _lib.ISG_NMS_MAX_BOXES); continue
+        if n_cand.max(initial=0) > plan.cap:
+            raise RuntimeError("decode_boxes: %d candidates above cls_th exceed the supported %d per image"
+                               % (int(n_cand.max()), plan.cap))
+        if n_keep.max(initial=0) > plan.N:
+            max_keep = min(max_keep * 4, plan.cap); continue
+        break
+    rois, scores, cls = plan.rois.cpu().numpy(), plan.scores.cpu().numpy(), plan.cls.cpu().numpy()
+    dets = []
+    for b in range(plan.B):
+        n = int(n_keep[b])
+        if n == 0:
+            dets.append(dict(_EMPTY))                               # :389-393, :413-417
+        else:
+            dets.append({'rois': rois[b, :n].copy(), 'class_ids': cls[b, :n].astype(np.int64), 'scores': scores[b, :n].copy()})
+    return dets
+
+
+def decode_single(kp_heat, ae_mat, boxes, info, transforms, decode_cfg, device):
+    """:422-441"""
+    hm_kp_mat = kp_heat[0]
+    center_cls = boxes["class_ids"]
+    if center_cls.shape[0] == 0:
+        return ([],)
+    lt = boxes["rois"][:, :2][:, ::-1]
+    rb = boxes["rois"][:, 2:][:, ::-1]
+    center_indexes = (lt + rb) / 2
+    center_confs = boxes["scores"]
+    center_whs = rb - lt
+    if decode_cfg.draw_flag:
+        draw_box(center_whs, center_indexes, info, transforms)
+    center_cls, center_confs, center_indexes, groups = group_kp(hm_kp_mat, ae_mat, transforms, center_whs, center_indexes,
+                                                                center_cls, center_confs, info, decode_cfg, device)
+    return ([e for e in zip(center_cls, center_confs, center_indexes, groups)],)
+
+
+def decode_ct_hm(conf_mat, cls_mat, wh, num_classes, cls_th, transforms, info):
+    """:254-285 (dead code in the reference; the only caller of py_cpu_nms)."""
+    cat, height, width = wh.size()
+    center_mask = select_points(conf_mat, cls_th).bool()
+    cls_mat, conf_mat, wh = cls_mat.to(center_mask.device), conf_mat.to(center_mask.device), wh.to(center_mask.device)
+    center_cls = to_numpy(cls_mat.masked_select(center_mask))
+    center_indexes = to_numpy(center_mask.nonzero())
+    center_confs = to_numpy(conf_mat.masked_select(center_mask)).astype(np.float32)
+    center_whs = to_numpy(wh.masked_select(center_mask)).reshape(cat, -1)
+    keep_cls, keep_idx, keep_confs, keep_whs = [], [], [], []
+    for c_i in range(0, num_classes):
+        sel = center_cls == c_i
+        if sel.sum() == 0:
+            continue
+        cls, confs, whs, centers = center_cls[sel], center_confs[sel], center_whs[:, sel], center_indexes[sel, :]
+        tc = transforms.detransform_pixel(centers, info)[:, ::-1]
+        swh = whs * compute_scale(info)
+        boxes = np.array([[*(tc[j] - swh[:, j] / 2), *(tc[j] + swh[:, j] / 2), confs[j]] for j in range(tc.shape[0])],
+                         dtype=np.float32)
+        keep = py_cpu_nms(boxes, thresh=0.5)
+        keep_cls.extend(cls[keep]); keep_idx.extend(centers[keep]); keep_confs.extend(confs[keep]); keep_whs.extend(whs[:, keep].T)
+    return keep_cls, keep_idx, keep_confs, keep_whs
+
+
+def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
+    """:444-461 — decode the model output of a batch into per-image lists of
+    (class id, confidence, centre (x,y) fp32[2], polygon fp32[K,2] (x,y))."""
+    kp_out, regression, classification, anchors = outs
+    dev = require_cuda(device if device is not None else globals()["device"])
+    kp = engine.as_f32_planes(kp_out[0], dev)
+    ae = engine.as_f32_planes(kp_out[1], dev)
+    B, H, W = kp.shape[0], kp.shape[-2], kp.shape[-1]
+    height, width = inputs.shape[2], inputs.shape[3]
+    cap, max_keep = 4096, 256
+    while True:
+        bplan = _decode_boxes_device(height, width, anchors, regression, classification, decode_cfg.cls_th,
+                                     decode_cfg.iou_th, dev, cap, max_keep)
+        plan, identity = _run_plan(kp, ae, bplan.rois, bplan.n_seeds, _lib.ISG_BOX_XYXY, decode_cfg, transforms, dev,
+                                   bplan.N)
+        # one read-back for the whole batch
+        n_cand = bplan.cand_count.cpu().numpy()
+        n_keep = bplan.n_keep.cpu().numpy()
+        if n_cand.max(initial=0) > bplan.cap:
+            if bplan.cap >= min(_lib.ISG_NMS_MAX_BOXES, bplan.A):
+                raise RuntimeError("decode_output: %d candidates above cls_th exceed the supported %d per image"
+                                   % (int(n_cand.max()), bplan.cap))
+            cap = min(cap * 4, _lib.ISG_NMS_MAX_BOXES); continue
+        if n_keep.max(initial=0) > bplan.N:
+            max_keep = min(max(max_keep * 4, int(n_keep.max())), bplan.cap); continue
+        break
+    rois = bplan.rois.cpu().numpy(); scores = bplan.scores.cpu().numpy(); cls = bplan.cls.cpu().numpy()
+    counts = plan.count.cpu().numpy()
+    offsets = plan.offsets.cpu().numpy()
+    tot = int(offsets[np.arange(B), np.minimum(n_keep, bplan.N)].max(initial=0))
+    points = plan.points[:, :max(tot, 1)].cpu().numpy()
+    dets = []
+    for b in range(B):
+        n = int(n_keep[b])
+        if n == 0 or counts[b] == 0:                                # :426-427, :300
+            dets.append([]); continue
+        r = rois[b, :n]
+        lt, rb = r[:, :2][:, ::-1], r[:, 2:][:, ::-1]
+        centres, whs = (lt + rb) / 2, rb - lt                       # :428-432
+        if decode_cfg.draw_flag:
+            draw_box(whs, centres, infos[b], transforms)
+        c, f, ctr, g = _polygons_for_image(points[b], offsets[b], n, centres, whs, cls[b, :n].astype(np.int64),
+                                           scores[b, :n], transforms, infos[b], decode_cfg, identity)
+        dets.append([e for e in zip(c, f, ctr, g)])
+    return dets

@@ -1,0 +1,422 @@
+"""GPU parity: libisg.so (through the drop-in modules, i.e. through the C ABI) against the oracle and the
+reference-run golden fixtures.  Integer / index results must be bit-exact; floating-point results within the
+tolerance north_star states (1e-5 relative, 1e-7 absolute for the far tail)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import DecodeCfg, IdentityTransforms, TransInfo, unpack_bits
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-7
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import isg_b200
+    from isg_b200 import _lib, engine, synth
+    from isg_b200.utils import decode, image, kmeans, nms, utils
+    _lib.lib()
+    return dict(lib=_lib, engine=engine, synth=synth, decode=decode, image=image, kmeans=kmeans, nms=nms, utils=utils)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import ref_decode, ref_kmeans_nms
+    return ref_decode, ref_kmeans_nms
+
+
+DEV = "cuda:0"
+
+
+# ---------------------------------------------------------------------------------------------- K2
+def test_select_points_golden(mods, golden):
+    g = golden("select_points")
+    for name in "abcd":
+        out = mods["decode"].select_points(torch.from_numpy(g["in_" + name]).to(DEV), int(g["k_" + name]))
+        assert out.dtype == torch.uint8 and out.is_cuda
+        assert np.array_equal(out.cpu().numpy(), g["out_" + name]), name
+
+
+@pytest.mark.parametrize("shape,k", [((64, 128), 0), ((64, 128), 64 * 128), ((5, 7), 3), ((1, 1), 1), ((3, 300), 17),
+                                     ((130, 36), 999), ((257, 515), 20000)])
+def test_select_points_shapes_vs_oracle(mods, oracle, shape, k):
+    rd, _ = oracle
+    rs = np.random.RandomState(shape[0] * 1000 + shape[1])
+    m = mods["synth"]._distinct_float32(rs.normal(0.0, 2.0, size=shape).astype(np.float32))
+    want = rd.select_points(torch.from_numpy(m), k).numpy()
+    got = mods["decode"].select_points(torch.from_numpy(m).to(DEV), k).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_select_points_k_too_large_raises(mods):
+    with pytest.raises(RuntimeError):
+        mods["decode"].select_points(torch.zeros(4, 4, device=DEV), 17)
+
+
+def test_select_points_ties_select_all_tied(mods):
+    # documented tie rule: every pixel tied with the k-th value is selected
+    m = torch.zeros(8, 8, device=DEV)
+    m[2, 2] = 5.0
+    m[6, 6] = 5.0
+    out = mods["decode"].select_points(m, 1).cpu().numpy()
+    assert out[2, 2] == 1 and out[6, 6] == 1 and out.sum() == 2
+
+
+def test_topk_count_property_full_size(mods):
+    """size-independent property at BASELINE size: exactly k pixels are >= the selected threshold."""
+    lib, eng = mods["lib"], mods["engine"]
+    H, W, k = 1024, 2048, 20000
+    g = torch.Generator(device="cpu").manual_seed(5)
+    kp = torch.randn((2, H, W), generator=g).to(DEV)
+    kp = kp + torch.arange(H * W, device=DEV).view(1, H, W) * 1e-9   # still may tie; count property allows >= k
+    ws_bytes = int(lib.lib().isg_topk_workspace_bytes(2))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    thr = torch.empty(2, dtype=torch.int32, device=DEV)
+    lib.call("isg_topk_threshold", kp.data_ptr(), 2, H, W, H * W, k, thr.data_ptr(), ws.data_ptr(), ws_bytes,
+             eng.stream_ptr(torch.device(DEV)))
+    for b in range(2):
+        kth = torch.topk(kp[b].reshape(-1), k).values[-1]
+        u = np.array([thr[b].item()], dtype=np.int32).view(np.uint32)[0]
+        f = np.array([u & 0x7FFFFFFF if u & 0x80000000 else ~u], dtype=np.uint32).view(np.float32)[0]
+        assert f == kth.item()
+
+
+def test_nms_hm_golden(mods, golden):
+    g = golden("select_points")
+    heat = torch.from_numpy(g["heat"]).to(DEV)
+    assert np.array_equal(mods["decode"].nms_hm(heat, 3).cpu().numpy(), g["heat_keep3"])
+    assert np.array_equal(mods["decode"].nms_hm(heat, 5).cpu().numpy(), g["heat_keep5"])
+
+
+# ---------------------------------------------------------------------------------------------- K1/K3
+def _run_plan(mods, img, kp_th, mode, want_score=True):
+    eng = mods["engine"]
+    H, W = img.kp.shape[-2:]
+    N = len(img.rois)
+    plan = eng.DecodePlan(1, H, W, N, kp_th, DEV, mode, want_score=want_score)
+    kp = torch.from_numpy(img.kp)[None].to(DEV)
+    ae = torch.from_numpy(img.ae)[None].to(DEV)
+    rois = torch.from_numpy(img.rois)[None].to(DEV).contiguous()
+    n = torch.tensor([N], dtype=torch.int32, device=DEV)
+    plan.run(kp, ae, rois, n)
+    torch.cuda.synchronize()
+    return plan
+
+
+@pytest.mark.parametrize("mode", ["sparse", "dense"])
+@pytest.mark.parametrize("shape,N,kp_th", [((256, 512), 20, 20000), ((96, 160), 5, 100), ((130, 257), 6, 3000)])
+def test_group_core_vs_oracle(mods, oracle, mode, shape, N, kp_th):
+    rd, _ = oracle
+    img = mods["synth"].make_image(77 + N, shape[0], shape[1], N)
+    core = rd.group_core(torch.from_numpy(img.kp[0]), torch.from_numpy(img.ae), img.rois, kp_th)
+    plan = _run_plan(mods, img, kp_th, mode)
+    M = int(plan.count[0].item())
+    assert M == core["idx"].shape[0]
+    assert np.array_equal(unpack_bits(plan.keepbits[0].cpu().numpy(), shape[1]), core["mask"].numpy())
+    assert np.array_equal(plan.idx[0, :M].cpu().numpy(), core["idx"].numpy().astype(np.int32))
+    assert np.array_equal(plan.label[0, :M].cpu().numpy(), core["label"].numpy().astype(np.int32))     # bit-exact
+    np.testing.assert_allclose(plan.score[0, :M].cpu().numpy(), core["score"].numpy(), rtol=RTOL, atol=ATOL)
+    # per-instance point sets (ghost filter + grouping) — exact
+    want = rd.instance_points(core["idx"], core["label"], core["centres"], core["whs"], 0.1)
+    off = plan.offsets[0].cpu().numpy()
+    pts = plan.points[0].cpu().numpy()
+    stats = plan.stats[0].cpu().numpy()
+    for i, (p, _) in enumerate(want):
+        got = pts[off[i]:off[i + 1]]
+        assert np.array_equal(got, p), i
+        assert stats[i, 0] == p.shape[0]
+        if p.shape[0]:
+            assert (stats[i, 1], stats[i, 2], stats[i, 3], stats[i, 4]) == (p[:, 1].min(), p[:, 0].min(), p[:, 1].max(), p[:, 0].max())
+
+
+@pytest.mark.parametrize("shape,N", [((128, 256), 6), ((130, 257), 5), ((256, 512), 40)])
+def test_dense_label_map_vs_oracle(mods, oracle, shape, N):
+    rd, _ = oracle
+    img = mods["synth"].make_image(5 + N, shape[0], shape[1], N)
+    score, label = rd.dense_labels(torch.from_numpy(img.ae), img.rois)
+    plan = _run_plan(mods, img, 2000, "dense")
+    got_l = plan.label_map[0].cpu().numpy()
+    got_s = plan.score_map[0].cpu().numpy()
+    np.testing.assert_allclose(got_s, score.numpy(), rtol=RTOL, atol=ATOL)
+    # labels are bit-exact wherever the oracle's best/second-best margin is not a float-rounding tie
+    P = _all_memberships(rd, img)
+    top2 = np.sort(P, axis=2)[:, :, -2:] if P.shape[2] > 1 else np.concatenate([np.zeros_like(P), P], axis=2)
+    safe = (top2[:, :, 1] - top2[:, :, 0]) > 1e-5 * np.maximum(top2[:, :, 1], 1e-30)
+    safe |= top2[:, :, 1] == 0
+    assert safe.mean() > 0.99
+    assert np.array_equal(got_l[safe], label.numpy()[safe].astype(np.int32))
+    # the dense map restricted to the keep pixels equals the sparse labels
+    M = int(plan.count[0].item())
+    idx = plan.idx[0, :M].cpu().numpy()
+    assert np.array_equal(got_l[idx[:, 0], idx[:, 1]], plan.label[0, :M].cpu().numpy())
+
+
+def _all_memberships(rd, img):
+    """fp32 P[H,W,N] per the oracle's formulas (for margin masks only)."""
+    ae = torch.from_numpy(img.ae)
+    _, h, w = ae.shape
+    ys = torch.linspace(0, 1, 1024)[:h]; xs = torch.linspace(0, 2, 2048)[:w]
+    centres, whs = rd.box_geometry(img.rois)
+    ci = torch.from_numpy(centres).long()
+    C = torch.stack((ys[ci[:, 0]], xs[ci[:, 1]]), dim=1)
+    e0 = torch.tanh(ae[0]) + ys[:, None]; e1 = torch.tanh(ae[1]) + xs[None, :]
+    s0, s1 = torch.exp(ae[2]), torch.exp(ae[3])
+    c_t, wh_t = torch.from_numpy(centres), torch.from_numpy(whs)
+    lt, rb = c_t - wh_t / 2, c_t + wh_t / 2
+    yy = torch.arange(h).float()[:, None, None]; xx = torch.arange(w).float()[None, :, None]
+    inb = (yy - lt[:, 0] >= 0) & (xx - lt[:, 1] >= 0) & (rb[:, 0] - yy >= 0) & (rb[:, 1] - xx >= 0)
+    P = torch.exp(-((e0[..., None] - C[:, 0]) ** 2 * s0[..., None] + (e1[..., None] - C[:, 1]) ** 2 * s1[..., None])) * inb
+    return P.numpy()
+
+
+@pytest.mark.parametrize("name", ["s0", "s1", "s2", "s3"])
+@pytest.mark.parametrize("mode", ["sparse", "dense"])
+def test_decode_single_golden(mods, golden, name, mode):
+    """the drop-in decode_single against polygons produced by the reference itself"""
+    g = golden("decode_single_" + name)
+    dec = mods["decode"]
+    dec.decode_mode = mode
+    try:
+        h, w = g["kp"].shape[-2:]
+        boxes = {"rois": g["rois"], "class_ids": g["class_ids"], "scores": g["scores"]}
+        (dets,) = dec.decode_single(torch.from_numpy(g["kp"]).to(DEV), torch.from_numpy(g["ae"]).to(DEV), boxes,
+                                    TransInfo("/nonexistent.png", (h, w)), IdentityTransforms(),
+                                    DecodeCfg(kp_th=int(g["kp_th"])), torch.device(DEV))
+    finally:
+        dec.decode_mode = "sparse"
+    assert len(dets) == int(g["n_dets"])
+    for i, (cls, conf, ctr, poly) in enumerate(dets):
+        assert int(cls) == int(g["det_cls_%d" % i])
+        assert np.float32(conf) == g["det_conf_%d" % i]
+        assert np.array_equal(ctr, g["det_ctr_%d" % i])
+        assert np.array_equal(poly, g["det_poly_%d" % i])
+
+
+def test_decode_single_no_boxes(mods):
+    dec = mods["decode"]
+    boxes = {"rois": np.array(()), "class_ids": np.array(()), "scores": np.array(())}
+    out = dec.decode_single(torch.zeros(1, 8, 8, device=DEV), torch.zeros(4, 8, 8, device=DEV), boxes,
+                            TransInfo("x", (8, 8)), IdentityTransforms(), DecodeCfg(), torch.device(DEV))
+    assert out == ([],)
+
+
+def test_cpu_device_is_refused(mods):
+    with pytest.raises(RuntimeError):
+        mods["decode"].group_kp(torch.zeros(8, 8), torch.zeros(4, 8, 8), IdentityTransforms(), [np.zeros(2, np.float32)],
+                                [np.zeros(2, np.float32)], [0], [0.5], TransInfo("x", (8, 8)), DecodeCfg(), torch.device("cpu"))
+
+
+# ---------------------------------------------------------------------------------------------- a2 / K5
+def test_decode_boxes_golden(mods, golden):
+    g = golden("decode_boxes")
+    H, W = int(g["H"]), int(g["W"])
+    x = torch.zeros((3, 3, H, W))
+    dets = mods["decode"].decode_boxes(x, torch.from_numpy(g["anchors"]).to(DEV), torch.from_numpy(g["regression"]).to(DEV),
+                                       torch.from_numpy(g["classification"]).to(DEV), 0.3, 0.2)
+    for b, det in enumerate(dets):
+        assert np.array_equal(det["class_ids"], g["cls_%d" % b])
+        assert np.array_equal(det["scores"], g["scores_%d" % b])
+        np.testing.assert_allclose(det["rois"], g["rois_%d" % b].reshape(det["rois"].shape), rtol=1e-6, atol=1e-4)
+    assert dets[2]["rois"].shape == (0,)
+
+
+def test_bbox_transform_and_clip_vs_oracle(mods, oracle, golden):
+    rd, _ = oracle
+    g = golden("decode_boxes")
+    anchors, reg = torch.from_numpy(g["anchors"]), torch.from_numpy(g["regression"])
+    want = rd.bbox_transform(anchors, reg)
+    got = mods["utils"].BBoxTransform()(anchors.to(DEV), reg.to(DEV))
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-6, atol=1e-4)
+    img = torch.zeros((3, 3, int(g["H"]), int(g["W"])))
+    clipped = mods["utils"].ClipBoxes()(got, img)
+    assert clipped.data_ptr() == got.data_ptr()
+    np.testing.assert_allclose(clipped.cpu().numpy(), rd.clip_boxes(want, int(g["H"]), int(g["W"])).numpy(), rtol=1e-6, atol=1e-4)
+
+
+def test_py_cpu_nms_golden(mods, golden):
+    g = golden("nms")
+    for name in "abc":
+        keep = mods["nms"].py_cpu_nms(g["dets_" + name], float(g["thr_" + name]))
+        assert isinstance(keep, list)
+        assert np.array_equal(np.asarray(keep, dtype=np.int64), g["keep_" + name]), name
+    assert mods["nms"].py_cpu_nms(np.zeros((0, 5), np.float32), 0.5) == []
+
+
+@pytest.mark.parametrize("n,thr", [(1000, 0.5), (2500, 0.3), (65, 0.7)])
+def test_py_cpu_nms_vs_oracle(mods, oracle, n, thr):
+    _, rk = oracle
+    dets = mods["synth"].make_nms_boxes(n, n, extent=1500.0, thr=thr, plus1=True)
+    assert np.array_equal(np.asarray(mods["nms"].py_cpu_nms(dets, thr)), np.asarray(rk.py_cpu_nms(dets, thr)))
+
+
+def test_boxes_nms_intended_semantics(mods, oracle):
+    _, rk = oracle
+    dets = mods["synth"].make_nms_boxes(9, 400, extent=500.0, thr=0.4, plus1=True)
+    rs = np.random.RandomState(1)
+    d = {"rois": dets[:, :4], "scores": dets[:, 4], "class_ids": rs.randint(0, 5, size=len(dets))}
+    c1, b1, s1 = mods["nms"].boxes_nms(d, 0.4)
+    c2, b2, s2 = rk.boxes_nms(d, 0.4)
+    assert np.array_equal(np.asarray(c1), np.asarray(c2)) and np.array_equal(np.asarray(b1), np.asarray(b2))
+    assert np.array_equal(np.asarray(s1), np.asarray(s2))
+    assert mods["nms"].boxes_nms({"class_ids": np.array(()), "rois": np.array(()), "scores": np.array(())}, 0.5) == ([], [], [])
+
+
+def test_tv_nms_vs_torchvision(mods):
+    from torchvision.ops.boxes import batched_nms
+    lib, eng = mods["lib"], mods["engine"]
+    n, thr = 3000, 0.2
+    dets = mods["synth"].make_nms_boxes(4, n, extent=2000.0, thr=thr, plus1=False)
+    n = len(dets)
+    rs = np.random.RandomState(2)
+    cls = rs.randint(0, 8, size=n).astype(np.int32)
+    want = batched_nms(torch.from_numpy(dets[:, :4].copy()), torch.from_numpy(dets[:, 4].copy()), torch.from_numpy(cls).long(), thr).numpy()
+    d = torch.device(DEV)
+    boxes = torch.from_numpy(dets[:, :4].copy()).to(d).contiguous(); scores = torch.from_numpy(dets[:, 4].copy()).to(d)
+    clsd = torch.from_numpy(cls).to(d); count = torch.tensor([n], dtype=torch.int32, device=d)
+    keep = torch.empty(n, dtype=torch.int32, device=d); nk = torch.empty(1, dtype=torch.int32, device=d)
+    wsb = int(lib.lib().isg_box_nms_workspace_bytes(1, n)); ws = torch.empty(wsb + 256, dtype=torch.uint8, device=d)
+    off = (-ws.data_ptr()) % 256
+    lib.call("isg_box_nms", boxes.data_ptr(), scores.data_ptr(), clsd.data_ptr(), 0, count.data_ptr(), 1, n, thr,
+             lib.ISG_NMS_TV_GT, keep.data_ptr(), nk.data_ptr(), ws.data_ptr() + off, wsb, eng.stream_ptr(d))
+    got = keep[:int(nk.item())].cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------- full decode
+@pytest.mark.parametrize("mode", ["sparse", "dense"])
+def test_decode_output_vs_oracle(mods, oracle, mode):
+    rd, _ = oracle
+    synth, dec = mods["synth"], mods["decode"]
+    H, W, C, B = 256, 512, 8, 3
+    anchors = synth.make_anchors(H, W)
+    scenes = [synth.make_scene(300 + b, H, W, [12, 0, 25][b], C, anchors) for b in range(B)]
+    kp = torch.from_numpy(np.stack([s[0].kp for s in scenes])); ae = torch.from_numpy(np.stack([s[0].ae for s in scenes]))
+    reg = torch.from_numpy(np.stack([s[1] for s in scenes])); cls = torch.from_numpy(np.stack([s[2] for s in scenes]))
+    anc = torch.from_numpy(anchors)
+    want = rd.decode_output(H, W, ((kp, ae, None), reg, cls, anc), kp_th=3000)
+    dec.decode_mode = mode
+    try:
+        inputs = torch.zeros((B, 3, H, W))
+        infos = [TransInfo("/nonexistent.png", (H, W))] * B
+        got = dec.decode_output(inputs, ((kp.to(DEV), ae.to(DEV), None), reg.to(DEV), cls.to(DEV), anc.to(DEV)), infos,
+                                IdentityTransforms(), DecodeCfg(kp_th=3000), torch.device(DEV))
+    finally:
+        dec.decode_mode = "sparse"
+    assert len(got) == B and len(got[1]) == 0
+    for b in range(B):
+        assert len(got[b]) == len(want[b]) and (b == 1 or len(got[b]) > 0)
+        for (c1, f1, ctr1, p1), (c2, f2, ctr2, p2) in zip(got[b], want[b]):
+            assert int(c1) == int(c2) and np.float32(f1) == np.float32(f2)
+            assert np.array_equal(ctr1, ctr2) and np.array_equal(p1, p2)
+
+
+def test_decode_output_from_host_tensors(mods):
+    """the e2e entry: pinned host tensors in, python lists out"""
+    synth, dec = mods["synth"], mods["decode"]
+    H, W = 128, 256
+    anchors = synth.make_anchors(H, W)
+    img, reg, cls, _ = synth.make_scene(9, H, W, 6, 8, anchors)
+    outs = ((torch.from_numpy(img.kp)[None].pin_memory(), torch.from_numpy(img.ae)[None].pin_memory(), None),
+            torch.from_numpy(reg)[None].pin_memory(), torch.from_numpy(cls)[None].pin_memory(), torch.from_numpy(anchors))
+    got = dec.decode_output(torch.zeros((1, 3, H, W)), outs, [TransInfo("x", (H, W))], IdentityTransforms(),
+                            DecodeCfg(kp_th=2000), torch.device(DEV))
+    assert len(got) == 1 and len(got[0]) >= 1
+    assert got[0][0][3].dtype == np.float32 and got[0][0][3].shape[1] == 2
+
+
+# ---------------------------------------------------------------------------------------------- K4
+def test_kmeans_golden(mods, golden):
+    g = golden("kmeans")
+    km = mods["kmeans"]
+    lab, ctr = km.kmeans(torch.from_numpy(g["X"]), 10, torch.from_numpy(g["init"]), g["allow"], device=torch.device(DEV))
+    assert lab.dtype == torch.int64
+    assert np.array_equal(lab.cpu().numpy(), g["labels"])
+    np.testing.assert_allclose(ctr.cpu().numpy(), g["centers"], rtol=RTOL, atol=ATOL)
+    lab, ctr = km.kmeans(torch.from_numpy(g["X"] + 1.0), 10, torch.from_numpy(g["init"] + 1.0), np.full(10, 0.002, dtype=np.float32),
+                         distance="cosine", device=torch.device(DEV))
+    assert np.array_equal(lab.cpu().numpy(), g["labels_cos"])
+    np.testing.assert_allclose(ctr.cpu().numpy(), g["centers_cos"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(km.pairwise_distance(torch.from_numpy(g["X"][:40]), torch.from_numpy(g["init"]), torch.device(DEV)).cpu().numpy(),
+                               g["pd"], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(km.pairwise_cosine(torch.from_numpy(g["X"][:40] + 1.0), torch.from_numpy(g["init"] + 1.0), torch.device(DEV)).cpu().numpy(),
+                               g["pc"], rtol=0, atol=2e-7)
+    with pytest.raises(NotImplementedError):
+        km.kmeans(torch.zeros(4, 2), 2, torch.zeros(2, 2), np.ones(2, np.float32), distance="manhattan")
+
+
+def test_kmeans_dense_crowd_vs_oracle(mods, oracle):
+    """BASELINE config 4 shape: M = 20000 embeddings, N = 500 seeds, allow = 0.05"""
+    _, rk = oracle
+    rs = np.random.RandomState(4)
+    N, M = 500, 20000
+    cen = np.stack([rs.uniform(0.05, 0.95, N), rs.uniform(0.05, 1.95, N)], axis=1).astype(np.float32)
+    X = (cen[rs.randint(0, N, size=M)] + rs.normal(0, 0.004, size=(M, 2))).astype(np.float32)
+    init = (cen + rs.normal(0, 0.002, size=cen.shape)).astype(np.float32)
+    allow = np.full(N, 0.05, dtype=np.float32)
+    lab_w, ctr_w, it_w = rk.kmeans(torch.from_numpy(X), N, torch.from_numpy(init), allow)
+    lab, ctr = mods["kmeans"].kmeans(torch.from_numpy(X), N, torch.from_numpy(init), allow, device=torch.device(DEV))
+    # labels are exact except where two centres are equidistant within fp32 rounding (not present in this draw)
+    assert (lab.cpu().numpy() != lab_w.numpy()).mean() < 1e-3
+    np.testing.assert_allclose(ctr.cpu().numpy(), ctr_w.numpy(), rtol=RTOL, atol=1e-6)
+    assert abs(mods["kmeans"].kmeans.last_iterations - it_w) <= 1
+
+
+# ---------------------------------------------------------------------------------------------- K6
+def test_mask_iou_golden(mods, golden):
+    g = golden("mask_iou")
+    H, W = int(g["H"]), int(g["W"])
+    dense = unpack_bits(g["masks"], W).astype(np.int32)
+    im = mods["image"]
+    bits = im.pack_masks(dense)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), g["masks"])
+    for i in range(len(dense)):
+        for j in range(len(dense)):
+            assert im.compute_iou_for_mask(dense[i], dense[j]) == g["iou"][i, j]
+            assert im.is_cover(dense[i], dense[j]) == bool(g["cover"][i, j])
+
+
+@pytest.mark.parametrize("n,H,W,C,thr,with_boxes", [(60, 96, 130, 3, 0.5, True), (200, 200, 333, 10, 0.3, False), (33, 64, 64, 1, 0.7, True)])
+def test_mask_nms_vs_oracle(mods, oracle, n, H, W, C, thr, with_boxes):
+    _, rk = oracle
+    masks, boxes, scores, cls = mods["synth"].make_masks(n + H, n, H, W, C)
+    want = rk.mask_nms(masks, scores, cls, thr)
+    got = mods["nms"].mask_nms(masks, scores, cls, thr, bboxes=boxes if with_boxes else None)
+    assert np.array_equal(got, np.asarray(want, dtype=np.int64))
+    got_agn = mods["nms"].mask_nms(masks, scores, None, thr)
+    assert np.array_equal(got_agn, np.asarray(rk.mask_nms(masks, scores, None, thr), dtype=np.int64))
+
+
+# ---------------------------------------------------------------------------------------------- full size
+def test_full_size_batch_properties(mods, oracle):
+    """BASELINE full size (1024x2048, ~100 seeds): dense and sparse agree with each other on every keep pixel,
+    labels of keep pixels match the oracle on one image, and the per-instance counts are consistent."""
+    rd, _ = oracle
+    synth, eng = mods["synth"], mods["engine"]
+    H, W, N, B = 1024, 2048, 100, 2
+    imgs = [synth.make_image(1000 + b, H, W, N) for b in range(B)]
+    kp = torch.from_numpy(np.stack([i.kp for i in imgs])).to(DEV)
+    ae = torch.from_numpy(np.stack([i.ae for i in imgs])).to(DEV)
+    rois = torch.from_numpy(np.stack([i.rois for i in imgs])).to(DEV).contiguous()
+    n = torch.full((B,), N, dtype=torch.int32, device=DEV)
+    out = {}
+    for mode in ("sparse", "dense"):
+        plan = eng.DecodePlan(B, H, W, N, 20000, DEV, mode, want_score=True)
+        plan.run(kp, ae, rois, n)
+        torch.cuda.synchronize()
+        out[mode] = {k: getattr(plan, k).cpu().numpy() for k in ("count", "idx", "label", "score", "flag", "offsets", "points", "stats")}
+    for k in ("count", "offsets", "stats"):
+        assert np.array_equal(out["sparse"][k], out["dense"][k]), k
+    for b in range(B):
+        M = int(out["sparse"]["count"][b]); T = int(out["sparse"]["offsets"][b, N])
+        for k in ("idx", "label", "flag"):
+            assert np.array_equal(out["sparse"][k][b, :M], out["dense"][k][b, :M]), k
+        assert np.array_equal(out["sparse"]["points"][b, :T], out["dense"]["points"][b, :T])
+    core = rd.group_core(torch.from_numpy(imgs[0].kp[0]), torch.from_numpy(imgs[0].ae), imgs[0].rois, 20000)
+    M = int(out["sparse"]["count"][0])
+    assert M == core["idx"].shape[0]
+    assert np.array_equal(out["sparse"]["idx"][0, :M], core["idx"].numpy().astype(np.int32))
+    assert np.array_equal(out["sparse"]["label"][0, :M], core["label"].numpy().astype(np.int32))
+    np.testing.assert_allclose(out["sparse"]["score"][0, :M], core["score"].numpy(), rtol=RTOL, atol=ATOL)
+    assert out["sparse"]["stats"][0, :, 0].sum() == out["sparse"]["flag"][0, :M].sum() == out["sparse"]["offsets"][0, N]
