@@ -117,7 +117,7 @@ hist_pass_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, uint
   __syncthreads();
   for (int i = t; i < kHistBins; i += kHistThreads) {
     const uint32_t c = sh[i];
-    if (c) atomicAdd(&hist[i], c);
+    if (c) atomicAdd(&hist[PASS * kHistBins + i], c);
   }
 }
 

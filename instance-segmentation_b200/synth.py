@@ -175,7 +175,7 @@ def make_anchors(H: int, W: int, strides=(8, 16, 32, 64, 128), anchor_scale: flo
 
 
 def _iou_matrix(b: np.ndarray) -> np.ndarray:
-    b = b.astype(np.float64)
+    b = b.astype(np.float64).reshape(-1, 4)
     area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
     x1 = np.maximum(b[:, None, 0], b[None, :, 0]); y1 = np.maximum(b[:, None, 1], b[None, :, 1])
     x2 = np.minimum(b[:, None, 2], b[None, :, 2]); y2 = np.minimum(b[:, None, 3], b[None, :, 3])
@@ -295,7 +295,7 @@ def make_scene(seed: int, H: int, W: int, N: int, C: int = 8, anchors: np.ndarra
             if bx[0] < 0 or bx[1] < 0 or bx[2] > W - 1 or bx[3] > H - 1 or bx[2] - bx[0] < 4 or bx[3] - bx[1] < 4:
                 continue
             cand.append((bx, float(img.scores[j]) * float(rs.uniform(0.45, 0.95)), int(img.class_ids[j])))
-    boxes = np.array([c[0] for c in cand], dtype=np.float64)
+    boxes = np.array([c[0] for c in cand], dtype=np.float64).reshape(-1, 4)
     scores = _distinct_float32(np.array([c[1] for c in cand], dtype=np.float32))
     classes = np.array([c[2] for c in cand], dtype=np.int64)
     ok = scores > cls_th + 1e-3
