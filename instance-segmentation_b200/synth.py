@@ -171,7 +171,7 @@ def make_anchors(H: int, W: int, strides=(8, 16, 32, 64, 128), anchor_scale: flo
                 xv, yv = xv.reshape(-1), yv.reshape(-1)
                 per.append(np.vstack((yv - ay2, xv - ax2, yv + ay2, xv + ax2)).T[:, None, :])
         levels.append(np.concatenate(per, axis=1).reshape(-1, 4))
-    return np.vstack(levels).astype(np.float32)[None]
+    return np.ascontiguousarray(np.vstack(levels), dtype=np.float32)[None]
 
 
 def _iou_matrix(b: np.ndarray) -> np.ndarray:
