@@ -43,16 +43,20 @@ class Image:
 
 
 def _distinct_float32(v: np.ndarray) -> np.ndarray:
-    """Return a float32 array with the same ordering as `v` (ties broken by position) and no duplicates."""
-    flat = v.astype(np.float32).ravel()
+    """Return a float32 array with the same ordering as `v` (ties broken by position) and no two EQUAL values
+    (-0.0 never appears, so key-distinct implies value-distinct)."""
+    flat = v.astype(np.float32).ravel() + np.float32(0.0)                 # -0.0 -> +0.0
     u = flat.view(np.uint32)
     key = np.where(u & 0x80000000, ~u, u | 0x80000000).astype(np.int64)  # monotone in the float value
+    k0 = 0x7FFFFFFF                                                      # key of -0.0: removed from the key space
+    key = key - (key > k0)
     order = np.argsort(key, kind="stable")
     ks = key[order]
     i = np.arange(ks.size, dtype=np.int64)
     ks2 = np.maximum.accumulate(ks - i) + i                              # strictly increasing
     out_key = np.empty_like(ks2)
     out_key[order] = ks2
+    out_key = out_key + (out_key >= k0)
     ku = out_key.astype(np.uint64).astype(np.uint32)
     back = np.where(ku & 0x80000000, ku & 0x7FFFFFFF, ~ku).astype(np.uint32)
     return back.view(np.float32).reshape(v.shape)

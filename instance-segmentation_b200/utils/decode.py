@@ -174,6 +174,17 @@ def smooth_polygon(polar_pts, sorted_inds, k=360):
     return selected
 
 
+def _polygon_area_is_zero(sorted_kp) -> bool:
+    """`image.poly_to_mask(sorted_kp).sum() == 0` (:187-189) evaluated on the polygon's own bounding box:
+    fillPoly on integer vertices is invariant under integer translation, so rasterising the polygon shifted
+    to the origin gives the same pixel count without allocating a canvas as large as the image."""
+    import cv2
+    poly = sorted_kp.astype(np.int32)
+    lo = poly.min(0)
+    size = (poly.max(0) - lo + 1)[::-1]
+    return not cv2.fillPoly(np.zeros(size, dtype=np.uint8), [poly - lo], 1).any()
+
+
 def aug_group(pts, center_loc):
     """:167-204 — order the points by polar angle about an internal point; None if degenerate."""
     import cv2
@@ -182,7 +193,7 @@ def aug_group(pts, center_loc):
     polar_pts = cartesian2polar(pts, internal_point)
     sorted_inds = np.argsort(polar_pts[:, 0])
     sorted_kp = pts[sorted_inds]
-    if image.poly_to_mask(sorted_kp).sum() == 0:
+    if _polygon_area_is_zero(sorted_kp):
         return None
     if cv2.pointPolygonTest(sorted_kp, tuple(center_loc), False) > 0:
         return sorted_kp

@@ -1,0 +1,127 @@
+"""CPU: host-side logic of the drop-in modules (polygon glue, generator guarantees, API surface)."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import DecodeCfg, IdentityTransforms, TransInfo
+
+
+@pytest.fixture(scope="module")
+def dec():
+    import isg_b200  # noqa: F401
+    from isg_b200.utils import decode
+    return decode
+
+
+def test_call_surface_matches_reference(dec):
+    """names and argument order of SURVEY.md §8b"""
+    from isg_b200.utils import kmeans, nms
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(dec.decode_output) == ["inputs", "outs", "infos", "transforms", "decode_cfg", "device"]
+    assert sig(dec.decode_single) == ["kp_heat", "ae_mat", "boxes", "info", "transforms", "decode_cfg", "device"]
+    assert sig(dec.decode_boxes) == ["x", "anchors", "regression", "classification", "threshold", "iou_threshold"]
+    assert sig(dec.group_kp) == ["hm_kp", "hm_ae", "transforms", "center_whs", "center_indexes", "center_cls", "center_confs",
+                                 "info", "decode_cfg", "device"]
+    assert sig(dec.select_points) == ["mat", "k"] and sig(dec.nms_hm) == ["heat", "kernel"]
+    assert sig(dec.decode_ct_hm) == ["conf_mat", "cls_mat", "wh", "num_classes", "cls_th", "transforms", "info"]
+    assert sig(kmeans.kmeans) == ["X", "num_clusters", "cluster_centers", "allow_distances", "distance", "tol", "device"]
+    assert sig(kmeans.pairwise_distance) == ["data1", "data2", "device"] and sig(kmeans.pairwise_cosine) == ["data1", "data2", "device"]
+    assert sig(nms.py_cpu_nms) == ["dets", "thresh"] and sig(nms.boxes_nms) == ["dets", "thresh"]
+    assert dec.base_dir == "" and dec.target_size == 1 and dec.xym.shape == (2, 1024, 2048)
+
+
+def test_cartesian2polar_matches_scalar_loop(dec):
+    """the vectorised form against the reference's per-point control flow (utils/decode.py:96-112)"""
+    rs = np.random.RandomState(0)
+    pts = rs.randint(0, 50, size=(400, 2)).astype(np.float32)
+    for c in (np.array([25.0, 25.0], np.float32), np.array([24.5, 10.5], np.float32), pts[7].copy()):
+        want = []
+        with np.errstate(divide="ignore", invalid="ignore"):
+            for p in pts:
+                d_x, d_y = tuple(p - c)
+                if d_x == 0 and d_y > 0:
+                    seta = np.pi / 2
+                elif d_x == 0 and d_y < 0:
+                    seta = 3 * np.pi / 2
+                else:
+                    seta = np.arctan(d_y / d_x)
+                    if d_x < 0:
+                        seta = seta + np.pi
+                    elif d_x > 0 and d_y < 0:
+                        seta = seta + 2 * np.pi
+                want.append(np.array([[seta, np.sqrt(d_x ** 2 + d_y ** 2)]], dtype=np.float32))
+        want = np.vstack(want)
+        got = dec.cartesian2polar(pts, c)
+        assert np.array_equal(got, want, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["s0", "s1", "s2", "s3"])
+def test_aug_group_reproduces_reference_polygons(dec, golden, name):
+    """host polygon glue fed with the point sets the reference handed to its own aug_group"""
+    g = golden("decode_single_" + name)
+    polys = [g["det_poly_%d" % i] for i in range(int(g["n_dets"]))]
+    out = []
+    for i in range(int(g["n_groups"])):
+        p = dec.aug_group(g["grp_pts_%d" % i], g["grp_ctr_%d" % i])
+        if p is not None:
+            out.append(p)
+    assert len(out) == len(polys)
+    for a, b in zip(out, polys):
+        assert np.array_equal(a, b)
+
+
+def test_polygon_area_predicate_equals_full_canvas(dec):
+    from isg_b200.utils import image
+    rs = np.random.RandomState(3)
+    for _ in range(300):
+        k = rs.randint(1, 30)
+        p = (rs.randint(0, 40, size=(k, 2)) + rs.randint(0, 300, size=2)).astype(np.float32)
+        assert dec._polygon_area_is_zero(p) == (image.poly_to_mask(p).sum() == 0)
+
+
+def test_degenerate_polygon_is_dropped(dec):
+    # centre outside the point set -> pointPolygonTest fails -> None (utils/decode.py:201-204)
+    pts = np.array([[10, 10], [20, 10], [20, 20], [10, 20]], np.float32)
+    assert dec.aug_group(pts, np.array([50.0, 50.0], np.float32)) is None
+    assert dec.aug_group(pts, np.array([15.0, 15.0], np.float32)) is not None
+
+
+def test_no_cpu_path(dec):
+    with pytest.raises(RuntimeError):
+        dec.select_points(torch.zeros(8, 8), 3)
+    with pytest.raises(RuntimeError):
+        dec.decode_output(torch.zeros(1, 3, 8, 8), ((torch.zeros(1, 1, 8, 8), torch.zeros(1, 4, 8, 8), None), torch.zeros(1, 4, 4),
+                                                    torch.zeros(1, 4, 2), torch.zeros(1, 4, 4)), [TransInfo("x", (8, 8))],
+                          IdentityTransforms(), DecodeCfg(), torch.device("cpu"))
+
+
+def test_generator_guarantees():
+    import isg_b200  # noqa: F401
+    from isg_b200 import synth
+    a = synth.make_image(5, 96, 160, 5)
+    b = synth.make_image(5, 96, 160, 5)
+    assert np.array_equal(a.kp, b.kp) and np.array_equal(a.ae, b.ae) and np.array_equal(a.rois, b.rois)   # deterministic
+    assert np.unique(a.kp).size == a.kp.size                                                              # tie-free
+    c = (a.rois[:, :2] + a.rois[:, 2:]) / 2
+    assert np.all(c - np.floor(c) == 0.5) and np.all((a.rois[:, 2:] - a.rois[:, :2]) % 2 == 0)
+    assert np.unique(a.scores).size == a.scores.size and np.all(np.diff(a.scores) < 0)
+    x = synth._distinct_float32(np.array([1.0, 1.0, -0.0, 0.0, 1.0, np.float32(1.0000001)], np.float32))
+    assert np.unique(x).size == 6 and np.all(np.argsort(x, kind="stable") == np.argsort(np.array([1, 1, -0.0, 0.0, 1, 1.0000001], np.float32), kind="stable"))
+    anc = synth.make_anchors(128, 256)
+    assert anc.shape == (1, 9 * (16 * 32 + 8 * 16 + 4 * 8 + 2 * 4 + 1 * 2), 4) and anc.flags["C_CONTIGUOUS"]
+
+
+def test_scene_box_head_decodes_to_the_image_boxes():
+    """oracle decode_boxes on a synthetic scene returns (a subset of) the image's instance boxes, exactly"""
+    import isg_b200  # noqa: F401
+    from isg_b200 import synth
+    from oracle import ref_decode as rd
+    img, reg, cls, anc = synth.make_scene(11, 128, 256, 6)
+    det = rd.decode_boxes(128, 256, torch.from_numpy(anc), torch.from_numpy(reg)[None], torch.from_numpy(cls)[None], 0.3, 0.2)[0]
+    assert 1 <= len(det["class_ids"]) <= 6
+    ctr = (det["rois"][:, :2] + det["rois"][:, 2:]) / 2
+    assert np.all(ctr - np.floor(ctr) == 0.5)
+    empty = synth.make_scene(12, 128, 256, 0)
+    assert (empty[2].max(axis=1) > 0.3).sum() == 0
