@@ -195,7 +195,7 @@ def run_ours(args, wl, rank, world, local_rank):
     d = {k: v.to(dev) for k, v in host.items()}
     A, C = d["classification"].shape[1], d["classification"].shape[2]
     max_keep = max(64, 1 << int(np.ceil(np.log2(N * 1.3))))
-    bplan = engine.BoxPlan(B, A, C, H, W, dev, cap=4096, max_keep=max_keep)
+    bplan = engine.BoxPlan(B, A, C, H, W, dev, cap=1024, max_keep=max_keep)
     dplan = engine.DecodePlan(B, H, W, bplan.N, wl["kp_th"], dev, args.mode, want_score=False, wh_delta=WH_DELTA)
     dplan.events = []
 

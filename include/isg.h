@@ -68,7 +68,7 @@ int         isg_device_supported(int device);
  *   keep(p) = sel(p) && v(p) == max over the 3x3 window clipped to the image of v   (:45-47,85)
  * With ties at the k-th value every tied pixel is selected (torch.topk's choice is unspecified).
  * ------------------------------------------------------------------------------------------ */
-size_t isg_topk_workspace_bytes(int B);
+size_t isg_topk_workspace_bytes(int B, int H, int W, int k);
 /* k-th largest value per image as an order-preserving uint32 key (see isg_float_key in DESIGN.md).
  * kp: [B] images of H*W fp32, image b at kp + b*img_stride.  k in [0, H*W]; k > H*W -> ISG_EINVAL
  * (the reference's topk raises).  k == 0 selects nothing (key = 0xFFFFFFFF). */
@@ -78,8 +78,8 @@ int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t img_stride,
  * mask_u8 (nullable): [B,H,W] uint8 0/1, the tensor select_points returns. */
 int isg_keep_points(const float* kp, int B, int H, int W, int64_t img_stride, const uint32_t* thr_key,
                     uint32_t* keepbits, uint8_t* mask_u8, isg_stream_t stream);
-/* isg_topk_threshold + isg_keep_points; workspace = isg_topk_workspace_bytes(B) + 4*B bytes */
-size_t isg_select_points_workspace_bytes(int B);
+/* isg_topk_threshold + isg_keep_points.  Workspaces must be 256-byte aligned. */
+size_t isg_select_points_workspace_bytes(int B, int H, int W, int k);
 int isg_select_points(const float* kp, int B, int H, int W, int64_t img_stride, int k,
                       uint32_t* keepbits, uint8_t* mask_u8, void* ws, size_t ws_bytes, isg_stream_t stream);
 /* nms_hm (utils/decode.py:42-48): keep[p] = heat[p] == max over kernel x kernel window (stride 1,

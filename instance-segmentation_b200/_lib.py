@@ -19,10 +19,10 @@ PROTOTYPES = {
     "isg_abi_version": (I, []),
     "isg_strerror": (C.c_char_p, [I]),
     "isg_device_supported": (I, [I]),
-    "isg_topk_workspace_bytes": (SZ, [I]),
+    "isg_topk_workspace_bytes": (SZ, [I, I, I, I]),
     "isg_topk_threshold": (I, [P, I, I, I, I64, I, P, P, SZ, P]),
     "isg_keep_points": (I, [P, I, I, I, I64, P, P, P, P]),
-    "isg_select_points_workspace_bytes": (SZ, [I]),
+    "isg_select_points_workspace_bytes": (SZ, [I, I, I, I]),
     "isg_select_points": (I, [P, I, I, I, I64, I, P, P, P, SZ, P]),
     "isg_nms_hm": (I, [P, I, I, I, I, P, P]),
     "isg_compact_points": (I, [P, I, I, I, I, P, P, P]),
@@ -91,13 +91,18 @@ def check(code: int, where: str) -> None:
 # number of kernels/launches enqueued through this binding (the bench's `gpu_launches` claim)
 launch_count = 0
 
-# kernels each entry point enqueues (excluding memsets); keep in sync with csrc/
+# kernels each entry point enqueues (excluding memsets); an int, or a function of the call's arguments where
+# the entry point picks a path by size.  Keep in sync with csrc/.
 _LAUNCHES = {
-    "isg_topk_threshold": 4, "isg_keep_points": 1, "isg_select_points": 5, "isg_nms_hm": 1,
+    "isg_topk_threshold": 3, "isg_keep_points": 1, "isg_select_points": 4, "isg_nms_hm": 1,
     "isg_compact_points": 1, "isg_build_seeds": 1, "isg_stats_init": 1, "isg_assign_sparse": 1,
-    "isg_assign_dense": 1, "isg_gather_labels": 1, "isg_group_points": 3, "isg_decode_boxes": 1,
-    "isg_gather_kept": 1, "isg_box_nms": 3, "isg_mask_nms": 5, "isg_mask_pair_counts": 1, "isg_pairwise": 1,
+    "isg_assign_dense": 1, "isg_gather_labels": 1, "isg_decode_boxes": 1,
+    "isg_gather_kept": 1, "isg_mask_nms": 5, "isg_mask_pair_counts": 1, "isg_pairwise": 1,
     "isg_bbox_transform": 1, "isg_clip_boxes": 1, "isg_pack_masks": 1,
+    # (idx,label,flag,count,cap,n_seeds,B,Nmax,...): one multisplit kernel unless the seed table is huge
+    "isg_group_points": lambda a: 1 if (16 * a[7] + a[7] + 1) * 4 <= 200 * 1024 else 3,
+    # (boxes,scores,cls,tiebreak,count,B,cap,...): fused single-CTA kernel for cap <= 1024
+    "isg_box_nms": lambda a: 1 if a[6] <= 1024 else 3,
 }
 
 
@@ -107,4 +112,5 @@ def call(name: str, *args) -> None:
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise IsgError(rc, name)
-    launch_count += _LAUNCHES.get(name, 0)
+    n = _LAUNCHES.get(name, 0)
+    launch_count += n(args) if callable(n) else n

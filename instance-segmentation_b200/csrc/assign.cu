@@ -429,6 +429,88 @@ group_scatter_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// grouping v2: stable multisplit by label, one CTA per image.  Warp w owns a contiguous segment of the
+// row-major keep list; per-warp label histograms (phase 1) are prefix-summed across warps and labels
+// (phase 2) and each warp then scatters its segment in order (phase 3).  __match_any_sync gives every lane
+// its rank among the lanes of the same label, so the output order inside an instance stays row-major.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSplitWarps = 16;
+
+__global__ void __launch_bounds__(32 * kSplitWarps)
+group_split_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ label,
+                   const uint8_t* __restrict__ flag, const int32_t* __restrict__ count, int cap,
+                   const int32_t* __restrict__ n_seeds, int Nmax, int32_t* __restrict__ offsets,
+                   float* __restrict__ points) {
+  extern __shared__ int sm_split[];
+  int* hist = sm_split;                       // [kSplitWarps][Nmax]
+  int* tot = sm_split + kSplitWarps * Nmax;   // [Nmax + 1]
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = min(count[b], cap), n = min(n_seeds[b], Nmax);
+  const int32_t* lb = label + (size_t)b * cap;
+  const uint8_t* fb = flag + (size_t)b * cap;
+  const int32_t* ib = idx + (size_t)b * cap * 2;
+  float2* out = reinterpret_cast<float2*>(points) + (size_t)b * cap;
+  int32_t* off_g = offsets + (size_t)b * (Nmax + 1);
+  for (int i = tid; i < kSplitWarps * Nmax; i += 32 * kSplitWarps) hist[i] = 0;
+  __syncthreads();
+  const int seg = ((M + kSplitWarps * 32 - 1) / (kSplitWarps * 32)) * 32;
+  const int m0 = warp * seg, m1 = min(m0 + seg, M);
+  int* myhist = hist + warp * Nmax;
+  // phase 1
+  for (int mb = m0; mb < m1; mb += 32) {
+    const int m = mb + lane;
+    int l = -1;
+    if (m < m1 && fb[m]) { l = lb[m]; if (l < 0 || l >= n) l = -1; }
+    const unsigned peers = __match_any_sync(0xffffffffu, l);
+    if (l >= 0 && lane == __ffs(peers) - 1) myhist[l] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // phase 2a: exclusive prefix across warps, per label
+  for (int l = tid; l < n; l += 32 * kSplitWarps) {
+    int run = 0;
+#pragma unroll
+    for (int w = 0; w < kSplitWarps; ++w) { const int c = hist[w * Nmax + l]; hist[w * Nmax + l] = run; run += c; }
+    tot[l] = run;
+  }
+  __syncthreads();
+  // phase 2b: exclusive scan over labels (warp 0)
+  if (warp == 0) {
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const int v = i < n ? tot[i] : 0;
+      int sc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, sc, o);
+        if (lane >= o) sc += u;
+      }
+      if (i < n) { tot[i] = carry + sc - v; off_g[i] = carry + sc - v; }
+      carry += __shfl_sync(0xffffffffu, sc, 31);
+    }
+    for (int i = n + lane; i <= Nmax; i += 32) off_g[i] = carry;
+  }
+  __syncthreads();
+  // phase 3: ordered scatter
+  for (int mb = m0; mb < m1; mb += 32) {
+    const int m = mb + lane;
+    int l = -1;
+    if (m < m1 && fb[m]) { l = lb[m]; if (l < 0 || l >= n) l = -1; }
+    const unsigned peers = __match_any_sync(0xffffffffu, l);
+    int pos = 0;
+    if (l >= 0) pos = tot[l] + myhist[l] + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+    if (l >= 0) {
+      out[pos] = make_float2((float)ib[2 * m + 1], (float)ib[2 * m]);   // (x,y) flip
+      if (lane == __ffs(peers) - 1) myhist[l] += __popc(peers);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace isg
 
 using namespace isg;
@@ -538,10 +620,16 @@ extern "C" int isg_group_points(const int32_t* idx, const int32_t* label, const 
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!idx || !label || !flag || !count || !n_seeds || !offsets || !points) return ISG_EINVAL;
   if (B <= 0 || Nmax <= 0 || cap <= 0 || B > 65535) return ISG_EINVAL;
-  dim3 block(32, kGroupWarps), grid(cdiv(Nmax, kGroupWarps), B);
-  group_count_kernel<<<grid, block, 0, stream>>>(label, flag, count, cap, n_seeds, Nmax, offsets);
-  group_scan_kernel<<<B, 32, 0, stream>>>(offsets, Nmax);
-  group_scatter_kernel<<<grid, block, 0, stream>>>(idx, label, flag, count, cap, n_seeds, Nmax, offsets, points);
+  const size_t smem = ((size_t)kSplitWarps * Nmax + Nmax + 1) * sizeof(int);
+  if (smem <= 200 * 1024) {
+    ISG_CUDA(cudaFuncSetAttribute(group_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    group_split_kernel<<<B, 32 * kSplitWarps, smem, stream>>>(idx, label, flag, count, cap, n_seeds, Nmax, offsets, points);
+  } else {   // very large seed tables: one warp per instance scans the list
+    dim3 block(32, kGroupWarps), grid(cdiv(Nmax, kGroupWarps), B);
+    group_count_kernel<<<grid, block, 0, stream>>>(label, flag, count, cap, n_seeds, Nmax, offsets);
+    group_scan_kernel<<<B, 32, 0, stream>>>(offsets, Nmax);
+    group_scatter_kernel<<<grid, block, 0, stream>>>(idx, label, flag, count, cap, n_seeds, Nmax, offsets, points);
+  }
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }

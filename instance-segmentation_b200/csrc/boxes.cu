@@ -174,33 +174,42 @@ __device__ __forceinline__ bool suppresses_plus1(const float4 a, const float4 c,
   return !(ovr <= thr);
 }
 
+constexpr int kMaskCtasPerImage = 128;
+
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const int32_t* __restrict__ count, int cap, double thr, int convention, void* ws) {
-  const int rb = blockIdx.y, cb = blockIdx.x, b = blockIdx.z;
-  if (cb < rb) return;
+  const int b = blockIdx.y;
   const int n = min(max(count[b], 0), cap);
-  if (rb * 64 >= n || cb * 64 >= n) return;
+  const int nb = (n + 63) / 64;
+  const int npairs = nb * (nb + 1) / 2;
   const NmsWs v = nms_ws_view(ws, b, cap);
   const int nw = (cap + 63) / 64;
   __shared__ float4 cbox[64];
   __shared__ int ccls[64];
   const int t = threadIdx.x;
-  const int j = cb * 64 + t;
-  if (j < n) { cbox[t] = v.sbox[j]; ccls[t] = v.scls[j]; }
-  __syncthreads();
-  const int i = rb * 64 + t;
-  if (i >= n) return;
-  const float4 a = v.sbox[i];
-  const int ac = v.scls[i];
-  const int ncol = min(64, n - cb * 64);
-  unsigned long long bits = 0ull;
   const float thr_f = (float)thr;
-  for (int c = (rb == cb ? t + 1 : 0); c < ncol; ++c) {
-    if (ccls[c] != ac) continue;   // class aware (batched_nms); class-agnostic callers pass cls = NULL -> all 0
-    const bool s = (convention == ISG_NMS_TV_GT) ? suppresses_tv(a, cbox[c], thr) : suppresses_plus1(a, cbox[c], thr_f);
-    if (s) bits |= 1ull << c;
+  for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
+    // linear index over the upper triangle -> (row block, column block)
+    int rb = 0, rem = p;
+    while (rem >= nb - rb) { rem -= nb - rb; ++rb; }
+    const int cb = rb + rem;
+    __syncthreads();
+    const int j = cb * 64 + t;
+    if (j < n) { cbox[t] = v.sbox[j]; ccls[t] = v.scls[j]; }
+    __syncthreads();
+    const int i = rb * 64 + t;
+    if (i >= n) continue;
+    const float4 a = v.sbox[i];
+    const int ac = v.scls[i];
+    const int ncol = min(64, n - cb * 64);
+    unsigned long long bits = 0ull;
+    for (int c = (rb == cb ? t + 1 : 0); c < ncol; ++c) {
+      if (ccls[c] != ac) continue;   // class aware (batched_nms); class-agnostic callers pass cls = NULL -> all 0
+      const bool s = (convention == ISG_NMS_TV_GT) ? suppresses_tv(a, cbox[c], thr) : suppresses_plus1(a, cbox[c], thr_f);
+      if (s) bits |= 1ull << c;
+    }
+    v.mask[(size_t)i * nw + cb] = bits;
   }
-  v.mask[(size_t)i * nw + cb] = bits;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -252,6 +261,110 @@ nms_scan_kernel(const int32_t* __restrict__ count, int cap, void* ws, int32_t* _
         acc |= v.mask[(size_t)(base + q) * nw + w];
       }
       remv[w] |= acc;
+    }
+    __syncthreads();
+  }
+  if (t == 0) n_keep[b] = nk;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NMS, small problems (cap <= 1024): sort + bitmask + greedy scan fused in ONE CTA per image, everything in
+// shared memory.  The three-kernel path above remains for larger candidate sets.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmallMax = 1024;
+
+__global__ void __launch_bounds__(kSortThreads)
+nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int32_t* __restrict__ cls,
+                 const int32_t* __restrict__ tiebreak, const int32_t* __restrict__ count, int cap, int P,
+                 double thr, int convention, int32_t* __restrict__ keep, int32_t* __restrict__ n_keep) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nwP = P / 64 > 0 ? P / 64 : 1;
+  float4* sbox = reinterpret_cast<float4*>(smem_raw);                               // [P]
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(sbox + P);        // [P]
+  unsigned long long* mask = key + P;                                               // [P][nwP]
+  uint32_t* val = reinterpret_cast<uint32_t*>(mask + (size_t)P * nwP);              // [P]
+  int* scls = reinterpret_cast<int*>(val + P);                                      // [P]
+  __shared__ unsigned long long remv[kSmallMax / 64];
+  __shared__ unsigned long long s_kept;
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int n = min(max(count[b], 0), cap);
+  int Pn = 1;
+  while (Pn < n) Pn <<= 1;
+  for (int i = t; i < Pn; i += kSortThreads) {
+    unsigned long long k = 0ull;
+    if (i < n) {
+      const size_t o = (size_t)b * cap + i;
+      const uint32_t tb = tiebreak ? (uint32_t)tiebreak[o] : (uint32_t)i;
+      const uint32_t low = (convention == ISG_NMS_PLUS1_LE) ? tb : (0xffffffffu - tb);
+      k = ((unsigned long long)float_key(scores[o]) << 32) | low;
+    }
+    key[i] = k; val[i] = (uint32_t)i;
+  }
+  __syncthreads();
+  for (int size = 2; size <= Pn; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = t; i < (Pn >> 1); i += kSortThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = key[lo], c = key[hi];
+        if ((a < c) == desc) {
+          key[lo] = c; key[hi] = a;
+          const uint32_t va = val[lo]; val[lo] = val[hi]; val[hi] = va;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = t; r < n; r += kSortThreads) {
+    const size_t o = (size_t)b * cap + val[r];
+    sbox[r] = boxes[o];
+    scls[r] = cls ? cls[o] : 0;
+  }
+  if (t < kSmallMax / 64) remv[t] = 0ull;
+  __syncthreads();
+  // suppression bits: task = (row i, word w >= i/64)
+  const int nw = (n + 63) / 64;
+  const float thr_f = (float)thr;
+  for (int task = t; task < n * nw; task += kSortThreads) {
+    const int i = task / nw, w = task - i * nw;
+    if (w < (i >> 6)) continue;
+    const float4 a = sbox[i];
+    const int ac = scls[i];
+    const int c0 = w * 64, c1 = min(c0 + 64, n);
+    unsigned long long bits = 0ull;
+    for (int c = max(c0, i + 1); c < c1; ++c) {
+      if (scls[c] != ac) continue;
+      const bool sup = (convention == ISG_NMS_TV_GT) ? suppresses_tv(a, sbox[c], thr) : suppresses_plus1(a, sbox[c], thr_f);
+      if (sup) bits |= 1ull << (c - c0);
+    }
+    mask[(size_t)i * nwP + w] = bits;
+  }
+  __syncthreads();
+  // greedy scan, 64-box chunks
+  int nk = 0;
+  int32_t* out = keep + (size_t)b * cap;
+  for (int c = 0; c < nw; ++c) {
+    const int base = c * 64;
+    const int m = min(64, n - base);
+    if (t == 0) {
+      unsigned long long word = remv[c], kept = 0ull;
+      for (int q = 0; q < m; ++q)
+        if (!((word >> q) & 1ull)) { kept |= 1ull << q; word |= mask[(size_t)(base + q) * nwP + c]; }
+      s_kept = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = s_kept;
+    if (t < m && ((kept >> t) & 1ull)) out[nk + __popcll(kept & ((1ull << t) - 1ull))] = (int32_t)val[base + t];
+    nk += __popcll(kept);
+    if (t > c && t < nw) {
+      unsigned long long acc = 0ull, kk = kept;
+      while (kk) {
+        const int q = __ffsll((long long)kk) - 1;
+        kk &= kk - 1;
+        acc |= mask[(size_t)(base + q) * nwP + t];
+      }
+      remv[t] |= acc;
     }
     __syncthreads();
   }
@@ -525,8 +638,7 @@ static int run_nms_stages(const float* boxes, const float* scores, const int32_t
   nms_sort_kernel<<<B, kSortThreads, smem, stream>>>(reinterpret_cast<const float4*>(boxes), scores, cls, tiebreak,
                                                      count, cap, P, convention, ws);
   if (box_mask) {
-    const int nw = cdiv(cap, 64);
-    dim3 grid(nw, nw, B);
+    dim3 grid(kMaskCtasPerImage, B);
     nms_mask_kernel<<<grid, 64, 0, stream>>>(count, cap, thr, convention, ws);
     nms_scan_kernel<<<B, kScanThreads, 0, stream>>>(count, cap, ws, keep, n_keep);
   }
@@ -542,6 +654,16 @@ extern "C" int isg_box_nms(const float* boxes, const float* scores, const int32_
   if (convention != ISG_NMS_PLUS1_LE && convention != ISG_NMS_TV_GT) return ISG_EINVAL;
   if (cap > ISG_NMS_MAX_BOXES) return ISG_EUNSUPPORTED;
   if (!aligned16(boxes)) return ISG_EINVAL;
+  if (cap <= kSmallMax) {   // fused single-CTA path, no workspace needed
+    const int P = next_pow2(cap);
+    const int nwP = P / 64 > 0 ? P / 64 : 1;
+    const size_t smem = (size_t)P * (16 + 8 + 4 + 4) + (size_t)P * nwP * 8;
+    ISG_CUDA(cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_small_kernel<<<B, kSortThreads, smem, stream>>>(reinterpret_cast<const float4*>(boxes), scores, cls, tiebreak, count,
+                                                        cap, P, thr, convention, keep, n_keep);
+    ISG_LAUNCH_CHECK();
+    return ISG_OK;
+  }
   if (!ws || ws_bytes < isg_box_nms_workspace_bytes(B, cap) || ((uintptr_t)ws & 255)) return ISG_EWORKSPACE;
   return run_nms_stages(boxes, scores, cls, tiebreak, count, B, cap, thr, convention, keep, n_keep, ws, stream, true);
 }

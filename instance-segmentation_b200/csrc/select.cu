@@ -13,17 +13,18 @@ __device__ __forceinline__ uint32_t digit_of(uint32_t key, int pass) {
   return pass == 0 ? (key >> 21) : pass == 1 ? ((key >> 10) & 0x7ffu) : (key & 0x3ffu);
 }
 
-// Block-wide (256 threads): find the digit d with  #(digit > d) < krem <= #(digit >= d)
-// in a 2048-bin histogram; returns d and the rank remaining inside that bin.
-__device__ void resolve_digit(const uint32_t* __restrict__ hist, uint32_t krem, uint32_t* out_digit,
-                              uint32_t* out_krem) {
+// Block-wide: find the digit d with  #(digit > d) < krem <= #(digit >= d)  in a 2048-bin histogram;
+// returns d and the rank remaining inside that bin.  The first 256 threads own 8 bins each; any further
+// threads of the block only take part in the barriers.
+__device__ void resolve_digit(const uint32_t* hist, uint32_t krem, uint32_t* out_digit, uint32_t* out_krem) {
   __shared__ uint32_t warp_tot[kHistThreads / 32];
   __shared__ uint32_t res[2];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const bool own = t < kHistThreads;
   uint32_t h[8];
   uint32_t s = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { h[i] = hist[t * 8 + i]; s += h[i]; }
+  for (int i = 0; i < 8; ++i) { h[i] = own ? hist[t * 8 + i] : 0u; s += h[i]; }
   // inclusive suffix sum over threads (thread t gets sum over t' >= t)
   uint32_t suf = s;
 #pragma unroll
@@ -31,16 +32,18 @@ __device__ void resolve_digit(const uint32_t* __restrict__ hist, uint32_t krem, 
     uint32_t v = __shfl_down_sync(0xffffffffu, suf, o);
     if (lane + o < 32) suf += v;
   }
-  if (lane == 0) warp_tot[warp] = suf;
+  if (own && lane == 0) warp_tot[warp] = suf;
   if (t == 0) { res[0] = 0; res[1] = 0; }
   __syncthreads();
-  uint32_t above = 0;
-  for (int w = warp + 1; w < kHistThreads / 32; ++w) above += warp_tot[w];
-  uint32_t cum = suf - s + above;  // count of keys in bins owned by higher threads
+  if (own) {
+    uint32_t above = 0;
+    for (int w = warp + 1; w < kHistThreads / 32; ++w) above += warp_tot[w];
+    uint32_t cum = suf - s + above;  // count of keys in bins owned by higher threads
 #pragma unroll
-  for (int i = 7; i >= 0; --i) {
-    if (cum < krem && krem <= cum + h[i]) { res[0] = (uint32_t)(t * 8 + i); res[1] = krem - cum; }
-    cum += h[i];
+    for (int i = 7; i >= 0; --i) {
+      if (cum < krem && krem <= cum + h[i]) { res[0] = (uint32_t)(t * 8 + i); res[1] = krem - cum; }
+      cum += h[i];
+    }
   }
   __syncthreads();
   *out_digit = res[0];
@@ -68,10 +71,10 @@ __device__ __forceinline__ void hist_add(uint32_t* sh, uint32_t bin, bool valid,
 template <int PASS>
 __global__ void __launch_bounds__(kHistThreads)
 hist_pass_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, uint32_t k,
-                 uint32_t* __restrict__ hist_all, bool vec) {
+                 uint32_t* __restrict__ hist_all, int64_t hist_stride, bool vec) {
   __shared__ uint32_t sh[kHistBins];
   const int b = blockIdx.y;
-  uint32_t* hist = hist_all + (size_t)b * 3 * kHistBins;
+  uint32_t* hist = hist_all + (size_t)b * hist_stride;
   const int t = threadIdx.x, lane = t & 31;
   for (int i = t; i < kHistBins; i += kHistThreads) sh[i] = 0;
 
@@ -122,9 +125,10 @@ hist_pass_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, uint
 }
 
 __global__ void __launch_bounds__(kHistThreads)
-finish_threshold_kernel(const uint32_t* __restrict__ hist_all, uint32_t k, uint32_t* __restrict__ thr_key) {
+finish_threshold_kernel(const uint32_t* __restrict__ hist_all, int64_t hist_stride, uint32_t k,
+                        uint32_t* __restrict__ thr_key) {
   const int b = blockIdx.x;
-  const uint32_t* hist = hist_all + (size_t)b * 3 * kHistBins;
+  const uint32_t* hist = hist_all + (size_t)b * hist_stride;
   uint32_t d0, d1, d2, k1, k2, k3;
   resolve_digit(hist, k, &d0, &k1);
   resolve_digit(hist + kHistBins, k1, &d1, &k2);
@@ -135,6 +139,167 @@ finish_threshold_kernel(const uint32_t* __restrict__ hist_all, uint32_t k, uint3
 __global__ void fill_u32_kernel(uint32_t* p, int n, uint32_t v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+
+// ---- fast path: sample -> filter -> select ----------------------------------------------------
+// Only ~k of the H*W pixels can matter.  (1) one CTA per image radix-selects, on a 1/64 sample, a
+// conservative lower bound L (the sample rank that corresponds to ~2k pixels); (2) one full pass copies the
+// keys >= L into a per-image candidate list (block-aggregated appends); (3) one CTA per image selects the
+// exact k-th largest key among the candidates.  If the candidate list does not provably contain the answer
+// (fewer than k candidates, or overflow) step (3) falls back to scanning the whole image, so the result
+// is always exact.
+constexpr int kSelThreads = 1024;
+constexpr int kSampleMax = 32768;        // sample keys kept in shared memory (128 KB)
+constexpr int kFilterThreads = 256;
+constexpr int kFilterPxPerBlock = 8192;  // 8 float4 per thread; the block's candidates always fit in smem
+
+struct TopkWs {            // per-image views
+  uint32_t* hist;          // [3][2048]   (legacy multi-CTA path)
+  uint32_t* lower;         // [1]
+  uint32_t* ncand;         // [1]
+  uint32_t* cand;          // [cap_c]
+};
+__host__ __device__ inline size_t topk_cand_cap(int npx, int k) {
+  size_t c = (size_t)8 * (size_t)k + 8192;
+  return c < (size_t)npx ? c : (size_t)npx;
+}
+__host__ __device__ inline size_t topk_ws_per_image(int npx, int k) {
+  size_t s = 3 * kHistBins * sizeof(uint32_t) + 64 + topk_cand_cap(npx, k) * sizeof(uint32_t);
+  return (s + 255) & ~(size_t)255;
+}
+__host__ __device__ inline TopkWs topk_ws_view(void* ws, int b, int npx, int k) {
+  char* p = (char*)ws + (size_t)b * topk_ws_per_image(npx, k);
+  TopkWs v;
+  v.hist = (uint32_t*)p; p += 3 * kHistBins * sizeof(uint32_t);
+  v.lower = (uint32_t*)p; v.ncand = (uint32_t*)(p + 32); p += 64;
+  v.cand = (uint32_t*)p;
+  return v;
+}
+
+// block-wide exact select of the `rank`-th largest of n keys produced by key_at(i); 1024 threads.
+template <typename KeyAt>
+__device__ uint32_t block_radix_select(uint32_t* sh_hist, int n, uint32_t rank, KeyAt key_at) {
+  const int t = threadIdx.x, lane = t & 31;
+  uint32_t prefix = 0, pmask = 0, krem = rank;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int i = t; i < kHistBins; i += kSelThreads) sh_hist[i] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += kSelThreads) {   // warp-uniform trip count
+      const int i = i0 + t;
+      const bool in = i < n;
+      const uint32_t key = in ? key_at(i) : 0u;
+      hist_add(sh_hist, digit_of(key, pass), in && (key & pmask) == prefix, lane);
+    }
+    __syncthreads();
+    uint32_t d, k2;
+    resolve_digit(sh_hist, krem, &d, &k2);
+    krem = k2;
+    if (pass == 0) { prefix = d << 21; pmask = 0xffe00000u; }
+    else if (pass == 1) { prefix |= d << 10; pmask = 0xfffffc00u; }
+    else prefix |= d;
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+topk_sample_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, int stride, void* ws) {
+  extern __shared__ uint32_t skeys[];   // [<= kSampleMax]
+  __shared__ uint32_t sh_hist[kHistBins];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* img = kp + (int64_t)b * img_stride;
+  const int S = npx / stride;           // sample i reads pixel i*stride + (i*37 % stride)
+  for (int i = t; i < S; i += kSelThreads) {
+    const int p = i * stride + (int)(((unsigned)i * 37u) % (unsigned)stride);
+    skeys[i] = float_key(__ldg(img + p));
+  }
+  __syncthreads();
+  // sample rank that corresponds to ~2k pixels, plus 8 sigma and a constant
+  const double expect = 2.0 * (double)k * (double)S / (double)npx;
+  long long r = (long long)(expect + 8.0 * sqrt(expect) + 16.0);
+  TopkWs v = topk_ws_view(ws, b, npx, k);
+  uint32_t lower = 0u;                  // 0: every pixel is a candidate (step 3 then falls back if needed)
+  if (r < (long long)S) lower = block_radix_select(sh_hist, S, (uint32_t)r, [&](int i) { return skeys[i]; });
+  if (t == 0) { *v.lower = lower; *v.ncand = 0u; }
+}
+
+__global__ void __launch_bounds__(kFilterThreads)
+topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, void* ws, bool vec) {
+  __shared__ uint32_t buf[kFilterPxPerBlock];
+  __shared__ uint32_t s_count, s_base;
+  const int b = blockIdx.y, t = threadIdx.x, lane = t & 31;
+  const TopkWs v = topk_ws_view(ws, b, npx, k);
+  const uint32_t lower = *v.lower;
+  const float* img = kp + (int64_t)b * img_stride;
+  if (t == 0) s_count = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kFilterPxPerBlock;
+  const int end = min(base + kFilterPxPerBlock, npx);
+  for (int p0 = base; p0 < end; p0 += kFilterThreads * 4) {   // warp-uniform trip count
+    uint32_t key[4];
+    int c = 0;
+    if (vec) {
+      const int p = p0 + t * 4;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool in = p < end;
+      if (in) q = ldg_stream4(img + p);
+      key[0] = float_key(q.x); key[1] = float_key(q.y); key[2] = float_key(q.z); key[3] = float_key(q.w);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { if (!in || key[i] < lower) key[i] = 0xffffffffu; else ++c; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int p = p0 + i * kFilterThreads + t;
+        key[i] = 0xffffffffu;
+        if (p < end) { const uint32_t kk = float_key(__ldg(img + p)); if (kk >= lower) { key[i] = kk; ++c; } }
+      }
+    }
+    // NOTE: 0xffffffff marks "not a candidate"; a real key of 0xffffffff (a NaN payload) is dropped, NaNs are
+    // outside the contract.
+    if (__any_sync(0xffffffffu, c > 0)) {
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      uint32_t wbase = 0;
+      if (lane == 31) wbase = atomicAdd(&s_count, (uint32_t)inc);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      uint32_t o2 = wbase + inc - c;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (key[i] != 0xffffffffu) buf[o2++] = key[i];
+    }
+  }
+  __syncthreads();
+  const uint32_t n = s_count;
+  if (n == 0) return;
+  if (t == 0) s_base = atomicAdd(v.ncand, n);
+  __syncthreads();
+  const size_t capc = topk_cand_cap(npx, k);
+  const uint32_t g = s_base;
+  for (uint32_t i = t; i < n; i += kFilterThreads)
+    if ((size_t)g + i < capc) v.cand[g + i] = buf[i];
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, void* ws,
+                   uint32_t* __restrict__ thr_key) {
+  __shared__ uint32_t sh_hist[kHistBins];
+  const int b = blockIdx.x;
+  const TopkWs v = topk_ws_view(ws, b, npx, k);
+  const uint32_t nc = *v.ncand;
+  const bool use_cand = nc >= (uint32_t)k && (size_t)nc <= topk_cand_cap(npx, k);
+  uint32_t key;
+  if (use_cand) {
+    const uint32_t* cand = v.cand;
+    key = block_radix_select(sh_hist, (int)nc, (uint32_t)k, [&](int i) { return cand[i]; });
+  } else {
+    const float* img = kp + (int64_t)b * img_stride;
+    key = block_radix_select(sh_hist, npx, (uint32_t)k, [&](int i) { return float_key(__ldg(img + i)); });
+  }
+  if (threadIdx.x == 0) thr_key[b] = key;
 }
 
 // ---- stand-alone keep kernel ---------------------------------------------------------------
@@ -196,52 +361,130 @@ __global__ void nms_hm_kernel(const float* __restrict__ heat, int H, int W, int 
   keep[(size_t)blockIdx.z * H * W + (size_t)y * W + x] = (m == c) ? 1 : 0;
 }
 
-// ---- ordered compaction: one CTA per image ---------------------------------------------------
+// ---- ordered compaction: one CTA (32 warps) per image ----------------------------------------
+// Warp w owns rows w, w+32, ...; a row's words are read with one coalesced request per 32 words, eight rows
+// in flight per warp.  Phase 1 counts the set bits per row, a block scan turns the counts into row offsets,
+// phase 2 re-reads the rows (L2 hits) and emits the (y,x) pairs in row-major order.
 constexpr int kCompactThreads = 1024;
+constexpr int kCompactBatch = 8;   // rows in flight per warp
 
-__global__ void __launch_bounds__(kCompactThreads)
+// WL = words per lane (Wwords <= 32*WL); WL == 0 selects the generic any-width path
+template <int WL>
+__global__ void __launch_bounds__(kCompactThreads, 1)
 compact_kernel(const uint32_t* __restrict__ keepbits, int H, int Wwords, int W, int cap,
                int32_t* __restrict__ idx, int32_t* __restrict__ count) {
-  __shared__ int warp_tot[kCompactThreads / 32];
+  extern __shared__ int row_off[];   // [H + 1]
+  __shared__ int warp_tot[32];
   const int b = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int nwords = H * Wwords;
-  const uint32_t* bits = keepbits + (size_t)b * nwords;
-  const int per = (nwords + kCompactThreads - 1) / kCompactThreads;
-  const int w0 = min(t * per, nwords), w1 = min(w0 + per, nwords);
+  const uint32_t* bits = keepbits + (size_t)b * H * Wwords;
+  constexpr int WLc = WL > 0 ? WL : 1;
+
+  // phase 1: per-row popcounts
+  if (WL > 0) {
+    for (int yb = warp; yb < H; yb += 32 * kCompactBatch) {
+      uint32_t v[kCompactBatch][WLc];
+#pragma unroll
+      for (int r = 0; r < kCompactBatch; ++r)
+#pragma unroll
+        for (int j = 0; j < WLc; ++j) {
+          const int y = yb + 32 * r, w = lane + 32 * j;
+          v[r][j] = (y < H && w < Wwords) ? __ldg(bits + (size_t)y * Wwords + w) : 0u;
+        }
+#pragma unroll
+      for (int r = 0; r < kCompactBatch; ++r) {
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < WLc; ++j) c += __popc(v[r][j]);
+        c = warp_sum(c);
+        const int y = yb + 32 * r;
+        if (lane == 0 && y < H) row_off[y] = c;
+      }
+    }
+  } else {
+    for (int y = warp; y < H; y += 32) {
+      int c = 0;
+      for (int w = lane; w < Wwords; w += 32) c += __popc(__ldg(bits + (size_t)y * Wwords + w));
+      c = warp_sum(c);
+      if (lane == 0) row_off[y] = c;
+    }
+  }
+  __syncthreads();
+
+  // block exclusive scan over the H row counts (thread t owns a contiguous run of rows)
+  const int per = (H + kCompactThreads - 1) / kCompactThreads;
+  const int y0 = min(t * per, H), y1 = min(y0 + per, H);
   int c = 0;
-  for (int w = w0; w < w1; ++w) c += __popc(bits[w]);
-  // block exclusive scan
+  for (int y = y0; y < y1; ++y) c += row_off[y];
   int inc = c;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, inc, o);
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += v;
   }
   if (lane == 31) warp_tot[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    int v = warp_tot[lane];
-    int s = v;
+    const int v = warp_tot[lane];
+    int s2 = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int u = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += u;
+      const int u = __shfl_up_sync(0xffffffffu, s2, o);
+      if (lane >= o) s2 += u;
     }
-    warp_tot[lane] = s - v;  // exclusive
+    warp_tot[lane] = s2 - v;
   }
   __syncthreads();
-  int off = warp_tot[warp] + inc - c;
-  if (t == kCompactThreads - 1) count[b] = off + c;
+  int run = warp_tot[warp] + inc - c;
+  for (int y = y0; y < y1; ++y) { const int v = row_off[y]; row_off[y] = run; run += v; }
+  if (t == kCompactThreads - 1) count[b] = run;
+  __syncthreads();
+
+  // phase 2: emit.  `off` = first output slot of the 32-word group held by the warp.
   int32_t* out = idx + (size_t)b * cap * 2;
-  for (int w = w0; w < w1; ++w) {
-    uint32_t m = bits[w];
-    const int y = w / Wwords, xb = (w - y * Wwords) * 32;
+  auto emit_group = [&](int y, int w, uint32_t m, int& off) {
+    const int n = __popc(m);
+    int pre = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    int o2 = off + pre - n;
+    off += __shfl_sync(0xffffffffu, pre, 31);
     while (m) {
       const int i = __ffs(m) - 1;
       m &= m - 1;
-      if (off < cap) { out[2 * off] = y; out[2 * off + 1] = xb + i; }
-      ++off;
+      if (o2 < cap) { out[2 * o2] = y; out[2 * o2 + 1] = w * 32 + i; }
+      ++o2;
+    }
+  };
+  if (WL > 0) {
+    for (int yb = warp; yb < H; yb += 32 * kCompactBatch) {
+      uint32_t v[kCompactBatch][WLc];
+#pragma unroll
+      for (int r = 0; r < kCompactBatch; ++r)
+#pragma unroll
+        for (int j = 0; j < WLc; ++j) {
+          const int y = yb + 32 * r, w = lane + 32 * j;
+          v[r][j] = (y < H && w < Wwords) ? __ldg(bits + (size_t)y * Wwords + w) : 0u;
+        }
+#pragma unroll
+      for (int r = 0; r < kCompactBatch; ++r) {
+        const int y = yb + 32 * r;
+        if (y >= H) break;   // warp-uniform
+        int off = row_off[y];
+#pragma unroll
+        for (int j = 0; j < WLc; ++j) emit_group(y, lane + 32 * j, v[r][j], off);
+      }
+    }
+  } else {
+    for (int y = warp; y < H; y += 32) {
+      int off = row_off[y];
+      for (int w0 = 0; w0 < Wwords; w0 += 32) {
+        const int w = w0 + lane;
+        emit_group(y, w, (w < Wwords) ? __ldg(bits + (size_t)y * Wwords + w) : 0u, off);
+      }
     }
   }
 }
@@ -250,14 +493,15 @@ compact_kernel(const uint32_t* __restrict__ keepbits, int H, int Wwords, int W, 
 
 using namespace isg;
 
-extern "C" size_t isg_topk_workspace_bytes(int B) {
-  return B > 0 ? (size_t)B * 3 * kHistBins * sizeof(uint32_t) : 0;
+extern "C" size_t isg_topk_workspace_bytes(int B, int H, int W, int k) {
+  if (B <= 0 || H <= 0 || W <= 0 || k < 0 || (int64_t)H * W > ((int64_t)1 << 30)) return 0;
+  return (size_t)B * topk_ws_per_image(H * W, k);
 }
 
 extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t img_stride, int k,
                                   uint32_t* thr_key, void* ws, size_t ws_bytes, isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!kp || !thr_key || B <= 0 || H <= 0 || W <= 0 || k < 0) return ISG_EINVAL;
+  if (!kp || !thr_key || B <= 0 || H <= 0 || W <= 0 || k < 0 || B > 65535) return ISG_EINVAL;
   const int64_t npx64 = (int64_t)H * W;
   if (npx64 > (int64_t)1 << 30 || img_stride < npx64) return ISG_EINVAL;
   if ((int64_t)k > npx64) return ISG_EINVAL;  // torch.topk raises (utils/decode.py:81)
@@ -267,15 +511,37 @@ extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t 
     ISG_LAUNCH_CHECK();
     return ISG_OK;
   }
-  if (!ws || ws_bytes < isg_topk_workspace_bytes(B) || ((uintptr_t)ws & 15)) return ISG_EWORKSPACE;
-  uint32_t* hist = (uint32_t*)ws;
-  ISG_CUDA(cudaMemsetAsync(hist, 0, isg_topk_workspace_bytes(B), stream));
+  if (!ws || ws_bytes < isg_topk_workspace_bytes(B, H, W, k) || ((uintptr_t)ws & 255)) return ISG_EWORKSPACE;
   const bool vec = (npx % 4 == 0) && (img_stride % 4 == 0) && (((uintptr_t)kp & 15) == 0);
-  dim3 grid(cdiv(npx, kHistPxPerBlock), B);
-  hist_pass_kernel<0><<<grid, kHistThreads, 0, stream>>>(kp, img_stride, npx, (uint32_t)k, hist, vec);
-  hist_pass_kernel<1><<<grid, kHistThreads, 0, stream>>>(kp, img_stride, npx, (uint32_t)k, hist, vec);
-  hist_pass_kernel<2><<<grid, kHistThreads, 0, stream>>>(kp, img_stride, npx, (uint32_t)k, hist, vec);
-  finish_threshold_kernel<<<B, kHistThreads, 0, stream>>>(hist, (uint32_t)k, thr_key);
+  if ((int64_t)4 * k > npx64 && npx >= 65536) {
+    // large k: most pixels are candidates; the multi-CTA three-pass radix select is the efficient form
+    const size_t per = topk_ws_per_image(npx, k);
+    for (int b = 0; b < B; ++b)
+      ISG_CUDA(cudaMemsetAsync((char*)ws + (size_t)b * per, 0, 3 * kHistBins * sizeof(uint32_t), stream));
+    dim3 grid(cdiv(npx, kHistPxPerBlock), B);
+    const int64_t hist_stride = (int64_t)(per / sizeof(uint32_t));
+    hist_pass_kernel<0><<<grid, kHistThreads, 0, stream>>>(kp, img_stride, npx, (uint32_t)k, (uint32_t*)ws, hist_stride, vec);
+    hist_pass_kernel<1><<<grid, kHistThreads, 0, stream>>>(kp, img_stride, npx, (uint32_t)k, (uint32_t*)ws, hist_stride, vec);
+    hist_pass_kernel<2><<<grid, kHistThreads, 0, stream>>>(kp, img_stride, npx, (uint32_t)k, (uint32_t*)ws, hist_stride, vec);
+    finish_threshold_kernel<<<B, kHistThreads, 0, stream>>>((uint32_t*)ws, hist_stride, (uint32_t)k, thr_key);
+    ISG_LAUNCH_CHECK();
+    return ISG_OK;
+  }
+  if (npx >= 65536) {
+    int stride = 64;
+    while (npx / stride > kSampleMax) stride *= 2;
+    const size_t smem = (size_t)(npx / stride) * sizeof(uint32_t);
+    ISG_CUDA(cudaFuncSetAttribute(topk_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_sample_kernel<<<B, kSelThreads, smem, stream>>>(kp, img_stride, npx, k, stride, ws);
+    dim3 grid(cdiv(npx, kFilterPxPerBlock), B);
+    topk_filter_kernel<<<grid, kFilterThreads, 0, stream>>>(kp, img_stride, npx, k, ws, vec);
+  } else {
+    // small image: one CTA per image selects over all pixels directly (ncand = 0 -> full-image mode)
+    const size_t per = topk_ws_per_image(npx, k);
+    for (int b = 0; b < B; ++b)
+      ISG_CUDA(cudaMemsetAsync((char*)ws + (size_t)b * per + 3 * kHistBins * sizeof(uint32_t), 0, 64, stream));
+  }
+  topk_select_kernel<<<B, kSelThreads, 0, stream>>>(kp, img_stride, npx, k, ws, thr_key);
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }
@@ -296,17 +562,20 @@ extern "C" int isg_keep_points(const float* kp, int B, int H, int W, int64_t img
   return ISG_OK;
 }
 
-extern "C" size_t isg_select_points_workspace_bytes(int B) {
-  return B > 0 ? isg_topk_workspace_bytes(B) + (((size_t)B * 4 + 15) & ~(size_t)15) : 0;
+extern "C" size_t isg_select_points_workspace_bytes(int B, int H, int W, int k) {
+  const size_t t = isg_topk_workspace_bytes(B, H, W, k);
+  return t ? t + (((size_t)B * 4 + 255) & ~(size_t)255) : 0;
 }
 
 extern "C" int isg_select_points(const float* kp, int B, int H, int W, int64_t img_stride, int k,
                                  uint32_t* keepbits, uint8_t* mask_u8, void* ws, size_t ws_bytes,
                                  isg_stream_t stream) {
-  if (B <= 0) return ISG_EINVAL;
-  if (!ws || ws_bytes < isg_select_points_workspace_bytes(B) || ((uintptr_t)ws & 15)) return ISG_EWORKSPACE;
-  uint32_t* thr = (uint32_t*)((char*)ws + isg_topk_workspace_bytes(B));
-  int rc = isg_topk_threshold(kp, B, H, W, img_stride, k, thr, ws, isg_topk_workspace_bytes(B), stream);
+  if (B <= 0 || H <= 0 || W <= 0 || k < 0) return ISG_EINVAL;
+  if ((int64_t)k > (int64_t)H * W) return ISG_EINVAL;
+  const size_t tb = isg_topk_workspace_bytes(B, H, W, k);
+  if (!ws || tb == 0 || ws_bytes < isg_select_points_workspace_bytes(B, H, W, k) || ((uintptr_t)ws & 255)) return ISG_EWORKSPACE;
+  uint32_t* thr = (uint32_t*)((char*)ws + tb);
+  int rc = isg_topk_threshold(kp, B, H, W, img_stride, k, thr, ws, tb, stream);
   if (rc) return rc;
   return isg_keep_points(kp, B, H, W, img_stride, thr, keepbits, mask_u8, stream);
 }
@@ -327,7 +596,18 @@ extern "C" int isg_compact_points(const uint32_t* keepbits, int B, int H, int W,
                                   int32_t* count, isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!keepbits || !idx || !count || B <= 0 || H <= 0 || W <= 0 || cap < 0) return ISG_EINVAL;
-  compact_kernel<<<B, kCompactThreads, 0, stream>>>(keepbits, H, cdiv(W, 32), W, cap, idx, count);
+  const int Wwords = cdiv(W, 32);
+  const size_t smem = (size_t)(H + 1) * sizeof(int);
+  if (smem > 160 * 1024) return ISG_EUNSUPPORTED;
+#define ISG_COMPACT_LAUNCH(WL_)                                                                                 \
+  do {                                                                                                          \
+    ISG_CUDA(cudaFuncSetAttribute(compact_kernel<WL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    compact_kernel<WL_><<<B, kCompactThreads, smem, stream>>>(keepbits, H, Wwords, W, cap, idx, count);         \
+  } while (0)
+  if (Wwords <= 32) ISG_COMPACT_LAUNCH(1);
+  else if (Wwords <= 64) ISG_COMPACT_LAUNCH(2);
+  else ISG_COMPACT_LAUNCH(0);
+#undef ISG_COMPACT_LAUNCH
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }

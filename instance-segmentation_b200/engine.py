@@ -76,6 +76,12 @@ def as_f32_planes(t: torch.Tensor, device: torch.device) -> torch.Tensor:
     return t
 
 
+def aligned_workspace(nbytes: int, device: torch.device):
+    """(tensor, 256-byte aligned device pointer) of at least `nbytes`"""
+    t = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+    return t, t.data_ptr() + ((-t.data_ptr()) % 256)
+
+
 class DecodePlan:
     """select -> assign (dense or sparse) -> compact -> group for a batch of B images of HxW."""
 
@@ -111,8 +117,8 @@ class DecodePlan:
         self.ghost = torch.empty((B, N, _lib.GHOST_WORDS), dtype=f32, device=d)
         self.offsets = torch.empty((B, N + 1), dtype=i32, device=d)
         self.points = torch.empty((B, cap, 2), dtype=f32, device=d)
-        self.ws_bytes = int(_lib.lib().isg_topk_workspace_bytes(B))
-        self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=d)
+        self.ws_bytes = int(_lib.lib().isg_topk_workspace_bytes(B, H, W, self.kp_th))
+        self.ws, self.ws_ptr = aligned_workspace(self.ws_bytes, d)
         if mode == "dense":
             self.label_map = torch.empty((B, H, W), dtype=i32, device=d)
             self.score_map = torch.empty((B, H, W), dtype=f32, device=d) if want_score else None
@@ -140,7 +146,7 @@ class DecodePlan:
         call("isg_build_seeds", ptr(rois), layout, ptr(n_seeds), B, N, ptr(self.ys), ptr(self.xs), H, W, self.ghost_k,
              self.scale, ptr(self.seeds), ptr(self.ghost), s)
         call("isg_stats_init", ptr(self.stats), B, N, s)
-        call("isg_topk_threshold", ptr(kp), B, H, W, kp_stride, self.kp_th, ptr(self.thr_key), ptr(self.ws),
+        call("isg_topk_threshold", ptr(kp), B, H, W, kp_stride, self.kp_th, ptr(self.thr_key), self.ws_ptr,
              self.ws_bytes, s)
         ev = None
         if time_main:
@@ -195,8 +201,7 @@ class BoxPlan:
         self.cls = torch.empty((B, N), dtype=i32, device=d)
         self.n_seeds = torch.empty(B, dtype=i32, device=d)
         self.ws_bytes = int(_lib.lib().isg_box_nms_workspace_bytes(B, cap))
-        self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=d)
-        self.ws_off = (-self.ws.data_ptr()) % 256
+        self.ws, self.ws_ptr = aligned_workspace(self.ws_bytes, d)
 
     def run(self, anchors: torch.Tensor, regression: torch.Tensor, classification: torch.Tensor, cls_th: float,
             iou_th: float) -> None:
@@ -209,7 +214,7 @@ class BoxPlan:
              ptr(self.cand_anchor), ptr(self.cand_count), s)
         call("isg_box_nms", ptr(self.cand_boxes), ptr(self.cand_scores), ptr(self.cand_cls), ptr(self.cand_anchor),
              ptr(self.cand_count), B, self.cap, float(iou_th), _lib.ISG_NMS_TV_GT, ptr(self.keep), ptr(self.n_keep),
-             self.ws.data_ptr() + self.ws_off, self.ws_bytes, s)
+             self.ws_ptr, self.ws_bytes, s)
         call("isg_gather_kept", ptr(self.cand_boxes), ptr(self.cand_scores), ptr(self.cand_cls), ptr(self.keep),
              ptr(self.n_keep), B, self.cap, self.N, ptr(self.rois), ptr(self.scores), ptr(self.cls), ptr(self.n_seeds), s)
 

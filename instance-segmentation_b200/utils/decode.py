@@ -94,11 +94,11 @@ def select_points(mat, k):
     if k > H * W:
         raise RuntimeError("selected index k out of range")     # what torch.topk raises at :81
     lib = _lib.lib()
-    ws_bytes = int(lib.isg_select_points_workspace_bytes(1))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws_bytes = int(lib.isg_select_points_workspace_bytes(1, H, W, k))
+    ws, ws_ptr = engine.aligned_workspace(ws_bytes, dev)
     keepbits = torch.empty((H, (W + 31) // 32), dtype=torch.int32, device=dev)
     mask = torch.empty((H, W), dtype=torch.uint8, device=dev)
-    call("isg_select_points", ptr(m), 1, H, W, H * W, k, ptr(keepbits), ptr(mask), ptr(ws), ws_bytes, stream_ptr(dev))
+    call("isg_select_points", ptr(m), 1, H, W, H * W, k, ptr(keepbits), ptr(mask), ws_ptr, ws_bytes, stream_ptr(dev))
     return mask
 
 
@@ -357,10 +357,9 @@ def _decode_boxes_device(height, width, anchors, regression, classification, thr
     cls = engine.as_f32_planes(classification, dev).contiguous()
     anc = engine.as_f32_planes(anchors, dev).contiguous()
     B, A, C = cls.shape
-    while True:
-        plan = engine.get_box_plan(B, A, C, height, width, dev, cap, max_keep)
-        plan.run(anc, reg, cls, threshold, iou_threshold)
-        return plan
+    plan = engine.get_box_plan(B, A, C, height, width, dev, cap, max_keep)
+    plan.run(anc, reg, cls, threshold, iou_threshold)
+    return plan
 
 
 def decode_boxes(x, anchors, regression, classification, threshold, iou_threshold):
@@ -368,7 +367,7 @@ def decode_boxes(x, anchors, regression, classification, threshold, iou_threshol
     sorted by score descending; empty images give three empty arrays."""
     dev = _device_of(classification)
     height, width = x.shape[2], x.shape[3]
-    cap, max_keep = 4096, 1024
+    cap, max_keep = 1024, 1024
     while True:
         plan = _decode_boxes_device(height, width, anchors, regression, classification, threshold, iou_threshold, dev,
                                     cap, max_keep)
@@ -444,7 +443,7 @@ def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
     ae = engine.as_f32_planes(kp_out[1], dev)
     B, H, W = kp.shape[0], kp.shape[-2], kp.shape[-1]
     height, width = inputs.shape[2], inputs.shape[3]
-    cap, max_keep = 4096, 256
+    cap, max_keep = 1024, 256
     while True:
         bplan = _decode_boxes_device(height, width, anchors, regression, classification, decode_cfg.cls_th,
                                      decode_cfg.iou_th, dev, cap, max_keep)

@@ -43,8 +43,9 @@ def test_binding_table_matches_header(built):
 
 def test_host_side_queries_need_no_gpu(built):
     lib = built.lib()
-    assert lib.isg_topk_workspace_bytes(8) == 8 * 3 * 2048 * 4
-    assert lib.isg_select_points_workspace_bytes(1) >= lib.isg_topk_workspace_bytes(1) + 4
+    assert lib.isg_topk_workspace_bytes(8, 1024, 2048, 20000) >= 8 * (3 * 2048 * 4 + 8 * 20000 * 4)
+    assert lib.isg_topk_workspace_bytes(1, 0, 4, 1) == 0
+    assert lib.isg_select_points_workspace_bytes(1, 64, 64, 10) >= lib.isg_topk_workspace_bytes(1, 64, 64, 10) + 4
     assert lib.isg_box_nms_workspace_bytes(2, 1000) > 2 * 1000 * 16 * 8
     assert lib.isg_kmeans_workspace_bytes(100, 10, 2) > 0
     assert lib.isg_mask_nms_workspace_bytes(100) > 0

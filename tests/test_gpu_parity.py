@@ -71,16 +71,41 @@ def test_topk_count_property_full_size(mods):
     g = torch.Generator(device="cpu").manual_seed(5)
     kp = torch.randn((2, H, W), generator=g).to(DEV)
     kp = kp + torch.arange(H * W, device=DEV).view(1, H, W) * 1e-9   # still may tie; count property allows >= k
-    ws_bytes = int(lib.lib().isg_topk_workspace_bytes(2))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    ws_bytes = int(lib.lib().isg_topk_workspace_bytes(2, H, W, k))
+    ws, ws_ptr = eng.aligned_workspace(ws_bytes, torch.device(DEV))
     thr = torch.empty(2, dtype=torch.int32, device=DEV)
-    lib.call("isg_topk_threshold", kp.data_ptr(), 2, H, W, H * W, k, thr.data_ptr(), ws.data_ptr(), ws_bytes,
+    lib.call("isg_topk_threshold", kp.data_ptr(), 2, H, W, H * W, k, thr.data_ptr(), ws_ptr, ws_bytes,
              eng.stream_ptr(torch.device(DEV)))
     for b in range(2):
         kth = torch.topk(kp[b].reshape(-1), k).values[-1]
         u = np.array([thr[b].item()], dtype=np.int32).view(np.uint32)[0]
         f = np.array([u & 0x7FFFFFFF if u & 0x80000000 else ~u], dtype=np.uint32).view(np.float32)[0]
         assert f == kth.item()
+
+
+@pytest.mark.parametrize("shape,k,kind", [((1024, 2048), 1, "normal"), ((1024, 2048), 700000, "normal"), ((512, 1024), 20000, "flat"),
+                                          ((512, 1024), 5000, "sorted"), ((300, 500), 149999, "normal"), ((256, 256), 65536, "flat")])
+def test_topk_threshold_paths(mods, shape, k, kind):
+    """every host-selected path (sample/filter/select, legacy multi-CTA, single-CTA) and the in-kernel
+    fallback (flat / sorted images defeat the sample bound) return the exact k-th largest value"""
+    lib, eng = mods["lib"], mods["engine"]
+    H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(H + k)
+    if kind == "normal":
+        kp = torch.randn((1, H, W), generator=g)
+    elif kind == "flat":      # two values only: the k-th largest is heavily tied
+        kp = (torch.rand((1, H, W), generator=g) < 0.01).float() * 3.0 - 1.0
+    else:                     # monotone ramp: the strided sample sees a biased subset
+        kp = torch.arange(H * W, dtype=torch.float32).view(1, H, W) * 1e-3
+    kp = kp.to(DEV)
+    ws_bytes = int(lib.lib().isg_topk_workspace_bytes(1, H, W, k))
+    ws, ws_ptr = eng.aligned_workspace(ws_bytes, torch.device(DEV))
+    thr = torch.empty(1, dtype=torch.int32, device=DEV)
+    lib.call("isg_topk_threshold", kp.data_ptr(), 1, H, W, H * W, k, thr.data_ptr(), ws_ptr, ws_bytes, eng.stream_ptr(torch.device(DEV)))
+    kth = torch.topk(kp[0].reshape(-1), k).values[-1].item()
+    u = np.array([thr[0].item()], dtype=np.int32).view(np.uint32)[0]
+    f = np.array([u & 0x7FFFFFFF if u & 0x80000000 else ~u], dtype=np.uint32).view(np.float32)[0]
+    assert f == np.float32(kth)
 
 
 def test_nms_hm_golden(mods, golden):
