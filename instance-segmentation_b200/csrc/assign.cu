@@ -91,7 +91,7 @@ __device__ __forceinline__ float membership(float ey, float ex, float sy, float 
   const float dy = __fsub_rn(ey, cy), dx = __fsub_rn(ex, cx);
   const float qy = __fmul_rn(__fmul_rn(dy, dy), sy);
   const float qx = __fmul_rn(__fmul_rn(dx, dx), sx);
-  return expf(-__fadd_rn(qy, qx));
+  return exp_fast(-__fadd_rn(qy, qx));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -131,8 +131,8 @@ assign_sparse_kernel(const float* __restrict__ ae, int64_t img_stride, int64_t p
     const float* p = ae + (int64_t)b * img_stride + (int64_t)y * W + x;
     const float a0 = __ldg(p), a1 = __ldg(p + plane_stride), a2 = __ldg(p + 2 * plane_stride),
                 a3 = __ldg(p + 3 * plane_stride);
-    ey = __fadd_rn(tanhf(a0), ys[y]); ex = __fadd_rn(tanhf(a1), xs[x]);   // :305
-    sy = expf(a2); sx = expf(a3);                                         // :315
+    ey = __fadd_rn(tanh_fast(a0), ys[y]); ex = __fadd_rn(tanh_fast(a1), xs[x]);   // :305
+    sy = exp_fast(a2); sx = exp_fast(a3);                                         // :315
   }
   if (n > 0) mbar_wait(&bar, 0);
   if (m >= M) return;
@@ -212,24 +212,21 @@ assign_dense_kernel(const float* __restrict__ kp, int64_t kp_img_stride,
     }
   }
 
-  // (3) keep bits from kp (threshold + 3x3 peak); hides the ae latency
-  const int thr = skey_from_ukey(thr_key[b]);
+  // (3) keep bits from kp (threshold + separable 3x3 peak); hides the ae latency
+  const Thr thr = make_thr(thr_key[b]);
   const float* kpb = kp + (int64_t)b * kp_img_stride;
   uint32_t nib[RW];
   {
-    float raw_up[4], raw_mid[4], raw_dn[4];
-    Row6 up = load_vrow<VEC>(kpb, ybeg - 1, x0, H, W, thr, lane, raw_up);
-    Row6 mid = load_vrow<VEC>(kpb, ybeg, x0, H, W, thr, lane, raw_mid);
+    RowH up = load_rowh<VEC>(kpb, ybeg - 1, x0, H, W, thr, lane);
+    RowH mid = load_rowh<VEC>(kpb, ybeg, x0, H, W, thr, lane);
 #pragma unroll
     for (int r = 0; r < RW; ++r) {
-      Row6 dn = load_vrow<VEC>(kpb, ybeg + r + 1, x0, H, W, thr, lane, raw_dn);
-      nib[r] = (ybeg + r < H) ? keep_nibble(up, mid, dn, raw_mid, x0, W, thr) : 0u;
+      const RowH dn = load_rowh<VEC>(kpb, ybeg + r + 1, x0, H, W, thr, lane);
+      nib[r] = (ybeg + r < H) ? keep_nibble(up, mid, dn) : 0u;
       const uint32_t word = nibbles_to_word(nib[r], lane);
       if ((lane & 7) == 0 && x0 < W && ybeg + r < H)
         keepbits[((size_t)b * H + ybeg + r) * Wwords + (x0 >> 5)] = word;
       up = mid; mid = dn;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) raw_mid[i] = raw_dn[i];
     }
   }
 
@@ -265,15 +262,25 @@ assign_dense_kernel(const float* __restrict__ kp, int64_t kp_img_stride,
   float xs4[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) xs4[i] = (x0 + i < W) ? __ldg(xs + x0 + i) : 0.0f;
+  {
+    float amax = 0.0f;
 #pragma unroll
-  for (int r = 0; r < RW; ++r) {
-    const float yv = (ybeg + r < H) ? __ldg(ys + ybeg + r) : 0.0f;
+    for (int r = 0; r < RW; ++r)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      a[r][0][i] = __fadd_rn(tanhf(a[r][0][i]), yv);
-      a[r][1][i] = __fadd_rn(tanhf(a[r][1][i]), xs4[i]);
-      a[r][2][i] = expf(a[r][2][i]);
-      a[r][3][i] = expf(a[r][3][i]);
+      for (int i = 0; i < 4; ++i) amax = fmaxf(amax, fmaxf(fabsf(a[r][0][i]), fabsf(a[r][1][i])));
+    const bool small = __all_sync(0xffffffffu, amax < 0.55f);   // warp-uniform: polynomial branch only
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      const float yv = (ybeg + r < H) ? __ldg(ys + ybeg + r) : 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float t0 = small ? tanh_poly(a[r][0][i]) : tanh_fast(a[r][0][i]);
+        const float t1 = small ? tanh_poly(a[r][1][i]) : tanh_fast(a[r][1][i]);
+        a[r][0][i] = __fadd_rn(t0, yv);
+        a[r][1][i] = __fadd_rn(t1, xs4[i]);
+        a[r][2][i] = exp_fast(a[r][2][i]);
+        a[r][3][i] = exp_fast(a[r][3][i]);
+      }
     }
   }
 

@@ -84,6 +84,43 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- fast, accurate transcendentals ----------------------------------------------------------
+// exp(x) = 2^(x*log2e): the product is split into its rounded value t and the exact rounding residual e
+// (one FMA), so the only remaining error is ex2.approx's (<= 2 ulp); subnormal results are kept.
+__device__ __forceinline__ float ex2_approx(float t) {
+  float r;
+  asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(t));
+  return r;
+}
+// The argument is clamped to [-104, 88.7]: below, the result rounds to 0 anyway; above, the result would be
+// +inf (the clamp returns ~FLT_MAX instead; only reachable with log-sigma > 88).
+__device__ __forceinline__ float exp_fast(float x) {
+  const float L2E_HI = 1.44269502162933349609375f, L2E_LO = 1.925963033500011e-8f;
+  x = fminf(fmaxf(x, -104.0f), 88.7f);
+  const float t = x * L2E_HI;
+  float e = fmaf(x, L2E_HI, -t);
+  e = fmaf(x, L2E_LO, e);
+  const float r = ex2_approx(t);
+  return fmaf(r * 0.693147182464599609375f, e, r);   // 2^(t+e) ~ 2^t * (1 + e*ln2)
+}
+// tanh: |x| < 0.55 -> x + x^3 * P(x^2) (degree-4 minimax fit, < 1 ulp); otherwise 1 - 2/(1 + e^{2|x|})
+__device__ __forceinline__ float tanh_poly(float x) {
+  const float u = x * x;
+  float p = -0.00661575747653842f;
+  p = fmaf(p, u, 0.02131274715065956f);
+  p = fmaf(p, u, -0.053910065442323685f);
+  p = fmaf(p, u, 0.13333117961883545f);
+  p = fmaf(p, u, -0.3333333134651184f);
+  return fmaf(x * u, p, x);
+}
+__device__ __forceinline__ float tanh_large(float x) {
+  const float a = fabsf(x);
+  const float e = exp_fast(2.0f * fminf(a, 44.0f));
+  const float r = 1.0f - __fdividef(2.0f, e + 1.0f);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float tanh_fast(float x) { return fabsf(x) < 0.55f ? tanh_poly(x) : tanh_large(x); }
+
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

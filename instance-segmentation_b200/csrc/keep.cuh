@@ -1,5 +1,10 @@
 // 3x3 peak test on the thresholded boundary-keypoint map, shared by the stand-alone keep kernel
 // and the fused dense kernel.  Reference: select_points / nms_hm, utils/decode.py:42-48,71-85.
+//
+//   v(p)    = selected(p) ? kp[p] : 0            (mat * mask, :84)
+//   keep(p) = selected(p) && v(p) == max3x3(v)   (max_pool2d with -inf padding, :45-47,85)
+// The 3x3 maximum is evaluated separably: h(p) = max(v(x-1), v(x), v(x+1)) per row, then the maximum of
+// h over the three rows; the centre is part of its own window, so keep <=> v(p) >= that maximum.
 #pragma once
 #include "common.cuh"
 
@@ -11,17 +16,33 @@ __device__ __forceinline__ int skey(float x) {
   return s ^ ((s >> 31) & 0x7fffffff);
 }
 __device__ __forceinline__ int skey_from_ukey(uint32_t k) { return (int)(k ^ 0x80000000u); }
+__device__ __forceinline__ float float_from_ukey(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
 
-// v(p) = selected ? value : 0   (mat * mask, utils/decode.py:84)
-__device__ __forceinline__ float selv(float x, int thr_skey) { return skey(x) >= thr_skey ? x : 0.0f; }
+// Selection threshold.  Selection is defined on the total order of the keys (that is what the radix select
+// counted); for every threshold except +-0 that is exactly the float comparison x >= thr, which is cheaper.
+struct Thr {
+  float f;
+  int s;
+  bool use_int;   // threshold is +-0: -0 and +0 compare equal as floats but are distinct keys
+};
+__device__ __forceinline__ Thr make_thr(uint32_t ukey) {
+  Thr t;
+  t.f = float_from_ukey(ukey);
+  t.s = skey_from_ukey(ukey);
+  t.use_int = (t.f == 0.0f) || (ukey == 0xffffffffu) || (t.f != t.f);   // +-0, "select nothing", NaN keys
+  return t;
+}
+__device__ __forceinline__ bool selected(float x, const Thr& t) { return t.use_int ? (skey(x) >= t.s) : (x >= t.f); }
 
-// One row of the thresholded map as seen by a thread owning pixels x0..x0+3:
-// r[0] = v(x0-1), r[1..4] = v(x0..x0+3), r[5] = v(x0+4); out-of-image -> -inf (max_pool2d padding).
-struct Row6 { float r[6]; };
+// One image row as seen by a lane owning pixels x0..x0+3.
+struct RowH {
+  float h[4];      // horizontal 3-max of v centred on the lane's 4 pixels
+  float v[4];      // v of the lane's 4 pixels (-inf outside the image)
+  uint32_t sel;    // bit i: pixel x0+i is inside the image and selected
+};
 
-// raw4: the thread's 4 raw pixel values (only meaningful where in-image).
-// The lanes of a warp own consecutive 4-pixel groups of ONE row, so the halo comes from the
-// neighbouring lanes by shuffle; only lane 0 / lane 31 touch memory for it.
 template <bool VEC>
 __device__ __forceinline__ void load_raw4(const float* __restrict__ row, int x0, int W, float (&v)[4]) {
   if (VEC && x0 + 3 < W) {
@@ -33,44 +54,56 @@ __device__ __forceinline__ void load_raw4(const float* __restrict__ row, int x0,
   }
 }
 
+// The lanes of a warp own consecutive 4-pixel groups of ONE row, so the 1-pixel halo comes from the
+// neighbouring lanes by shuffle; only lane 0 / lane 31 touch memory for it.
 template <bool VEC>
-__device__ __forceinline__ Row6 load_vrow(const float* __restrict__ img, int y, int x0, int H, int W,
-                                          int thr_skey, int lane, float (&raw)[4]) {
-  Row6 o;
+__device__ __forceinline__ RowH load_rowh(const float* __restrict__ img, int y, int x0, int H, int W, const Thr& thr,
+                                          int lane) {
+  RowH o;
   const float ninf = __int_as_float(0xff800000);
   if (y < 0 || y >= H) {  // warp-uniform
 #pragma unroll
-    for (int i = 0; i < 6; ++i) o.r[i] = ninf;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) raw[i] = 0.0f;
+    for (int i = 0; i < 4; ++i) { o.h[i] = ninf; o.v[i] = ninf; }
+    o.sel = 0;
     return o;
   }
   const float* row = img + (int64_t)y * W;
+  float raw[4];
   load_raw4<VEC>(row, x0, W, raw);
+  o.sel = 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) o.r[i + 1] = (x0 + i < W) ? selv(raw[i], thr_skey) : ninf;
-  float left = __shfl_up_sync(0xffffffffu, o.r[4], 1);
-  float right = __shfl_down_sync(0xffffffffu, o.r[1], 1);
-  if (lane == 0) left = (x0 - 1 >= 0 && x0 - 1 < W) ? selv(__ldg(row + x0 - 1), thr_skey) : ninf;
-  if (lane == 31) right = (x0 + 4 < W) ? selv(__ldg(row + x0 + 4), thr_skey) : ninf;
-  o.r[0] = left;
-  o.r[5] = right;
+  for (int i = 0; i < 4; ++i) {
+    const bool in = x0 + i < W;
+    const bool s = in && selected(raw[i], thr);
+    o.sel |= (s ? 1u : 0u) << i;
+    o.v[i] = in ? (s ? raw[i] : 0.0f) : ninf;
+  }
+  float left = __shfl_up_sync(0xffffffffu, o.v[3], 1);
+  float right = __shfl_down_sync(0xffffffffu, o.v[0], 1);
+  if (lane == 0) {
+    left = ninf;
+    if (x0 - 1 >= 0 && x0 - 1 < W) { const float t = __ldg(row + x0 - 1); left = selected(t, thr) ? t : 0.0f; }
+  }
+  if (lane == 31) {
+    right = ninf;
+    if (x0 + 4 < W) { const float t = __ldg(row + x0 + 4); right = selected(t, thr) ? t : 0.0f; }
+  }
+  o.h[0] = fmaxf(fmaxf(left, o.v[0]), o.v[1]);
+  o.h[1] = fmaxf(fmaxf(o.v[0], o.v[1]), o.v[2]);
+  o.h[2] = fmaxf(fmaxf(o.v[1], o.v[2]), o.v[3]);
+  o.h[3] = fmaxf(fmaxf(o.v[2], o.v[3]), right);
   return o;
 }
 
-// keep nibble of the thread's 4 pixels: bit i = selected(x0+i) && v == max3x3(v)
-__device__ __forceinline__ uint32_t keep_nibble(const Row6& up, const Row6& mid, const Row6& down,
-                                                const float (&raw)[4], int x0, int W, int thr_skey) {
+// keep nibble of the lane's 4 pixels of the middle row
+__device__ __forceinline__ uint32_t keep_nibble(const RowH& up, const RowH& mid, const RowH& dn) {
   uint32_t nib = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float m = fmaxf(fmaxf(up.r[i], up.r[i + 1]), up.r[i + 2]);
-    m = fmaxf(m, fmaxf(mid.r[i], mid.r[i + 2]));
-    m = fmaxf(m, fmaxf(fmaxf(down.r[i], down.r[i + 1]), down.r[i + 2]));
-    const bool sel = (x0 + i < W) && (skey(raw[i]) >= thr_skey);
-    if (sel && mid.r[i + 1] >= m) nib |= 1u << i;
+    const float m = fmaxf(fmaxf(up.h[i], mid.h[i]), dn.h[i]);
+    if (mid.v[i] >= m) nib |= 1u << i;
   }
-  return nib;
+  return nib & mid.sel;
 }
 
 // Combine the nibbles of 8 consecutive lanes into one 32-bit word (valid in lanes with lane%8==0).

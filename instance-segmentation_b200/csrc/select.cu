@@ -317,16 +317,15 @@ keep_kernel(const float* __restrict__ kp, int64_t img_stride, int H, int W, int 
   const int ybeg = (blockIdx.y * kKeepWarps + warp) * kKeepRowsPerWarp;
   if (ybeg >= H) return;  // warp-uniform
   const float* img = kp + (int64_t)b * img_stride;
-  const int thr = skey_from_ukey(thr_key[b]);
-  float raw_up[4], raw_mid[4], raw_dn[4];
-  Row6 up = load_vrow<VEC>(img, ybeg - 1, x0, H, W, thr, lane, raw_up);
-  Row6 mid = load_vrow<VEC>(img, ybeg, x0, H, W, thr, lane, raw_mid);
+  const Thr thr = make_thr(thr_key[b]);
+  RowH up = load_rowh<VEC>(img, ybeg - 1, x0, H, W, thr, lane);
+  RowH mid = load_rowh<VEC>(img, ybeg, x0, H, W, thr, lane);
 #pragma unroll
   for (int r = 0; r < kKeepRowsPerWarp; ++r) {
     const int y = ybeg + r;
     if (y >= H) break;
-    Row6 dn = load_vrow<VEC>(img, y + 1, x0, H, W, thr, lane, raw_dn);
-    const uint32_t nib = keep_nibble(up, mid, dn, raw_mid, x0, W, thr);
+    const RowH dn = load_rowh<VEC>(img, y + 1, x0, H, W, thr, lane);
+    const uint32_t nib = keep_nibble(up, mid, dn);
     const uint32_t word = nibbles_to_word(nib, lane);
     if ((lane & 7) == 0 && x0 < W) keepbits[((size_t)b * H + y) * Wwords + (x0 >> 5)] = word;
     if (mask_u8) {
@@ -336,8 +335,6 @@ keep_kernel(const float* __restrict__ kp, int64_t img_stride, int H, int W, int 
         if (x0 + i < W) mrow[x0 + i] = (nib >> i) & 1u;
     }
     up = mid; mid = dn;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) raw_mid[i] = raw_dn[i];
   }
 }
 

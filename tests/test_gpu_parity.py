@@ -445,3 +445,34 @@ def test_full_size_batch_properties(mods, oracle):
     assert np.array_equal(out["sparse"]["label"][0, :M], core["label"].numpy().astype(np.int32))
     np.testing.assert_allclose(out["sparse"]["score"][0, :M], core["score"].numpy(), rtol=RTOL, atol=ATOL)
     assert out["sparse"]["stats"][0, :, 0].sum() == out["sparse"]["flag"][0, :M].sum() == out["sparse"]["offsets"][0, N]
+
+
+# ---------------------------------------------------------------------------------------------- transcendentals
+def test_fast_tanh_exp_accuracy(mods):
+    """tanh_fast / exp_fast (csrc/common.cuh) observed through the sparse kernel: a 1-seed image whose score is
+    exp(-(tanh(a0)+y - cy)^2 * exp(a2)); compared with fp64 over a sweep of arguments."""
+    eng = mods["engine"]
+    H, W = 64, 256
+    rs = np.random.RandomState(0)
+    a0 = rs.uniform(-3.0, 3.0, size=(H, W)).astype(np.float32)
+    a0[:8] = rs.uniform(-0.6, 0.6, size=(8, W)).astype(np.float32)
+    a0[8:12] = rs.uniform(-1e-3, 1e-3, size=(4, W)).astype(np.float32)
+    a2 = rs.uniform(-3.0, 6.0, size=(H, W)).astype(np.float32)
+    ae = np.zeros((4, H, W), np.float32); ae[0] = a0; ae[1] = 0.0; ae[2] = a2; ae[3] = -30.0   # x term ~ 0
+    kp = mods["synth"]._distinct_float32(rs.normal(0, 1, size=(1, H, W)).astype(np.float32))
+    rois = np.array([[-0.5, -0.5, W - 0.5, H - 0.5]], np.float32)          # one box covering the image
+    plan = eng.DecodePlan(1, H, W, 1, H * W, DEV, "dense", want_score=True)
+    plan.run(torch.from_numpy(kp)[None].to(DEV), torch.from_numpy(ae)[None].to(DEV), torch.from_numpy(rois)[None].to(DEV),
+             torch.tensor([1], dtype=torch.int32, device=DEV))
+    torch.cuda.synchronize()
+    got = plan.score_map[0].cpu().numpy().astype(np.float64)
+    ys = torch.linspace(0, 1, 1024)[:H].double().numpy(); xs = torch.linspace(0, 2, 2048)[:W].double().numpy()
+    cy, cx = ys[int((H - 1) / 2)], xs[int((W - 1) / 2)]
+    ey = (np.tanh(a0.astype(np.float64)).astype(np.float32) + ys.astype(np.float32)[:, None]).astype(np.float64)
+    q = (ey - cy) ** 2 * np.exp(a2.astype(np.float64)) + (xs[None, :] - cx) ** 2 * np.exp(-30.0)
+    want = np.exp(-q)
+    ok = want > 1e-30
+    rel = np.abs(got[ok] - want[ok]) / want[ok]
+    # error budget: fp32 rounding of (e-c), its square, the product and the sum (~4 * 6e-8 * q) plus 2-ulp exp
+    bound = 4e-6 + 1e-6 * q[ok]
+    assert np.all(rel < bound), float((rel / bound).max())
