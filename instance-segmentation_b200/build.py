@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libisg.so")
 SOURCES = ["api.cu", "select.cu", "assign.cu", "boxes.cu", "kmeans.cu"]
-HEADERS = ["common.cuh", "keep.cuh", os.path.join("..", "..", "include", "isg.h")]
+HEADERS = ["common.cuh", "keep.cuh", "dense_tma.cuh", os.path.join("..", "..", "include", "isg.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -32,7 +32,8 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+    extra = os.environ.get("ISG_NVCC_EXTRA", "").split()   # e.g. -DISG_TMA_GROUPS=3 for tuning experiments
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -3,6 +3,8 @@
 //
 // Parity-critical arithmetic uses __f*_rn intrinsics so that nvcc never contracts it into FMAs:
 // torch evaluates  (e - c)^2 * sigma  and the 2-term sum with separate roundings (:326-327).
+#include <algorithm>
+#include <cstdlib>
 #include "keep.cuh"
 
 namespace isg {
@@ -31,7 +33,9 @@ __global__ void build_seeds_kernel(const float* __restrict__ rois, int layout, c
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Nmax) return;
   SeedRec s;
-  s.y0 = 1; s.y1 = 0; s.x0 = 1; s.x1 = 0; s.cy = 0.f; s.cx = 0.f; s.id = j; s.pad = 0;
+  // empty box: no tile overlaps it, so the per-pixel range tests never see it
+  s.y0 = 0x7fffffff; s.y1 = -0x7fffffff - 1; s.x0 = 0x7fffffff; s.x1 = -0x7fffffff - 1;
+  s.cy = 0.f; s.cx = 0.f; s.id = j; s.pad = 0;
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
   if (j < n_seeds[b]) {
     const float4 r = reinterpret_cast<const float4*>(rois)[(size_t)b * Nmax + j];
@@ -49,8 +53,9 @@ __global__ void build_seeds_kernel(const float* __restrict__ rois, int layout, c
     // p is an integer-valued float, so  p - lt >= 0  <=>  p >= ceil(lt)  and  rb - p >= 0  <=>  p <= floor(rb)
     const bool finite = (lty == lty) && (ltx == ltx) && (rby == rby) && (rbx == rbx);
     if (finite) {
-      s.y0 = clamp_to_int(ceilf(lty)); s.y1 = clamp_to_int(floorf(rby));
-      s.x0 = clamp_to_int(ceilf(ltx)); s.x1 = clamp_to_int(floorf(rbx));
+      const int y0 = clamp_to_int(ceilf(lty)), y1 = clamp_to_int(floorf(rby));
+      const int x0 = clamp_to_int(ceilf(ltx)), x1 = clamp_to_int(floorf(rbx));
+      if (y0 <= y1 && x0 <= x1) { s.y0 = y0; s.y1 = y1; s.x0 = x0; s.x1 = x1; }
     }
     // seed coordinate = grid value at the truncated centre (:316-317); clamped into the image
     int iy = clamp_to_int(cy), ix = clamp_to_int(cx);
@@ -92,6 +97,39 @@ __device__ __forceinline__ float membership(float ey, float ex, float sy, float 
   const float qy = __fmul_rn(__fmul_rn(dy, dy), sy);
   const float qx = __fmul_rn(__fmul_rn(dx, dx), sx);
   return exp_fast(-__fadd_rn(qy, qx));
+}
+
+// keep nibbles of RW consecutive rows starting at ybeg (rows are re-used through a rolling window)
+template <int RW, bool VEC, bool USE_INT>
+__device__ __forceinline__ void keep_rows_global(const float* __restrict__ img, int ybeg, int x0, int H, int W,
+                                                 const Thr& thr, int lane, uint32_t (&nib)[RW]) {
+  RowH up = load_rowh<VEC, USE_INT>(img, ybeg - 1, x0, H, W, thr, lane);
+  RowH mid = load_rowh<VEC, USE_INT>(img, ybeg, x0, H, W, thr, lane);
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const RowH dn = load_rowh<VEC, USE_INT>(img, ybeg + r + 1, x0, H, W, thr, lane);
+    nib[r] = (ybeg + r < H) ? keep_nibble(up, mid, dn) : 0u;
+    up = mid; mid = dn;
+  }
+}
+
+// One culled seed against the lane's RW x 4 pixels.  bx = {y0,y1,x0,x1}; the caller has established that the
+// seed overlaps the lane's columns and the warp's rows.  Branch-free inside: pixels outside the box compute a
+// probability that the range predicate discards.
+template <int RW>
+__device__ __forceinline__ void seed_update(const int4 bx, float cy, float cx, int id, int ybeg, int x0,
+                                            const float (&a)[RW][4][4], float (&best)[RW][4], int (&lab)[RW][4]) {
+  const unsigned hy = (unsigned)(bx.y - bx.x), hx = (unsigned)(bx.w - bx.z);
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const bool rowin = (unsigned)(ybeg + r - bx.x) <= hy;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool in = rowin && ((unsigned)(x0 + i - bx.z) <= hx);
+      const float P = membership(a[r][0][i], a[r][1][i], a[r][2][i], a[r][3][i], cy, cx);
+      if (in && P > best[r][i]) { best[r][i] = P; lab[r][i] = id; }   // strict: first index wins ties (:328)
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -216,18 +254,13 @@ assign_dense_kernel(const float* __restrict__ kp, int64_t kp_img_stride,
   const Thr thr = make_thr(thr_key[b]);
   const float* kpb = kp + (int64_t)b * kp_img_stride;
   uint32_t nib[RW];
-  {
-    RowH up = load_rowh<VEC>(kpb, ybeg - 1, x0, H, W, thr, lane);
-    RowH mid = load_rowh<VEC>(kpb, ybeg, x0, H, W, thr, lane);
+  if (thr.use_int) keep_rows_global<RW, VEC, true>(kpb, ybeg, x0, H, W, thr, lane, nib);
+  else keep_rows_global<RW, VEC, false>(kpb, ybeg, x0, H, W, thr, lane, nib);
 #pragma unroll
-    for (int r = 0; r < RW; ++r) {
-      const RowH dn = load_rowh<VEC>(kpb, ybeg + r + 1, x0, H, W, thr, lane);
-      nib[r] = (ybeg + r < H) ? keep_nibble(up, mid, dn) : 0u;
-      const uint32_t word = nibbles_to_word(nib[r], lane);
-      if ((lane & 7) == 0 && x0 < W && ybeg + r < H)
-        keepbits[((size_t)b * H + ybeg + r) * Wwords + (x0 >> 5)] = word;
-      up = mid; mid = dn;
-    }
+  for (int r = 0; r < RW; ++r) {
+    const uint32_t word = nibbles_to_word(nib[r], lane);
+    if ((lane & 7) == 0 && x0 < W && ybeg + r < H)
+      keepbits[((size_t)b * H + ybeg + r) * Wwords + (x0 >> 5)] = word;
   }
 
   // (4) cull the seed table against this tile, preserving seed order (first-index rule)
@@ -297,20 +330,7 @@ assign_dense_kernel(const float* __restrict__ kp, int64_t kp_img_stride,
     if (bx.x > ybeg + RW - 1 || bx.y < ybeg) continue;                   // warp-uniform row cull
     if (bx.z > x0 + 3 || bx.w < x0) continue;                            // lane column cull
     const float4 cc = *reinterpret_cast<const float4*>(&s_hit[t].cy);   // cy,cx,id,pad
-    const int id = __float_as_int(cc.z);
-#pragma unroll
-    for (int r = 0; r < RW; ++r) {
-      const int y = ybeg + r;
-      if (y < bx.x || y > bx.y) continue;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int x = x0 + i;
-        if (x >= bx.z && x <= bx.w) {
-          const float P = membership(a[r][0][i], a[r][1][i], a[r][2][i], a[r][3][i], cc.x, cc.y);
-          if (P > best[r][i]) { best[r][i] = P; lab[r][i] = id; }
-        }
-      }
-    }
+    seed_update<RW>(bx, cc.x, cc.y, __float_as_int(cc.z), ybeg, x0, a, best, lab);
   }
 
   // (7) stores + statistics of the keep pixels
@@ -520,6 +540,8 @@ group_split_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ 
 
 }  // namespace isg
 
+#include "dense_tma.cuh"
+
 using namespace isg;
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -605,6 +627,21 @@ extern "C" int isg_assign_dense(const float* kp, int64_t kp_img_stride, const fl
   if ((size_t)Nmax * sizeof(SeedRec) * 2 > 200 * 1024) return ISG_EUNSUPPORTED;
   const bool vec = (W % 4 == 0) && (kp_img_stride % 4 == 0) && (ae_img_stride % 4 == 0) && (ae_plane_stride % 4 == 0) &&
                    aligned16(kp) && aligned16(ae) && aligned16(label_map) && (!score_map || aligned16(score_map));
+  // v2 (persistent, TMA-fed) whenever the layout allows tensor maps; v1 otherwise or when ISG_DENSE_V1 is set
+  const char* v1_env = getenv("ISG_DENSE_V1");
+  if (vec && !(v1_env && v1_env[0] == '1')) {
+    const int rc = launch_dense_tma(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
+                                    Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, stream);
+    if (rc != ISG_EUNSUPPORTED) return rc;
+  }
+  const char* rw_env = getenv("ISG_DENSE_RW");   // v1 tuning knob (rows per warp); default 4
+  const int rw = rw_env ? atoi(rw_env) : 4;
+  if (rw == 2)
+    return launch_dense<2>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
+                           Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, vec, stream);
+  if (rw == 1)
+    return launch_dense<1>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
+                           Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, vec, stream);
   return launch_dense<4>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
                          Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, vec, stream);
 }

@@ -92,11 +92,11 @@ __device__ __forceinline__ float ex2_approx(float t) {
   asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(t));
   return r;
 }
-// The argument is clamped to [-104, 88.7]: below, the result rounds to 0 anyway; above, the result would be
-// +inf (the clamp returns ~FLT_MAX instead; only reachable with log-sigma > 88).
+// Finite arguments only: for |x| beyond ~2e38 (or an overflowing result) the residual term turns the result
+// into NaN instead of 0 / +inf.  In the membership that is harmless: a NaN probability never wins the
+// `P > best` comparison, exactly like the 0 the reference would produce.
 __device__ __forceinline__ float exp_fast(float x) {
   const float L2E_HI = 1.44269502162933349609375f, L2E_LO = 1.925963033500011e-8f;
-  x = fminf(fmaxf(x, -104.0f), 88.7f);
   const float t = x * L2E_HI;
   float e = fmaf(x, L2E_HI, -t);
   e = fmaf(x, L2E_LO, e);

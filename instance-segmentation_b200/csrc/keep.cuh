@@ -34,7 +34,8 @@ __device__ __forceinline__ Thr make_thr(uint32_t ukey) {
   t.use_int = (t.f == 0.0f) || (ukey == 0xffffffffu) || (t.f != t.f);   // +-0, "select nothing", NaN keys
   return t;
 }
-__device__ __forceinline__ bool selected(float x, const Thr& t) { return t.use_int ? (skey(x) >= t.s) : (x >= t.f); }
+template <bool USE_INT>
+__device__ __forceinline__ bool selected(float x, const Thr& t) { return USE_INT ? (skey(x) >= t.s) : (x >= t.f); }
 
 // One image row as seen by a lane owning pixels x0..x0+3.
 struct RowH {
@@ -42,6 +43,47 @@ struct RowH {
   float v[4];      // v of the lane's 4 pixels (-inf outside the image)
   uint32_t sel;    // bit i: pixel x0+i is inside the image and selected
 };
+
+__device__ __forceinline__ RowH rowh_outside() {
+  RowH o;
+  const float ninf = __int_as_float(0xff800000);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { o.h[i] = ninf; o.v[i] = ninf; }
+  o.sel = 0;
+  return o;
+}
+
+// Build a RowH from the lane's 4 raw pixels.  `nin` = number of the lane's pixels inside the image (0..4),
+// `left_raw`/`right_raw` are only read by lane 0 / lane 31 (halo pixels the neighbouring lanes do not own) and
+// `has_left`/`has_right` say whether those halo pixels exist.  The interior halo comes from the neighbouring
+// lanes by shuffle (the lanes of a warp own consecutive 4-pixel groups of ONE row).
+template <bool USE_INT>
+__device__ __forceinline__ RowH make_rowh(const float (&raw)[4], int nin, float left_raw, bool has_left, float right_raw,
+                                          bool has_right, const Thr& thr, int lane) {
+  RowH o;
+  const float ninf = __int_as_float(0xff800000);
+  o.sel = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool s = selected<USE_INT>(raw[i], thr);
+    o.v[i] = s ? raw[i] : 0.0f;
+    o.sel |= (s ? 1u : 0u) << i;
+  }
+  if (nin < 4) {   // only the lanes straddling / beyond the right image border
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i >= nin) { o.v[i] = ninf; o.sel &= ~(1u << i); }
+  }
+  float left = __shfl_up_sync(0xffffffffu, o.v[3], 1);
+  float right = __shfl_down_sync(0xffffffffu, o.v[0], 1);
+  if (lane == 0) left = has_left ? (selected<USE_INT>(left_raw, thr) ? left_raw : 0.0f) : ninf;
+  if (lane == 31) right = has_right ? (selected<USE_INT>(right_raw, thr) ? right_raw : 0.0f) : ninf;
+  o.h[0] = fmaxf(fmaxf(left, o.v[0]), o.v[1]);
+  o.h[1] = fmaxf(fmaxf(o.v[0], o.v[1]), o.v[2]);
+  o.h[2] = fmaxf(fmaxf(o.v[1], o.v[2]), o.v[3]);
+  o.h[3] = fmaxf(fmaxf(o.v[2], o.v[3]), right);
+  return o;
+}
 
 template <bool VEC>
 __device__ __forceinline__ void load_raw4(const float* __restrict__ row, int x0, int W, float (&v)[4]) {
@@ -54,45 +96,19 @@ __device__ __forceinline__ void load_raw4(const float* __restrict__ row, int x0,
   }
 }
 
-// The lanes of a warp own consecutive 4-pixel groups of ONE row, so the 1-pixel halo comes from the
-// neighbouring lanes by shuffle; only lane 0 / lane 31 touch memory for it.
-template <bool VEC>
+// row `y` of a global-memory image
+template <bool VEC, bool USE_INT>
 __device__ __forceinline__ RowH load_rowh(const float* __restrict__ img, int y, int x0, int H, int W, const Thr& thr,
                                           int lane) {
-  RowH o;
-  const float ninf = __int_as_float(0xff800000);
-  if (y < 0 || y >= H) {  // warp-uniform
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { o.h[i] = ninf; o.v[i] = ninf; }
-    o.sel = 0;
-    return o;
-  }
+  if (y < 0 || y >= H) return rowh_outside();   // warp-uniform
   const float* row = img + (int64_t)y * W;
   float raw[4];
   load_raw4<VEC>(row, x0, W, raw);
-  o.sel = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool in = x0 + i < W;
-    const bool s = in && selected(raw[i], thr);
-    o.sel |= (s ? 1u : 0u) << i;
-    o.v[i] = in ? (s ? raw[i] : 0.0f) : ninf;
-  }
-  float left = __shfl_up_sync(0xffffffffu, o.v[3], 1);
-  float right = __shfl_down_sync(0xffffffffu, o.v[0], 1);
-  if (lane == 0) {
-    left = ninf;
-    if (x0 - 1 >= 0 && x0 - 1 < W) { const float t = __ldg(row + x0 - 1); left = selected(t, thr) ? t : 0.0f; }
-  }
-  if (lane == 31) {
-    right = ninf;
-    if (x0 + 4 < W) { const float t = __ldg(row + x0 + 4); right = selected(t, thr) ? t : 0.0f; }
-  }
-  o.h[0] = fmaxf(fmaxf(left, o.v[0]), o.v[1]);
-  o.h[1] = fmaxf(fmaxf(o.v[0], o.v[1]), o.v[2]);
-  o.h[2] = fmaxf(fmaxf(o.v[1], o.v[2]), o.v[3]);
-  o.h[3] = fmaxf(fmaxf(o.v[2], o.v[3]), right);
-  return o;
+  const bool has_left = x0 - 1 >= 0 && x0 - 1 < W, has_right = x0 + 4 < W;
+  float lr = 0.0f, rr = 0.0f;
+  if (lane == 0 && has_left) lr = __ldg(row + x0 - 1);
+  if (lane == 31 && has_right) rr = __ldg(row + x0 + 4);
+  return make_rowh<USE_INT>(raw, min(max(W - x0, 0), 4), lr, has_left, rr, has_right, thr, lane);
 }
 
 // keep nibble of the lane's 4 pixels of the middle row

@@ -318,13 +318,15 @@ keep_kernel(const float* __restrict__ kp, int64_t img_stride, int H, int W, int 
   if (ybeg >= H) return;  // warp-uniform
   const float* img = kp + (int64_t)b * img_stride;
   const Thr thr = make_thr(thr_key[b]);
-  RowH up = load_rowh<VEC>(img, ybeg - 1, x0, H, W, thr, lane);
-  RowH mid = load_rowh<VEC>(img, ybeg, x0, H, W, thr, lane);
+  RowH up, mid;
+  if (thr.use_int) { up = load_rowh<VEC, true>(img, ybeg - 1, x0, H, W, thr, lane); mid = load_rowh<VEC, true>(img, ybeg, x0, H, W, thr, lane); }
+  else { up = load_rowh<VEC, false>(img, ybeg - 1, x0, H, W, thr, lane); mid = load_rowh<VEC, false>(img, ybeg, x0, H, W, thr, lane); }
 #pragma unroll
   for (int r = 0; r < kKeepRowsPerWarp; ++r) {
     const int y = ybeg + r;
     if (y >= H) break;
-    const RowH dn = load_rowh<VEC>(img, y + 1, x0, H, W, thr, lane);
+    const RowH dn = thr.use_int ? load_rowh<VEC, true>(img, y + 1, x0, H, W, thr, lane)
+                                : load_rowh<VEC, false>(img, y + 1, x0, H, W, thr, lane);
     const uint32_t nib = keep_nibble(up, mid, dn);
     const uint32_t word = nibbles_to_word(nib, lane);
     if ((lane & 7) == 0 && x0 < W) keepbits[((size_t)b * H + y) * Wwords + (x0 >> 5)] = word;
