@@ -198,10 +198,10 @@ def run_ours(args, wl, rank, world, local_rank):
     bplan = engine.BoxPlan(B, A, C, H, W, dev, cap=1024, max_keep=max_keep)
     dplan = engine.DecodePlan(B, H, W, bplan.N, wl["kp_th"], dev, args.mode, want_score=False, wh_delta=WH_DELTA)
     dplan.events = []
+    pipe = engine.DecodePipeline(bplan, dplan)
 
     def step(timed_kernel=False):
-        bplan.run(d["anchors"], d["regression"], d["classification"], CLS_TH, IOU_TH)
-        dplan.run(d["kp"], d["ae"], bplan.rois, bplan.n_seeds, time_main=timed_kernel)
+        pipe.run(d["kp"], d["ae"], d["anchors"], d["regression"], d["classification"], CLS_TH, IOU_TH, time_main=timed_kernel)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -249,10 +249,20 @@ def run_ours(args, wl, rank, world, local_rank):
             import torch.distributed as dist
             dist.barrier()
         t0 = time.perf_counter()
+        host_s = 0.0
         for _ in range(args.e2e_steps):
             res = dec.decode_output(inputs, outs, infos, tf, cfg, dev)
+            host_s += dec.last_timing.get("host_polygons_s", 0.0)
         torch.cuda.synchronize(dev)
         te = time.perf_counter() - t0
+        # the H2D copy alone, for the split reported next to the e2e number
+        hc0, hc1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        hc0.record()
+        _tmp = [pinned[k].to(dev, non_blocking=True) for k in ("kp", "ae", "regression", "classification")]
+        hc1.record()
+        torch.cuda.synchronize(dev)
+        h2d_ms = hc0.elapsed_time(hc1)
+        del _tmp
         if world > 1:
             tt = torch.tensor([te], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -263,7 +273,8 @@ def run_ours(args, wl, rank, world, local_rank):
                   dplan.offsets.numel() * 4 + B * max(int(counts.max()), 1) * 8)
         e2e = {"value": world * B * H * W * args.e2e_steps / te / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * te / args.e2e_steps,
-               "instances_per_step": n_inst, "polygons": "host (cv2/numpy) this round"}
+               "instances_per_step": n_inst, "h2d_ms_per_step": h2d_ms, "host_polygon_ms_per_step": 1e3 * host_s / args.e2e_steps,
+               "polygons": "host (cv2/numpy) this round"}
 
     if rank != 0:
         return

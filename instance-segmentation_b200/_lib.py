@@ -100,7 +100,7 @@ _LAUNCHES = {
     "isg_gather_kept": 1, "isg_mask_nms": 5, "isg_mask_pair_counts": 1, "isg_pairwise": 1,
     "isg_bbox_transform": 1, "isg_clip_boxes": 1, "isg_pack_masks": 1,
     # (idx,label,flag,count,cap,n_seeds,B,Nmax,...): one multisplit kernel unless the seed table is huge
-    "isg_group_points": lambda a: 1 if (16 * a[7] + a[7] + 1) * 4 <= 200 * 1024 else 3,
+    "isg_group_points": lambda a: 1 if (16 * a[7] + a[7] + 1 + a[4]) * 4 <= 200 * 1024 else 3,
     # (boxes,scores,cls,tiebreak,count,B,cap,...): fused single-CTA kernel for cap <= 1024
     "isg_box_nms": lambda a: 1 if a[6] <= 1024 else 3,
 }

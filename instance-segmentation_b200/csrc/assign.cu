@@ -470,8 +470,9 @@ group_split_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ 
                    const int32_t* __restrict__ n_seeds, int Nmax, int32_t* __restrict__ offsets,
                    float* __restrict__ points) {
   extern __shared__ int sm_split[];
-  int* hist = sm_split;                       // [kSplitWarps][Nmax]
-  int* tot = sm_split + kSplitWarps * Nmax;   // [Nmax + 1]
+  int* hist = sm_split;                                           // [kSplitWarps][Nmax]
+  int* tot = sm_split + kSplitWarps * Nmax;                       // [Nmax + 1]
+  int* slab = tot + Nmax + 1;                                     // [M]: label (or -1), later the output slot
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = min(count[b], cap), n = min(n_seeds[b], Nmax);
@@ -481,15 +482,20 @@ group_split_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ 
   float2* out = reinterpret_cast<float2*>(points) + (size_t)b * cap;
   int32_t* off_g = offsets + (size_t)b * (Nmax + 1);
   for (int i = tid; i < kSplitWarps * Nmax; i += 32 * kSplitWarps) hist[i] = 0;
+  // stage the (flag-filtered) labels in shared memory: independent, coalesced loads
+  for (int m = tid; m < M; m += 32 * kSplitWarps) {
+    int l = -1;
+    if (fb[m]) { l = lb[m]; if (l < 0 || l >= n) l = -1; }
+    slab[m] = l;
+  }
   __syncthreads();
   const int seg = ((M + kSplitWarps * 32 - 1) / (kSplitWarps * 32)) * 32;
   const int m0 = warp * seg, m1 = min(m0 + seg, M);
   int* myhist = hist + warp * Nmax;
-  // phase 1
+  // phase 1: per-warp label histogram of the warp's contiguous segment
   for (int mb = m0; mb < m1; mb += 32) {
     const int m = mb + lane;
-    int l = -1;
-    if (m < m1 && fb[m]) { l = lb[m]; if (l < 0 || l >= n) l = -1; }
+    const int l = m < m1 ? slab[m] : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, l);
     if (l >= 0 && lane == __ffs(peers) - 1) myhist[l] += __popc(peers);
     __syncwarp();
@@ -521,20 +527,26 @@ group_split_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ 
     for (int i = n + lane; i <= Nmax; i += 32) off_g[i] = carry;
   }
   __syncthreads();
-  // phase 3: ordered scatter
+  // phase 3: output slot of every element, in order (shared memory only)
   for (int mb = m0; mb < m1; mb += 32) {
     const int m = mb + lane;
-    int l = -1;
-    if (m < m1 && fb[m]) { l = lb[m]; if (l < 0 || l >= n) l = -1; }
+    const int l = m < m1 ? slab[m] : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, l);
-    int pos = 0;
+    int pos = -1;
     if (l >= 0) pos = tot[l] + myhist[l] + __popc(peers & ((1u << lane) - 1u));
     __syncwarp();
-    if (l >= 0) {
-      out[pos] = make_float2((float)ib[2 * m + 1], (float)ib[2 * m]);   // (x,y) flip
-      if (lane == __ffs(peers) - 1) myhist[l] += __popc(peers);
-    }
+    if (l >= 0 && lane == __ffs(peers) - 1) myhist[l] += __popc(peers);
+    if (m < m1) slab[m] = pos;
     __syncwarp();
+  }
+  __syncthreads();
+  // phase 4: scatter (independent loads / stores)
+  for (int m = tid; m < M; m += 32 * kSplitWarps) {
+    const int pos = slab[m];
+    if (pos >= 0) {
+      const int2 yx = *reinterpret_cast<const int2*>(ib + 2 * m);
+      out[pos] = make_float2((float)yx.y, (float)yx.x);   // (x,y) flip
+    }
   }
 }
 
@@ -664,7 +676,7 @@ extern "C" int isg_group_points(const int32_t* idx, const int32_t* label, const 
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!idx || !label || !flag || !count || !n_seeds || !offsets || !points) return ISG_EINVAL;
   if (B <= 0 || Nmax <= 0 || cap <= 0 || B > 65535) return ISG_EINVAL;
-  const size_t smem = ((size_t)kSplitWarps * Nmax + Nmax + 1) * sizeof(int);
+  const size_t smem = ((size_t)kSplitWarps * Nmax + Nmax + 1 + cap) * sizeof(int);
   if (smem <= 200 * 1024) {
     ISG_CUDA(cudaFuncSetAttribute(group_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     group_split_kernel<<<B, 32 * kSplitWarps, smem, stream>>>(idx, label, flag, count, cap, n_seeds, Nmax, offsets, points);

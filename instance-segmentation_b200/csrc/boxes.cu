@@ -341,30 +341,33 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
     mask[(size_t)i * nwP + w] = bits;
   }
   __syncthreads();
-  // greedy scan, 64-box chunks
+  // greedy scan, 64-box chunks.  Inside a chunk only the KEPT boxes cost a (dependent) step: the next kept box
+  // is the lowest still-alive bit.  The kept rows are then OR-ed into the later words by (row, word) threads.
   int nk = 0;
   int32_t* out = keep + (size_t)b * cap;
   for (int c = 0; c < nw; ++c) {
     const int base = c * 64;
     const int m = min(64, n - base);
     if (t == 0) {
-      unsigned long long word = remv[c], kept = 0ull;
-      for (int q = 0; q < m; ++q)
-        if (!((word >> q) & 1ull)) { kept |= 1ull << q; word |= mask[(size_t)(base + q) * nwP + c]; }
+      const unsigned long long valid = (m == 64) ? ~0ull : ((1ull << m) - 1ull);
+      unsigned long long alive = ~remv[c] & valid, kept = 0ull;
+      while (alive) {
+        const int q = __ffsll((long long)alive) - 1;
+        kept |= 1ull << q;
+        alive &= ~(mask[(size_t)(base + q) * nwP + c] | (1ull << q));
+      }
       s_kept = kept;
     }
     __syncthreads();
     const unsigned long long kept = s_kept;
     if (t < m && ((kept >> t) & 1ull)) out[nk + __popcll(kept & ((1ull << t) - 1ull))] = (int32_t)val[base + t];
     nk += __popcll(kept);
-    if (t > c && t < nw) {
-      unsigned long long acc = 0ull, kk = kept;
-      while (kk) {
-        const int q = __ffsll((long long)kk) - 1;
-        kk &= kk - 1;
-        acc |= mask[(size_t)(base + q) * nwP + t];
+    {
+      const int q = t & 63, w = c + 1 + (t >> 6);   // 1024 threads cover 64 rows x 16 words
+      if (w < nw && ((kept >> q) & 1ull)) {
+        const unsigned long long bits = mask[(size_t)(base + q) * nwP + w];
+        if (bits) atomicOr(&remv[w], bits);
       }
-      remv[t] |= acc;
     }
     __syncthreads();
   }

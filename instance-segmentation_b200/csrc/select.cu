@@ -1,7 +1,10 @@
 // K2 — boundary-keypoint selection: exact k-th largest (3-pass radix select), 3x3 peak test,
 // row-major compaction.  Reference: select_points / nms_hm (utils/decode.py:42-48,71-85) and
 // kp_mask.nonzero() (utils/decode.py:312).
+#include <cooperative_groups.h>
 #include "keep.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace isg {
 
@@ -176,51 +179,116 @@ __host__ __device__ inline TopkWs topk_ws_view(void* ws, int b, int npx, int k) 
   return v;
 }
 
-// block-wide exact select of the `rank`-th largest of n keys produced by key_at(i); 1024 threads.
+constexpr int kSelCluster = 8;   // CTAs per image in the sample / select kernels (one thread-block cluster)
+
+// histogram increment aggregated with match.any: one shared-memory atomic per distinct bin per warp
+__device__ __forceinline__ void hist_add_match(uint32_t* sh, uint32_t bin, bool valid, int lane) {
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? bin : 0xffffffffu);
+  if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[bin], (uint32_t)__popc(peers));
+}
+
+// resolve_digit over the SUM of the cluster's per-CTA histograms (read through distributed shared memory)
+__device__ void resolve_digit_cluster(cg::cluster_group& cluster, uint32_t* sh_hist, uint32_t krem, uint32_t* out_digit,
+                                      uint32_t* out_krem) {
+  __shared__ uint32_t warp_tot[kHistThreads / 32];
+  __shared__ uint32_t res[2];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const bool own = t < kHistThreads;
+  uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (own) {
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) {
+      const uint4* peer = reinterpret_cast<const uint4*>(cluster.map_shared_rank(sh_hist, r)) + t * 2;
+      const uint4 a = peer[0], c = peer[1];
+      h[0] += a.x; h[1] += a.y; h[2] += a.z; h[3] += a.w; h[4] += c.x; h[5] += c.y; h[6] += c.z; h[7] += c.w;
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += h[i];
+  uint32_t suf = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t v = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += v;
+  }
+  if (own && lane == 0) warp_tot[warp] = suf;
+  if (t == 0) { res[0] = 0; res[1] = 0; }
+  __syncthreads();
+  if (own) {
+    uint32_t above = 0;
+    for (int w = warp + 1; w < kHistThreads / 32; ++w) above += warp_tot[w];
+    uint32_t cum = suf - s + above;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      if (cum < krem && krem <= cum + h[i]) { res[0] = (uint32_t)(t * 8 + i); res[1] = krem - cum; }
+      cum += h[i];
+    }
+  }
+  __syncthreads();
+  *out_digit = res[0];
+  *out_krem = res[1];
+  __syncthreads();
+}
+
+// Cluster-wide exact select of the `rank`-th largest of n keys produced by key_at(i).  Every CTA of the
+// cluster (1024 threads each) histograms a contiguous slice; the per-CTA histograms are summed through
+// DSMEM, so all CTAs resolve the same digit.  sh_hist: this CTA's 2048-bin histogram (shared memory).
 template <typename KeyAt>
-__device__ uint32_t block_radix_select(uint32_t* sh_hist, int n, uint32_t rank, KeyAt key_at) {
+__device__ uint32_t cluster_radix_select(cg::cluster_group& cluster, uint32_t* sh_hist, int n, uint32_t rank, KeyAt key_at) {
   const int t = threadIdx.x, lane = t & 31;
+  const int nb = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+  const int chunk = (n + nb - 1) / nb;
+  const int lo = min(r * chunk, n), hi = min(lo + chunk, n);
   uint32_t prefix = 0, pmask = 0, krem = rank;
 #pragma unroll 1
   for (int pass = 0; pass < 3; ++pass) {
     for (int i = t; i < kHistBins; i += kSelThreads) sh_hist[i] = 0;
     __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += kSelThreads) {   // warp-uniform trip count
-      const int i = i0 + t;
-      const bool in = i < n;
-      const uint32_t key = in ? key_at(i) : 0u;
-      hist_add(sh_hist, digit_of(key, pass), in && (key & pmask) == prefix, lane);
+    for (int i0 = lo; i0 < hi; i0 += kSelThreads * 4) {   // warp-uniform trip count, 4 independent loads in flight
+      uint32_t key[4];
+      bool in[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * kSelThreads + t; in[u] = i < hi; key[u] = in[u] ? key_at(i) : 0u; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) hist_add_match(sh_hist, digit_of(key[u], pass), in[u] && (key[u] & pmask) == prefix, lane);
     }
-    __syncthreads();
+    cluster.sync();   // every CTA's histogram is complete and visible
     uint32_t d, k2;
-    resolve_digit(sh_hist, krem, &d, &k2);
+    resolve_digit_cluster(cluster, sh_hist, krem, &d, &k2);
     krem = k2;
     if (pass == 0) { prefix = d << 21; pmask = 0xffe00000u; }
     else if (pass == 1) { prefix |= d << 10; pmask = 0xfffffc00u; }
     else prefix |= d;
+    cluster.sync();   // nobody still reads this CTA's histogram when the next pass clears it
   }
   return prefix;
 }
 
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
 topk_sample_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, int stride, void* ws) {
-  extern __shared__ uint32_t skeys[];   // [<= kSampleMax]
+  extern __shared__ uint32_t skeys[];   // this CTA's slice of the sample, [ceil(S / cluster)]
   __shared__ uint32_t sh_hist[kHistBins];
-  const int b = blockIdx.x, t = threadIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int b = blockIdx.y, t = threadIdx.x;
+  const int r = (int)cluster.block_rank(), nb = (int)cluster.num_blocks();
   const float* img = kp + (int64_t)b * img_stride;
   const int S = npx / stride;           // sample i reads pixel i*stride + (i*37 % stride)
-  for (int i = t; i < S; i += kSelThreads) {
+  const int chunk = (S + nb - 1) / nb;
+  const int lo = min(r * chunk, S), hi = min(lo + chunk, S);
+  for (int i = lo + t; i < hi; i += kSelThreads) {
     const int p = i * stride + (int)(((unsigned)i * 37u) % (unsigned)stride);
-    skeys[i] = float_key(__ldg(img + p));
+    skeys[i - lo] = float_key(__ldg(img + p));
   }
   __syncthreads();
-  // sample rank that corresponds to ~2k pixels, plus 8 sigma and a constant
-  const double expect = 2.0 * (double)k * (double)S / (double)npx;
-  long long r = (long long)(expect + 8.0 * sqrt(expect) + 16.0);
+  // sample rank that corresponds to ~1.2k pixels, plus 6 sigma and a constant: the number of pixels above the
+  // sample value of that rank then exceeds k with a margin of ~9 sigma (and step 3 falls back if it ever did not)
+  const double expect = 1.2 * (double)k * (double)S / (double)npx;
+  long long rk = (long long)(expect + 6.0 * sqrt(expect) + 8.0);
   TopkWs v = topk_ws_view(ws, b, npx, k);
   uint32_t lower = 0u;                  // 0: every pixel is a candidate (step 3 then falls back if needed)
-  if (r < (long long)S) lower = block_radix_select(sh_hist, S, (uint32_t)r, [&](int i) { return skeys[i]; });
-  if (t == 0) { *v.lower = lower; *v.ncand = 0u; }
+  if (rk < (long long)S)                // cluster-uniform
+    lower = cluster_radix_select(cluster, sh_hist, S, (uint32_t)rk, [&](int i) { return skeys[i - lo]; });
+  if (r == 0 && t == 0) { *v.lower = lower; *v.ncand = 0u; }
 }
 
 __global__ void __launch_bounds__(kFilterThreads)
@@ -283,23 +351,24 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
     if ((size_t)g + i < capc) v.cand[g + i] = buf[i];
 }
 
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
 topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, void* ws,
                    uint32_t* __restrict__ thr_key) {
   __shared__ uint32_t sh_hist[kHistBins];
-  const int b = blockIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int b = blockIdx.y;
   const TopkWs v = topk_ws_view(ws, b, npx, k);
   const uint32_t nc = *v.ncand;
   const bool use_cand = nc >= (uint32_t)k && (size_t)nc <= topk_cand_cap(npx, k);
   uint32_t key;
-  if (use_cand) {
+  if (use_cand) {   // cluster-uniform
     const uint32_t* cand = v.cand;
-    key = block_radix_select(sh_hist, (int)nc, (uint32_t)k, [&](int i) { return cand[i]; });
+    key = cluster_radix_select(cluster, sh_hist, (int)nc, (uint32_t)k, [&](int i) { return cand[i]; });
   } else {
     const float* img = kp + (int64_t)b * img_stride;
-    key = block_radix_select(sh_hist, npx, (uint32_t)k, [&](int i) { return float_key(__ldg(img + i)); });
+    key = cluster_radix_select(cluster, sh_hist, npx, (uint32_t)k, [&](int i) { return float_key(__ldg(img + i)); });
   }
-  if (threadIdx.x == 0) thr_key[b] = key;
+  if (cluster.block_rank() == 0 && threadIdx.x == 0) thr_key[b] = key;
 }
 
 // ---- stand-alone keep kernel ---------------------------------------------------------------
@@ -360,35 +429,44 @@ __global__ void nms_hm_kernel(const float* __restrict__ heat, int H, int W, int 
   keep[(size_t)blockIdx.z * H * W + (size_t)y * W + x] = (m == c) ? 1 : 0;
 }
 
-// ---- ordered compaction: one CTA (32 warps) per image ----------------------------------------
-// Warp w owns rows w, w+32, ...; a row's words are read with one coalesced request per 32 words, eight rows
-// in flight per warp.  Phase 1 counts the set bits per row, a block scan turns the counts into row offsets,
-// phase 2 re-reads the rows (L2 hits) and emits the (y,x) pairs in row-major order.
+// ---- ordered compaction: one 8-CTA thread-block cluster per image ----------------------------
+// CTA r of the cluster owns a contiguous band of rows; inside it warp w owns rows w, w+32, ...  A row's words are
+// read with one coalesced request per 32 words, eight rows in flight per warp.  Phase 1 counts the set bits per
+// row, a block scan gives row offsets inside the band, the band totals are exchanged through distributed shared
+// memory (exclusive prefix over the lower-ranked CTAs), and phase 2 re-reads the rows (L2 hits) and emits the
+// (y,x) pairs in row-major order.
 constexpr int kCompactThreads = 1024;
-constexpr int kCompactBatch = 8;   // rows in flight per warp
+constexpr int kCompactBatch = 8;     // rows in flight per warp
+constexpr int kCompactCluster = 8;   // CTAs per image
 
 // WL = words per lane (Wwords <= 32*WL); WL == 0 selects the generic any-width path
 template <int WL>
-__global__ void __launch_bounds__(kCompactThreads, 1)
+__global__ void __cluster_dims__(kCompactCluster, 1, 1) __launch_bounds__(kCompactThreads, 1)
 compact_kernel(const uint32_t* __restrict__ keepbits, int H, int Wwords, int W, int cap,
                int32_t* __restrict__ idx, int32_t* __restrict__ count) {
-  extern __shared__ int row_off[];   // [H + 1]
+  extern __shared__ int row_off[];   // [band rows + 1]
   __shared__ int warp_tot[32];
-  const int b = blockIdx.x;
+  __shared__ int s_total;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int b = blockIdx.y;
+  const int rank = (int)cluster.block_rank();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const uint32_t* bits = keepbits + (size_t)b * H * Wwords;
   constexpr int WLc = WL > 0 ? WL : 1;
+  const int Hc = (H + kCompactCluster - 1) / kCompactCluster;
+  const int yb0 = min(rank * Hc, H), yb1 = min(yb0 + Hc, H);   // this CTA's band [yb0, yb1)
+  const int nrows = yb1 - yb0;
 
   // phase 1: per-row popcounts
   if (WL > 0) {
-    for (int yb = warp; yb < H; yb += 32 * kCompactBatch) {
+    for (int yr = warp; yr < nrows; yr += 32 * kCompactBatch) {
       uint32_t v[kCompactBatch][WLc];
 #pragma unroll
       for (int r = 0; r < kCompactBatch; ++r)
 #pragma unroll
         for (int j = 0; j < WLc; ++j) {
-          const int y = yb + 32 * r, w = lane + 32 * j;
-          v[r][j] = (y < H && w < Wwords) ? __ldg(bits + (size_t)y * Wwords + w) : 0u;
+          const int y = yb0 + yr + 32 * r, w = lane + 32 * j;
+          v[r][j] = (yr + 32 * r < nrows && w < Wwords) ? __ldg(bits + (size_t)y * Wwords + w) : 0u;
         }
 #pragma unroll
       for (int r = 0; r < kCompactBatch; ++r) {
@@ -396,23 +474,22 @@ compact_kernel(const uint32_t* __restrict__ keepbits, int H, int Wwords, int W, 
 #pragma unroll
         for (int j = 0; j < WLc; ++j) c += __popc(v[r][j]);
         c = warp_sum(c);
-        const int y = yb + 32 * r;
-        if (lane == 0 && y < H) row_off[y] = c;
+        if (lane == 0 && yr + 32 * r < nrows) row_off[yr + 32 * r] = c;
       }
     }
   } else {
-    for (int y = warp; y < H; y += 32) {
+    for (int yr = warp; yr < nrows; yr += 32) {
       int c = 0;
-      for (int w = lane; w < Wwords; w += 32) c += __popc(__ldg(bits + (size_t)y * Wwords + w));
+      for (int w = lane; w < Wwords; w += 32) c += __popc(__ldg(bits + (size_t)(yb0 + yr) * Wwords + w));
       c = warp_sum(c);
-      if (lane == 0) row_off[y] = c;
+      if (lane == 0) row_off[yr] = c;
     }
   }
   __syncthreads();
 
-  // block exclusive scan over the H row counts (thread t owns a contiguous run of rows)
-  const int per = (H + kCompactThreads - 1) / kCompactThreads;
-  const int y0 = min(t * per, H), y1 = min(y0 + per, H);
+  // block exclusive scan over the band's row counts (thread t owns a contiguous run of rows)
+  const int per = (nrows + kCompactThreads - 1) / kCompactThreads;
+  const int y0 = min(t * per, nrows), y1 = min(y0 + per, nrows);
   int c = 0;
   for (int y = y0; y < y1; ++y) c += row_off[y];
   int inc = c;
@@ -432,12 +509,22 @@ compact_kernel(const uint32_t* __restrict__ keepbits, int H, int Wwords, int W, 
       if (lane >= o) s2 += u;
     }
     warp_tot[lane] = s2 - v;
+    if (lane == 31) s_total = s2;
   }
   __syncthreads();
   int run = warp_tot[warp] + inc - c;
   for (int y = y0; y < y1; ++y) { const int v = row_off[y]; row_off[y] = run; run += v; }
-  if (t == kCompactThreads - 1) count[b] = run;
-  __syncthreads();
+
+  // exchange the band totals: offset of this band = sum of the totals of the lower-ranked CTAs
+  cluster.sync();
+  int band_base = 0, grand = 0;
+  for (int r = 0; r < kCompactCluster; ++r) {
+    const int v = *cluster.map_shared_rank(&s_total, r);
+    if (r < rank) band_base += v;
+    grand += v;
+  }
+  if (rank == 0 && t == 0) count[b] = grand;
+  cluster.sync();   // peers have read s_total (nobody exits early), and row_off is complete for this CTA
 
   // phase 2: emit.  `off` = first output slot of the 32-word group held by the warp.
   int32_t* out = idx + (size_t)b * cap * 2;
@@ -459,30 +546,29 @@ compact_kernel(const uint32_t* __restrict__ keepbits, int H, int Wwords, int W, 
     }
   };
   if (WL > 0) {
-    for (int yb = warp; yb < H; yb += 32 * kCompactBatch) {
+    for (int yr = warp; yr < nrows; yr += 32 * kCompactBatch) {
       uint32_t v[kCompactBatch][WLc];
 #pragma unroll
       for (int r = 0; r < kCompactBatch; ++r)
 #pragma unroll
         for (int j = 0; j < WLc; ++j) {
-          const int y = yb + 32 * r, w = lane + 32 * j;
-          v[r][j] = (y < H && w < Wwords) ? __ldg(bits + (size_t)y * Wwords + w) : 0u;
+          const int y = yb0 + yr + 32 * r, w = lane + 32 * j;
+          v[r][j] = (yr + 32 * r < nrows && w < Wwords) ? __ldg(bits + (size_t)y * Wwords + w) : 0u;
         }
 #pragma unroll
       for (int r = 0; r < kCompactBatch; ++r) {
-        const int y = yb + 32 * r;
-        if (y >= H) break;   // warp-uniform
-        int off = row_off[y];
+        if (yr + 32 * r >= nrows) break;   // warp-uniform
+        int off = band_base + row_off[yr + 32 * r];
 #pragma unroll
-        for (int j = 0; j < WLc; ++j) emit_group(y, lane + 32 * j, v[r][j], off);
+        for (int j = 0; j < WLc; ++j) emit_group(yb0 + yr + 32 * r, lane + 32 * j, v[r][j], off);
       }
     }
   } else {
-    for (int y = warp; y < H; y += 32) {
-      int off = row_off[y];
+    for (int yr = warp; yr < nrows; yr += 32) {
+      int off = band_base + row_off[yr];
       for (int w0 = 0; w0 < Wwords; w0 += 32) {
         const int w = w0 + lane;
-        emit_group(y, w, (w < Wwords) ? __ldg(bits + (size_t)y * Wwords + w) : 0u, off);
+        emit_group(yb0 + yr, w, (w < Wwords) ? __ldg(bits + (size_t)(yb0 + yr) * Wwords + w) : 0u, off);
       }
     }
   }
@@ -529,9 +615,9 @@ extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t 
   if (npx >= 65536) {
     int stride = 64;
     while (npx / stride > kSampleMax) stride *= 2;
-    const size_t smem = (size_t)(npx / stride) * sizeof(uint32_t);
+    const size_t smem = (size_t)cdiv(npx / stride, kSelCluster) * sizeof(uint32_t);
     ISG_CUDA(cudaFuncSetAttribute(topk_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_sample_kernel<<<B, kSelThreads, smem, stream>>>(kp, img_stride, npx, k, stride, ws);
+    topk_sample_kernel<<<dim3(kSelCluster, B), kSelThreads, smem, stream>>>(kp, img_stride, npx, k, stride, ws);
     dim3 grid(cdiv(npx, kFilterPxPerBlock), B);
     topk_filter_kernel<<<grid, kFilterThreads, 0, stream>>>(kp, img_stride, npx, k, ws, vec);
   } else {
@@ -540,7 +626,7 @@ extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t 
     for (int b = 0; b < B; ++b)
       ISG_CUDA(cudaMemsetAsync((char*)ws + (size_t)b * per + 3 * kHistBins * sizeof(uint32_t), 0, 64, stream));
   }
-  topk_select_kernel<<<B, kSelThreads, 0, stream>>>(kp, img_stride, npx, k, ws, thr_key);
+  topk_select_kernel<<<dim3(kSelCluster, B), kSelThreads, 0, stream>>>(kp, img_stride, npx, k, ws, thr_key);
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }
@@ -594,14 +680,14 @@ extern "C" int isg_nms_hm(const float* heat, int planes, int H, int W, int kerne
 extern "C" int isg_compact_points(const uint32_t* keepbits, int B, int H, int W, int cap, int32_t* idx,
                                   int32_t* count, isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!keepbits || !idx || !count || B <= 0 || H <= 0 || W <= 0 || cap < 0) return ISG_EINVAL;
+  if (!keepbits || !idx || !count || B <= 0 || H <= 0 || W <= 0 || cap < 0 || B > 65535) return ISG_EINVAL;
   const int Wwords = cdiv(W, 32);
-  const size_t smem = (size_t)(H + 1) * sizeof(int);
+  const size_t smem = (size_t)(cdiv(H, kCompactCluster) + 1) * sizeof(int);
   if (smem > 160 * 1024) return ISG_EUNSUPPORTED;
 #define ISG_COMPACT_LAUNCH(WL_)                                                                                 \
   do {                                                                                                          \
     ISG_CUDA(cudaFuncSetAttribute(compact_kernel<WL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    compact_kernel<WL_><<<B, kCompactThreads, smem, stream>>>(keepbits, H, Wwords, W, cap, idx, count);         \
+    compact_kernel<WL_><<<dim3(kCompactCluster, B), kCompactThreads, smem, stream>>>(keepbits, H, Wwords, W, cap, idx, count); \
   } while (0)
   if (Wwords <= 32) ISG_COMPACT_LAUNCH(1);
   else if (Wwords <= 64) ISG_COMPACT_LAUNCH(2);

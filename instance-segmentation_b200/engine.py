@@ -126,19 +126,31 @@ class DecodePlan:
             self.label_map = self.score_map = None
 
     # ------------------------------------------------------------------------------------------
-    def run(self, kp: torch.Tensor, ae: torch.Tensor, rois: torch.Tensor, n_seeds: torch.Tensor,
-            layout: int = _lib.ISG_BOX_XYXY, time_main: bool = False) -> None:
-        """kp [B,1,H,W] or [B,H,W]; ae [B,4,H,W]; rois [B,N,4] fp32 ((x1,y1,x2,y2) or (cy,cx,h,w), see `layout`);
-        n_seeds [B] int32 — all on the plan's device.  Enqueues the kernels on the current stream and returns
-        without synchronising.  time_main=True brackets the assignment kernel with CUDA events on the launching
-        stream and appends the pair to self.events (bench.py's roofline measurement)."""
-        B, H, W, N, cap = self.B, self.H, self.W, self.N, self.cap
+    def _check(self, kp, ae):
+        B, H, W = self.B, self.H, self.W
         if kp.dim() == 4:
             kp = kp[:, 0]
-        assert kp.shape == (B, H, W) and ae.shape == (B, 4, H, W), (kp.shape, ae.shape)
+        assert kp.shape == (B, H, W), kp.shape
+        assert kp.dtype == torch.float32 and _rows_contiguous(kp)
+        if ae is not None:
+            assert ae.shape == (B, 4, H, W) and ae.dtype == torch.float32 and _rows_contiguous(ae), ae.shape
+        return kp
+
+    def run_topk(self, kp: torch.Tensor) -> None:
+        """Stage 1 (independent of the boxes): exact k-th largest kp value per image -> self.thr_key."""
+        kp = self._check(kp, None)
+        B, H, W = self.B, self.H, self.W
+        kp_stride = kp.stride(0) if B > 1 else H * W
+        call("isg_topk_threshold", ptr(kp), B, H, W, kp_stride, self.kp_th, ptr(self.thr_key), self.ws_ptr,
+             self.ws_bytes, stream_ptr(self.device))
+
+    def run_assign(self, kp: torch.Tensor, ae: torch.Tensor, rois: torch.Tensor, n_seeds: torch.Tensor,
+                   layout: int = _lib.ISG_BOX_XYXY, time_main: bool = False) -> None:
+        """Stage 2: seeds -> assignment (dense or sparse) -> compaction -> grouping.  Needs self.thr_key."""
+        B, H, W, N, cap = self.B, self.H, self.W, self.N, self.cap
+        kp = self._check(kp, ae)
         assert rois.shape == (B, N, 4) and rois.is_contiguous() and rois.dtype == torch.float32
         assert n_seeds.shape == (B,) and n_seeds.dtype == torch.int32
-        assert kp.dtype == torch.float32 and ae.dtype == torch.float32 and _rows_contiguous(kp) and _rows_contiguous(ae)
         s = stream_ptr(self.device)
         kp_stride = kp.stride(0) if B > 1 else H * W
         ae_img = ae.stride(0) if B > 1 else 4 * H * W
@@ -146,8 +158,6 @@ class DecodePlan:
         call("isg_build_seeds", ptr(rois), layout, ptr(n_seeds), B, N, ptr(self.ys), ptr(self.xs), H, W, self.ghost_k,
              self.scale, ptr(self.seeds), ptr(self.ghost), s)
         call("isg_stats_init", ptr(self.stats), B, N, s)
-        call("isg_topk_threshold", ptr(kp), B, H, W, kp_stride, self.kp_th, ptr(self.thr_key), self.ws_ptr,
-             self.ws_bytes, s)
         ev = None
         if time_main:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -176,6 +186,15 @@ class DecodePlan:
              B, N, ptr(self.offsets), ptr(self.points), s)
         if ev:
             self.events.append(ev)
+
+    def run(self, kp: torch.Tensor, ae: torch.Tensor, rois: torch.Tensor, n_seeds: torch.Tensor,
+            layout: int = _lib.ISG_BOX_XYXY, time_main: bool = False) -> None:
+        """kp [B,1,H,W] or [B,H,W]; ae [B,4,H,W]; rois [B,N,4] fp32 ((x1,y1,x2,y2) or (cy,cx,h,w), see `layout`);
+        n_seeds [B] int32 — all on the plan's device.  Enqueues the kernels on the current stream and returns
+        without synchronising.  time_main=True brackets the assignment kernel with CUDA events on the launching
+        stream and appends the pair to self.events (bench.py's roofline measurement)."""
+        self.run_topk(kp)
+        self.run_assign(kp, ae, rois, n_seeds, layout, time_main)
 
 
 class BoxPlan:
@@ -240,3 +259,38 @@ def get_box_plan(B, A, C, H, W, device, cap=4096, max_keep=1024) -> BoxPlan:
             _plans.clear()
         _plans[key] = BoxPlan(B, A, C, H, W, device, cap, max_keep)
     return _plans[key]
+
+
+class DecodePipeline:
+    """box head + decode for one batch.  The top-k threshold does not depend on the boxes, so it runs on a side
+    stream concurrently with the box head / NMS branch and joins before the assignment kernel."""
+
+    def __init__(self, bplan: BoxPlan, dplan: DecodePlan):
+        assert bplan.device == dplan.device and bplan.B == dplan.B and bplan.N == dplan.N
+        self.bplan, self.dplan, self.device = bplan, dplan, dplan.device
+        self.side = torch.cuda.Stream(device=self.device)
+        self.fork = torch.cuda.Event()
+        self.join = torch.cuda.Event()
+
+    def run(self, kp, ae, anchors, regression, classification, cls_th, iou_th, time_main: bool = False) -> None:
+        main = torch.cuda.current_stream(self.device)
+        self.fork.record(main)
+        self.side.wait_event(self.fork)
+        with torch.cuda.stream(self.side):
+            self.dplan.run_topk(kp)
+            self.join.record(self.side)
+        self.bplan.run(anchors, regression, classification, cls_th, iou_th)
+        main.wait_event(self.join)
+        self.dplan.run_assign(kp, ae, self.bplan.rois, self.bplan.n_seeds, _lib.ISG_BOX_XYXY, time_main)
+
+
+_pipes = {}
+
+
+def get_pipeline(bplan: BoxPlan, dplan: DecodePlan) -> DecodePipeline:
+    key = (id(bplan), id(dplan))
+    if key not in _pipes:
+        if len(_pipes) > 8:
+            _pipes.clear()
+        _pipes[key] = DecodePipeline(bplan, dplan)
+    return _pipes[key]

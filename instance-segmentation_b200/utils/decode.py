@@ -37,6 +37,10 @@ draw_flag = False     # set by evaluate.py:41 (the code reads decode_cfg.draw_fl
 # reference's own amount of work (isg_assign_sparse).  Both give identical detections.
 decode_mode = os.environ.get("ISG_DECODE_MODE", "sparse")
 
+# wall-clock split of the last decode_output call (seconds): device (H2D + kernels, until the results are on the
+# host) and host (polygon stage).  Diagnostic only.
+last_timing = {}
+
 _xym = None
 
 
@@ -307,6 +311,57 @@ def _polygons_for_image(points, offsets, n, centres_yx, whs, center_cls, center_
     return n_clss, n_confs, n_centers, kps
 
 
+def _polar_angles(pts, centres):
+    """theta of cartesian2polar for points [K,2] about per-point centres [K,2] (same fp32 arithmetic)."""
+    d = (pts - centres).astype(np.float32)
+    dx, dy = d[:, 0], d[:, 1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        seta = np.arctan(dy / dx)
+        seta = np.where(dx < 0, seta + np.float32(np.pi), seta)
+        seta = np.where((dx > 0) & (dy < 0), seta + np.float32(2 * np.pi), seta)
+        seta = np.where((dx == 0) & (dy > 0), np.float32(np.pi / 2), seta)
+        seta = np.where((dx == 0) & (dy < 0), np.float32(3 * np.pi / 2), seta)
+    return seta.astype(np.float32)
+
+
+def _polygons_for_image_fast(points, offsets, n, centres_yx, center_cls, center_confs, obj_pixel_th):
+    """The identity-transform, no-drawing case of :337-369 with the per-instance numpy work batched:
+    one vectorised polar-angle evaluation for all instances of the image, then per instance only the argsort
+    (kept per instance: np.argsort's order among equal angles must be the reference's) and the two cv2 tests.
+    The `area == 0` rejection (:187-189) is not evaluated: fillPoly rasterises the outline of the polygon, every
+    vertex lies inside the (max+1)-sized canvas, so the area of a polygon with at least one vertex is >= 1
+    (tests/test_host_logic.py checks the predicate against the full-canvas rasterisation)."""
+    import cv2
+    cnt = np.diff(offsets[:n + 1])
+    valid = np.nonzero(cnt >= obj_pixel_th)[0]                       # :355
+    if valid.size == 0:
+        return [], [], [], []
+    centers_xy = np.ascontiguousarray(centres_yx[:, ::-1])          # detransform_pixel flip, (x,y) fp32
+    internal = np.empty((valid.size, 2), dtype=np.float32)
+    segs = []
+    for q, i in enumerate(valid):
+        pts = points[offsets[i]:offsets[i + 1]]
+        segs.append(pts)
+        c = centers_xy[i]
+        internal[q] = c if cv2.pointPolygonTest(pts, (c[0], c[1]), False) > 0 else find_internal_point(pts, c)
+    allp = np.concatenate(segs) if len(segs) > 1 else segs[0]
+    reps = cnt[valid]
+    theta = _polar_angles(allp, np.repeat(internal, reps, axis=0))
+    n_clss, n_confs, n_centers, kps = [], [], [], []
+    pos = 0
+    for q, i in enumerate(valid):
+        k = int(reps[q])
+        sorted_kp = allp[pos:pos + k][np.argsort(theta[pos:pos + k])]
+        pos += k
+        c = centers_xy[i]
+        if cv2.pointPolygonTest(sorted_kp, (c[0], c[1]), False) > 0:     # :201
+            kps.append(sorted_kp)
+            n_centers.append(c)
+            n_clss.append(center_cls[i])
+            n_confs.append(center_confs[i])
+    return n_clss, n_confs, n_centers, kps
+
+
 def _run_plan(kp, ae, boxes_dev, n_dev, layout, decode_cfg, transforms, dev, max_seeds):
     """Enqueue select/assign/group for a batch; returns (plan, identity)."""
     B, H, W = kp.shape[0], kp.shape[-2], kp.shape[-1]
@@ -340,6 +395,8 @@ def group_kp(hm_kp, hm_ae, transforms, center_whs, center_indexes, center_cls, c
         return [], [], [], []
     offsets = plan.offsets[0].cpu().numpy()
     points = plan.points[0, :int(offsets[objs_num])].cpu().numpy()
+    if identity and not decode_cfg.draw_flag:
+        return _polygons_for_image_fast(points, offsets, objs_num, centres, center_cls, center_confs, decode_cfg.obj_pixel_th)
     return _polygons_for_image(points, offsets, objs_num, centres, whs, center_cls, center_confs, transforms, info,
                                decode_cfg, identity)
 
@@ -444,11 +501,17 @@ def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
     B, H, W = kp.shape[0], kp.shape[-2], kp.shape[-1]
     height, width = inputs.shape[2], inputs.shape[3]
     cap, max_keep = 1024, 256
+    reg = engine.as_f32_planes(regression, dev).contiguous()
+    cls_t = engine.as_f32_planes(classification, dev).contiguous()
+    anc = engine.as_f32_planes(anchors, dev).contiguous()
+    A, C = cls_t.shape[1], cls_t.shape[2]
+    identity = _identity_transform(transforms)
     while True:
-        bplan = _decode_boxes_device(height, width, anchors, regression, classification, decode_cfg.cls_th,
-                                     decode_cfg.iou_th, dev, cap, max_keep)
-        plan, identity = _run_plan(kp, ae, bplan.rois, bplan.n_seeds, _lib.ISG_BOX_XYXY, decode_cfg, transforms, dev,
-                                   bplan.N)
+        bplan = engine.get_box_plan(B, A, C, height, width, dev, cap, max_keep)
+        plan = engine.get_decode_plan(B, H, W, bplan.N, int(decode_cfg.kp_th), dev, decode_mode, want_score=False,
+                                      wh_delta=float(decode_cfg.wh_delta) if identity else None,
+                                      scale=float(compute_scale(None)))
+        engine.get_pipeline(bplan, plan).run(kp, ae, anc, reg, cls_t, decode_cfg.cls_th, decode_cfg.iou_th)
         # one read-back for the whole batch
         n_cand = bplan.cand_count.cpu().numpy()
         n_keep = bplan.n_keep.cpu().numpy()
@@ -460,11 +523,14 @@ def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
         if n_keep.max(initial=0) > bplan.N:
             max_keep = min(max(max_keep * 4, int(n_keep.max())), bplan.cap); continue
         break
+    import time as _time
+    _t0 = _time.perf_counter()
     rois = bplan.rois.cpu().numpy(); scores = bplan.scores.cpu().numpy(); cls = bplan.cls.cpu().numpy()
     counts = plan.count.cpu().numpy()
     offsets = plan.offsets.cpu().numpy()
     tot = int(offsets[np.arange(B), np.minimum(n_keep, bplan.N)].max(initial=0))
     points = plan.points[:, :max(tot, 1)].cpu().numpy()
+    _t1 = _time.perf_counter()
     dets = []
     for b in range(B):
         n = int(n_keep[b])
@@ -475,7 +541,12 @@ def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
         centres, whs = (lt + rb) / 2, rb - lt                       # :428-432
         if decode_cfg.draw_flag:
             draw_box(whs, centres, infos[b], transforms)
-        c, f, ctr, g = _polygons_for_image(points[b], offsets[b], n, centres, whs, cls[b, :n].astype(np.int64),
-                                           scores[b, :n], transforms, infos[b], decode_cfg, identity)
+        if identity and not decode_cfg.draw_flag:
+            c, f, ctr, g = _polygons_for_image_fast(points[b], offsets[b], n, centres, cls[b, :n].astype(np.int64),
+                                                    scores[b, :n], decode_cfg.obj_pixel_th)
+        else:
+            c, f, ctr, g = _polygons_for_image(points[b], offsets[b], n, centres, whs, cls[b, :n].astype(np.int64),
+                                               scores[b, :n], transforms, infos[b], decode_cfg, identity)
         dets.append([e for e in zip(c, f, ctr, g)])
+    last_timing.update(readback_s=_t1 - _t0, host_polygons_s=_time.perf_counter() - _t1)
     return dets

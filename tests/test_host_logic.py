@@ -125,3 +125,26 @@ def test_scene_box_head_decodes_to_the_image_boxes():
     assert np.all(ctr - np.floor(ctr) == 0.5)
     empty = synth.make_scene(12, 128, 256, 0)
     assert (empty[2].max(axis=1) > 0.3).sum() == 0
+
+
+def test_fast_polygon_path_equals_per_instance_aug_group(dec):
+    """the batched host polygon path against the per-instance reference-shaped path, on a full-size image"""
+    import isg_b200  # noqa: F401
+    from isg_b200 import synth
+    from oracle import ref_decode as rd
+    img = synth.make_image(77, 512, 1024, 40)
+    core = rd.group_core(torch.from_numpy(img.kp[0]), torch.from_numpy(img.ae), img.rois, 20000)
+    groups = rd.instance_points(core["idx"], core["label"], core["centres"], core["whs"], 0.1)
+    offsets = np.concatenate([[0], np.cumsum([len(p) for p, _ in groups])]).astype(np.int32)
+    points = np.concatenate([p for p, _ in groups]).astype(np.float32)
+    n = len(groups)
+    cls, conf = np.arange(n, dtype=np.int64), np.linspace(0.9, 0.4, n).astype(np.float32)
+    c1, f1, ctr1, p1 = dec._polygons_for_image_fast(points, offsets, n, core["centres"], cls, conf, 2)
+    c2, f2, ctr2, p2 = dec._polygons_for_image(points, offsets, n, core["centres"], core["whs"], cls, conf, IdentityTransforms(),
+                                               TransInfo("x", (512, 1024)), DecodeCfg(), True)
+    assert len(p1) == len(p2) > 10
+    assert list(c1) == list(c2) and list(f1) == list(f2)
+    for a, b in zip(ctr1, ctr2):
+        assert np.array_equal(a, b)
+    for a, b in zip(p1, p2):
+        assert np.array_equal(a, b)
