@@ -224,6 +224,22 @@ int isg_kmeans(const float* X, int M, int D, float* centers, const float* allow,
 int isg_pairwise(const float* X, int M, const float* Y, int N, int D, int metric, float* out,
                  isg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * HOST helpers of the polygon stage (aug_group / find_internal_point, utils/decode.py:51-68,167-204).
+ * Host pointers, no device work: the polygon stage is host glue this round (SURVEY.md §8 f1 is next).
+ * They restate cv2.pointPolygonTest(contour fp32 [K,2], pt, measureDist=False) so that whole images are
+ * processed per call instead of one cv2 call per test.
+ * ------------------------------------------------------------------------------------------ */
+/* +1 inside, 0 on the polyline, -1 outside */
+int isg_host_point_in_polygon(const float* pts, int K, float px, float py);
+/* find_internal_point for n instances; points [*,2] (x,y) grouped by instance, offsets [n+1], centers [n,2] (x,y),
+ * internal [n,2] out.  Instances with fewer than min_pts points keep their centre. */
+int isg_host_internal_points(const float* points, const int32_t* offsets, int n, const float* centers,
+                             int min_pts, float* internal);
+/* inside[i] = pointPolygonTest(polygon i, centers[i]) > 0 for n polygons stored back to back */
+int isg_host_centres_inside(const float* points, const int32_t* offsets, int n, const float* centers,
+                            uint8_t* inside);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,9 @@ PROTOTYPES = {
     "isg_kmeans_workspace_bytes": (SZ, [I, I, I]),
     "isg_kmeans": (I, [P, I, I, P, P, I, F, I, I, P, P, P, SZ, P]),
     "isg_pairwise": (I, [P, I, P, I, I, I, P, P]),
+    "isg_host_point_in_polygon": (I, [P, I, F, F]),
+    "isg_host_internal_points": (I, [P, P, I, P, I, P]),
+    "isg_host_centres_inside": (I, [P, P, I, P, P]),
 }
 
 ISG_NMS_PLUS1_LE = 0

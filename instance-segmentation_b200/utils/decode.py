@@ -325,38 +325,52 @@ def _polar_angles(pts, centres):
 
 
 def _polygons_for_image_fast(points, offsets, n, centres_yx, center_cls, center_confs, obj_pixel_th):
-    """The identity-transform, no-drawing case of :337-369 with the per-instance numpy work batched:
-    one vectorised polar-angle evaluation for all instances of the image, then per instance only the argsort
-    (kept per instance: np.argsort's order among equal angles must be the reference's) and the two cv2 tests.
+    """The identity-transform, no-drawing case of :337-369 with the per-instance work batched per image:
+      * internal points of all instances: one call of libisg's host helper (restates cv2.pointPolygonTest and the
+        search of find_internal_point, :51-68);
+      * polar angles of all points: one vectorised numpy evaluation (same fp32 arithmetic as cartesian2polar);
+      * per instance only np.argsort (kept per instance: its order among equal angles must be the reference's);
+      * centre-inside test of all sorted polygons (:201): one helper call.
     The `area == 0` rejection (:187-189) is not evaluated: fillPoly rasterises the outline of the polygon, every
     vertex lies inside the (max+1)-sized canvas, so the area of a polygon with at least one vertex is >= 1
     (tests/test_host_logic.py checks the predicate against the full-canvas rasterisation)."""
-    import cv2
-    cnt = np.diff(offsets[:n + 1])
-    valid = np.nonzero(cnt >= obj_pixel_th)[0]                       # :355
-    if valid.size == 0:
+    lib = _lib.lib()
+    offsets = np.ascontiguousarray(offsets[:n + 1], dtype=np.int32)
+    tot = int(offsets[n])
+    cnt = np.diff(offsets)
+    valid = cnt >= obj_pixel_th                                      # :355
+    if tot == 0 or not valid.any():
         return [], [], [], []
-    centers_xy = np.ascontiguousarray(centres_yx[:, ::-1])          # detransform_pixel flip, (x,y) fp32
-    internal = np.empty((valid.size, 2), dtype=np.float32)
-    segs = []
-    for q, i in enumerate(valid):
-        pts = points[offsets[i]:offsets[i + 1]]
-        segs.append(pts)
-        c = centers_xy[i]
-        internal[q] = c if cv2.pointPolygonTest(pts, (c[0], c[1]), False) > 0 else find_internal_point(pts, c)
-    allp = np.concatenate(segs) if len(segs) > 1 else segs[0]
-    reps = cnt[valid]
-    theta = _polar_angles(allp, np.repeat(internal, reps, axis=0))
+    pts = np.ascontiguousarray(points[:tot], dtype=np.float32)
+    centers_xy = np.ascontiguousarray(centres_yx[:n, ::-1], dtype=np.float32)   # detransform_pixel flip, (x,y)
+    internal = np.empty((n, 2), dtype=np.float32)
+    rc = lib.isg_host_internal_points(pts.ctypes.data, offsets.ctypes.data, n, centers_xy.ctypes.data, int(obj_pixel_th),
+                                      internal.ctypes.data)
+    if rc != 0:
+        raise _lib.IsgError(rc, "isg_host_internal_points")
+    theta = _polar_angles(pts, np.repeat(internal, cnt, axis=0))
+    offs = offsets.tolist()                                          # python ints: no numpy-scalar overhead in the loops
+    is_valid = valid.tolist()
+    parts = []
+    for i in range(n):
+        o0, o1 = offs[i], offs[i + 1]
+        if is_valid[i]:
+            a = theta[o0:o1].argsort()                               # :183
+            a += o0
+            parts.append(a)
+        elif o1 > o0:
+            parts.append(np.arange(o0, o1))
+    sorted_pts = pts[np.concatenate(parts)]
+    inside = np.empty(n, dtype=np.uint8)
+    rc = lib.isg_host_centres_inside(sorted_pts.ctypes.data, offsets.ctypes.data, n, centers_xy.ctypes.data, inside.ctypes.data)
+    if rc != 0:
+        raise _lib.IsgError(rc, "isg_host_centres_inside")
     n_clss, n_confs, n_centers, kps = [], [], [], []
-    pos = 0
-    for q, i in enumerate(valid):
-        k = int(reps[q])
-        sorted_kp = allp[pos:pos + k][np.argsort(theta[pos:pos + k])]
-        pos += k
-        c = centers_xy[i]
-        if cv2.pointPolygonTest(sorted_kp, (c[0], c[1]), False) > 0:     # :201
-            kps.append(sorted_kp)
-            n_centers.append(c)
+    ok = (valid & (inside != 0)).tolist()
+    for i in range(n):
+        if ok[i]:                                                    # :201
+            kps.append(sorted_pts[offs[i]:offs[i + 1]].copy())
+            n_centers.append(centers_xy[i])
             n_clss.append(center_cls[i])
             n_confs.append(center_confs[i])
     return n_clss, n_confs, n_centers, kps

@@ -148,3 +148,56 @@ def test_fast_polygon_path_equals_per_instance_aug_group(dec):
         assert np.array_equal(a, b)
     for a, b in zip(p1, p2):
         assert np.array_equal(a, b)
+
+
+def test_host_point_in_polygon_equals_cv2():
+    """libisg's host restatement of cv2.pointPolygonTest (measureDist=False, fp32 contour) against cv2 itself,
+    including points on edges / vertices and degenerate contours"""
+    import ctypes
+    import cv2
+    import isg_b200  # noqa: F401
+    from isg_b200 import _lib
+    lib = _lib.lib()
+    rs = np.random.RandomState(0)
+    n_checked = 0
+    for trial in range(400):
+        K = int(rs.randint(1, 40))
+        pts = rs.randint(0, 24, size=(K, 2)).astype(np.float32)
+        if trial % 3 == 0:
+            pts += rs.choice([0.0, 0.5], size=(K, 2)).astype(np.float32)
+        tests = [pts[rs.randint(0, K)], pts.mean(axis=0), (pts[0] + pts[-1]) / 2]
+        tests += [rs.uniform(-2, 26, size=2).astype(np.float32) for _ in range(6)]
+        tests += [rs.randint(0, 24, size=2).astype(np.float32) for _ in range(6)]
+        for t in tests:
+            want = cv2.pointPolygonTest(pts, (np.float32(t[0]), np.float32(t[1])), False)
+            got = lib.isg_host_point_in_polygon(pts.ctypes.data, K, float(t[0]), float(t[1]))
+            assert got == int(want), (pts, t, got, want)
+            n_checked += 1
+    assert n_checked > 5000
+
+
+def test_host_internal_points_equal_reference_search(dec):
+    import isg_b200  # noqa: F401
+    from isg_b200 import _lib
+    lib = _lib.lib()
+    rs = np.random.RandomState(1)
+    segs, ctrs = [], []
+    for _ in range(120):
+        K = int(rs.randint(2, 30))
+        base = rs.randint(0, 400, size=2)
+        # ring-like and random clouds, sorted row-major like the device emits them
+        p = (base + rs.randint(0, 30, size=(K, 2))).astype(np.float32)
+        p = p[np.lexsort((p[:, 0], p[:, 1]))]
+        segs.append(p)
+        ctrs.append((p.mean(axis=0) + rs.uniform(-8, 8, size=2)).astype(np.float32))
+    offsets = np.concatenate([[0], np.cumsum([len(p) for p in segs])]).astype(np.int32)
+    points = np.ascontiguousarray(np.concatenate(segs), dtype=np.float32)
+    centers = np.ascontiguousarray(np.stack(ctrs), dtype=np.float32)
+    internal = np.empty_like(centers)
+    assert lib.isg_host_internal_points(points.ctypes.data, offsets.ctypes.data, len(segs), centers.ctypes.data, 2, internal.ctypes.data) == 0
+    n_fallback = 0
+    for i, (p, c) in enumerate(zip(segs, ctrs)):
+        want = dec.find_internal_point(p, c)
+        assert np.array_equal(internal[i], np.asarray(want, dtype=np.float32)), i
+        n_fallback += not np.array_equal(want, c)
+    assert n_fallback > 10
