@@ -553,6 +553,7 @@ group_split_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ 
 }  // namespace isg
 
 #include "dense_tma.cuh"
+#include "dense_v3.cuh"
 
 using namespace isg;
 
@@ -641,6 +642,12 @@ extern "C" int isg_assign_dense(const float* kp, int64_t kp_img_stride, const fl
                    aligned16(kp) && aligned16(ae) && aligned16(label_map) && (!score_map || aligned16(score_map));
   // v2 (persistent, TMA-fed) whenever the layout allows tensor maps; v1 otherwise or when ISG_DENSE_V1 is set
   const char* v1_env = getenv("ISG_DENSE_V1");
+  const char* v2_env = getenv("ISG_DENSE_V2");
+  if (vec && !(v1_env && v1_env[0] == '1') && !(v2_env && v2_env[0] == '1')) {
+    const int rc = launch_dense_v3(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
+                                   Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, stream);
+    if (rc != ISG_EUNSUPPORTED) return rc;
+  }
   if (vec && !(v1_env && v1_env[0] == '1')) {
     const int rc = launch_dense_tma(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
                                     Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, stream);
