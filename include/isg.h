@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ISG_ABI_VERSION 1
+#define ISG_ABI_VERSION 2
 
 #define ISG_OK            0
 #define ISG_EINVAL       (-1)  /* bad argument (null pointer, negative extent, k > H*W ...) */
@@ -130,18 +130,25 @@ int isg_assign_sparse(const float* ae, int64_t img_stride, int64_t plane_stride,
  * top-k threshold and the 3x3 peak test, assigns every pixel, writes label_map [B,H,W] int32,
  * keepbits [B,H,ceil(W/32)], optional score_map [B,H,W] fp32 (nullable), and accumulates stats
  * for the keep pixels.  label_map[keep] equals isg_assign_sparse's label (rows are independent). */
+/* workspace: isg_assign_dense_workspace_bytes() bytes, 16-byte aligned.  Its first 256 bytes (the tile scheduler)
+ * must be ZERO-FILLED by the caller once when the workspace is allocated; the kernel leaves them zero-filled when
+ * the launch completes, so the same workspace serves every later call.  The rest holds the per-tile seed lists
+ * (rebuilt by every call).  One workspace per concurrently running call. */
+size_t isg_assign_dense_workspace_bytes(int B, int Nmax, int H, int W);
 int isg_assign_dense(const float* kp, int64_t kp_img_stride,
                      const float* ae, int64_t ae_img_stride, int64_t ae_plane_stride,
                      const uint32_t* thr_key,
                      const uint32_t* seeds, const float* ghost, const int32_t* n_seeds, int B, int Nmax,
                      int H, int W, const float* ys, const float* xs,
                      int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats,
-                     isg_stream_t stream);
+                     void* workspace, size_t workspace_bytes, isg_stream_t stream);
 /* dense mode: labels / scores / ghost flags of the compacted keep pixels read back from the maps.
- * score_map nullable (then score is not written). */
+ * score_map nullable (then score is not written).  stats (nullable, pre-initialised by isg_stats_init): count /
+ * bbox of the flagged pixels per instance - the same numbers isg_assign_dense accumulates when it is given a stats
+ * pointer; pass it to exactly one of the two. */
 int isg_gather_labels(const int32_t* label_map, const float* score_map, const int32_t* idx,
                       const int32_t* count, int cap, const float* ghost, int B, int Nmax, int H, int W,
-                      int32_t* label, float* score, uint8_t* flag, isg_stream_t stream);
+                      int32_t* label, float* score, uint8_t* flag, int32_t* stats, isg_stream_t stream);
 /* per-instance point sets (utils/decode.py:342-353): the flagged pixels of instance i, in row-major
  * order, as fp32 (x,y) pairs (detransform_pixel's flip, utils/tranform.py:157-159).
  * offsets: [B,Nmax+1] int32 exclusive prefix of the per-instance counts; points: [B,cap,2] fp32. */

@@ -29,8 +29,9 @@ PROTOTYPES = {
     "isg_build_seeds": (I, [P, I, P, I, I, P, P, I, I, F, F, P, P, P]),
     "isg_stats_init": (I, [P, I, I, P]),
     "isg_assign_sparse": (I, [P, I64, I64, P, P, I, P, P, P, I, I, I, I, P, P, P, P, P, P, P]),
-    "isg_assign_dense": (I, [P, I64, P, I64, I64, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P]),
-    "isg_gather_labels": (I, [P, P, P, P, I, P, I, I, I, I, P, P, P, P]),
+    "isg_assign_dense_workspace_bytes": (SZ, [I, I, I, I]),
+    "isg_assign_dense": (I, [P, I64, P, I64, I64, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P, SZ, P]),
+    "isg_gather_labels": (I, [P, P, P, P, I, P, I, I, I, I, P, P, P, P, P]),
     "isg_group_points": (I, [P, P, P, P, I, P, I, I, P, P, P]),
     "isg_decode_boxes": (I, [P, P, P, I, I, I, I, I, F, I, P, P, P, P, P, P]),
     "isg_bbox_transform": (I, [P, P, I, I, I, I, I, P, P]),

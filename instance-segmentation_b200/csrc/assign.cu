@@ -369,7 +369,7 @@ __global__ void gather_labels_kernel(const int32_t* __restrict__ label_map, cons
                                      const int32_t* __restrict__ idx, const int32_t* __restrict__ count, int cap,
                                      const float4* __restrict__ ghost, int Nmax, int H, int W,
                                      int32_t* __restrict__ label, float* __restrict__ score,
-                                     uint8_t* __restrict__ flag) {
+                                     uint8_t* __restrict__ flag, int32_t* __restrict__ stats) {
   const int b = blockIdx.y;
   const int M = min(count[b], cap);
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -380,7 +380,9 @@ __global__ void gather_labels_kernel(const int32_t* __restrict__ label_map, cons
   const int l = label_map[p];
   label[o] = l;
   if (score && score_map) score[o] = score_map[p];
-  if (flag) flag[o] = (Nmax > 0 && l >= 0 && l < Nmax && ghost_pass(ghost[(size_t)b * Nmax + l], y, x)) ? 1 : 0;
+  const bool pass = Nmax > 0 && l >= 0 && l < Nmax && ghost_pass(ghost[(size_t)b * Nmax + l], y, x);
+  if (flag) flag[o] = pass ? 1 : 0;
+  if (stats && pass) stats_add(stats + ((size_t)b * Nmax + l) * ISG_STAT_WORDS, y, x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -553,7 +555,7 @@ group_split_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ 
 }  // namespace isg
 
 #include "dense_tma.cuh"
-#include "dense_v3.cuh"
+#include "dense_v4.cuh"
 
 using namespace isg;
 
@@ -627,25 +629,33 @@ static int launch_dense(const float* kp, int64_t kp_img_stride, const float* ae,
   return ISG_OK;
 }
 
+extern "C" size_t isg_assign_dense_workspace_bytes(int B, int Nmax, int H, int W) {
+  if (B <= 0 || Nmax <= 0 || H <= 0 || W <= 0) return 0;
+  return dense_workspace_bytes(B, Nmax, H, W);
+}
+
 extern "C" int isg_assign_dense(const float* kp, int64_t kp_img_stride, const float* ae, int64_t ae_img_stride,
                                 int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds,
                                 const float* ghost, const int32_t* n_seeds, int B, int Nmax, int H, int W,
                                 const float* ys, const float* xs, int32_t* label_map, float* score_map,
-                                uint32_t* keepbits, int32_t* stats, isg_stream_t stream_) {
+                                uint32_t* keepbits, int32_t* stats, void* workspace, size_t workspace_bytes,
+                                isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!kp || !ae || !thr_key || !seeds || !ghost || !n_seeds || !ys || !xs || !label_map || !keepbits) return ISG_EINVAL;
   if (B <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
   if (kp_img_stride < (int64_t)H * W || ae_plane_stride < (int64_t)H * W) return ISG_EINVAL;
   if (!aligned16(seeds) || !aligned16(ghost)) return ISG_EINVAL;
+  if (!workspace || workspace_bytes < dense_workspace_bytes(B, Nmax, H, W) || !aligned16(workspace)) return ISG_EINVAL;
   if ((size_t)Nmax * sizeof(SeedRec) * 2 > 200 * 1024) return ISG_EUNSUPPORTED;
   const bool vec = (W % 4 == 0) && (kp_img_stride % 4 == 0) && (ae_img_stride % 4 == 0) && (ae_plane_stride % 4 == 0) &&
                    aligned16(kp) && aligned16(ae) && aligned16(label_map) && (!score_map || aligned16(score_map));
-  // v2 (persistent, TMA-fed) whenever the layout allows tensor maps; v1 otherwise or when ISG_DENSE_V1 is set
+  // v4 (persistent, TMA-fed, dynamic scheduler) whenever the layout allows tensor maps; ISG_DENSE_V2 / ISG_DENSE_V1
+  // select the older kernels for A/B measurements; v1 also serves the layouts TMA cannot describe (W % 4 != 0)
   const char* v1_env = getenv("ISG_DENSE_V1");
   const char* v2_env = getenv("ISG_DENSE_V2");
   if (vec && !(v1_env && v1_env[0] == '1') && !(v2_env && v2_env[0] == '1')) {
-    const int rc = launch_dense_v3(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
-                                   Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, stream);
+    const int rc = launch_dense_v4(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
+                                   Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, workspace, workspace_bytes, stream);
     if (rc != ISG_EUNSUPPORTED) return rc;
   }
   if (vec && !(v1_env && v1_env[0] == '1')) {
@@ -667,12 +677,12 @@ extern "C" int isg_assign_dense(const float* kp, int64_t kp_img_stride, const fl
 
 extern "C" int isg_gather_labels(const int32_t* label_map, const float* score_map, const int32_t* idx,
                                  const int32_t* count, int cap, const float* ghost, int B, int Nmax, int H, int W,
-                                 int32_t* label, float* score, uint8_t* flag, isg_stream_t stream_) {
+                                 int32_t* label, float* score, uint8_t* flag, int32_t* stats, isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!label_map || !idx || !count || !ghost || !label || B <= 0 || cap <= 0 || H <= 0 || W <= 0 || Nmax <= 0) return ISG_EINVAL;
   dim3 grid(cdiv(cap, 256), B);
   gather_labels_kernel<<<grid, 256, 0, stream>>>(label_map, score_map, idx, count, cap,
-                                                 reinterpret_cast<const float4*>(ghost), Nmax, H, W, label, score, flag);
+                                                 reinterpret_cast<const float4*>(ghost), Nmax, H, W, label, score, flag, stats);
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }

@@ -1,0 +1,600 @@
+// Fused dense kernel, v4: persistent CTAs, dynamic tile scheduler, producer-side seed culling.
+//
+// What one launch does for every pixel of the batch (reference: select_points / nms_hm, utils/decode.py:42-48,71-85,
+// and the core of group_kp, :303-328):
+//   keep bit  = selected (kp >= k-th largest) and 3x3 maximum of the thresholded map,
+//   embedding = tanh(ae[0:2]) + grid, sigma = exp(ae[2:4]),
+//   label     = first seed (in index order) with the largest membership exp(-q) among the seeds whose box
+//               contains the pixel, q = (e_y-c_y)^2*s_y + (e_x-c_x)^2*s_x; 0 when no membership is > 0,
+//   per-instance count / bbox of the keep pixels that pass the ghost filter.
+// Every input pixel is read from HBM once (kp halo rows/columns are re-read from L2), the label is written once.
+//
+// Structure
+//   * one CTA per SM.  The last warp is the PRODUCER: it takes tile indices from a global counter (dynamic
+//     scheduling, in image order), stages the seed table of the tile's image in shared memory (1-D bulk copy, two
+//     buffers), culls it against the tile (ordered, so that the first-index tie rule survives), writes a small
+//     header + hit list next to the stage and issues the two TMA box loads of the tile (kp with a 1-pixel halo,
+//     out-of-image elements NaN-filled = the reference's -inf padding because fmax ignores NaN; the four ae
+//     planes as one 4-D box);
+//   * the other warps are CONSUMERS in G groups of WG warps; group g takes the stages k = g (mod G).  Inside a
+//     tile a warp owns RW consecutive rows and walks down them two at a time with a rolling window of the
+//     separable 3x3 maximum; a lane owns 4 consecutive pixels of each row;
+//   * consumers are stateless with respect to images: everything they need is in the stage header;
+//   * the membership loop tracks the SMALLEST exponent q instead of the largest exp(-q): exp is monotone, so the
+//     winner is the same seed whenever two memberships differ as fp32 numbers, and the transcendental per
+//     (pixel, seed) pair disappears.  q >= ln(2^150) is where exp(-q) rounds to 0 in fp32 (label stays 0).
+#pragma once
+#include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include "keep.cuh"
+
+namespace isg {
+
+constexpr int kD4TileW = 128;
+constexpr int kD4KpW = kD4TileW + 8;          // 4 columns of padding on each side keep the box 16-byte granular
+constexpr int kD4MaxStages = 8;
+constexpr float kQZero = 103.97207708f;       // ln(2^150): exp(-q) == 0 in fp32 (round to nearest, subnormals kept)
+
+template <int RW, int WG>
+struct D4Geom {
+  static constexpr int TH = RW * WG;                                  // tile rows
+  static constexpr int kKpRows = TH + 2;
+  static constexpr int kKpBytes = kD4KpW * kKpRows * 4;
+  static constexpr int kKpStage = (kKpBytes + 127) / 128 * 128;
+  static constexpr int kAePlane = kD4TileW * TH;                      // floats
+  static constexpr int kAeBytes = kAePlane * 16;
+  static constexpr int kStage = kKpStage + kAeBytes;
+  static constexpr uint32_t kTx = kKpBytes + kAeBytes;
+};
+
+// Per-tile work list, built by tile_lists_kernel and copied next to the tile by the producer (one 1-D bulk copy):
+// a 32-byte header followed by the first `cap` seed records overlapping the tile, in ascending seed index.
+struct __align__(16) TileHdr {
+  int b, y0, x0, nhit;            // image, first row / column of the tile, seeds overlapping the tile (< 0: end marker)
+  uint32_t thr_key;               // selection threshold of image b
+  int n_seeds;                    // seeds of image b
+  int tile;                       // tile index (locates the overflow list when nhit > cap)
+  int pad;
+};
+static_assert(sizeof(TileHdr) == 32, "tile header layout");
+
+struct RowK {
+  float h[4];      // horizontal 3-max of v centred on the lane's 4 pixels
+  float v[4];      // thresholded value (0 when not selected, NaN outside the image)
+  uint32_t sel;    // bit i: pixel i is selected
+};
+
+// One staged kp row -> RowK.  `row` points at the first float of the box row; the lane's pixels start at
+// row[4 + 4*lane]; row[3] / row[132] are the halo pixels of lane 0 / lane 31 (`halo_off` selects one per lane).
+template <bool USE_INT>
+__device__ __forceinline__ RowK d4_prep_row(const float* __restrict__ row, int lane, int halo_off, const Thr& thr) {
+  RowK o;
+  const float4 t = *reinterpret_cast<const float4*>(row + 4 + lane * 4);
+  const float hv = row[halo_off];
+  const float raw[4] = {t.x, t.y, t.z, t.w};
+  o.sel = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool below = USE_INT ? (skey(raw[i]) < thr.s) : (raw[i] < thr.f);   // NaN (outside) is never below
+    o.v[i] = below ? 0.0f : raw[i];
+    o.sel |= (below ? 0u : 1u) << i;
+  }
+  const bool hbelow = USE_INT ? (skey(hv) < thr.s) : (hv < thr.f);
+  const float hvv = hbelow ? 0.0f : hv;
+  float left = __shfl_up_sync(0xffffffffu, o.v[3], 1);
+  float right = __shfl_down_sync(0xffffffffu, o.v[0], 1);
+  if (lane == 0) left = hvv;
+  if (lane == 31) right = hvv;
+  o.h[0] = fmaxf(fmaxf(left, o.v[0]), o.v[1]);
+  o.h[1] = fmaxf(fmaxf(o.v[0], o.v[1]), o.v[2]);
+  o.h[2] = fmaxf(fmaxf(o.v[1], o.v[2]), o.v[3]);
+  o.h[3] = fmaxf(fmaxf(o.v[2], o.v[3]), right);
+  return o;
+}
+__device__ __forceinline__ RowK d4_prep(const float* __restrict__ row, int lane, int halo_off, const Thr& thr) {
+  return thr.use_int ? d4_prep_row<true>(row, lane, halo_off, thr) : d4_prep_row<false>(row, lane, halo_off, thr);
+}
+// keep nibble of the middle row's 4 pixels
+__device__ __forceinline__ uint32_t d4_keep(const RowK& up, const RowK& mid, const RowK& dn) {
+  uint32_t nib = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float m = fmaxf(fmaxf(up.h[i], mid.h[i]), dn.h[i]);
+    if (mid.v[i] >= m) nib |= 1u << i;
+  }
+  return nib & mid.sel;
+}
+
+__device__ __forceinline__ void mbar_arrive_plain(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// Waits used by this kernel.  With -DISG_D4_WATCHDOG a wait that does not complete within ~2 s prints where it is
+// stuck and traps (debug builds only; the production build spins without a bound).
+__device__ __forceinline__ bool d4_try_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  return done != 0;
+}
+// producer-side wait: the hardware parks the thread until the phase completes or the hint (ns) expires, so a
+// waiting producer costs its scheduler almost no issue slots
+__device__ __forceinline__ bool d4_try_wait_hint(uint64_t* bar, uint32_t phase, uint32_t hint_ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(phase), "r"(hint_ns) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void d4_wait_parked(uint64_t* bar, uint32_t phase) {
+  while (!d4_try_wait_hint(bar, phase, 20000u)) {}
+}
+__device__ __forceinline__ void d4_wait(uint64_t* bar, uint32_t phase, unsigned sleep_ns, int site, int a0, int a1) {
+#ifdef ISG_D4_WATCHDOG
+  const long long t0 = clock64();
+  bool said = false;
+  while (!d4_try_wait(bar, phase)) {
+    if (sleep_ns) __nanosleep(sleep_ns);
+    const long long dt = clock64() - t0;
+    if (dt > 4000000000ll && !said) {
+      said = true;
+      if ((threadIdx.x & 31) == 0 || site == 1)
+        printf("[d4 watchdog] site=%d block=%d warp=%d lane=%d phase=%u a0=%d a1=%d\n", site, blockIdx.x, threadIdx.x >> 5,
+               threadIdx.x & 31, phase, a0, a1);
+    }
+    if (dt > 8000000000ll) __trap();
+  }
+#else
+  (void)site; (void)a0; (void)a1;
+  while (!d4_try_wait(bar, phase)) {
+    if (sleep_ns) __nanosleep(sleep_ns);
+  }
+#endif
+}
+__device__ __forceinline__ void d4_tma_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void d4_tma_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// shared-memory layout (byte offsets from the dynamic shared base)
+template <int RW, int WG>
+struct D4Smem {
+  int stage, list, list_stride, bars, total;
+  __host__ __device__ D4Smem(int cap, int nstages) {
+    using Geo = D4Geom<RW, WG>;
+    int o = 0;
+    stage = o; o += nstages * Geo::kStage;
+    list_stride = (int)sizeof(TileHdr) + cap * (int)sizeof(SeedRec);
+    list = o;  o += nstages * list_stride;
+    bars = o;  o += 2 * kD4MaxStages * 8;
+    total = o;
+  }
+};
+
+// Pre-pass: one warp per tile collects, in ascending seed index, the seeds of the tile's image whose boxes overlap
+// the tile.  lists: [T] x (TileHdr + cap records); ovf: [T][Nmax] seed indices of ALL hits (read by the dense kernel
+// only for the rare tiles with more than cap hits).
+__global__ void __launch_bounds__(256)
+tile_lists_kernel(const SeedRec* __restrict__ seeds, const int32_t* __restrict__ n_seeds,
+                  const uint32_t* __restrict__ thr_key, int Nmax, int B, int H, int W, int TH, int tilesX, int tilesY,
+                  int cap, unsigned char* __restrict__ lists, uint16_t* __restrict__ ovf) {
+  const int lane = threadIdx.x & 31;
+  const long long T = (long long)B * tilesX * tilesY;
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const int tiles_per_img = tilesX * tilesY;
+  const int b = (int)(t / tiles_per_img);
+  const int rem = (int)(t - (long long)b * tiles_per_img);
+  const int ty = rem / tilesX, tx = rem - ty * tilesX;
+  const int y0 = ty * TH, x0 = tx * kD4TileW;
+  const int y1 = min(y0 + TH - 1, H - 1), x1 = min(x0 + kD4TileW - 1, W - 1);
+  const int n = min(n_seeds[b], Nmax);
+  const size_t stride = sizeof(TileHdr) + (size_t)cap * sizeof(SeedRec);
+  unsigned char* out = lists + (size_t)t * stride;
+  int4* recs = reinterpret_cast<int4*>(out + sizeof(TileHdr));
+  uint16_t* ov = ovf + (size_t)t * Nmax;
+  const int4* src = reinterpret_cast<const int4*>(seeds + (size_t)b * Nmax);
+  int cnt = 0;
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    const int j = j0 + lane;
+    bool hit = false;
+    int4 lo = make_int4(0, 0, 0, 0);
+    if (j < n) { lo = __ldg(src + 2 * j); hit = lo.x <= y1 && lo.y >= y0 && lo.z <= x1 && lo.w >= x0 && lo.x <= lo.y && lo.z <= lo.w; }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+      ov[pos] = (uint16_t)j;
+      if (pos < cap) { recs[2 * pos] = lo; recs[2 * pos + 1] = __ldg(src + 2 * j + 1); }
+    }
+    cnt += __popc(bal);
+  }
+  if (lane == 0) {
+    TileHdr h;
+    h.b = b; h.y0 = y0; h.x0 = x0; h.nhit = cnt; h.thr_key = thr_key[b]; h.n_seeds = n; h.tile = (int)t; h.pad = 0;
+    *reinterpret_cast<TileHdr*>(out) = h;
+  }
+}
+
+template <int RW, int WG, int G, bool SCORE>
+__global__ void __launch_bounds__(32 * (WG * G + 1), 1)
+dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant__ CUtensorMap tm_ae,
+                const SeedRec* __restrict__ seeds, const float4* __restrict__ ghost, int Nmax, int B, int H, int W,
+                int Wwords, int tilesX, int tilesY, int nstages, int cap, const unsigned char* __restrict__ lists,
+                const uint16_t* __restrict__ ovf, const float* __restrict__ ys, const float* __restrict__ xs,
+                int32_t* __restrict__ label_map, float* __restrict__ score_map, uint32_t* __restrict__ keepbits,
+                int32_t* __restrict__ stats, unsigned int* __restrict__ sched, int dyn_tail, int dbg_flags) {
+  static_assert(RW % 2 == 0, "rows are processed in pairs");
+  using Geo = D4Geom<RW, WG>;
+  constexpr int kConsumers = WG * G;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const D4Smem<RW, WG> L(cap, nstages);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);           // [kD4MaxStages]
+  uint64_t* empty = full + kD4MaxStages;                                 // [kD4MaxStages]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], WG); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kConsumers) {
+    // ============================ producer: one thread feeds the ring ============================
+    if (lane != 0) return;
+    const int tiles_per_img = tilesX * tilesY;
+    const unsigned T = (unsigned)B * (unsigned)tiles_per_img;
+    const uint32_t list_bytes = (uint32_t)L.list_stride;
+    int slot = 0, round = 0;
+    // Tile order: the first n_static tiles of a CTA are c, c + P, c + 2P, ... (P = grid size; neighbouring CTAs work
+    // on neighbouring tiles, no scheduling traffic); the last `dyn_tail` tiles per CTA (and the remainder of T / P)
+    // come from a global counter so that CTAs that finish early take over work from the slow ones.  The counter
+    // value is always requested one tile ahead: an atomic round trip under full memory load is ~2 us, a CTA that
+    // waited for it on every tile would be latency-bound.
+    const unsigned P = gridDim.x;
+    const unsigned n_static = (T / P > (unsigned)dyn_tail) ? (T / P - (unsigned)dyn_tail) : 0u;
+    const unsigned T_s = n_static * P;
+    unsigned i_static = 0;
+    unsigned dyn = T_s + atomicAdd(&sched[0], 1u);
+    unsigned t;
+    if (n_static > 0) { t = blockIdx.x; i_static = 1; }
+    else { t = dyn; dyn = (t < T) ? T_s + atomicAdd(&sched[0], 1u) : T; }
+    while (t < T) {
+      const int b = (int)(t / (unsigned)tiles_per_img);
+      const int rem = (int)t - b * tiles_per_img;
+      const int ty = rem / tilesX, tx = rem - ty * tilesX;
+      const int y0t = ty * Geo::TH, x0t = tx * kD4TileW;
+      // the slot must have been released by the consumers of its previous tile
+      if (round >= 1) d4_wait_parked(&empty[slot], (uint32_t)((round - 1) & 1));
+      unsigned char* st = smem + L.stage + (size_t)slot * Geo::kStage;
+      mbar_expect_tx(&full[slot], Geo::kTx + list_bytes);
+      bulk_g2s(smem + L.list + (size_t)slot * L.list_stride, lists + (size_t)t * list_bytes, list_bytes, &full[slot]);
+      d4_tma_3d(st, &tm_kp, x0t - 4, y0t - 1, b, &full[slot]);
+      d4_tma_4d(st + Geo::kKpStage, &tm_ae, x0t, y0t, 0, b, &full[slot]);
+      if (++slot == nstages) { slot = 0; ++round; }
+      if (i_static < n_static) {
+        t = blockIdx.x + (i_static++) * P;
+      } else {
+        t = dyn;
+        dyn = (t < T) ? T_s + atomicAdd(&sched[0], 1u) : T;
+      }
+    }
+    // one end marker per consumer group (the next G stages cover every group once)
+    for (int g = 0; g < G; ++g) {
+      if (round >= 1) d4_wait_parked(&empty[slot], (uint32_t)((round - 1) & 1));
+      reinterpret_cast<TileHdr*>(smem + L.list + (size_t)slot * L.list_stride)->nhit = -1;
+      mbar_arrive_plain(&full[slot]);
+      if (++slot == nstages) { slot = 0; ++round; }
+    }
+    // the last CTA to finish leaves the scheduler words zeroed for the next launch
+    __threadfence();
+    const unsigned done = atomicAdd(&sched[1], 1u);
+    if (done == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
+    return;
+  }
+
+  // ========================================= consumers =========================================
+  const int grp = warp / WG, wl = warp % WG;
+  const int halo_off = (lane == 31) ? (4 + kD4TileW) : 3;
+  int slot = grp, rnd = 0;
+  while (true) {
+    // Slots are shared between groups over time and TMA completions are not ordered, so the previous fill of this
+    // slot (another group's tile) may not have landed when this group gets here; a parity wait only tells "this
+    // phase" from "the one before".  The previous occupant's RELEASE (empty phase rnd-1) implies its fill completed,
+    // and it cannot be more than one phase away (the release of fill rnd is ours): wait for it first.
+    if (rnd > 0) d4_wait(&empty[slot], (uint32_t)((rnd - 1) & 1), 0, 6, slot, rnd);
+    d4_wait(&full[slot], (uint32_t)(rnd & 1), 0, 5, slot, rnd);
+    const unsigned char* lst = smem + L.list + (size_t)slot * L.list_stride;
+    const int4 h0 = *reinterpret_cast<const int4*>(lst);                    // b, y0, x0, nhit
+    const int nhit = h0.w;
+    if (nhit < 0) break;
+    const int b = h0.x;
+    const int ybeg = h0.y + wl * RW;
+    if (ybeg < H && !(dbg_flags & 1)) {                                     // warp-uniform (ragged bottom)
+      const int4 h1 = *reinterpret_cast<const int4*>(lst + 16);             // thr_key, n_seeds, tile, pad
+      const Thr thr = make_thr((uint32_t)h1.x);
+      const int x0 = h0.z + lane * 4;
+      const bool colvalid = x0 < W;                                         // W % 4 == 0: a lane is all in or all out
+      float xs4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (colvalid) { const float4 v = __ldg(reinterpret_cast<const float4*>(xs + x0)); xs4[0] = v.x; xs4[1] = v.y; xs4[2] = v.z; xs4[3] = v.w; }
+      const unsigned char* st = smem + L.stage + (size_t)slot * Geo::kStage;
+      const float* krow = reinterpret_cast<const float*>(st) + (wl * RW) * kD4KpW;     // box row = tile row + 1
+      const float* arow = reinterpret_cast<const float*>(st + Geo::kKpStage) + (wl * RW) * kD4TileW + lane * 4;
+      const unsigned char* recs = lst + sizeof(TileHdr);
+      const int nsm = min(nhit, cap);
+      const size_t pix0 = ((size_t)b * H + ybeg) * W + x0;
+      uint32_t* kbrow = keepbits + ((size_t)b * H + ybeg) * Wwords + (x0 >> 5);
+      const bool kbwriter = ((lane & 7) == 0) && colvalid;
+
+      RowK up = d4_prep(krow, lane, halo_off, thr);
+      RowK mid = d4_prep(krow + kD4KpW, lane, halo_off, thr);
+#pragma unroll
+      for (int rp = 0; rp < RW; rp += 2) {
+        const int y = ybeg + rp;
+        if (y >= H) break;                                                  // warp-uniform
+        const bool row1 = y + 1 < H;
+        // --- keep bits of rows y, y+1 ---
+        const RowK dn0 = d4_prep(krow + (rp + 2) * kD4KpW, lane, halo_off, thr);
+        const RowK dn1 = d4_prep(krow + (rp + 3) * kD4KpW, lane, halo_off, thr);
+        uint32_t nib0 = d4_keep(up, mid, dn0);
+        uint32_t nib1 = d4_keep(mid, dn0, dn1);
+        up = dn0; mid = dn1;
+        if (!colvalid) { nib0 = 0; nib1 = 0; }
+        if (!row1) nib1 = 0;
+        {
+          const uint32_t w0 = nibbles_to_word(nib0, lane), w1 = nibbles_to_word(nib1, lane);
+          if (kbwriter) {
+            kbrow[(size_t)rp * Wwords] = w0;
+            if (row1) kbrow[(size_t)(rp + 1) * Wwords] = w1;
+          }
+        }
+
+        // --- embedding of the lane's 2 x 4 pixels ---
+        float ey[2][4], ex[2][4], sy[2][4], sx[2][4];
+        {
+          float t0[2][4], t1[2][4];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const float* ar = arow + (rp + r) * kD4TileW;
+            const float4 a0 = *reinterpret_cast<const float4*>(ar);
+            const float4 a1 = *reinterpret_cast<const float4*>(ar + Geo::kAePlane);
+            const float4 a2 = *reinterpret_cast<const float4*>(ar + 2 * Geo::kAePlane);
+            const float4 a3 = *reinterpret_cast<const float4*>(ar + 3 * Geo::kAePlane);
+            t0[r][0] = a0.x; t0[r][1] = a0.y; t0[r][2] = a0.z; t0[r][3] = a0.w;
+            t1[r][0] = a1.x; t1[r][1] = a1.y; t1[r][2] = a1.z; t1[r][3] = a1.w;
+            sy[r][0] = exp_fast_ftz(a2.x); sy[r][1] = exp_fast_ftz(a2.y); sy[r][2] = exp_fast_ftz(a2.z); sy[r][3] = exp_fast_ftz(a2.w);
+            sx[r][0] = exp_fast_ftz(a3.x); sx[r][1] = exp_fast_ftz(a3.y); sx[r][2] = exp_fast_ftz(a3.z); sx[r][3] = exp_fast_ftz(a3.w);
+          }
+          float amax = 0.0f;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) amax = fmaxf(amax, fmaxf(fabsf(t0[r][i]), fabsf(t1[r][i])));
+          const bool small = __all_sync(0xffffffffu, amax < 0.55f);       // warp-uniform: polynomial branch only
+          const float yv0 = __ldg(ys + y), yv1 = __ldg(ys + min(y + 1, H - 1));
+          if (small) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              ey[0][i] = __fadd_rn(tanh_poly(t0[0][i]), yv0); ex[0][i] = __fadd_rn(tanh_poly(t1[0][i]), xs4[i]);
+              ey[1][i] = __fadd_rn(tanh_poly(t0[1][i]), yv1); ex[1][i] = __fadd_rn(tanh_poly(t1[1][i]), xs4[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              ey[0][i] = __fadd_rn(tanh_fast(t0[0][i]), yv0); ex[0][i] = __fadd_rn(tanh_fast(t1[0][i]), xs4[i]);
+              ey[1][i] = __fadd_rn(tanh_fast(t0[1][i]), yv1); ex[1][i] = __fadd_rn(tanh_fast(t1[1][i]), xs4[i]);
+            }
+          }
+        }
+
+        // --- membership: smallest exponent among the seeds whose box contains the pixel, ascending seed index ---
+        float bq[2][4];
+        int lab[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { bq[r][i] = kQZero; lab[r][i] = 0; }
+        auto visit = [&](const int4 bx, const int4 cw) {                      // y0,y1,x0,x1 | cy,cx,id,pad (warp-uniform)
+          const bool in0 = (y >= bx.x) && (y <= bx.y), in1 = (y + 1 >= bx.x) && (y + 1 <= bx.y);
+          if (!(in0 || in1)) return;                                           // row test
+          const float cy = __int_as_float(cw.x), cx = __int_as_float(cw.y);
+          const int id = cw.z;
+          const int lo = bx.z - x0, hi = bx.w - x0;                            // pixel i is inside iff lo <= i <= hi
+          bool pin[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pin[i] = (lo <= i) && (hi >= i);
+          if (in0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float dy = __fsub_rn(ey[0][i], cy), dx = __fsub_rn(ex[0][i], cx);
+              const float qq = __fadd_rn(__fmul_rn(__fmul_rn(dy, dy), sy[0][i]), __fmul_rn(__fmul_rn(dx, dx), sx[0][i]));
+              if (pin[i] && qq < bq[0][i]) { bq[0][i] = qq; lab[0][i] = id; }   // strict: first index wins ties (:328)
+            }
+          }
+          if (in1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float dy = __fsub_rn(ey[1][i], cy), dx = __fsub_rn(ex[1][i], cx);
+              const float qq = __fadd_rn(__fmul_rn(__fmul_rn(dy, dy), sy[1][i]), __fmul_rn(__fmul_rn(dx, dx), sx[1][i]));
+              if (pin[i] && qq < bq[1][i]) { bq[1][i] = qq; lab[1][i] = id; }
+            }
+          }
+        };
+        for (int q = 0; q < nsm; ++q)
+          visit(*reinterpret_cast<const int4*>(recs + q * (int)sizeof(SeedRec)),
+                *reinterpret_cast<const int4*>(recs + q * (int)sizeof(SeedRec) + 16));
+        for (int q = nsm; q < nhit; ++q) {                                     // rare: more hits than staged records
+          const int id = __ldg(ovf + (size_t)h1.z * Nmax + q);
+          const int4* g = reinterpret_cast<const int4*>(seeds + (size_t)b * Nmax + id);
+          visit(__ldg(g), __ldg(g + 1));
+        }
+
+        // --- stores + statistics of the keep pixels ---
+        if (colvalid) {
+          int32_t* lp = label_map + pix0 + (size_t)rp * W;
+          stg_stream4(lp, lab[0][0], lab[0][1], lab[0][2], lab[0][3]);
+          if (row1) stg_stream4(lp + W, lab[1][0], lab[1][1], lab[1][2], lab[1][3]);
+          if (SCORE) {
+            float p[2][4];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) p[r][i] = (bq[r][i] < kQZero) ? exp_fast(-bq[r][i]) : 0.0f;
+            float* sp = score_map + pix0 + (size_t)rp * W;
+            stg_stream4f(sp, p[0][0], p[0][1], p[0][2], p[0][3]);
+            if (row1) stg_stream4f(sp + W, p[1][0], p[1][1], p[1][2], p[1][3]);
+          }
+        }
+        uint32_t nib = nib0 | (nib1 << 4);
+        if (nib && stats && h1.y > 0) {
+          while (nib) {
+            const int bit = __ffs(nib) - 1;
+            nib &= nib - 1;
+            const int r = bit >> 2, i = bit & 3;
+            const int l = (r == 0) ? ((i == 0) ? lab[0][0] : (i == 1) ? lab[0][1] : (i == 2) ? lab[0][2] : lab[0][3])
+                                   : ((i == 0) ? lab[1][0] : (i == 1) ? lab[1][1] : (i == 2) ? lab[1][2] : lab[1][3]);
+            if (ghost_pass(ghost[(size_t)b * Nmax + l], y + r, x0 + i))
+              stats_add(stats + ((size_t)b * Nmax + l) * ISG_STAT_WORDS, y + r, x0 + i);
+          }
+        }
+      }
+    }
+    // every read of the stage and of its list is done: hand the slot back to the producer
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);
+    slot += G;
+    if (slot >= nstages) { slot -= nstages; ++rnd; }
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+// Workspace: [0,256) scheduler words | tile lists [T_max] x (32 + cap*32) | overflow indices [T_max][Nmax] u16.
+// T_max is the tile count of the smallest compiled tile (8 rows), so that every geometry fits.
+constexpr size_t kDenseSchedBytes = 256;
+constexpr int kD4MinTileRows = 8;
+inline int dense_list_cap(int Nmax) { return Nmax <= 16 ? 16 : (Nmax <= 160 ? 16 : 32); }
+inline size_t dense_lists_bytes(long long T, int Nmax) {
+  const size_t stride = sizeof(TileHdr) + (size_t)dense_list_cap(Nmax) * sizeof(SeedRec);
+  return ((size_t)T * stride + 255) & ~(size_t)255;
+}
+inline size_t dense_workspace_bytes(int B, int Nmax, int H, int W) {
+  const long long T = (long long)B * cdiv(W, kD4TileW) * cdiv(H, kD4MinTileRows);
+  return kDenseSchedBytes + dense_lists_bytes(T, Nmax) + (((size_t)T * Nmax * 2 + 255) & ~(size_t)255);
+}
+
+template <int RW, int WG, int G>
+inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const float* ae, int64_t ae_img_stride,
+                               int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds, const float* ghost,
+                               const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys, const float* xs,
+                               int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats, void* workspace,
+                               size_t workspace_bytes, int max_stages, cudaStream_t stream) {
+  using Geo = D4Geom<RW, WG>;
+  static_assert(Geo::TH >= kD4MinTileRows, "workspace is sized for tiles of at least kD4MinTileRows rows");
+  if (Nmax > 65535) return ISG_EUNSUPPORTED;
+  const int cap = dense_list_cap(Nmax);
+  int nstages = std::min(max_stages, kD4MaxStages);
+  while (nstages > 1 && D4Smem<RW, WG>(cap, nstages).total > 227 * 1024) --nstages;
+  if (nstages < G + 1) return ISG_EUNSUPPORTED;
+  const int tilesX = cdiv(W, kD4TileW), tilesY = cdiv(H, Geo::TH);
+  const long long T = (long long)B * tilesX * tilesY;
+  if (T >= (1ll << 31) - 65536) return ISG_EUNSUPPORTED;
+  if (workspace_bytes < dense_workspace_bytes(B, Nmax, H, W)) return ISG_EINVAL;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  unsigned int* sched = reinterpret_cast<unsigned int*>(ws);
+  unsigned char* lists = ws + kDenseSchedBytes;
+  const long long T_max = (long long)B * tilesX * cdiv(H, kD4MinTileRows);
+  uint16_t* ovf = reinterpret_cast<uint16_t*>(lists + dense_lists_bytes(T_max, Nmax));
+  static isg_encode_tiled_fn encode = get_encode_tiled();
+  if (!encode) return ISG_EUNSUPPORTED;
+  CUtensorMap tm_kp, tm_ae;
+  {
+    const cuuint64_t dim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t str[2] = {(cuuint64_t)W * 4, (cuuint64_t)kp_img_stride * 4};
+    const cuuint32_t box[3] = {kD4KpW, (cuuint32_t)Geo::kKpRows, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    if (encode(&tm_kp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(kp), dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) != CUDA_SUCCESS)
+      return ISG_EUNSUPPORTED;
+  }
+  {
+    const cuuint64_t dim[4] = {(cuuint64_t)W, (cuuint64_t)H, 4, (cuuint64_t)B};
+    const cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)ae_plane_stride * 4, (cuuint64_t)ae_img_stride * 4};
+    const cuuint32_t box[4] = {kD4TileW, (cuuint32_t)Geo::TH, 4, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    if (encode(&tm_ae, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ae), dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ISG_EUNSUPPORTED;
+  }
+  int dev = 0, sms = kSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)std::min<long long>(T, sms);
+  const size_t smem = (size_t)D4Smem<RW, WG>(cap, nstages).total;
+  const int Wwords = cdiv(W, 32);
+  const int threads = 32 * (WG * G + 1);
+  int dyn_tail = 4;                                   // tiles per CTA left to the dynamic scheduler
+  if (const char* e = getenv("ISG_DENSE_TAIL")) dyn_tail = std::max(0, atoi(e));
+  int dbg_flags = 0;                                  // measurement aid: bit 0 = consumers release tiles without computing
+  if (const char* e = getenv("ISG_DENSE_DEBUG")) dbg_flags = atoi(e);
+  const SeedRec* srec = reinterpret_cast<const SeedRec*>(seeds);
+  tile_lists_kernel<<<(unsigned)cdiv64(T, 8), 256, 0, stream>>>(srec, n_seeds, thr_key, Nmax, B, H, W, Geo::TH, tilesX, tilesY, cap,
+                                                                lists, ovf);
+  ISG_LAUNCH_CHECK();
+  if (score_map) {
+    ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dense_v4_kernel<RW, WG, G, true><<<grid, threads, smem, stream>>>(
+        tm_kp, tm_ae, srec, reinterpret_cast<const float4*>(ghost), Nmax, B, H, W, Wwords, tilesX, tilesY, nstages, cap, lists,
+        ovf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail, dbg_flags);
+  } else {
+    ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dense_v4_kernel<RW, WG, G, false><<<grid, threads, smem, stream>>>(
+        tm_kp, tm_ae, srec, reinterpret_cast<const float4*>(ghost), Nmax, B, H, W, Wwords, tilesX, tilesY, nstages, cap, lists,
+        ovf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail, dbg_flags);
+  }
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+// Tuning knob for experiments: ISG_DENSE_CFG = "<RW>x<WG>x<G>[:stages]" selects one of the compiled geometries.
+inline int launch_dense_v4(const float* kp, int64_t kp_img_stride, const float* ae, int64_t ae_img_stride,
+                           int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds, const float* ghost,
+                           const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys, const float* xs,
+                           int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream) {
+  int rw = 2, wg = 8, g = 2, st = kD4MaxStages;
+  if (const char* e = getenv("ISG_DENSE_CFG")) {
+    int a = 0, b_ = 0, c = 0, d = 0;
+    const int got = sscanf(e, "%dx%dx%d:%d", &a, &b_, &c, &d);
+    if (got >= 3) { rw = a; wg = b_; g = c; }
+    if (got >= 4 && d > 0) st = d;
+  }
+#define ISG_V4_CASE(RW_, WG_, G_)                                                                                      \
+  if (rw == RW_ && wg == WG_ && g == G_)                                                                               \
+    return launch_dense_v4_cfg<RW_, WG_, G_>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, \
+                                             n_seeds, B, Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, workspace, workspace_bytes, st, stream);
+  ISG_V4_CASE(2, 8, 2)
+  ISG_V4_CASE(4, 4, 3)
+  ISG_V4_CASE(4, 4, 4)
+  ISG_V4_CASE(4, 2, 6)
+  ISG_V4_CASE(2, 4, 4)
+  ISG_V4_CASE(2, 4, 6)
+  ISG_V4_CASE(2, 8, 3)
+#undef ISG_V4_CASE
+  return ISG_EUNSUPPORTED;
+}
+
+}  // namespace isg

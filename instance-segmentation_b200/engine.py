@@ -86,7 +86,7 @@ class DecodePlan:
     """select -> assign (dense or sparse) -> compact -> group for a batch of B images of HxW."""
 
     def __init__(self, B: int, H: int, W: int, max_seeds: int, kp_th: int, device, mode: str = "sparse",
-                 want_score: bool = True, wh_delta: float = 0.1, scale: float = 1.0):
+                 want_score: bool = True, wh_delta: float = 0.1, scale: float = 1.0, fused_stats: bool = False):
         if mode not in ("dense", "sparse"):
             raise ValueError("mode must be 'dense' or 'sparse'")
         self.device = require_cuda(device)
@@ -97,6 +97,9 @@ class DecodePlan:
             raise RuntimeError("selected index k out of range")   # torch.topk, utils/decode.py:81
         self.cap = max(min(self.kp_th, H * W), 1)
         self.mode, self.want_score = mode, bool(want_score)
+        # dense mode: per-instance count/bbox either inside the fused kernel (one atomic set per keep pixel in the hot
+        # loop) or in the gather pass over the compacted keep pixels (default: same numbers, cheaper)
+        self.fused_stats = bool(fused_stats)
         # wh_delta None disables the device ghost filter (non-identity val transforms filter on the host)
         self.ghost_k = -1.0 if wh_delta is None else float(np.float32(0.5 + wh_delta))
         self.scale = float(scale)
@@ -121,6 +124,9 @@ class DecodePlan:
         self.ws, self.ws_ptr = aligned_workspace(self.ws_bytes, d)
         if mode == "dense":
             self.label_map = torch.empty((B, H, W), dtype=i32, device=d)
+            # tile scheduler of the dense kernel: zero-filled once, the kernel leaves it zero-filled
+            self.dense_ws_bytes = int(_lib.lib().isg_assign_dense_workspace_bytes(B, N, H, W))
+            self.dense_ws = torch.zeros(self.dense_ws_bytes, dtype=torch.uint8, device=d)
             self.score_map = torch.empty((B, H, W), dtype=f32, device=d) if want_score else None
         else:
             self.label_map = self.score_map = None
@@ -166,12 +172,14 @@ class DecodePlan:
                 ev[0].record()
             call("isg_assign_dense", ptr(kp), kp_stride, ptr(ae), ae_img, ae_plane, ptr(self.thr_key), ptr(self.seeds),
                  ptr(self.ghost), ptr(n_seeds), B, N, H, W, ptr(self.ys), ptr(self.xs), ptr(self.label_map),
-                 ptr(self.score_map), ptr(self.keepbits), ptr(self.stats), s)
+                 ptr(self.score_map), ptr(self.keepbits), ptr(self.stats) if self.fused_stats else 0, ptr(self.dense_ws),
+                 self.dense_ws_bytes, s)
             if ev:
                 ev[1].record()
             call("isg_compact_points", ptr(self.keepbits), B, H, W, cap, ptr(self.idx), ptr(self.count), s)
             call("isg_gather_labels", ptr(self.label_map), ptr(self.score_map), ptr(self.idx), ptr(self.count), cap,
-                 ptr(self.ghost), B, N, H, W, ptr(self.label), ptr(self.score), ptr(self.flag), s)
+                 ptr(self.ghost), B, N, H, W, ptr(self.label), ptr(self.score), ptr(self.flag),
+                 0 if self.fused_stats else ptr(self.stats), s)
         else:
             call("isg_keep_points", ptr(kp), B, H, W, kp_stride, ptr(self.thr_key), ptr(self.keepbits), 0, s)
             call("isg_compact_points", ptr(self.keepbits), B, H, W, cap, ptr(self.idx), ptr(self.count), s)

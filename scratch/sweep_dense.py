@@ -9,7 +9,7 @@ from isg_b200 import _lib, engine
 
 def main():
     wlname = sys.argv[1] if len(sys.argv) > 1 else "cityscapes_1024x2048_b8_n100"
-    cfgs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["v2", "2x8x2", "4x4x3", "4x2x6", "2x4x4", "2x4x6", "8x2x3", "8x1x8", "4x1x12", "4x2x8"]
+    cfgs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["v2", "2x8x2", "4x4x3", "4x4x4", "4x2x6", "2x4x4", "2x4x6", "2x8x3"]
     wl = bench.WORKLOADS[wlname]
     dev = torch.device("cuda", 0)
     B, H, W, N = wl["B"], wl["H"], wl["W"], wl["N"]
@@ -23,8 +23,16 @@ def main():
     ref = None
     for cfg in cfgs:
         os.environ.pop("ISG_DENSE_V2", None); os.environ.pop("ISG_DENSE_CFG", None)
+        os.environ.pop("ISG_DENSE_TAIL", None)
         if cfg == "v2": os.environ["ISG_DENSE_V2"] = "1"
-        else: os.environ["ISG_DENSE_CFG"] = cfg
+        else:
+            c = cfg
+            os.environ.pop("ISG_DENSE_DEBUG", None)
+            if "!" in c:
+                c, dbg = c.split("!"); os.environ["ISG_DENSE_DEBUG"] = dbg
+            if "@" in c:
+                c, tail = c.split("@"); os.environ["ISG_DENSE_TAIL"] = tail
+            os.environ["ISG_DENSE_CFG"] = c
         dplan.label_map.fill_(-7); dplan.keepbits.fill_(0)
         try:
             for _ in range(3):

@@ -116,11 +116,11 @@ def test_nms_hm_golden(mods, golden):
 
 
 # ---------------------------------------------------------------------------------------------- K1/K3
-def _run_plan(mods, img, kp_th, mode, want_score=True):
+def _run_plan(mods, img, kp_th, mode, want_score=True, fused_stats=False):
     eng = mods["engine"]
     H, W = img.kp.shape[-2:]
     N = len(img.rois)
-    plan = eng.DecodePlan(1, H, W, N, kp_th, DEV, mode, want_score=want_score)
+    plan = eng.DecodePlan(1, H, W, N, kp_th, DEV, mode, want_score=want_score, fused_stats=fused_stats)
     kp = torch.from_numpy(img.kp)[None].to(DEV)
     ae = torch.from_numpy(img.ae)[None].to(DEV)
     rois = torch.from_numpy(img.rois)[None].to(DEV).contiguous()
@@ -130,13 +130,14 @@ def _run_plan(mods, img, kp_th, mode, want_score=True):
     return plan
 
 
-@pytest.mark.parametrize("mode", ["sparse", "dense"])
+@pytest.mark.parametrize("mode", ["sparse", "dense", "dense-fused-stats"])
 @pytest.mark.parametrize("shape,N,kp_th", [((256, 512), 20, 20000), ((96, 160), 5, 100), ((130, 257), 6, 3000)])
 def test_group_core_vs_oracle(mods, oracle, mode, shape, N, kp_th):
     rd, _ = oracle
     img = mods["synth"].make_image(77 + N, shape[0], shape[1], N)
     core = rd.group_core(torch.from_numpy(img.kp[0]), torch.from_numpy(img.ae), img.rois, kp_th)
-    plan = _run_plan(mods, img, kp_th, mode)
+    # dense mode: per-instance statistics from the gather pass (default) or accumulated inside the fused kernel
+    plan = _run_plan(mods, img, kp_th, mode.split("-")[0], fused_stats=mode.endswith("fused-stats"))
     M = int(plan.count[0].item())
     assert M == core["idx"].shape[0]
     assert np.array_equal(unpack_bits(plan.keepbits[0].cpu().numpy(), shape[1]), core["mask"].numpy())
