@@ -232,6 +232,26 @@ int isg_pairwise(const float* X, int M, const float* Y, int N, int D, int metric
                  isg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f1 — per-instance point sets + polygon extraction on the device (identity val-transform).  Replaces the per-instance
+ * loop of group_kp (utils/decode.py:337-356) and aug_group (:167-204, with find_internal_point :51-68 and
+ * cartesian2polar :88-113).  One CTA per (image, instance) collects, in row-major order, the keep pixels (keepbits,
+ * label_map of isg_assign_dense) labelled with the instance that lie strictly inside its ghost bounds; instances with
+ * at least obj_pixel_th points get their internal point, the polar-angle sort of their points (equal angles keep
+ * row-major order; numpy's order among equal keys is unspecified) and the centre-inside test of the sorted polygon.
+ *   rois [B,Nmax,4] fp32 in `layout` (ISG_BOX_XYXY / ISG_BOX_CYCXHW, as given to isg_build_seeds); ghost [B,Nmax,4] from isg_build_seeds; cap = capacity of poly_points per image
+ *   poly_points [B,cap,2] fp32 (x,y): instance i of image b occupies [inst_start, inst_start+inst_count) of image b's
+ *     block - angle-sorted when a polygon was computed, row-major otherwise; blocks are allocated in completion order
+ *   inst_flags [B,Nmax] uint8: 1 = polygon valid (centre strictly inside), 0 = no polygon, 2 = more than 2048 points:
+ *     the raw row-major set was written and the caller finishes this instance (aug_group on the host)
+ *   inst_internal [B,Nmax,2] fp32 (nullable): the internal point used;  img_total [B] int32: points per image
+ *   stats (nullable, pre-initialised by isg_stats_init): count / bbox per instance
+ * ------------------------------------------------------------------------------------------ */
+int isg_instance_polygons(const uint32_t* keepbits, const int32_t* label_map, const float* rois, int layout, const float* ghost,
+                          const int32_t* n_seeds, int B, int Nmax, int H, int W, int cap, int obj_pixel_th,
+                          float* poly_points, int32_t* inst_start, int32_t* inst_count, uint8_t* inst_flags,
+                          float* inst_internal, int32_t* img_total, int32_t* stats, isg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * HOST helpers of the polygon stage (aug_group / find_internal_point, utils/decode.py:51-68,167-204).
  * Host pointers, no device work: the polygon stage is host glue this round (SURVEY.md §8 f1 is next).
  * They restate cv2.pointPolygonTest(contour fp32 [K,2], pt, measureDist=False) so that whole images are

@@ -1,0 +1,335 @@
+// f1 — per-instance point sets and polygon extraction on the device.
+// Reference: the per-instance loop of group_kp (utils/decode.py:337-356) and aug_group (:167-204) with
+// find_internal_point (:51-68) and cartesian2polar (:88-113), for the identity val-transform (the default).
+//
+// One CTA per (image, instance):
+//   1. collect, in row-major order, the keep pixels (keepbits) whose label_map entry is the instance and that lie
+//      strictly inside its ghost bounds (:351-352); the scan is restricted to the integer pixel range of the bounds;
+//   2. fewer than obj_pixel_th points -> no polygon (:355);
+//   3. internal point: the box centre if cv2.pointPolygonTest(points, centre) > 0, else the fp32 mean of the
+//      points, else the first pair midpoint (kps[i]+kps[j])/2 (i outer, j from 1) that is inside, else the centre;
+//   4. polar angle of every point about the internal point in fp32 (same branches as cartesian2polar), ascending
+//      sort; EQUAL angles keep their row-major order (np.argsort's order among equal keys is unspecified);
+//   5. polygon is valid iff the box centre is strictly inside the sorted polygon (:201).
+// The `area == 0` rejection (:187-189) cannot fire for a polygon with at least one vertex (fillPoly rasterises the
+// outline) and is not evaluated.  pointPolygonTest is restated from OpenCV's float branch (crossing count with the
+// on-edge cases returning 0, the cross product in double) - the same restatement as csrc/host_polygon.cpp, which
+// tests/test_host_logic.py checks against cv2 itself.
+#include "common.cuh"
+
+namespace isg {
+
+constexpr int kPolyThreads = 256;
+constexpr int kPolyWarps = kPolyThreads / 32;
+constexpr int kPolyMaxPoints = 2048;     // points of one instance handled on the device (more: flagged, host fallback)
+constexpr int kPolyMaskWords = 4096;     // matched-bit masks cached in shared memory between the two passes
+
+struct PolySmem {
+  float2 pts[kPolyMaxPoints];
+  unsigned long long keys[kPolyMaxPoints];
+  uint32_t masks[kPolyMaskWords];
+  int warp_tot[kPolyWarps];
+  int red_i[kPolyWarps];
+  int red_j[kPolyWarps];
+  float misc[8];
+};
+
+// crossing-count contribution of edge (v0 -> v) for the query point; returns 0 / 1 to add to the counter and sets
+// on_edge when the point lies on the edge (pointPolygonTest returns 0 then)
+__device__ __forceinline__ int pip_edge(float v0x, float v0y, float vx, float vy, float px, float py, bool& on_edge) {
+  if ((v0y <= py && vy <= py) || (v0y > py && vy > py) || (v0x < px && vx < px)) {
+    if (py == vy && (px == vx || (py == v0y && ((v0x <= px && px <= vx) || (vx <= px && px <= v0x))))) on_edge = true;
+    return 0;
+  }
+  double dist = (double)(py - v0y) * (double)(vx - v0x) - (double)(px - v0x) * (double)(vy - v0y);
+  if (dist == 0) { on_edge = true; return 0; }
+  if (vy < v0y) dist = -dist;
+  return dist > 0 ? 1 : 0;
+}
+
+// pointPolygonTest(pts[0..K), (px,py), False) by one warp: +1 inside, 0 on the polyline, -1 outside
+__device__ __forceinline__ int pip_warp(const float2* pts, int K, float px, float py, int lane) {
+  int cnt = 0;
+  bool on_edge = false;
+  for (int i = lane; i < K; i += 32) {
+    const float2 v0 = pts[i == 0 ? K - 1 : i - 1], v = pts[i];
+    cnt += pip_edge(v0.x, v0.y, v.x, v.y, px, py, on_edge);
+  }
+  cnt = warp_sum(cnt);
+  const bool any_on = __any_sync(0xffffffffu, on_edge);
+  if (any_on) return 0;
+  return (cnt & 1) ? 1 : -1;
+}
+
+// the same by the whole CTA (result broadcast to every thread); uses s.red_i / s.red_j
+__device__ __forceinline__ int pip_block(PolySmem& s, const float2* pts, int K, float px, float py) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int cnt = 0;
+  bool on_edge = false;
+  for (int i = tid; i < K; i += kPolyThreads) {
+    const float2 v0 = pts[i == 0 ? K - 1 : i - 1], v = pts[i];
+    cnt += pip_edge(v0.x, v0.y, v.x, v.y, px, py, on_edge);
+  }
+  cnt = warp_sum(cnt);
+  const bool any_on = __any_sync(0xffffffffu, on_edge);
+  __syncthreads();
+  if (lane == 0) { s.red_i[warp] = cnt; s.red_j[warp] = any_on ? 1 : 0; }
+  __syncthreads();
+  int tot = 0, on = 0;
+#pragma unroll
+  for (int w = 0; w < kPolyWarps; ++w) { tot += s.red_i[w]; on |= s.red_j[w]; }
+  if (on) return 0;
+  return (tot & 1) ? 1 : -1;
+}
+
+__device__ __forceinline__ float polar_theta(float dx, float dy) {
+  const float PI_F = 3.14159274101257324f;          // float32(np.pi)
+  if (dx == 0.0f && dy > 0.0f) return 1.57079637050628662f;    // float32(np.pi / 2)
+  if (dx == 0.0f && dy < 0.0f) return 4.71238899230957031f;    // float32(3 * np.pi / 2)
+  float seta = (float)atan((double)__fdiv_rn(dy, dx));         // fp32 arctan of the fp32 ratio (NaN for 0/0)
+  if (dx < 0.0f) seta = __fadd_rn(seta, PI_F);
+  else if (dx > 0.0f && dy < 0.0f) seta = __fadd_rn(seta, __fmul_rn(2.0f, PI_F));
+  return seta;
+}
+
+__global__ void __launch_bounds__(kPolyThreads)
+instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* __restrict__ label_map,
+                         const float4* __restrict__ rois, int layout, const float4* __restrict__ ghost,
+                         const int32_t* __restrict__ n_seeds, int Nmax, int H, int W, int Wwords, int cap,
+                         int obj_pixel_th, float2* __restrict__ poly_points, int32_t* __restrict__ inst_start,
+                         int32_t* __restrict__ inst_count, uint8_t* __restrict__ inst_flags,
+                         float2* __restrict__ inst_internal, int32_t* __restrict__ img_total,
+                         int32_t* __restrict__ stats) {
+  extern __shared__ __align__(16) unsigned char poly_smem_raw[];
+  PolySmem& s = *reinterpret_cast<PolySmem*>(poly_smem_raw);
+  const int b = blockIdx.y, inst = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t io = (size_t)b * Nmax + inst;
+  const int n = min(n_seeds[b], Nmax);
+  if (inst >= n) {
+    if (tid == 0) { inst_start[io] = 0; inst_count[io] = 0; inst_flags[io] = 0; }
+    return;
+  }
+  // ---- scan range: integer pixels strictly inside the ghost bounds ----
+  const float4 g = ghost[io];                                   // x_lo, x_hi, y_lo, y_hi (strict)
+  const float fx_lo = fmaxf(floorf(g.x) + 1.0f, 0.0f), fx_hi = fminf(ceilf(g.y) - 1.0f, (float)(W - 1));
+  const float fy_lo = fmaxf(floorf(g.z) + 1.0f, 0.0f), fy_hi = fminf(ceilf(g.w) - 1.0f, (float)(H - 1));
+  const bool empty_range = !(fx_lo <= fx_hi) || !(fy_lo <= fy_hi);          // also true for NaN bounds
+  const int x_lo = empty_range ? 0 : (int)fx_lo, x_hi = empty_range ? -1 : (int)fx_hi;
+  const int y_lo = empty_range ? 0 : (int)fy_lo, y_hi = empty_range ? -1 : (int)fy_hi;
+  const int w_lo = x_lo >> 5, w_hi = x_hi >> 5;
+  const int Wb = empty_range ? 0 : (w_hi - w_lo + 1), R = empty_range ? 0 : (y_hi - y_lo + 1);
+  const int NW = Wb * R;
+  const bool cached = NW <= kPolyMaskWords;
+  const uint32_t* kb = keepbits + (size_t)b * H * Wwords;
+  const int32_t* lm = label_map + (size_t)b * H * W;
+
+  auto matched_mask = [&](int w) -> uint32_t {                  // word w of the box (row-major), bits of this instance
+    const int r = w / Wb, c = w - r * Wb;
+    const int y = y_lo + r, wx = w_lo + c;
+    uint32_t m = __ldg(kb + (size_t)y * Wwords + wx);
+    if (wx == w_lo) m &= 0xffffffffu << (x_lo & 31);
+    if (wx == w_hi) m &= 0xffffffffu >> (31 - (x_hi & 31));
+    uint32_t out = 0;
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      if (__ldg(lm + (size_t)y * W + (wx << 5) + bit) == inst) out |= 1u << bit;
+    }
+    return out;
+  };
+
+  // ---- pass 1: count (blocked assignment keeps row-major order) ----
+  const int q = (NW + kPolyThreads - 1) / kPolyThreads;
+  const int w0 = min(tid * q, NW), w1 = min(w0 + q, NW);
+  int mine = 0;
+  for (int w = w0; w < w1; ++w) {
+    const uint32_t m = matched_mask(w);
+    if (cached) s.masks[w] = m;
+    mine += __popc(m);
+  }
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+  if (lane == 31) s.warp_tot[warp] = incl;
+  __syncthreads();
+  int base = incl - mine, K = 0;
+#pragma unroll
+  for (int w = 0; w < kPolyWarps; ++w) { const int t = s.warp_tot[w]; if (w < warp) base += t; K += t; }
+
+  __shared__ int s_start;
+  if (tid == 0) {
+    s_start = (K > 0) ? atomicAdd(img_total + b, K) : 0;
+    inst_count[io] = K;
+  }
+  __syncthreads();
+  const int start = s_start;
+  if (tid == 0) inst_start[io] = start;
+  const bool fits = K <= kPolyMaxPoints && start + K <= cap;
+  float2* out = poly_points + (size_t)b * cap + start;
+
+  // ---- pass 2: emit the points (x,y) fp32, row-major; bbox for the statistics ----
+  int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -1, by1 = -1;
+  {
+    int pos = base;
+    for (int w = w0; w < w1; ++w) {
+      uint32_t m = cached ? s.masks[w] : matched_mask(w);
+      if (!m) continue;
+      const int r = w / Wb, c = w - r * Wb;
+      const int y = y_lo + r, xb = (w_lo + c) << 5;
+      by0 = min(by0, y); by1 = max(by1, y);
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int x = xb + bit;
+        bx0 = min(bx0, x); bx1 = max(bx1, x);
+        const float2 p = make_float2((float)x, (float)y);
+        if (fits) s.pts[pos] = p;
+        else if (start + pos < cap) out[pos] = p;                 // too many points for the device stage: raw set
+        ++pos;
+      }
+    }
+  }
+  if (stats) {
+    int32_t* st = stats + io * ISG_STAT_WORDS;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+      bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    }
+    if (lane == 0 && bx1 >= 0) { atomicMin(st + 1, by0); atomicMin(st + 2, bx0); atomicMax(st + 3, by1); atomicMax(st + 4, bx1); }
+    if (tid == 0) st[0] = K;
+  }
+  __syncthreads();
+  if (!fits) { if (tid == 0) inst_flags[io] = (K >= obj_pixel_th) ? 2 : 0; return; }   // bit 1: host must finish this one
+  if (K < obj_pixel_th || K == 0) {                                                 // :355
+    for (int i = tid; i < K; i += kPolyThreads) out[i] = s.pts[i];
+    if (tid == 0) inst_flags[io] = 0;
+    return;
+  }
+
+  // ---- internal point (:51-68) ----
+  const float4 r4 = rois[io];
+  float cx, cy;
+  if (layout == ISG_BOX_XYXY) {   // x1,y1,x2,y2: centre = (lt+rb)/2 (:430)
+    cx = __fmul_rn(__fadd_rn(r4.x, r4.z), 0.5f); cy = __fmul_rn(__fadd_rn(r4.y, r4.w), 0.5f);
+  } else {                        // cy,cx,h,w: group_kp's center_indexes
+    cx = r4.y; cy = r4.x;
+  }
+  float ix = cx, iy = cy;
+  if (pip_block(s, s.pts, K, cx, cy) <= 0) {
+    if (tid == 0) {   // numpy mean(axis=0) of a C-contiguous [K,2] fp32 array: sequential fp32 sums, then / K
+      float sx = 0.0f, sy = 0.0f;
+      for (int i = 0; i < K; ++i) { sx = __fadd_rn(sx, s.pts[i].x); sy = __fadd_rn(sy, s.pts[i].y); }
+      s.misc[0] = __fdiv_rn(sx, (float)K); s.misc[1] = __fdiv_rn(sy, (float)K);
+    }
+    __syncthreads();
+    const float mx = s.misc[0], my = s.misc[1];
+    if (pip_block(s, s.pts, K, mx, my) > 0) { ix = mx; iy = my; }
+    else {
+      // pair midpoints in the reference's order (i outer over [0,K), j inner over [1,K)); one candidate per warp
+      const long long ncand = (long long)K * (K - 1);
+      long long found = -1;
+      for (long long c0 = 0; c0 < ncand && found < 0; c0 += kPolyWarps) {
+        const long long c = c0 + warp;
+        int hit = 0;
+        if (c < ncand) {
+          const int i = (int)(c / (K - 1)), j = 1 + (int)(c - (long long)i * (K - 1));
+          const float qx = __fdiv_rn(__fadd_rn(s.pts[i].x, s.pts[j].x), 2.0f), qy = __fdiv_rn(__fadd_rn(s.pts[i].y, s.pts[j].y), 2.0f);
+          hit = pip_warp(s.pts, K, qx, qy, lane) > 0;
+        }
+        __syncthreads();
+        if (lane == 0) s.red_i[warp] = hit;
+        __syncthreads();
+        for (int w = 0; w < kPolyWarps; ++w) if (s.red_i[w]) { found = c0 + w; break; }
+      }
+      if (found >= 0) {
+        const int i = (int)(found / (K - 1)), j = 1 + (int)(found - (long long)i * (K - 1));
+        ix = __fdiv_rn(__fadd_rn(s.pts[i].x, s.pts[j].x), 2.0f); iy = __fdiv_rn(__fadd_rn(s.pts[i].y, s.pts[j].y), 2.0f);
+      }
+    }
+  }
+  if (tid == 0 && inst_internal) inst_internal[io] = make_float2(ix, iy);
+
+  // ---- polar angles + stable ascending sort (bitonic on (angle bits, index)) ----
+  int Kp = 1;
+  while (Kp < K) Kp <<= 1;
+  for (int i = tid; i < Kp; i += kPolyThreads) {
+    unsigned long long key = ~0ull;
+    if (i < K) {
+      const float2 p = s.pts[i];
+      float th = polar_theta(__fsub_rn(p.x, ix), __fsub_rn(p.y, iy));
+      th = th + 0.0f;                                                 // -0 -> +0
+      uint32_t tb = __float_as_uint(th);
+      if (th != th) tb = 0x7fffffffu;                                 // NaN sorts last (np.argsort)
+      else if (tb & 0x80000000u) tb = 0;                              // defensive: angles are never negative
+      key = ((unsigned long long)tb << 32) | (unsigned)i;
+    }
+    s.keys[i] = key;
+  }
+  __syncthreads();
+  for (int k2 = 2; k2 <= Kp; k2 <<= 1) {
+    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      for (int i = tid; i < Kp; i += kPolyThreads) {
+        const int l = i ^ j2;
+        if (l > i) {
+          const unsigned long long a = s.keys[i], c = s.keys[l];
+          const bool up = (i & k2) == 0;
+          if ((a > c) == up) { s.keys[i] = c; s.keys[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // sorted polygon -> global, and keep a sorted copy in shared memory for the final test
+  float2 mine_pt[kPolyMaxPoints / kPolyThreads];
+#pragma unroll
+  for (int u = 0; u < kPolyMaxPoints / kPolyThreads; ++u) {
+    const int i = tid + u * kPolyThreads;
+    if (i < K) mine_pt[u] = s.pts[(int)(s.keys[i] & 0xffffffffu)];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < kPolyMaxPoints / kPolyThreads; ++u) {
+    const int i = tid + u * kPolyThreads;
+    if (i < K) { s.pts[i] = mine_pt[u]; out[i] = mine_pt[u]; }
+  }
+  __syncthreads();
+  // ---- centre strictly inside the sorted polygon (:201) ----
+  const int inside = pip_block(s, s.pts, K, cx, cy);
+  if (tid == 0) inst_flags[io] = inside > 0 ? 1 : 0;
+}
+
+__global__ void zero_i32_kernel(int32_t* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0;
+}
+
+}  // namespace isg
+
+using namespace isg;
+
+extern "C" int isg_instance_polygons(const uint32_t* keepbits, const int32_t* label_map, const float* rois,
+                                     int layout, const float* ghost, const int32_t* n_seeds, int B, int Nmax, int H, int W,
+                                     int cap, int obj_pixel_th, float* poly_points, int32_t* inst_start,
+                                     int32_t* inst_count, uint8_t* inst_flags, float* inst_internal,
+                                     int32_t* img_total, int32_t* stats, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!keepbits || !label_map || !rois || !ghost || !n_seeds || !poly_points || !inst_start || !inst_count || !inst_flags ||
+      !img_total)
+    return ISG_EINVAL;
+  if (B <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || cap <= 0 || B > 65535) return ISG_EINVAL;
+  if (layout != ISG_BOX_XYXY && layout != ISG_BOX_CYCXHW) return ISG_EINVAL;
+  if (((uintptr_t)rois & 15) || ((uintptr_t)ghost & 15) || ((uintptr_t)poly_points & 7)) return ISG_EINVAL;
+  zero_i32_kernel<<<cdiv(B, 256), 256, 0, stream>>>(img_total, B);
+  ISG_LAUNCH_CHECK();
+  const size_t smem = sizeof(PolySmem);
+  ISG_CUDA(cudaFuncSetAttribute(instance_polygons_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(Nmax, B);
+  instance_polygons_kernel<<<grid, kPolyThreads, smem, stream>>>(
+      keepbits, label_map, reinterpret_cast<const float4*>(rois), layout, reinterpret_cast<const float4*>(ghost), n_seeds, Nmax, H, W,
+      cdiv(W, 32), cap, obj_pixel_th, reinterpret_cast<float2*>(poly_points), inst_start, inst_count, inst_flags,
+      reinterpret_cast<float2*>(inst_internal), img_total, stats);
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}

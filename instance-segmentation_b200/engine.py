@@ -123,6 +123,13 @@ class DecodePlan:
         self.ws_bytes = int(_lib.lib().isg_topk_workspace_bytes(B, H, W, self.kp_th))
         self.ws, self.ws_ptr = aligned_workspace(self.ws_bytes, d)
         if mode == "dense":
+            # device polygon stage (isg_instance_polygons)
+            self.poly_points = torch.empty((B, cap, 2), dtype=f32, device=d)
+            self.inst_start = torch.empty((B, N), dtype=i32, device=d)
+            self.inst_count = torch.empty((B, N), dtype=i32, device=d)
+            self.inst_flags = torch.empty((B, N), dtype=torch.uint8, device=d)
+            self.inst_internal = torch.empty((B, N, 2), dtype=f32, device=d)
+            self.img_total = torch.empty(B, dtype=i32, device=d)
             self.label_map = torch.empty((B, H, W), dtype=i32, device=d)
             # tile scheduler of the dense kernel: zero-filled once, the kernel leaves it zero-filled
             self.dense_ws_bytes = int(_lib.lib().isg_assign_dense_workspace_bytes(B, N, H, W))
@@ -151,8 +158,16 @@ class DecodePlan:
              self.ws_bytes, stream_ptr(self.device))
 
     def run_assign(self, kp: torch.Tensor, ae: torch.Tensor, rois: torch.Tensor, n_seeds: torch.Tensor,
-                   layout: int = _lib.ISG_BOX_XYXY, time_main: bool = False) -> None:
-        """Stage 2: seeds -> assignment (dense or sparse) -> compaction -> grouping.  Needs self.thr_key."""
+                   layout: int = _lib.ISG_BOX_XYXY, time_main: bool = False, tail: str = "lists",
+                   obj_pixel_th: int = 0) -> None:
+        """Stage 2: seeds -> assignment (dense or sparse) -> tail.  Needs self.thr_key.
+        tail "lists": compaction + per-pixel labels + per-instance point sets (idx/label/flag/offsets/points);
+        tail "polygons" (dense mode, XYXY rois): isg_instance_polygons straight from the label map
+        (poly_points/inst_start/inst_count/inst_flags)."""
+        if tail not in ("lists", "polygons"):
+            raise ValueError("tail must be 'lists' or 'polygons'")
+        if tail == "polygons" and (self.mode != "dense" or self.ghost_k < 0):
+            raise ValueError("the device polygon stage needs dense mode and the device ghost filter")
         B, H, W, N, cap = self.B, self.H, self.W, self.N, self.cap
         kp = self._check(kp, ae)
         assert rois.shape == (B, N, 4) and rois.is_contiguous() and rois.dtype == torch.float32
@@ -176,6 +191,14 @@ class DecodePlan:
                  self.dense_ws_bytes, s)
             if ev:
                 ev[1].record()
+            if tail == "polygons":
+                call("isg_instance_polygons", ptr(self.keepbits), ptr(self.label_map), ptr(rois), layout, ptr(self.ghost), ptr(n_seeds),
+                     B, N, H, W, cap, int(obj_pixel_th), ptr(self.poly_points), ptr(self.inst_start), ptr(self.inst_count),
+                     ptr(self.inst_flags), ptr(self.inst_internal), ptr(self.img_total),
+                     0 if self.fused_stats else ptr(self.stats), s)
+                if ev:
+                    self.events.append(ev)
+                return
             call("isg_compact_points", ptr(self.keepbits), B, H, W, cap, ptr(self.idx), ptr(self.count), s)
             call("isg_gather_labels", ptr(self.label_map), ptr(self.score_map), ptr(self.idx), ptr(self.count), cap,
                  ptr(self.ghost), B, N, H, W, ptr(self.label), ptr(self.score), ptr(self.flag),
@@ -196,13 +219,13 @@ class DecodePlan:
             self.events.append(ev)
 
     def run(self, kp: torch.Tensor, ae: torch.Tensor, rois: torch.Tensor, n_seeds: torch.Tensor,
-            layout: int = _lib.ISG_BOX_XYXY, time_main: bool = False) -> None:
+            layout: int = _lib.ISG_BOX_XYXY, time_main: bool = False, tail: str = "lists", obj_pixel_th: int = 0) -> None:
         """kp [B,1,H,W] or [B,H,W]; ae [B,4,H,W]; rois [B,N,4] fp32 ((x1,y1,x2,y2) or (cy,cx,h,w), see `layout`);
         n_seeds [B] int32 — all on the plan's device.  Enqueues the kernels on the current stream and returns
         without synchronising.  time_main=True brackets the assignment kernel with CUDA events on the launching
         stream and appends the pair to self.events (bench.py's roofline measurement)."""
         self.run_topk(kp)
-        self.run_assign(kp, ae, rois, n_seeds, layout, time_main)
+        self.run_assign(kp, ae, rois, n_seeds, layout, time_main, tail, obj_pixel_th)
 
 
 class BoxPlan:
@@ -280,7 +303,8 @@ class DecodePipeline:
         self.fork = torch.cuda.Event()
         self.join = torch.cuda.Event()
 
-    def run(self, kp, ae, anchors, regression, classification, cls_th, iou_th, time_main: bool = False) -> None:
+    def run(self, kp, ae, anchors, regression, classification, cls_th, iou_th, time_main: bool = False,
+            tail: str = "lists", obj_pixel_th: int = 0) -> None:
         main = torch.cuda.current_stream(self.device)
         self.fork.record(main)
         self.side.wait_event(self.fork)
@@ -289,7 +313,7 @@ class DecodePipeline:
             self.join.record(self.side)
         self.bplan.run(anchors, regression, classification, cls_th, iou_th)
         main.wait_event(self.join)
-        self.dplan.run_assign(kp, ae, self.bplan.rois, self.bplan.n_seeds, _lib.ISG_BOX_XYXY, time_main)
+        self.dplan.run_assign(kp, ae, self.bplan.rois, self.bplan.n_seeds, _lib.ISG_BOX_XYXY, time_main, tail, obj_pixel_th)
 
 
 _pipes = {}

@@ -35,7 +35,10 @@ draw_flag = False     # set by evaluate.py:41 (the code reads decode_cfg.draw_fl
 
 # "dense": fused label map for every pixel (isg_assign_dense); "sparse": only the selected pixels, the
 # reference's own amount of work (isg_assign_sparse).  Both give identical detections.
-decode_mode = os.environ.get("ISG_DECODE_MODE", "sparse")
+decode_mode = os.environ.get("ISG_DECODE_MODE", "dense")
+# dense mode, identity val-transform, no drawing: run the per-instance polygon stage on the device
+# (isg_instance_polygons); False keeps it on the host (cv2/numpy, the reference's own calls)
+device_polygon_stage = os.environ.get("ISG_DEVICE_POLYGONS", "1") != "0"
 
 # wall-clock split of the last decode_output call (seconds): device (H2D + kernels, until the results are on the
 # host) and host (polygon stage).  Diagnostic only.
@@ -383,8 +386,10 @@ def _run_plan(kp, ae, boxes_dev, n_dev, layout, decode_cfg, transforms, dev, max
     plan = engine.get_decode_plan(B, H, W, max_seeds, int(decode_cfg.kp_th), dev, decode_mode, want_score=False,
                                   wh_delta=float(decode_cfg.wh_delta) if identity else None,
                                   scale=float(compute_scale(None)))
-    plan.run(kp, ae, boxes_dev, n_dev, layout)
-    return plan, identity
+    device_polygons = identity and not decode_cfg.draw_flag and decode_mode == "dense" and device_polygon_stage
+    plan.run(kp, ae, boxes_dev, n_dev, layout, tail="polygons" if device_polygons else "lists",
+             obj_pixel_th=int(decode_cfg.obj_pixel_th))
+    return plan, identity, device_polygons
 
 
 def group_kp(hm_kp, hm_ae, transforms, center_whs, center_indexes, center_cls, center_confs, info, decode_cfg, device):
@@ -400,7 +405,25 @@ def group_kp(hm_kp, hm_ae, transforms, center_whs, center_indexes, center_cls, c
     whs = np.vstack(center_whs).astype(np.float32).reshape(-1, 2)
     boxes = torch.from_numpy(np.ascontiguousarray(np.concatenate([centres, whs], axis=1))[None]).to(dev)
     n_dev = torch.tensor([objs_num], dtype=torch.int32, device=dev)
-    plan, identity = _run_plan(kp, ae, boxes, n_dev, _lib.ISG_BOX_CYCXHW, decode_cfg, transforms, dev, objs_num)
+    plan, identity, device_polygons = _run_plan(kp, ae, boxes, n_dev, _lib.ISG_BOX_CYCXHW, decode_cfg, transforms, dev, objs_num)
+    if device_polygons:
+        tot = int(plan.img_total[0].item())
+        if tot == 0:                                                 # :300
+            return [], [], [], []
+        st = plan.inst_start[0, :objs_num].cpu().tolist(); ct = plan.inst_count[0, :objs_num].cpu().tolist()
+        fl = plan.inst_flags[0, :objs_num].cpu().tolist()
+        pts = plan.poly_points[0, :tot].cpu().numpy()
+        centers_xy = np.ascontiguousarray(centres[:, ::-1])          # detransform_pixel flip, (x,y) fp32
+        n_clss, n_confs, n_centers, kps = [], [], [], []
+        for i in range(objs_num):
+            poly = None
+            if fl[i] == 1:
+                poly = pts[st[i]:st[i] + ct[i]].copy()
+            elif fl[i] == 2:                                         # more points than the device stage handles
+                poly = aug_group(pts[st[i]:st[i] + ct[i]].copy(), centers_xy[i])
+            if poly is not None:
+                kps.append(poly); n_centers.append(centers_xy[i]); n_clss.append(center_cls[i]); n_confs.append(center_confs[i])
+        return n_clss, n_confs, n_centers, kps
     if decode_cfg.draw_flag:
         mask = select_points(kp[0], decode_cfg.kp_th)
         draw_kp_mask(mask, transforms, decode_cfg.kp_th, info, "bound")
@@ -505,6 +528,34 @@ def decode_ct_hm(conf_mat, cls_mat, wh, num_classes, cls_th, transforms, info):
     return keep_cls, keep_idx, keep_confs, keep_whs
 
 
+def _dets_from_device_polygons(plan, B, n_keep, rois, scores, cls, decode_cfg):
+    """Assemble decode_output's result from isg_instance_polygons' buffers (one read-back per buffer)."""
+    totals = plan.img_total.cpu().numpy()
+    tot = int(totals.max(initial=0))
+    starts = plan.inst_start.cpu().numpy(); cnts = plan.inst_count.cpu().numpy(); flags = plan.inst_flags.cpu().numpy()
+    pts = plan.poly_points[:, :max(tot, 1)].cpu().numpy()
+    dets = []
+    for b in range(B):
+        n = int(n_keep[b])
+        if n == 0 or totals[b] == 0:                                # :426-427, :300
+            dets.append([]); continue
+        r = rois[b, :n]
+        centres_xy = (r[:, :2] + r[:, 2:]) / 2                       # :428-432 + detransform_pixel flip -> (x,y)
+        fl, st, ct = flags[b, :n].tolist(), starts[b, :n].tolist(), cnts[b, :n].tolist()
+        cls_b, sc_b, pb = cls[b, :n].astype(np.int64), scores[b, :n], pts[b]
+        out = []
+        for i in range(n):
+            f = fl[i]
+            if f == 1:
+                out.append((cls_b[i], sc_b[i], centres_xy[i], pb[st[i]:st[i] + ct[i]].copy()))
+            elif f == 2:                                            # more points than the device stage handles
+                poly = aug_group(pb[st[i]:st[i] + ct[i]].copy(), centres_xy[i])
+                if poly is not None:
+                    out.append((cls_b[i], sc_b[i], centres_xy[i], poly))
+        dets.append(out)
+    return dets
+
+
 def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
     """:444-461 — decode the model output of a batch into per-image lists of
     (class id, confidence, centre (x,y) fp32[2], polygon fp32[K,2] (x,y))."""
@@ -525,7 +576,12 @@ def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
         plan = engine.get_decode_plan(B, H, W, bplan.N, int(decode_cfg.kp_th), dev, decode_mode, want_score=False,
                                       wh_delta=float(decode_cfg.wh_delta) if identity else None,
                                       scale=float(compute_scale(None)))
-        engine.get_pipeline(bplan, plan).run(kp, ae, anc, reg, cls_t, decode_cfg.cls_th, decode_cfg.iou_th)
+        # identity val-transform without drawing: the whole per-instance stage (point sets, internal point, angular
+        # sort, centre test) runs on the device; otherwise the device emits the point sets and the host finishes
+        device_polygons = identity and not decode_cfg.draw_flag and decode_mode == "dense" and device_polygon_stage
+        engine.get_pipeline(bplan, plan).run(kp, ae, anc, reg, cls_t, decode_cfg.cls_th, decode_cfg.iou_th,
+                                             tail="polygons" if device_polygons else "lists",
+                                             obj_pixel_th=int(decode_cfg.obj_pixel_th))
         # one read-back for the whole batch
         n_cand = bplan.cand_count.cpu().numpy()
         n_keep = bplan.n_keep.cpu().numpy()
@@ -540,6 +596,10 @@ def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
     import time as _time
     _t0 = _time.perf_counter()
     rois = bplan.rois.cpu().numpy(); scores = bplan.scores.cpu().numpy(); cls = bplan.cls.cpu().numpy()
+    if device_polygons:
+        dets = _dets_from_device_polygons(plan, B, n_keep, rois, scores, cls, decode_cfg)
+        last_timing.update(readback_s=0.0, host_polygons_s=_time.perf_counter() - _t0)
+        return dets
     counts = plan.count.cpu().numpy()
     offsets = plan.offsets.cpu().numpy()
     tot = int(offsets[np.arange(B), np.minimum(n_keep, bplan.N)].max(initial=0))

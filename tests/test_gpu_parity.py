@@ -198,12 +198,13 @@ def _all_memberships(rd, img):
 
 
 @pytest.mark.parametrize("name", ["s0", "s1", "s2", "s3"])
-@pytest.mark.parametrize("mode", ["sparse", "dense"])
+@pytest.mark.parametrize("mode", ["sparse", "dense", "dense-host-polygons"])
 def test_decode_single_golden(mods, golden, name, mode):
     """the drop-in decode_single against polygons produced by the reference itself"""
     g = golden("decode_single_" + name)
     dec = mods["decode"]
-    dec.decode_mode = mode
+    saved = dec.decode_mode, dec.device_polygon_stage
+    dec.decode_mode, dec.device_polygon_stage = mode.split("-")[0], not mode.endswith("host-polygons")
     try:
         h, w = g["kp"].shape[-2:]
         boxes = {"rois": g["rois"], "class_ids": g["class_ids"], "scores": g["scores"]}
@@ -211,13 +212,16 @@ def test_decode_single_golden(mods, golden, name, mode):
                                     TransInfo("/nonexistent.png", (h, w)), IdentityTransforms(),
                                     DecodeCfg(kp_th=int(g["kp_th"])), torch.device(DEV))
     finally:
-        dec.decode_mode = "sparse"
+        dec.decode_mode, dec.device_polygon_stage = saved
     assert len(dets) == int(g["n_dets"])
     for i, (cls, conf, ctr, poly) in enumerate(dets):
         assert int(cls) == int(g["det_cls_%d" % i])
         assert np.float32(conf) == g["det_conf_%d" % i]
         assert np.array_equal(ctr, g["det_ctr_%d" % i])
-        assert np.array_equal(poly, g["det_poly_%d" % i])
+        if mode == "dense":      # device polygon stage: equal-angle points may come in a different order
+            assert_polygon_equivalent(dec, poly, g["det_poly_%d" % i], ctr)
+        else:
+            assert np.array_equal(poly, g["det_poly_%d" % i])
 
 
 def test_decode_single_no_boxes(mods):
@@ -311,7 +315,7 @@ def test_tv_nms_vs_torchvision(mods):
 
 
 # ---------------------------------------------------------------------------------------------- full decode
-@pytest.mark.parametrize("mode", ["sparse", "dense"])
+@pytest.mark.parametrize("mode", ["sparse", "dense", "dense-host-polygons"])
 def test_decode_output_vs_oracle(mods, oracle, mode):
     rd, _ = oracle
     synth, dec = mods["synth"], mods["decode"]
@@ -322,20 +326,36 @@ def test_decode_output_vs_oracle(mods, oracle, mode):
     reg = torch.from_numpy(np.stack([s[1] for s in scenes])); cls = torch.from_numpy(np.stack([s[2] for s in scenes]))
     anc = torch.from_numpy(anchors)
     want = rd.decode_output(H, W, ((kp, ae, None), reg, cls, anc), kp_th=3000)
-    dec.decode_mode = mode
+    saved = dec.decode_mode, dec.device_polygon_stage
+    dec.decode_mode, dec.device_polygon_stage = mode.split("-")[0], not mode.endswith("host-polygons")
     try:
         inputs = torch.zeros((B, 3, H, W))
         infos = [TransInfo("/nonexistent.png", (H, W))] * B
         got = dec.decode_output(inputs, ((kp.to(DEV), ae.to(DEV), None), reg.to(DEV), cls.to(DEV), anc.to(DEV)), infos,
                                 IdentityTransforms(), DecodeCfg(kp_th=3000), torch.device(DEV))
     finally:
-        dec.decode_mode = "sparse"
+        dec.decode_mode, dec.device_polygon_stage = saved
     assert len(got) == B and len(got[1]) == 0
     for b in range(B):
         assert len(got[b]) == len(want[b]) and (b == 1 or len(got[b]) > 0)
         for (c1, f1, ctr1, p1), (c2, f2, ctr2, p2) in zip(got[b], want[b]):
             assert int(c1) == int(c2) and np.float32(f1) == np.float32(f2)
-            assert np.array_equal(ctr1, ctr2) and np.array_equal(p1, p2)
+            assert np.array_equal(ctr1, ctr2)
+            assert_polygon_equivalent(dec, p1, p2, ctr2)
+
+
+def assert_polygon_equivalent(dec, got, want, centre_xy):
+    """Bit-exact, except that points with EQUAL polar angle about the internal point may come in any order
+    (np.argsort's order among equal keys is unspecified; the device sort keeps them row-major)."""
+    if np.array_equal(got, want):
+        return
+    assert got.shape == want.shape and got.dtype == want.dtype
+    key = lambda a: a[np.lexsort((a[:, 0], a[:, 1]))]
+    assert np.array_equal(key(got), key(want)), "different point sets"
+    internal = np.asarray(dec.find_internal_point(want, np.asarray(centre_xy, dtype=np.float32)), dtype=np.float32)
+    th_g = dec._polar_angles(got, np.repeat(internal[None], len(got), 0))
+    th_w = dec._polar_angles(want, np.repeat(internal[None], len(want), 0))
+    assert np.array_equal(th_g, th_w, equal_nan=True), "polygons differ beyond the order of equal-angle points"
 
 
 def test_decode_output_from_host_tensors(mods):
