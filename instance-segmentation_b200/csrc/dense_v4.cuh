@@ -209,18 +209,25 @@ tile_lists_kernel(const SeedRec* __restrict__ seeds, const int32_t* __restrict__
   uint16_t* ov = ovf + (size_t)t * Nmax;
   const int4* src = reinterpret_cast<const int4*>(seeds + (size_t)b * Nmax);
   int cnt = 0;
-  for (int j0 = 0; j0 < n; j0 += 32) {
-    const int j = j0 + lane;
-    bool hit = false;
-    int4 lo = make_int4(0, 0, 0, 0);
-    if (j < n) { lo = __ldg(src + 2 * j); hit = lo.x <= y1 && lo.y >= y0 && lo.z <= x1 && lo.w >= x0 && lo.x <= lo.y && lo.z <= lo.w; }
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (hit) {
-      const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-      ov[pos] = (uint16_t)j;
-      if (pos < cap) { recs[2 * pos] = lo; recs[2 * pos + 1] = __ldg(src + 2 * j + 1); }
+  for (int j0 = 0; j0 < n; j0 += 128) {            // 4 independent loads per lane in flight (the loop is latency-bound)
+    int4 lo[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 32 + lane;
+      lo[u] = (j < n) ? __ldg(src + 2 * j) : make_int4(1, 0, 1, 0);     // empty box
     }
-    cnt += __popc(bal);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 32 + lane;
+      const bool hit = lo[u].x <= y1 && lo[u].y >= y0 && lo[u].z <= x1 && lo[u].w >= x0 && lo[u].x <= lo[u].y && lo[u].z <= lo[u].w;
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+        ov[pos] = (uint16_t)j;
+        if (pos < cap) { recs[2 * pos] = lo[u]; recs[2 * pos + 1] = __ldg(src + 2 * j + 1); }
+      }
+      cnt += __popc(bal);
+    }
   }
   if (lane == 0) {
     TileHdr h;

@@ -22,12 +22,12 @@ namespace isg {
 constexpr int kPolyThreads = 256;
 constexpr int kPolyWarps = kPolyThreads / 32;
 constexpr int kPolyMaxPoints = 2048;     // points of one instance handled on the device (more: flagged, host fallback)
-constexpr int kPolyMaskWords = 4096;     // matched-bit masks cached in shared memory between the two passes
+constexpr int kPolyRankSort = 512;       // up to this many points: rank sort instead of the bitonic network
+constexpr int kPolyMaxCand = 4096;       // keep pixels inside one instance's ghost range listed in shared memory
 
 struct PolySmem {
   float2 pts[kPolyMaxPoints];
   unsigned long long keys[kPolyMaxPoints];
-  uint32_t masks[kPolyMaskWords];
   int warp_tot[kPolyWarps];
   int red_i[kPolyWarps];
   int red_j[kPolyWarps];
@@ -120,42 +120,74 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
   const int w_lo = x_lo >> 5, w_hi = x_hi >> 5;
   const int Wb = empty_range ? 0 : (w_hi - w_lo + 1), R = empty_range ? 0 : (y_hi - y_lo + 1);
   const int NW = Wb * R;
-  const bool cached = NW <= kPolyMaskWords;
   const uint32_t* kb = keepbits + (size_t)b * H * Wwords;
   const int32_t* lm = label_map + (size_t)b * H * W;
 
-  auto matched_mask = [&](int w) -> uint32_t {                  // word w of the box (row-major), bits of this instance
+  auto box_word = [&](int w, int& y, int& xb) -> uint32_t {     // keep bits of word w of the box (row-major), clipped
     const int r = w / Wb, c = w - r * Wb;
-    const int y = y_lo + r, wx = w_lo + c;
+    const int wx = w_lo + c;
+    y = y_lo + r; xb = wx << 5;
     uint32_t m = __ldg(kb + (size_t)y * Wwords + wx);
     if (wx == w_lo) m &= 0xffffffffu << (x_lo & 31);
     if (wx == w_hi) m &= 0xffffffffu >> (31 - (x_hi & 31));
-    uint32_t out = 0;
-    while (m) {
-      const int bit = __ffs(m) - 1;
-      m &= m - 1;
-      if (__ldg(lm + (size_t)y * W + (wx << 5) + bit) == inst) out |= 1u << bit;
-    }
-    return out;
+    return m;
+  };
+  // exclusive prefix of `v` over the CTA in thread order; `total` = sum (every thread calls it)
+  auto block_scan = [&](int v, int& total) -> int {
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    __syncthreads();
+    if (lane == 31) s.warp_tot[warp] = incl;
+    __syncthreads();
+    int base = incl - v;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < kPolyWarps; ++w) { const int t = s.warp_tot[w]; if (w < warp) base += t; total += t; }
+    return base;
   };
 
-  // ---- pass 1: count (blocked assignment keeps row-major order) ----
+  // ---- candidates: keep pixels inside the range, row-major (blocked word assignment keeps the order) ----
   const int q = (NW + kPolyThreads - 1) / kPolyThreads;
   const int w0 = min(tid * q, NW), w1 = min(w0 + q, NW);
-  int mine = 0;
-  for (int w = w0; w < w1; ++w) {
-    const uint32_t m = matched_mask(w);
-    if (cached) s.masks[w] = m;
-    mine += __popc(m);
+  int ncand_mine = 0;
+  for (int w = w0; w < w1; ++w) { int y, xb; ncand_mine += __popc(box_word(w, y, xb)); }
+  int C = 0;
+  const int cbase = block_scan(ncand_mine, C);
+  uint32_t* cand = reinterpret_cast<uint32_t*>(s.keys);          // [kPolyMaxCand] packed (y << 16 | x), shares the sort buffer
+  const bool listed = C <= kPolyMaxCand && H <= 65535 && W <= 65535;
+  int K = 0, base = 0;
+  if (listed) {
+    {
+      int pos = cbase;
+      for (int w = w0; w < w1; ++w) {
+        int y, xb;
+        uint32_t m = box_word(w, y, xb);
+        while (m) { const int bit = __ffs(m) - 1; m &= m - 1; cand[pos++] = ((uint32_t)y << 16) | (uint32_t)(xb + bit); }
+      }
+    }
+    __syncthreads();
+    // label look-ups: one candidate per thread, all in flight at once
+    for (int c = tid; c < C; c += kPolyThreads) {
+      const uint32_t v = cand[c];
+      if (__ldg(lm + (size_t)(v >> 16) * W + (v & 0xffffu)) != inst) cand[c] = 0xffffffffu;
+    }
+    __syncthreads();
+    const int qc = (C + kPolyThreads - 1) / kPolyThreads;
+    const int c0 = min(tid * qc, C), c1 = min(c0 + qc, C);
+    int mine = 0;
+    for (int c = c0; c < c1; ++c) mine += cand[c] != 0xffffffffu;
+    base = block_scan(mine, K);
+  } else {
+    // very many keep pixels in the range: test the labels word by word
+    int mine = 0;
+    for (int w = w0; w < w1; ++w) {
+      int y, xb;
+      uint32_t m = box_word(w, y, xb);
+      while (m) { const int bit = __ffs(m) - 1; m &= m - 1; mine += __ldg(lm + (size_t)y * W + xb + bit) == inst; }
+    }
+    base = block_scan(mine, K);
   }
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-  if (lane == 31) s.warp_tot[warp] = incl;
-  __syncthreads();
-  int base = incl - mine, K = 0;
-#pragma unroll
-  for (int w = 0; w < kPolyWarps; ++w) { const int t = s.warp_tot[w]; if (w < warp) base += t; K += t; }
 
   __shared__ int s_start;
   if (tid == 0) {
@@ -168,25 +200,30 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
   const bool fits = K <= kPolyMaxPoints && start + K <= cap;
   float2* out = poly_points + (size_t)b * cap + start;
 
-  // ---- pass 2: emit the points (x,y) fp32, row-major; bbox for the statistics ----
+  // ---- emit the points (x,y) fp32, row-major; bbox for the statistics ----
   int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -1, by1 = -1;
-  {
+  auto emit = [&](int pos, int x, int y) {
+    bx0 = min(bx0, x); bx1 = max(bx1, x); by0 = min(by0, y); by1 = max(by1, y);
+    const float2 p = make_float2((float)x, (float)y);
+    if (fits) s.pts[pos] = p;
+    else if (start + pos < cap) out[pos] = p;                     // too many points for the device stage: raw set
+  };
+  if (listed) {
+    const int qc = (C + kPolyThreads - 1) / kPolyThreads;
+    const int c0 = min(tid * qc, C), c1 = min(c0 + qc, C);
+    int pos = base;
+    for (int c = c0; c < c1; ++c) {
+      const uint32_t v = cand[c];
+      if (v != 0xffffffffu) emit(pos++, (int)(v & 0xffffu), (int)(v >> 16));
+    }
+  } else {
     int pos = base;
     for (int w = w0; w < w1; ++w) {
-      uint32_t m = cached ? s.masks[w] : matched_mask(w);
-      if (!m) continue;
-      const int r = w / Wb, c = w - r * Wb;
-      const int y = y_lo + r, xb = (w_lo + c) << 5;
-      by0 = min(by0, y); by1 = max(by1, y);
+      int y, xb;
+      uint32_t m = box_word(w, y, xb);
       while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        const int x = xb + bit;
-        bx0 = min(bx0, x); bx1 = max(bx1, x);
-        const float2 p = make_float2((float)x, (float)y);
-        if (fits) s.pts[pos] = p;
-        else if (start + pos < cap) out[pos] = p;                 // too many points for the device stage: raw set
-        ++pos;
+        const int bit = __ffs(m) - 1; m &= m - 1;
+        if (__ldg(lm + (size_t)y * W + xb + bit) == inst) emit(pos++, xb + bit, y);
       }
     }
   }
@@ -218,7 +255,22 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
   }
   float ix = cx, iy = cy;
   if (pip_block(s, s.pts, K, cx, cy) <= 0) {
-    if (tid == 0) {   // numpy mean(axis=0) of a C-contiguous [K,2] fp32 array: sequential fp32 sums, then / K
+    // numpy mean(axis=0) of a C-contiguous [K,2] fp32 array: sequential fp32 sums over the rows, then / K.  The
+    // coordinates are integers, so while K * max(W,H) < 2^24 every partial sum is an exactly representable integer
+    // and the sum does not depend on the order: reduce in parallel; otherwise add sequentially like numpy.
+    if ((long long)K * max(W, H) < (1ll << 24)) {
+      int sxi = 0, syi = 0;
+      for (int i = tid; i < K; i += kPolyThreads) { sxi += (int)s.pts[i].x; syi += (int)s.pts[i].y; }
+      sxi = warp_sum(sxi); syi = warp_sum(syi);
+      __syncthreads();
+      if (lane == 0) { s.red_i[warp] = sxi; s.red_j[warp] = syi; }
+      __syncthreads();
+      if (tid == 0) {
+        int tx = 0, ty = 0;
+        for (int w = 0; w < kPolyWarps; ++w) { tx += s.red_i[w]; ty += s.red_j[w]; }
+        s.misc[0] = __fdiv_rn((float)tx, (float)K); s.misc[1] = __fdiv_rn((float)ty, (float)K);
+      }
+    } else if (tid == 0) {
       float sx = 0.0f, sy = 0.0f;
       for (int i = 0; i < K; ++i) { sx = __fadd_rn(sx, s.pts[i].x); sy = __fadd_rn(sy, s.pts[i].y); }
       s.misc[0] = __fdiv_rn(sx, (float)K); s.misc[1] = __fdiv_rn(sy, (float)K);
@@ -268,17 +320,40 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
     s.keys[i] = key;
   }
   __syncthreads();
-  for (int k2 = 2; k2 <= Kp; k2 <<= 1) {
-    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-      for (int i = tid; i < Kp; i += kPolyThreads) {
-        const int l = i ^ j2;
-        if (l > i) {
-          const unsigned long long a = s.keys[i], c = s.keys[l];
-          const bool up = (i & k2) == 0;
-          if ((a > c) == up) { s.keys[i] = c; s.keys[l] = a; }
+  if (K <= kPolyRankSort) {
+    // small sets: rank sort - every key counts the keys below it (broadcast reads, no barriers); keys are distinct
+    // because they carry the index, so the ranks are a permutation
+    unsigned long long mykey[kPolyRankSort / kPolyThreads];
+    int myrank[kPolyRankSort / kPolyThreads];
+#pragma unroll
+    for (int u = 0; u < kPolyRankSort / kPolyThreads; ++u) {
+      const int i = tid + u * kPolyThreads;
+      mykey[u] = (i < K) ? s.keys[i] : ~0ull;
+      myrank[u] = 0;
+    }
+    for (int j = 0; j < K; ++j) {
+      const unsigned long long kj = s.keys[j];
+#pragma unroll
+      for (int u = 0; u < kPolyRankSort / kPolyThreads; ++u) myrank[u] += kj < mykey[u];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPolyRankSort / kPolyThreads; ++u)
+      if (tid + u * kPolyThreads < K) s.keys[myrank[u]] = mykey[u];
+    __syncthreads();
+  } else {
+    for (int k2 = 2; k2 <= Kp; k2 <<= 1) {
+      for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+        for (int i = tid; i < Kp; i += kPolyThreads) {
+          const int l = i ^ j2;
+          if (l > i) {
+            const unsigned long long a = s.keys[i], c = s.keys[l];
+            const bool up = (i & k2) == 0;
+            if ((a > c) == up) { s.keys[i] = c; s.keys[l] = a; }
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   // sorted polygon -> global, and keep a sorted copy in shared memory for the final test

@@ -528,12 +528,18 @@ def decode_ct_hm(conf_mat, cls_mat, wh, num_classes, cls_th, transforms, info):
     return keep_cls, keep_idx, keep_confs, keep_whs
 
 
+def _host(t):
+    """device tensor -> numpy, counting the bytes read back (bench.py reports them)"""
+    last_timing["d2h_bytes"] = last_timing.get("d2h_bytes", 0) + t.numel() * t.element_size()
+    return t.cpu().numpy()
+
+
 def _dets_from_device_polygons(plan, B, n_keep, rois, scores, cls, decode_cfg):
     """Assemble decode_output's result from isg_instance_polygons' buffers (one read-back per buffer)."""
-    totals = plan.img_total.cpu().numpy()
+    totals = _host(plan.img_total)
     tot = int(totals.max(initial=0))
-    starts = plan.inst_start.cpu().numpy(); cnts = plan.inst_count.cpu().numpy(); flags = plan.inst_flags.cpu().numpy()
-    pts = plan.poly_points[:, :max(tot, 1)].cpu().numpy()
+    starts = _host(plan.inst_start); cnts = _host(plan.inst_count); flags = _host(plan.inst_flags)
+    pts = _host(plan.poly_points[:, :max(tot, 1)])
     dets = []
     for b in range(B):
         n = int(n_keep[b])
@@ -556,9 +562,53 @@ def _dets_from_device_polygons(plan, B, n_keep, rois, scores, cls, decode_cfg):
     return dets
 
 
+# host-resident model outputs are uploaded and decoded in chunks of this many images, the upload of chunk k+1
+# overlapping the kernels / read-back / list assembly of chunk k (0 disables the chunking)
+host_chunk_images = int(os.environ.get("ISG_HOST_CHUNK", "2"))
+_copy_streams = {}
+
+
 def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
     """:444-461 — decode the model output of a batch into per-image lists of
-    (class id, confidence, centre (x,y) fp32[2], polygon fp32[K,2] (x,y))."""
+    (class id, confidence, centre (x,y) fp32[2], polygon fp32[K,2] (x,y)).
+    Outputs that live in (pinned) host memory are streamed to the device chunk by chunk."""
+    kp_out, regression, classification, anchors = outs
+    dev = require_cuda(device if device is not None else globals()["device"])
+    B = kp_out[0].shape[0]
+    cb = host_chunk_images
+    on_host = all(t.device.type == "cpu" for t in (kp_out[0], kp_out[1], regression, classification))
+    if not (on_host and cb > 0 and B > cb):
+        return _decode_output_batch(inputs, outs, infos, transforms, decode_cfg, dev)
+    if dev.index not in _copy_streams:
+        _copy_streams[dev.index] = torch.cuda.Stream(device=dev)
+    cs = _copy_streams[dev.index]
+    main = torch.cuda.current_stream(dev)
+    anc = engine.as_f32_planes(anchors, dev).contiguous()
+
+    def upload(b0):
+        b1 = min(b0 + cb, B)
+        with torch.cuda.stream(cs):
+            t = [x[b0:b1].to(dev, non_blocking=True) for x in (kp_out[0], kp_out[1], regression, classification)]
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        return b0, b1, t, ev
+
+    dets, timing = [], {}
+    nxt = upload(0)
+    while nxt is not None:
+        b0, b1, t, ev = nxt
+        nxt = upload(b1) if b1 < B else None                       # enqueue the next upload before decoding this chunk
+        main.wait_event(ev)
+        sub_inputs = inputs[b0:b1] if inputs.shape[0] == B else inputs
+        dets += _decode_output_batch(sub_inputs, ((t[0], t[1], None), t[2], t[3], anc), infos[b0:b1], transforms, decode_cfg, dev)
+        for k, v in last_timing.items():
+            timing[k] = timing.get(k, 0.0) + v
+    last_timing.update(timing)
+    return dets
+
+
+def _decode_output_batch(inputs, outs, infos, transforms, decode_cfg, device):
+    """decode_output for one device-sized batch"""
     kp_out, regression, classification, anchors = outs
     dev = require_cuda(device if device is not None else globals()["device"])
     kp = engine.as_f32_planes(kp_out[0], dev)
@@ -583,8 +633,9 @@ def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
                                              tail="polygons" if device_polygons else "lists",
                                              obj_pixel_th=int(decode_cfg.obj_pixel_th))
         # one read-back for the whole batch
-        n_cand = bplan.cand_count.cpu().numpy()
-        n_keep = bplan.n_keep.cpu().numpy()
+        last_timing["d2h_bytes"] = 0
+        n_cand = _host(bplan.cand_count)
+        n_keep = _host(bplan.n_keep)
         if n_cand.max(initial=0) > bplan.cap:
             if bplan.cap >= min(_lib.ISG_NMS_MAX_BOXES, bplan.A):
                 raise RuntimeError("decode_output: %d candidates above cls_th exceed the supported %d per image"
@@ -595,15 +646,15 @@ def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
         break
     import time as _time
     _t0 = _time.perf_counter()
-    rois = bplan.rois.cpu().numpy(); scores = bplan.scores.cpu().numpy(); cls = bplan.cls.cpu().numpy()
+    rois = _host(bplan.rois); scores = _host(bplan.scores); cls = _host(bplan.cls)
     if device_polygons:
         dets = _dets_from_device_polygons(plan, B, n_keep, rois, scores, cls, decode_cfg)
         last_timing.update(readback_s=0.0, host_polygons_s=_time.perf_counter() - _t0)
         return dets
-    counts = plan.count.cpu().numpy()
-    offsets = plan.offsets.cpu().numpy()
+    counts = _host(plan.count)
+    offsets = _host(plan.offsets)
     tot = int(offsets[np.arange(B), np.minimum(n_keep, bplan.N)].max(initial=0))
-    points = plan.points[:, :max(tot, 1)].cpu().numpy()
+    points = _host(plan.points[:, :max(tot, 1)])
     _t1 = _time.perf_counter()
     dets = []
     for b in range(B):
