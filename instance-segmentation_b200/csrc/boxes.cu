@@ -159,7 +159,10 @@ __device__ __forceinline__ bool suppresses_tv(const float4 a, const float4 c, do
   const float xx1 = fmaxf(a.x, c.x), yy1 = fmaxf(a.y, c.y), xx2 = fminf(a.z, c.z), yy2 = fminf(a.w, c.w);
   const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
   const float inter = __fmul_rn(w, h);
-  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(areaa, areac), inter));
+  const float uni = __fsub_rn(__fadd_rn(areaa, areac), inter);
+  // disjoint boxes (the common case): 0 / uni is exactly +0 for uni > 0; skipping the division avoids the slow
+  // special-operand path of the IEEE divide, which a zero numerator always takes
+  const float ovr = (inter == 0.0f && uni > 0.0f) ? 0.0f : __fdiv_rn(inter, uni);
   return (double)ovr > thr;
 }
 __device__ __forceinline__ bool suppresses_plus1(const float4 a, const float4 c, float thr) {
@@ -170,7 +173,8 @@ __device__ __forceinline__ bool suppresses_plus1(const float4 a, const float4 c,
   const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
   const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
   const float inter = __fmul_rn(w, h);
-  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(areaa, areac), inter));
+  const float uni = __fsub_rn(__fadd_rn(areaa, areac), inter);
+  const float ovr = (inter == 0.0f && uni > 0.0f) ? 0.0f : __fdiv_rn(inter, uni);   // see suppresses_tv
   return !(ovr <= thr);
 }
 

@@ -331,10 +331,15 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
       mykey[u] = (i < K) ? s.keys[i] : ~0ull;
       myrank[u] = 0;
     }
-    for (int j = 0; j < K; ++j) {
-      const unsigned long long kj = s.keys[j];
+    if (K <= kPolyThreads) {                    // one key per thread; warps without keys skip the loop
+      if ((tid & ~31) < K)
+        for (int j = 0; j < K; ++j) myrank[0] += s.keys[j] < mykey[0];
+    } else {
+      for (int j = 0; j < K; ++j) {
+        const unsigned long long kj = s.keys[j];
 #pragma unroll
-      for (int u = 0; u < kPolyRankSort / kPolyThreads; ++u) myrank[u] += kj < mykey[u];
+        for (int u = 0; u < kPolyRankSort / kPolyThreads; ++u) myrank[u] += kj < mykey[u];
+      }
     }
     __syncthreads();
 #pragma unroll
