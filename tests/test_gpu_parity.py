@@ -497,3 +497,85 @@ def test_fast_tanh_exp_accuracy(mods):
     # error budget: fp32 rounding of (e-c), its square, the product and the sum (~4 * 6e-8 * q) plus 2-ulp exp
     bound = 4e-6 + 1e-6 * q[ok]
     assert np.all(rel < bound), float((rel / bound).max())
+
+
+# ---------------------------------------------------------------------------------------------- round-1 additions
+def test_dense_tile_list_overflow(mods, oracle):
+    """crowded image: tiles overlapped by more seed boxes than the records staged next to a tile (16), so the dense
+    kernel walks the overflow index list; labels must still be the oracle's"""
+    rd, _ = oracle
+    H, W, N = 128, 256, 60
+    img = mods["synth"].make_image(4242, H, W, N)
+    x1, y1, x2, y2 = img.rois.T
+    worst = 0
+    for ty in range(0, H, 16):
+        for tx in range(0, W, 128):
+            hit = (np.ceil(y1) <= ty + 15) & (np.floor(y2) >= ty) & (np.ceil(x1) <= tx + 127) & (np.floor(x2) >= tx)
+            worst = max(worst, int(hit.sum()))
+    assert worst > 16, worst
+    core = rd.group_core(torch.from_numpy(img.kp[0]), torch.from_numpy(img.ae), img.rois, 3000)
+    plan = _run_plan(mods, img, 3000, "dense")
+    M = int(plan.count[0].item())
+    assert M == core["idx"].shape[0]
+    assert np.array_equal(plan.label[0, :M].cpu().numpy(), core["label"].numpy().astype(np.int32))
+    np.testing.assert_allclose(plan.score[0, :M].cpu().numpy(), core["score"].numpy(), rtol=RTOL, atol=ATOL)
+    score, label = rd.dense_labels(torch.from_numpy(img.ae), img.rois)
+    P = _all_memberships(rd, img)
+    top2 = np.sort(P, axis=2)[:, :, -2:]
+    safe = ((top2[:, :, 1] - top2[:, :, 0]) > 1e-5 * np.maximum(top2[:, :, 1], 1e-30)) | (top2[:, :, 1] == 0)
+    assert safe.mean() > 0.98
+    assert np.array_equal(plan.label_map[0].cpu().numpy()[safe], label.numpy()[safe].astype(np.int32))
+    # the sparse kernel (independent code path: exp + arg-max) agrees on every keep pixel
+    sp = _run_plan(mods, img, 3000, "sparse")
+    assert np.array_equal(sp.label[0, :M].cpu().numpy(), plan.label[0, :M].cpu().numpy())
+
+
+def test_decode_output_host_chunks_equal_device_batch(mods):
+    """host tensors are uploaded and decoded in chunks (uneven last chunk); same detections as one device batch"""
+    synth, dec = mods["synth"], mods["decode"]
+    H, W, C, B = 128, 256, 8, 5
+    anchors = synth.make_anchors(H, W)
+    scenes = [synth.make_scene(700 + b, H, W, [6, 3, 0, 9, 5][b], C, anchors) for b in range(B)]
+    kp = torch.from_numpy(np.stack([s[0].kp for s in scenes])); ae = torch.from_numpy(np.stack([s[0].ae for s in scenes]))
+    reg = torch.from_numpy(np.stack([s[1] for s in scenes])); cls = torch.from_numpy(np.stack([s[2] for s in scenes]))
+    anc = torch.from_numpy(anchors)
+    infos = [TransInfo("/nonexistent.png", (H, W))] * B
+    cfg, tf, inputs = DecodeCfg(kp_th=2000), IdentityTransforms(), torch.zeros((B, 3, H, W))
+    saved = dec.decode_mode, dec.host_chunk_images
+    dec.decode_mode, dec.host_chunk_images = "dense", 2
+    try:
+        got = dec.decode_output(inputs, ((kp.pin_memory(), ae.pin_memory(), None), reg.pin_memory(), cls.pin_memory(), anc),
+                                infos, tf, cfg, torch.device(DEV))
+        want = dec.decode_output(inputs, ((kp.to(DEV), ae.to(DEV), None), reg.to(DEV), cls.to(DEV), anc.to(DEV)), infos, tf,
+                                 cfg, torch.device(DEV))
+    finally:
+        dec.decode_mode, dec.host_chunk_images = saved
+    assert len(got) == len(want) == B and len(got[2]) == 0 and sum(len(g) for g in got) > 5
+    for g, w in zip(got, want):
+        assert len(g) == len(w)
+        for (c1, f1, k1, p1), (c2, f2, k2, p2) in zip(g, w):
+            assert int(c1) == int(c2) and f1 == f2 and np.array_equal(k1, k2) and np.array_equal(p1, p2)
+
+
+def test_polygon_stage_large_instance_falls_back(mods):
+    """an instance with more boundary points than the device polygon stage sorts (2048) is finished by the host from the
+    raw point set: same polygon as the all-host path"""
+    dec = mods["decode"]
+    H, W = 256, 512
+    rs = np.random.RandomState(11)
+    kp = torch.from_numpy(rs.permutation(H * W).astype(np.float32).reshape(H, W) / 1000.0)     # distinct values
+    ae = torch.zeros((4, H, W)); ae[2:] = np.log(200.0)
+    centre, wh = [np.array([128.5, 256.5], np.float32)], [np.array([250.0, 500.0], np.float32)]
+    cfg = DecodeCfg(kp_th=30000)
+    saved = dec.decode_mode, dec.device_polygon_stage
+    out = {}
+    try:
+        for name, flag in (("device", True), ("host", False)):
+            dec.decode_mode, dec.device_polygon_stage = "dense", flag
+            out[name] = dec.group_kp(kp.to(DEV), ae.to(DEV), IdentityTransforms(), wh, centre, [3], [0.9],
+                                     TransInfo("x", (H, W)), cfg, torch.device(DEV))
+    finally:
+        dec.decode_mode, dec.device_polygon_stage = saved
+    assert len(out["host"][3]) == len(out["device"][3])
+    for p1, p2 in zip(out["host"][3], out["device"][3]):
+        assert p1.shape[0] > 2048 and np.array_equal(p1, p2)
