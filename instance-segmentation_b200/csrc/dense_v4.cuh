@@ -192,6 +192,9 @@ __global__ void __launch_bounds__(256)
 tile_lists_kernel(const SeedRec* __restrict__ seeds, const int32_t* __restrict__ n_seeds,
                   const uint32_t* __restrict__ thr_key, int Nmax, int B, int H, int W, int TH, int tilesX, int tilesY,
                   int cap, unsigned char* __restrict__ lists, uint16_t* __restrict__ ovf) {
+  // programmatic dependent launch: let the dense kernel's CTAs start (barrier init, first kp/ae loads) while this
+  // grid is still running; its producer waits on the grid dependency before it touches a list
+  asm volatile("griddepcontrol.launch_dependents;");
   const int lane = threadIdx.x & 31;
   const long long T = (long long)B * tilesX * tilesY;
   const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -279,6 +282,8 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
     unsigned t;
     if (n_static > 0) { t = blockIdx.x; i_static = 1; }
     else { t = dyn; dyn = (t < T) ? T_s + atomicAdd(&sched[0], 1u) : T; }
+    // the tile lists come from the preceding grid (tile_lists_kernel): wait for it (no-op without PDL)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     while (t < T) {
       const int b = (int)(t / (unsigned)tiles_per_img);
       const int rem = (int)t - b * tiles_per_img;
@@ -561,16 +566,26 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   tile_lists_kernel<<<(unsigned)cdiv64(T, 8), 256, 0, stream>>>(srec, n_seeds, thr_key, Nmax, B, H, W, Geo::TH, tilesX, tilesY, cap,
                                                                 lists, ovf);
   ISG_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const char* pdl_env = getenv("ISG_DENSE_PDL");
+  cfg.attrs = attr; cfg.numAttrs = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
+  const float4* ghost4 = reinterpret_cast<const float4*>(ghost);
+  const unsigned char* clists = lists;
+  const uint16_t* covf = ovf;
   if (score_map) {
     ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dense_v4_kernel<RW, WG, G, true><<<grid, threads, smem, stream>>>(
-        tm_kp, tm_ae, srec, reinterpret_cast<const float4*>(ghost), Nmax, B, H, W, Wwords, tilesX, tilesY, nstages, cap, lists,
-        ovf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail, dbg_flags);
+    ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, true>, tm_kp, tm_ae, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
+                                tilesY, nstages, cap, clists, covf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail,
+                                dbg_flags));
   } else {
     ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dense_v4_kernel<RW, WG, G, false><<<grid, threads, smem, stream>>>(
-        tm_kp, tm_ae, srec, reinterpret_cast<const float4*>(ghost), Nmax, B, H, W, Wwords, tilesX, tilesY, nstages, cap, lists,
-        ovf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail, dbg_flags);
+    ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, false>, tm_kp, tm_ae, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
+                                tilesY, nstages, cap, clists, covf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail,
+                                dbg_flags));
   }
   ISG_LAUNCH_CHECK();
   return ISG_OK;
