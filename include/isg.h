@@ -241,15 +241,19 @@ int isg_pairwise(const float* X, int M, const float* Y, int N, int D, int metric
  *   rois [B,Nmax,4] fp32 in `layout` (ISG_BOX_XYXY / ISG_BOX_CYCXHW, as given to isg_build_seeds); ghost [B,Nmax,4] from isg_build_seeds; cap = capacity of poly_points per image
  *   poly_points [B,cap,2] fp32 (x,y): instance i of image b occupies [inst_start, inst_start+inst_count) of image b's
  *     block - angle-sorted when a polygon was computed, row-major otherwise; blocks are allocated in completion order
- *   inst_flags [B,Nmax] uint8: 1 = polygon valid (centre strictly inside), 0 = no polygon, 2 = more than 2048 points:
- *     the raw row-major set was written and the caller finishes this instance (aug_group on the host)
+ *   inst_flags [B,Nmax] uint8: 1 = polygon valid (centre strictly inside), 0 = no polygon; instances with more than
+ *     2048 points are finished by a second kernel that works in global memory (needs `workspace`); without a workspace
+ *     they keep flag 2 and their raw row-major set, and the caller finishes them (aug_group on the host)
  *   inst_internal [B,Nmax,2] fp32 (nullable): the internal point used;  img_total [B] int32: points per image
  *   stats (nullable, pre-initialised by isg_stats_init): count / bbox per instance
+ *   workspace (nullable): isg_instance_polygons_workspace_bytes(B, cap) bytes, 256-byte aligned
  * ------------------------------------------------------------------------------------------ */
+size_t isg_instance_polygons_workspace_bytes(int B, int cap);
 int isg_instance_polygons(const uint32_t* keepbits, const int32_t* label_map, const float* rois, int layout, const float* ghost,
                           const int32_t* n_seeds, int B, int Nmax, int H, int W, int cap, int obj_pixel_th,
                           float* poly_points, int32_t* inst_start, int32_t* inst_count, uint8_t* inst_flags,
-                          float* inst_internal, int32_t* img_total, int32_t* stats, isg_stream_t stream);
+                          float* inst_internal, int32_t* img_total, int32_t* stats, void* workspace, size_t workspace_bytes,
+                          isg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * HOST helpers of the polygon stage (aug_group / find_internal_point, utils/decode.py:51-68,167-204).

@@ -21,7 +21,7 @@ namespace isg {
 
 constexpr int kPolyThreads = 256;
 constexpr int kPolyWarps = kPolyThreads / 32;
-constexpr int kPolyMaxPoints = 2048;     // points of one instance handled on the device (more: flagged, host fallback)
+constexpr int kPolyMaxPoints = 2048;     // points of one instance held in shared memory (more: the global-memory variant)
 constexpr int kPolyRankSort = 512;       // up to this many points: rank sort instead of the bitonic network
 constexpr int kPolyMaxCand = 4096;       // keep pixels inside one instance's ghost range listed in shared memory
 
@@ -91,6 +91,164 @@ __device__ __forceinline__ float polar_theta(float dx, float dy) {
   else if (dx > 0.0f && dy < 0.0f) seta = __fadd_rn(seta, __fmul_rn(2.0f, PI_F));
   return seta;
 }
+
+__device__ __forceinline__ float2 box_centre(const float4 r4, int layout) {
+  if (layout == ISG_BOX_XYXY)     // x1,y1,x2,y2: centre = (lt+rb)/2 (:430)
+    return make_float2(__fmul_rn(__fadd_rn(r4.x, r4.z), 0.5f), __fmul_rn(__fadd_rn(r4.y, r4.w), 0.5f));
+  return make_float2(r4.y, r4.x);   // cy,cx,h,w: group_kp's center_indexes
+}
+
+// Steps 3-5 for one instance: internal point, polar angles, stable sort, centre test.  pts[0..K) holds the row-major
+// point set and receives the sorted polygon (also written to out); keys needs room for the next power of two >= K.
+// LARGE = false: pts / keys are the CTA's shared-memory arrays (K <= kPolyMaxPoints).  LARGE = true: global memory,
+// tmp[0..K) is scratch for the permutation (the sequential-mean fall-back stages chunks through s.pts).
+// Returns 1 when the polygon is valid.  Must be called by the whole CTA.
+template <bool LARGE>
+__device__ int finish_polygon(PolySmem& s, float2* pts, unsigned long long* keys, float2* tmp, float2* out, int K, int W, int H,
+                              float cx, float cy, float2* internal_out) {
+  // ---- internal point (:51-68) ----
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float ix = cx, iy = cy;
+  if (pip_block(s, pts, K, cx, cy) <= 0) {
+    // numpy mean(axis=0) of a C-contiguous [K,2] fp32 array: sequential fp32 sums over the rows, then / K.  The
+    // coordinates are integers, so while K * max(W,H) < 2^24 every partial sum is an exactly representable integer
+    // and the sum does not depend on the order: reduce in parallel; otherwise add sequentially like numpy.
+    if ((long long)K * max(W, H) < (1ll << 24)) {
+      int sxi = 0, syi = 0;
+      for (int i = tid; i < K; i += kPolyThreads) { sxi += (int)pts[i].x; syi += (int)pts[i].y; }
+      sxi = warp_sum(sxi); syi = warp_sum(syi);
+      __syncthreads();
+      if (lane == 0) { s.red_i[warp] = sxi; s.red_j[warp] = syi; }
+      __syncthreads();
+      if (tid == 0) {
+        int tx = 0, ty = 0;
+        for (int w = 0; w < kPolyWarps; ++w) { tx += s.red_i[w]; ty += s.red_j[w]; }
+        s.misc[0] = __fdiv_rn((float)tx, (float)K); s.misc[1] = __fdiv_rn((float)ty, (float)K);
+      }
+    } else {
+      // sequential like numpy; the points are staged through shared memory chunk by chunk so that the one adding
+      // thread only pays the dependent adds
+      float sx = 0.0f, sy = 0.0f;
+      for (int c0 = 0; c0 < K; c0 += kPolyMaxPoints) {
+        const int m = min(kPolyMaxPoints, K - c0);
+        __syncthreads();
+        for (int i = tid; i < m; i += kPolyThreads) s.pts[i] = pts[c0 + i];
+        __syncthreads();
+        if (tid == 0)
+          for (int i = 0; i < m; ++i) { sx = __fadd_rn(sx, s.pts[i].x); sy = __fadd_rn(sy, s.pts[i].y); }
+      }
+      if (tid == 0) { s.misc[0] = __fdiv_rn(sx, (float)K); s.misc[1] = __fdiv_rn(sy, (float)K); }
+    }
+    __syncthreads();
+    const float mx = s.misc[0], my = s.misc[1];
+    if (pip_block(s, pts, K, mx, my) > 0) { ix = mx; iy = my; }
+    else {
+      // pair midpoints in the reference's order (i outer over [0,K), j inner over [1,K)); one candidate per warp
+      const long long ncand = (long long)K * (K - 1);
+      long long found = -1;
+      for (long long c0 = 0; c0 < ncand && found < 0; c0 += kPolyWarps) {
+        const long long c = c0 + warp;
+        int hit = 0;
+        if (c < ncand) {
+          const int i = (int)(c / (K - 1)), j = 1 + (int)(c - (long long)i * (K - 1));
+          const float qx = __fdiv_rn(__fadd_rn(pts[i].x, pts[j].x), 2.0f), qy = __fdiv_rn(__fadd_rn(pts[i].y, pts[j].y), 2.0f);
+          hit = pip_warp(pts, K, qx, qy, lane) > 0;
+        }
+        __syncthreads();
+        if (lane == 0) s.red_i[warp] = hit;
+        __syncthreads();
+        for (int w = 0; w < kPolyWarps; ++w) if (s.red_i[w]) { found = c0 + w; break; }
+      }
+      if (found >= 0) {
+        const int i = (int)(found / (K - 1)), j = 1 + (int)(found - (long long)i * (K - 1));
+        ix = __fdiv_rn(__fadd_rn(pts[i].x, pts[j].x), 2.0f); iy = __fdiv_rn(__fadd_rn(pts[i].y, pts[j].y), 2.0f);
+      }
+    }
+  }
+  if (tid == 0 && internal_out) *internal_out = make_float2(ix, iy);
+
+  // ---- polar angles + stable ascending sort (bitonic on (angle bits, index)) ----
+  int Kp = 1;
+  while (Kp < K) Kp <<= 1;
+  for (int i = tid; i < Kp; i += kPolyThreads) {
+    unsigned long long key = ~0ull;
+    if (i < K) {
+      const float2 p = pts[i];
+      float th = polar_theta(__fsub_rn(p.x, ix), __fsub_rn(p.y, iy));
+      th = th + 0.0f;                                                 // -0 -> +0
+      uint32_t tb = __float_as_uint(th);
+      if (th != th) tb = 0x7fffffffu;                                 // NaN sorts last (np.argsort)
+      else if (tb & 0x80000000u) tb = 0;                              // defensive: angles are never negative
+      key = ((unsigned long long)tb << 32) | (unsigned)i;
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  if (!LARGE && K <= kPolyRankSort) {
+    // small sets: rank sort - every key counts the keys below it (broadcast reads, no barriers); keys are distinct
+    // because they carry the index, so the ranks are a permutation
+    unsigned long long mykey[kPolyRankSort / kPolyThreads];
+    int myrank[kPolyRankSort / kPolyThreads];
+#pragma unroll
+    for (int u = 0; u < kPolyRankSort / kPolyThreads; ++u) {
+      const int i = tid + u * kPolyThreads;
+      mykey[u] = (i < K) ? keys[i] : ~0ull;
+      myrank[u] = 0;
+    }
+    if (K <= kPolyThreads) {                    // one key per thread; warps without keys skip the loop
+      if ((tid & ~31) < K)
+        for (int j = 0; j < K; ++j) myrank[0] += keys[j] < mykey[0];
+    } else {
+      for (int j = 0; j < K; ++j) {
+        const unsigned long long kj = keys[j];
+#pragma unroll
+        for (int u = 0; u < kPolyRankSort / kPolyThreads; ++u) myrank[u] += kj < mykey[u];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPolyRankSort / kPolyThreads; ++u)
+      if (tid + u * kPolyThreads < K) keys[myrank[u]] = mykey[u];
+    __syncthreads();
+  } else {
+    for (int k2 = 2; k2 <= Kp; k2 <<= 1) {
+      for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+        for (int i = tid; i < Kp; i += kPolyThreads) {
+          const int l = i ^ j2;
+          if (l > i) {
+            const unsigned long long a = keys[i], c = keys[l];
+            const bool up = (i & k2) == 0;
+            if ((a > c) == up) { keys[i] = c; keys[l] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  // sorted polygon -> global (and, for the shared-memory variant, a sorted copy in place for the final test)
+  if (!LARGE) {
+    float2 mine_pt[kPolyMaxPoints / kPolyThreads];
+#pragma unroll
+    for (int u = 0; u < kPolyMaxPoints / kPolyThreads; ++u) {
+      const int i = tid + u * kPolyThreads;
+      if (i < K) mine_pt[u] = pts[(int)(keys[i] & 0xffffffffu)];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPolyMaxPoints / kPolyThreads; ++u) {
+      const int i = tid + u * kPolyThreads;
+      if (i < K) { pts[i] = mine_pt[u]; out[i] = mine_pt[u]; }
+    }
+  } else {
+    for (int i = tid; i < K; i += kPolyThreads) tmp[i] = pts[(int)(keys[i] & 0xffffffffu)];
+    __syncthreads();
+    for (int i = tid; i < K; i += kPolyThreads) { const float2 v = tmp[i]; pts[i] = v; out[i] = v; }
+  }
+  __syncthreads();
+  // ---- centre strictly inside the sorted polygon (:201) ----
+  return pip_block(s, pts, K, cx, cy) > 0 ? 1 : 0;
+}
+
 
 __global__ void __launch_bounds__(kPolyThreads)
 instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* __restrict__ label_map,
@@ -238,146 +396,40 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
     if (tid == 0) st[0] = K;
   }
   __syncthreads();
-  if (!fits) { if (tid == 0) inst_flags[io] = (K >= obj_pixel_th) ? 2 : 0; return; }   // bit 1: host must finish this one
+  if (!fits) { if (tid == 0) inst_flags[io] = (K >= obj_pixel_th) ? 2 : 0; return; }   // 2: finished by the large-instance kernel
   if (K < obj_pixel_th || K == 0) {                                                 // :355
     for (int i = tid; i < K; i += kPolyThreads) out[i] = s.pts[i];
     if (tid == 0) inst_flags[io] = 0;
     return;
   }
 
-  // ---- internal point (:51-68) ----
-  const float4 r4 = rois[io];
-  float cx, cy;
-  if (layout == ISG_BOX_XYXY) {   // x1,y1,x2,y2: centre = (lt+rb)/2 (:430)
-    cx = __fmul_rn(__fadd_rn(r4.x, r4.z), 0.5f); cy = __fmul_rn(__fadd_rn(r4.y, r4.w), 0.5f);
-  } else {                        // cy,cx,h,w: group_kp's center_indexes
-    cx = r4.y; cy = r4.x;
-  }
-  float ix = cx, iy = cy;
-  if (pip_block(s, s.pts, K, cx, cy) <= 0) {
-    // numpy mean(axis=0) of a C-contiguous [K,2] fp32 array: sequential fp32 sums over the rows, then / K.  The
-    // coordinates are integers, so while K * max(W,H) < 2^24 every partial sum is an exactly representable integer
-    // and the sum does not depend on the order: reduce in parallel; otherwise add sequentially like numpy.
-    if ((long long)K * max(W, H) < (1ll << 24)) {
-      int sxi = 0, syi = 0;
-      for (int i = tid; i < K; i += kPolyThreads) { sxi += (int)s.pts[i].x; syi += (int)s.pts[i].y; }
-      sxi = warp_sum(sxi); syi = warp_sum(syi);
-      __syncthreads();
-      if (lane == 0) { s.red_i[warp] = sxi; s.red_j[warp] = syi; }
-      __syncthreads();
-      if (tid == 0) {
-        int tx = 0, ty = 0;
-        for (int w = 0; w < kPolyWarps; ++w) { tx += s.red_i[w]; ty += s.red_j[w]; }
-        s.misc[0] = __fdiv_rn((float)tx, (float)K); s.misc[1] = __fdiv_rn((float)ty, (float)K);
-      }
-    } else if (tid == 0) {
-      float sx = 0.0f, sy = 0.0f;
-      for (int i = 0; i < K; ++i) { sx = __fadd_rn(sx, s.pts[i].x); sy = __fadd_rn(sy, s.pts[i].y); }
-      s.misc[0] = __fdiv_rn(sx, (float)K); s.misc[1] = __fdiv_rn(sy, (float)K);
-    }
-    __syncthreads();
-    const float mx = s.misc[0], my = s.misc[1];
-    if (pip_block(s, s.pts, K, mx, my) > 0) { ix = mx; iy = my; }
-    else {
-      // pair midpoints in the reference's order (i outer over [0,K), j inner over [1,K)); one candidate per warp
-      const long long ncand = (long long)K * (K - 1);
-      long long found = -1;
-      for (long long c0 = 0; c0 < ncand && found < 0; c0 += kPolyWarps) {
-        const long long c = c0 + warp;
-        int hit = 0;
-        if (c < ncand) {
-          const int i = (int)(c / (K - 1)), j = 1 + (int)(c - (long long)i * (K - 1));
-          const float qx = __fdiv_rn(__fadd_rn(s.pts[i].x, s.pts[j].x), 2.0f), qy = __fdiv_rn(__fadd_rn(s.pts[i].y, s.pts[j].y), 2.0f);
-          hit = pip_warp(s.pts, K, qx, qy, lane) > 0;
-        }
-        __syncthreads();
-        if (lane == 0) s.red_i[warp] = hit;
-        __syncthreads();
-        for (int w = 0; w < kPolyWarps; ++w) if (s.red_i[w]) { found = c0 + w; break; }
-      }
-      if (found >= 0) {
-        const int i = (int)(found / (K - 1)), j = 1 + (int)(found - (long long)i * (K - 1));
-        ix = __fdiv_rn(__fadd_rn(s.pts[i].x, s.pts[j].x), 2.0f); iy = __fdiv_rn(__fadd_rn(s.pts[i].y, s.pts[j].y), 2.0f);
-      }
-    }
-  }
-  if (tid == 0 && inst_internal) inst_internal[io] = make_float2(ix, iy);
+  const float2 centre = box_centre(rois[io], layout);
+  const int ok = finish_polygon<false>(s, s.pts, s.keys, nullptr, out, K, W, H, centre.x, centre.y,
+                                       inst_internal ? inst_internal + io : nullptr);
+  if (tid == 0) inst_flags[io] = ok ? 1 : 0;
+}
 
-  // ---- polar angles + stable ascending sort (bitonic on (angle bits, index)) ----
-  int Kp = 1;
-  while (Kp < K) Kp <<= 1;
-  for (int i = tid; i < Kp; i += kPolyThreads) {
-    unsigned long long key = ~0ull;
-    if (i < K) {
-      const float2 p = s.pts[i];
-      float th = polar_theta(__fsub_rn(p.x, ix), __fsub_rn(p.y, iy));
-      th = th + 0.0f;                                                 // -0 -> +0
-      uint32_t tb = __float_as_uint(th);
-      if (th != th) tb = 0x7fffffffu;                                 // NaN sorts last (np.argsort)
-      else if (tb & 0x80000000u) tb = 0;                              // defensive: angles are never negative
-      key = ((unsigned long long)tb << 32) | (unsigned)i;
-    }
-    s.keys[i] = key;
-  }
-  __syncthreads();
-  if (K <= kPolyRankSort) {
-    // small sets: rank sort - every key counts the keys below it (broadcast reads, no barriers); keys are distinct
-    // because they carry the index, so the ranks are a permutation
-    unsigned long long mykey[kPolyRankSort / kPolyThreads];
-    int myrank[kPolyRankSort / kPolyThreads];
-#pragma unroll
-    for (int u = 0; u < kPolyRankSort / kPolyThreads; ++u) {
-      const int i = tid + u * kPolyThreads;
-      mykey[u] = (i < K) ? s.keys[i] : ~0ull;
-      myrank[u] = 0;
-    }
-    if (K <= kPolyThreads) {                    // one key per thread; warps without keys skip the loop
-      if ((tid & ~31) < K)
-        for (int j = 0; j < K; ++j) myrank[0] += s.keys[j] < mykey[0];
-    } else {
-      for (int j = 0; j < K; ++j) {
-        const unsigned long long kj = s.keys[j];
-#pragma unroll
-        for (int u = 0; u < kPolyRankSort / kPolyThreads; ++u) myrank[u] += kj < mykey[u];
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < kPolyRankSort / kPolyThreads; ++u)
-      if (tid + u * kPolyThreads < K) s.keys[myrank[u]] = mykey[u];
-    __syncthreads();
-  } else {
-    for (int k2 = 2; k2 <= Kp; k2 <<= 1) {
-      for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-        for (int i = tid; i < Kp; i += kPolyThreads) {
-          const int l = i ^ j2;
-          if (l > i) {
-            const unsigned long long a = s.keys[i], c = s.keys[l];
-            const bool up = (i & k2) == 0;
-            if ((a > c) == up) { s.keys[i] = c; s.keys[l] = a; }
-          }
-        }
-        __syncthreads();
-      }
-    }
-  }
-  // sorted polygon -> global, and keep a sorted copy in shared memory for the final test
-  float2 mine_pt[kPolyMaxPoints / kPolyThreads];
-#pragma unroll
-  for (int u = 0; u < kPolyMaxPoints / kPolyThreads; ++u) {
-    const int i = tid + u * kPolyThreads;
-    if (i < K) mine_pt[u] = s.pts[(int)(s.keys[i] & 0xffffffffu)];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int u = 0; u < kPolyMaxPoints / kPolyThreads; ++u) {
-    const int i = tid + u * kPolyThreads;
-    if (i < K) { s.pts[i] = mine_pt[u]; out[i] = mine_pt[u]; }
-  }
-  __syncthreads();
-  // ---- centre strictly inside the sorted polygon (:201) ----
-  const int inside = pip_block(s, s.pts, K, cx, cy);
-  if (tid == 0) inst_flags[io] = inside > 0 ? 1 : 0;
+// Instances with more points than fit in shared memory (flag 2 from the kernel above): the same stage with the points,
+// the sort keys and the sorted copy in global memory.  One CTA per flagged instance; everything else exits at once.
+__global__ void __launch_bounds__(kPolyThreads)
+instance_polygons_large_kernel(const float4* __restrict__ rois, int layout, const int32_t* __restrict__ n_seeds, int Nmax,
+                               int H, int W, int cap, float2* __restrict__ poly_points,
+                               const int32_t* __restrict__ inst_start, const int32_t* __restrict__ inst_count,
+                               uint8_t* __restrict__ inst_flags, float2* __restrict__ inst_internal,
+                               unsigned long long* __restrict__ keys_ws, float2* __restrict__ tmp_ws) {
+  extern __shared__ __align__(16) unsigned char poly_smem_raw[];
+  PolySmem& s = *reinterpret_cast<PolySmem*>(poly_smem_raw);
+  const int b = blockIdx.y, inst = blockIdx.x;
+  const size_t io = (size_t)b * Nmax + inst;
+  if (inst >= min(n_seeds[b], Nmax) || inst_flags[io] != 2) return;
+  const int K = inst_count[io], start = inst_start[io];
+  float2* pts = poly_points + (size_t)b * cap + start;                       // raw row-major set, sorted in place
+  unsigned long long* keys = keys_ws + ((size_t)b * cap + start) * 2;        // room for the padded power of two
+  float2* tmp = tmp_ws + (size_t)b * cap + start;
+  const float2 centre = box_centre(rois[io], layout);
+  const int ok = finish_polygon<true>(s, pts, keys, tmp, pts, K, W, H, centre.x, centre.y,
+                                      inst_internal ? inst_internal + io : nullptr);
+  if (threadIdx.x == 0) inst_flags[io] = ok ? 1 : 0;
 }
 
 __global__ void zero_i32_kernel(int32_t* p, int n) {
@@ -389,11 +441,18 @@ __global__ void zero_i32_kernel(int32_t* p, int n) {
 
 using namespace isg;
 
+extern "C" size_t isg_instance_polygons_workspace_bytes(int B, int cap) {
+  if (B <= 0 || cap <= 0) return 0;
+  // large-instance stage: sort keys [B][2*cap] u64 + permutation scratch [B][cap] float2
+  return (size_t)B * cap * (2 * sizeof(unsigned long long) + sizeof(float2)) + 256;
+}
+
 extern "C" int isg_instance_polygons(const uint32_t* keepbits, const int32_t* label_map, const float* rois,
                                      int layout, const float* ghost, const int32_t* n_seeds, int B, int Nmax, int H, int W,
                                      int cap, int obj_pixel_th, float* poly_points, int32_t* inst_start,
                                      int32_t* inst_count, uint8_t* inst_flags, float* inst_internal,
-                                     int32_t* img_total, int32_t* stats, isg_stream_t stream_) {
+                                     int32_t* img_total, int32_t* stats, void* workspace, size_t workspace_bytes,
+                                     isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!keepbits || !label_map || !rois || !ghost || !n_seeds || !poly_points || !inst_start || !inst_count || !inst_flags ||
       !img_total)
@@ -401,6 +460,8 @@ extern "C" int isg_instance_polygons(const uint32_t* keepbits, const int32_t* la
   if (B <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || cap <= 0 || B > 65535) return ISG_EINVAL;
   if (layout != ISG_BOX_XYXY && layout != ISG_BOX_CYCXHW) return ISG_EINVAL;
   if (((uintptr_t)rois & 15) || ((uintptr_t)ghost & 15) || ((uintptr_t)poly_points & 7)) return ISG_EINVAL;
+  if (workspace && (workspace_bytes < isg_instance_polygons_workspace_bytes(B, cap) || ((uintptr_t)workspace & 255)))
+    return ISG_EWORKSPACE;
   zero_i32_kernel<<<cdiv(B, 256), 256, 0, stream>>>(img_total, B);
   ISG_LAUNCH_CHECK();
   const size_t smem = sizeof(PolySmem);
@@ -411,5 +472,14 @@ extern "C" int isg_instance_polygons(const uint32_t* keepbits, const int32_t* la
       cdiv(W, 32), cap, obj_pixel_th, reinterpret_cast<float2*>(poly_points), inst_start, inst_count, inst_flags,
       reinterpret_cast<float2*>(inst_internal), img_total, stats);
   ISG_LAUNCH_CHECK();
+  if (workspace) {   // instances above the shared-memory capacity (flag 2) are finished from global memory
+    unsigned long long* keys_ws = static_cast<unsigned long long*>(workspace);
+    float2* tmp_ws = reinterpret_cast<float2*>(keys_ws + (size_t)B * cap * 2);
+    ISG_CUDA(cudaFuncSetAttribute(instance_polygons_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    instance_polygons_large_kernel<<<grid, kPolyThreads, smem, stream>>>(
+        reinterpret_cast<const float4*>(rois), layout, n_seeds, Nmax, H, W, cap, reinterpret_cast<float2*>(poly_points), inst_start,
+        inst_count, inst_flags, reinterpret_cast<float2*>(inst_internal), keys_ws, tmp_ws);
+    ISG_LAUNCH_CHECK();
+  }
   return ISG_OK;
 }

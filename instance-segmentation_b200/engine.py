@@ -130,6 +130,8 @@ class DecodePlan:
             self.inst_flags = torch.empty((B, N), dtype=torch.uint8, device=d)
             self.inst_internal = torch.empty((B, N, 2), dtype=f32, device=d)
             self.img_total = torch.empty(B, dtype=i32, device=d)
+            self.poly_ws_bytes = int(_lib.lib().isg_instance_polygons_workspace_bytes(B, cap))
+            self.poly_ws, self.poly_ws_ptr = aligned_workspace(self.poly_ws_bytes, d)
             self.label_map = torch.empty((B, H, W), dtype=i32, device=d)
             # tile scheduler of the dense kernel: zero-filled once, the kernel leaves it zero-filled
             self.dense_ws_bytes = int(_lib.lib().isg_assign_dense_workspace_bytes(B, N, H, W))
@@ -195,7 +197,7 @@ class DecodePlan:
                 call("isg_instance_polygons", ptr(self.keepbits), ptr(self.label_map), ptr(rois), layout, ptr(self.ghost), ptr(n_seeds),
                      B, N, H, W, cap, int(obj_pixel_th), ptr(self.poly_points), ptr(self.inst_start), ptr(self.inst_count),
                      ptr(self.inst_flags), ptr(self.inst_internal), ptr(self.img_total),
-                     0 if self.fused_stats else ptr(self.stats), s)
+                     0 if self.fused_stats else ptr(self.stats), self.poly_ws_ptr, self.poly_ws_bytes, s)
                 if ev:
                     self.events.append(ev)
                 return

@@ -557,9 +557,9 @@ def test_decode_output_host_chunks_equal_device_batch(mods):
             assert int(c1) == int(c2) and f1 == f2 and np.array_equal(k1, k2) and np.array_equal(p1, p2)
 
 
-def test_polygon_stage_large_instance_falls_back(mods):
-    """an instance with more boundary points than the device polygon stage sorts (2048) is finished by the host from the
-    raw point set: same polygon as the all-host path"""
+def test_polygon_stage_large_instance(mods):
+    """an instance with more boundary points than fit in shared memory (2048) is finished by the global-memory variant
+    of the device stage: same polygon as the all-host path (up to the order of equal-angle points)"""
     dec = mods["decode"]
     H, W = 256, 512
     rs = np.random.RandomState(11)
@@ -576,6 +576,7 @@ def test_polygon_stage_large_instance_falls_back(mods):
                                      TransInfo("x", (H, W)), cfg, torch.device(DEV))
     finally:
         dec.decode_mode, dec.device_polygon_stage = saved
-    assert len(out["host"][3]) == len(out["device"][3])
-    for p1, p2 in zip(out["host"][3], out["device"][3]):
-        assert p1.shape[0] > 2048 and np.array_equal(p1, p2)
+    assert len(out["host"][3]) == len(out["device"][3]) == 1
+    for p_host, p_dev, ctr in zip(out["host"][3], out["device"][3], out["host"][2]):
+        assert p_host.shape[0] > 2048
+        assert_polygon_equivalent(dec, p_dev, p_host, ctr)
