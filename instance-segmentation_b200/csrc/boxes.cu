@@ -327,22 +327,60 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
   }
   if (t < kSmallMax / 64) remv[t] = 0ull;
   __syncthreads();
-  // suppression bits: task = (row i, word w >= i/64)
+  // suppression bits.  Only boxes of the same class can suppress each other, so the ranks are first bucketed by
+  // (class & 63), each bucket keeping rank order; row i then visits only the later members of its bucket instead of
+  // every later box.  The `key` array is free after the sort and holds the bucket lists.
   const int nw = (n + 63) / 64;
   const float thr_f = (float)thr;
-  for (int task = t; task < n * nw; task += kSortThreads) {
-    const int i = task / nw, w = task - i * nw;
-    if (w < (i >> 6)) continue;
+  __shared__ int bcnt[64], bstart[65];
+  uint16_t* memb = reinterpret_cast<uint16_t*>(key);            // [n] ranks grouped by bucket, ascending inside
+  uint16_t* posof = memb + P;                                   // [n] position of rank r inside memb
+  const int lane = t & 31, warp = t >> 5;
+  if (t < 64) bcnt[t] = 0;
+  for (int i = t; i < n * nw; i += kSortThreads) mask[(size_t)(i / nw) * nwP + (i % nw)] = 0ull;
+  __syncthreads();
+  for (int h = warp; h < 64; h += kSortThreads / 32) {          // bucket sizes (one warp per bucket, ballots)
+    int c = 0;
+    for (int r0 = 0; r0 < n; r0 += 32) {
+      const int r = r0 + lane;
+      c += __popc(__ballot_sync(0xffffffffu, r < n && (scls[r] & 63) == h));
+    }
+    if (lane == 0) bcnt[h] = c;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int run = 0;
+    for (int h = 0; h < 64; ++h) { bstart[h] = run; run += bcnt[h]; }
+    bstart[64] = run;
+  }
+  __syncthreads();
+  for (int h = warp; h < 64; h += kSortThreads / 32) {          // ordered fill
+    int pos = bstart[h];
+    for (int r0 = 0; r0 < n; r0 += 32) {
+      const int r = r0 + lane;
+      const bool in = r < n && (scls[r] & 63) == h;
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      if (in) { const int q = pos + __popc(bal & ((1u << lane) - 1u)); memb[q] = (uint16_t)r; posof[r] = (uint16_t)q; }
+      pos += __popc(bal);
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < n; i += kSortThreads) {                   // one row per thread; its words are private to it
     const float4 a = sbox[i];
     const int ac = scls[i];
-    const int c0 = w * 64, c1 = min(c0 + 64, n);
+    const int qend = bstart[(ac & 63) + 1];
+    int cur_w = -1;
     unsigned long long bits = 0ull;
-    for (int c = max(c0, i + 1); c < c1; ++c) {
-      if (scls[c] != ac) continue;
+    for (int q = posof[i] + 1; q < qend; ++q) {
+      const int c = memb[q];                                    // rank > i, ascending
+      if (scls[c] != ac) continue;                              // another class hashed into the same bucket
       const bool sup = (convention == ISG_NMS_TV_GT) ? suppresses_tv(a, sbox[c], thr) : suppresses_plus1(a, sbox[c], thr_f);
-      if (sup) bits |= 1ull << (c - c0);
+      if (!sup) continue;
+      const int w = c >> 6;
+      if (w != cur_w) { if (cur_w >= 0) mask[(size_t)i * nwP + cur_w] = bits; cur_w = w; bits = 0ull; }
+      bits |= 1ull << (c & 63);
     }
-    mask[(size_t)i * nwP + w] = bits;
+    if (cur_w >= 0) mask[(size_t)i * nwP + cur_w] = bits;
   }
   __syncthreads();
   // greedy scan, 64-box chunks.  Inside a chunk only the KEPT boxes cost a (dependent) step: the next kept box

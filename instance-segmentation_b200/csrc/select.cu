@@ -2,6 +2,7 @@
 // row-major compaction.  Reference: select_points / nms_hm (utils/decode.py:42-48,71-85) and
 // kp_mask.nonzero() (utils/decode.py:312).
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include "keep.cuh"
 
 namespace cg = cooperative_groups;
@@ -289,6 +290,53 @@ topk_sample_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   if (rk < (long long)S)                // cluster-uniform
     lower = cluster_radix_select(cluster, sh_hist, S, (uint32_t)rk, [&](int i) { return skeys[i - lo]; });
   if (r == 0 && t == 0) { *v.lower = lower; *v.ncand = 0u; }
+}
+
+// Single-CTA form of the sample step: at most kSample1Max samples per image, radix-selected with block barriers
+// only (no cluster synchronisation, no distributed shared memory) - the sample is small, so latency is what counts.
+constexpr int kSample1Max = 8192;
+
+__global__ void __launch_bounds__(kSelThreads)
+topk_sample1_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, int stride, void* ws) {
+  __shared__ uint32_t skeys[kSample1Max];
+  __shared__ uint32_t sh_hist[kHistBins];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
+  const float* img = kp + (int64_t)b * img_stride;
+  const int S = min(npx / stride, kSample1Max);   // sample i reads pixel i*stride + (i*37 % stride)
+  for (int i = t; i < S; i += kSelThreads) {
+    const int p = i * stride + (int)(((unsigned)i * 37u) % (unsigned)stride);
+    skeys[i] = float_key(__ldg(img + p));
+  }
+  __syncthreads();
+  // same bound as topk_sample_kernel: sample rank of ~1.2k pixels plus 6 sigma and a constant
+  const double expect = 1.2 * (double)k * (double)S / (double)npx;
+  const long long rk = (long long)(expect + 6.0 * sqrt(expect) + 8.0);
+  TopkWs v = topk_ws_view(ws, b, npx, k);
+  uint32_t lower = 0u;                  // 0: every pixel is a candidate (the select step then falls back if needed)
+  if (rk < (long long)S) {              // block-uniform
+    uint32_t prefix = 0, pmask = 0, krem = (uint32_t)rk;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+      for (int i = t; i < kHistBins; i += kSelThreads) sh_hist[i] = 0;
+      __syncthreads();
+      for (int i0 = 0; i0 < S; i0 += kSelThreads) {          // warp-uniform trip count
+        const int i = i0 + t;
+        const uint32_t key = i < S ? skeys[i] : 0u;
+        const bool valid = i < S && (key & pmask) == prefix;
+        if (!__any_sync(0xffffffffu, valid)) continue;       // later passes: most warps hold no key of the prefix
+        hist_add_match(sh_hist, digit_of(key, pass), valid, lane);
+      }
+      __syncthreads();
+      uint32_t d, k2;
+      resolve_digit(sh_hist, krem, &d, &k2);
+      krem = k2;
+      if (pass == 0) { prefix = d << 21; pmask = 0xffe00000u; }
+      else if (pass == 1) { prefix |= d << 10; pmask = 0xfffffc00u; }
+      else prefix |= d;
+    }
+    lower = prefix;
+  }
+  if (t == 0) { *v.lower = lower; *v.ncand = 0u; }
 }
 
 __global__ void __launch_bounds__(kFilterThreads)
@@ -614,10 +662,16 @@ extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t 
   }
   if (npx >= 65536) {
     int stride = 64;
-    while (npx / stride > kSampleMax) stride *= 2;
-    const size_t smem = (size_t)cdiv(npx / stride, kSelCluster) * sizeof(uint32_t);
-    ISG_CUDA(cudaFuncSetAttribute(topk_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_sample_kernel<<<dim3(kSelCluster, B), kSelThreads, smem, stream>>>(kp, img_stride, npx, k, stride, ws);
+    const char* samp_env = getenv("ISG_TOPK_SAMPLE");   // "cluster": the 8-CTA cluster form with a 4x larger sample (A/B)
+    if (samp_env && samp_env[0] == 'c') {
+      while (npx / stride > kSampleMax) stride *= 2;
+      const size_t smem = (size_t)cdiv(npx / stride, kSelCluster) * sizeof(uint32_t);
+      ISG_CUDA(cudaFuncSetAttribute(topk_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      topk_sample_kernel<<<dim3(kSelCluster, B), kSelThreads, smem, stream>>>(kp, img_stride, npx, k, stride, ws);
+    } else {
+      while (npx / stride > kSample1Max) stride *= 2;
+      topk_sample1_kernel<<<B, kSelThreads, 0, stream>>>(kp, img_stride, npx, k, stride, ws);
+    }
     dim3 grid(cdiv(npx, kFilterPxPerBlock), B);
     topk_filter_kernel<<<grid, kFilterThreads, 0, stream>>>(kp, img_stride, npx, k, ws, vec);
   } else {
