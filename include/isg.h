@@ -106,6 +106,15 @@ int isg_build_seeds(const float* rois, int layout, const int32_t* n_seeds, int B
                     const float* ys, const float* xs, int H, int W, float ghost_k, float scale,
                     uint32_t* seeds, float* ghost, isg_stream_t stream);
 
+/* isg_gather_kept + isg_build_seeds (XYXY) + isg_stats_init in one launch, for the batched pipeline: the kept
+ * candidates of isg_box_nms become the detection tables (rois / scores / cls / n_out, as isg_gather_kept) and, in the
+ * same pass, the seed records, ghost bounds and (stats nullable) reset statistics of the decode. */
+int isg_gather_build_seeds(const float* cand_boxes, const float* cand_scores, const int32_t* cand_cls,
+                           const int32_t* keep, const int32_t* n_keep, int B, int cap, int Nmax,
+                           const float* ys, const float* xs, int H, int W, float ghost_k, float scale,
+                           float* rois, float* scores, int32_t* cls, int32_t* n_out,
+                           uint32_t* seeds, float* ghost, int32_t* stats, isg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K1+K3 — embedding + Gaussian membership + assignment.  Replaces group_kp's arithmetic core
  * (utils/decode.py:303-328) and the per-instance ghost filter / pixel count (:337-356).
@@ -242,7 +251,7 @@ int isg_pairwise(const float* X, int M, const float* Y, int N, int D, int metric
  *   poly_points [B,cap,2] fp32 (x,y): instance i of image b occupies [inst_start, inst_start+inst_count) of image b's
  *     block - angle-sorted when a polygon was computed, row-major otherwise; blocks are allocated in completion order
  *   inst_flags [B,Nmax] uint8: 1 = polygon valid (centre strictly inside), 0 = no polygon; instances with more than
- *     2048 points are finished by a second kernel that works in global memory (needs `workspace`); without a workspace
+ *     2048 points are finished by the same CTA in global memory (needs `workspace`); without a workspace
  *     they keep flag 2 and their raw row-major set, and the caller finishes them (aug_group on the host)
  *   inst_internal [B,Nmax,2] fp32 (nullable): the internal point used;  img_total [B] int32: points per image
  *   stats (nullable, pre-initialised by isg_stats_init): count / bbox per instance

@@ -25,6 +25,47 @@ __device__ __forceinline__ int clamp_to_int(float v) {
 // ---------------------------------------------------------------------------------------------
 // seeds: one thread per (image, box)
 // ---------------------------------------------------------------------------------------------
+// seed record + ghost bounds of one box (`valid` false: an empty record no tile overlaps)
+__device__ __forceinline__ void make_seed(const float4 r, int layout, bool valid, int j, const float* __restrict__ ys,
+                                          const float* __restrict__ xs, int H, int W, float ghost_k, float scale,
+                                          SeedRec& s, float4& g) {
+  // empty box: no tile overlaps it, so the per-pixel range tests never see it
+  s.y0 = 0x7fffffff; s.y1 = -0x7fffffff - 1; s.x0 = 0x7fffffff; s.x1 = -0x7fffffff - 1;
+  s.cy = 0.f; s.cx = 0.f; s.id = j; s.pad = 0;
+  g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!valid) return;
+  float cy, cx, hy, wx;
+  if (layout == ISG_BOX_XYXY) {   // x1,y1,x2,y2
+    // decode_single: lt = (y1,x1), rb = (y2,x2); centre = (lt+rb)/2; wh = rb-lt   (:428-432)
+    cy = __fmul_rn(__fadd_rn(r.y, r.w), 0.5f); cx = __fmul_rn(__fadd_rn(r.x, r.z), 0.5f);
+    hy = __fsub_rn(r.w, r.y); wx = __fsub_rn(r.z, r.x);
+  } else {                        // cy,cx,h,w : group_kp's center_indexes / center_whs (:288)
+    cy = r.x; cx = r.y; hy = r.z; wx = r.w;
+  }
+  // group_kp: lt = c - wh/2, rb = c + wh/2 ; inbox = (p - lt >= 0) & (rb - p >= 0)   (:321-325)
+  const float lty = __fsub_rn(cy, __fmul_rn(hy, 0.5f)), ltx = __fsub_rn(cx, __fmul_rn(wx, 0.5f));
+  const float rby = __fadd_rn(cy, __fmul_rn(hy, 0.5f)), rbx = __fadd_rn(cx, __fmul_rn(wx, 0.5f));
+  // p is an integer-valued float, so  p - lt >= 0  <=>  p >= ceil(lt)  and  rb - p >= 0  <=>  p <= floor(rb)
+  const bool finite = (lty == lty) && (ltx == ltx) && (rby == rby) && (rbx == rbx);
+  if (finite) {
+    const int y0 = clamp_to_int(ceilf(lty)), y1 = clamp_to_int(floorf(rby));
+    const int x0 = clamp_to_int(ceilf(ltx)), x1 = clamp_to_int(floorf(rbx));
+    if (y0 <= y1 && x0 <= x1) { s.y0 = y0; s.y1 = y1; s.x0 = x0; s.x1 = x1; }
+  }
+  // seed coordinate = grid value at the truncated centre (:316-317); clamped into the image
+  int iy = clamp_to_int(cy), ix = clamp_to_int(cx);
+  iy = min(max(iy, 0), H - 1); ix = min(max(ix, 0), W - 1);
+  s.cy = ys[iy]; s.cx = xs[ix];
+  // ghost filter bounds (:339-352): x -/+ (0.5+wh_delta)*w, y -/+ (0.5+wh_delta)*h, fp32
+  const float w = __fmul_rn(wx, scale), h = __fmul_rn(hy, scale);
+  if (ghost_k < 0.0f) {   // ghost filter disabled: every pixel passes
+    g = make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY);
+  } else {
+    g.x = __fsub_rn(cx, __fmul_rn(ghost_k, w)); g.y = __fadd_rn(cx, __fmul_rn(ghost_k, w));
+    g.z = __fsub_rn(cy, __fmul_rn(ghost_k, h)); g.w = __fadd_rn(cy, __fmul_rn(ghost_k, h));
+  }
+}
+
 __global__ void build_seeds_kernel(const float* __restrict__ rois, int layout, const int32_t* __restrict__ n_seeds,
                                    int Nmax, const float* __restrict__ ys, const float* __restrict__ xs,
                                    int H, int W, float ghost_k, float scale, SeedRec* __restrict__ seeds,
@@ -32,46 +73,49 @@ __global__ void build_seeds_kernel(const float* __restrict__ rois, int layout, c
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Nmax) return;
+  const bool valid = j < n_seeds[b];
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) r = reinterpret_cast<const float4*>(rois)[(size_t)b * Nmax + j];
   SeedRec s;
-  // empty box: no tile overlaps it, so the per-pixel range tests never see it
-  s.y0 = 0x7fffffff; s.y1 = -0x7fffffff - 1; s.x0 = 0x7fffffff; s.x1 = -0x7fffffff - 1;
-  s.cy = 0.f; s.cx = 0.f; s.id = j; s.pad = 0;
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (j < n_seeds[b]) {
-    const float4 r = reinterpret_cast<const float4*>(rois)[(size_t)b * Nmax + j];
-    float cy, cx, hy, wx;
-    if (layout == ISG_BOX_XYXY) {   // x1,y1,x2,y2
-      // decode_single: lt = (y1,x1), rb = (y2,x2); centre = (lt+rb)/2; wh = rb-lt   (:428-432)
-      cy = __fmul_rn(__fadd_rn(r.y, r.w), 0.5f); cx = __fmul_rn(__fadd_rn(r.x, r.z), 0.5f);
-      hy = __fsub_rn(r.w, r.y); wx = __fsub_rn(r.z, r.x);
-    } else {                        // cy,cx,h,w : group_kp's center_indexes / center_whs (:288)
-      cy = r.x; cx = r.y; hy = r.z; wx = r.w;
-    }
-    // group_kp: lt = c - wh/2, rb = c + wh/2 ; inbox = (p - lt >= 0) & (rb - p >= 0)   (:321-325)
-    const float lty = __fsub_rn(cy, __fmul_rn(hy, 0.5f)), ltx = __fsub_rn(cx, __fmul_rn(wx, 0.5f));
-    const float rby = __fadd_rn(cy, __fmul_rn(hy, 0.5f)), rbx = __fadd_rn(cx, __fmul_rn(wx, 0.5f));
-    // p is an integer-valued float, so  p - lt >= 0  <=>  p >= ceil(lt)  and  rb - p >= 0  <=>  p <= floor(rb)
-    const bool finite = (lty == lty) && (ltx == ltx) && (rby == rby) && (rbx == rbx);
-    if (finite) {
-      const int y0 = clamp_to_int(ceilf(lty)), y1 = clamp_to_int(floorf(rby));
-      const int x0 = clamp_to_int(ceilf(ltx)), x1 = clamp_to_int(floorf(rbx));
-      if (y0 <= y1 && x0 <= x1) { s.y0 = y0; s.y1 = y1; s.x0 = x0; s.x1 = x1; }
-    }
-    // seed coordinate = grid value at the truncated centre (:316-317); clamped into the image
-    int iy = clamp_to_int(cy), ix = clamp_to_int(cx);
-    iy = min(max(iy, 0), H - 1); ix = min(max(ix, 0), W - 1);
-    s.cy = ys[iy]; s.cx = xs[ix];
-    // ghost filter bounds (:339-352): x -/+ (0.5+wh_delta)*w, y -/+ (0.5+wh_delta)*h, fp32
-    const float w = __fmul_rn(wx, scale), h = __fmul_rn(hy, scale);
-    if (ghost_k < 0.0f) {   // ghost filter disabled: every pixel passes
-      g = make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY);
-    } else {
-      g.x = __fsub_rn(cx, __fmul_rn(ghost_k, w)); g.y = __fadd_rn(cx, __fmul_rn(ghost_k, w));
-      g.z = __fsub_rn(cy, __fmul_rn(ghost_k, h)); g.w = __fadd_rn(cy, __fmul_rn(ghost_k, h));
-    }
-  }
+  float4 g;
+  make_seed(r, layout, valid, j, ys, xs, H, W, ghost_k, scale, s, g);
   seeds[(size_t)b * Nmax + j] = s;
   ghost[(size_t)b * Nmax + j] = g;
+}
+
+// gather_kept + build_seeds + stats_init of the batched pipeline in one launch: thread (b, r) copies the r-th kept
+// box of image b into the detection tables, derives its seed record / ghost bounds and resets its statistics
+__global__ void gather_build_seeds_kernel(const float4* __restrict__ cand_boxes, const float* __restrict__ cand_scores,
+                                          const int32_t* __restrict__ cand_cls, const int32_t* __restrict__ keep,
+                                          const int32_t* __restrict__ n_keep, int cap, int Nmax,
+                                          const float* __restrict__ ys, const float* __restrict__ xs, int H, int W,
+                                          float ghost_k, float scale, float4* __restrict__ rois,
+                                          float* __restrict__ scores, int32_t* __restrict__ cls,
+                                          int32_t* __restrict__ n_out, SeedRec* __restrict__ seeds,
+                                          float4* __restrict__ ghost, int32_t* __restrict__ stats) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(n_keep[b], Nmax);
+  if (r == 0) n_out[b] = n;
+  if (r >= Nmax) return;
+  float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sc = 0.f;
+  int c = 0;
+  if (r < n) {
+    const size_t o = (size_t)b * cap + keep[(size_t)b * cap + r];
+    bx = cand_boxes[o]; sc = cand_scores[o]; c = cand_cls[o];
+  }
+  const size_t d = (size_t)b * Nmax + r;
+  rois[d] = bx; scores[d] = sc; cls[d] = c;
+  SeedRec s;
+  float4 g;
+  make_seed(bx, ISG_BOX_XYXY, r < n, r, ys, xs, H, W, ghost_k, scale, s, g);
+  seeds[d] = s;
+  ghost[d] = g;
+  if (stats) {
+    int32_t* st = stats + d * ISG_STAT_WORDS;
+    st[0] = 0; st[1] = 0x7fffffff; st[2] = 0x7fffffff; st[3] = -1; st[4] = -1;
+  }
 }
 
 __global__ void stats_init_kernel(int32_t* stats, int n) {
@@ -580,6 +624,26 @@ extern "C" int isg_stats_init(int32_t* stats, int B, int Nmax, isg_stream_t stre
   if (!stats || B <= 0 || Nmax <= 0) return ISG_EINVAL;
   const int n = B * Nmax;
   stats_init_kernel<<<cdiv(n, 256), 256, 0, stream>>>(stats, n);
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+extern "C" int isg_gather_build_seeds(const float* cand_boxes, const float* cand_scores, const int32_t* cand_cls,
+                                      const int32_t* keep, const int32_t* n_keep, int B, int cap, int Nmax, const float* ys,
+                                      const float* xs, int H, int W, float ghost_k, float scale, float* rois, float* scores,
+                                      int32_t* cls, int32_t* n_out, uint32_t* seeds, float* ghost, int32_t* stats,
+                                      isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!cand_boxes || !cand_scores || !cand_cls || !keep || !n_keep || !ys || !xs || !rois || !scores || !cls || !n_out ||
+      !seeds || !ghost)
+    return ISG_EINVAL;
+  if (B <= 0 || cap <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
+  if (!aligned16(cand_boxes) || !aligned16(rois) || !aligned16(seeds) || !aligned16(ghost)) return ISG_EINVAL;
+  dim3 grid(cdiv(Nmax, 128), B);
+  gather_build_seeds_kernel<<<grid, 128, 0, stream>>>(
+      reinterpret_cast<const float4*>(cand_boxes), cand_scores, cand_cls, keep, n_keep, cap, Nmax, ys, xs, H, W, ghost_k, scale,
+      reinterpret_cast<float4*>(rois), scores, cls, n_out, reinterpret_cast<SeedRec*>(seeds), reinterpret_cast<float4*>(ghost),
+      stats);
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }

@@ -15,6 +15,7 @@
 // outline) and is not evaluated.  pointPolygonTest is restated from OpenCV's float branch (crossing count with the
 // on-edge cases returning 0, the cross product in double) - the same restatement as csrc/host_polygon.cpp, which
 // tests/test_host_logic.py checks against cv2 itself.
+#include <algorithm>
 #include "common.cuh"
 
 namespace isg {
@@ -257,7 +258,8 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
                          int obj_pixel_th, float2* __restrict__ poly_points, int32_t* __restrict__ inst_start,
                          int32_t* __restrict__ inst_count, uint8_t* __restrict__ inst_flags,
                          float2* __restrict__ inst_internal, int32_t* __restrict__ img_total,
-                         int32_t* __restrict__ stats) {
+                         int32_t* __restrict__ stats, unsigned long long* __restrict__ keys_ws,
+                         float2* __restrict__ tmp_ws) {
   extern __shared__ __align__(16) unsigned char poly_smem_raw[];
   PolySmem& s = *reinterpret_cast<PolySmem*>(poly_smem_raw);
   const int b = blockIdx.y, inst = blockIdx.x;
@@ -396,7 +398,18 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
     if (tid == 0) st[0] = K;
   }
   __syncthreads();
-  if (!fits) { if (tid == 0) inst_flags[io] = (K >= obj_pixel_th) ? 2 : 0; return; }   // 2: finished by the large-instance kernel
+  if (!fits) {
+    // more points than the shared-memory arrays hold: the raw row-major set is in `out`; finish it in global memory
+    // (sort keys / permutation scratch in the caller's workspace), or flag it for the caller when there is none
+    if (K < obj_pixel_th || start + K > cap) { if (tid == 0) inst_flags[io] = 0; return; }
+    if (!keys_ws) { if (tid == 0) inst_flags[io] = 2; return; }
+    const float2 centre = box_centre(rois[io], layout);
+    __threadfence_block();
+    const int ok = finish_polygon<true>(s, out, keys_ws + ((size_t)b * cap + start) * 2, tmp_ws + (size_t)b * cap + start, out, K,
+                                        W, H, centre.x, centre.y, inst_internal ? inst_internal + io : nullptr);
+    if (tid == 0) inst_flags[io] = ok ? 1 : 0;
+    return;
+  }
   if (K < obj_pixel_th || K == 0) {                                                 // :355
     for (int i = tid; i < K; i += kPolyThreads) out[i] = s.pts[i];
     if (tid == 0) inst_flags[io] = 0;
@@ -407,29 +420,6 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
   const int ok = finish_polygon<false>(s, s.pts, s.keys, nullptr, out, K, W, H, centre.x, centre.y,
                                        inst_internal ? inst_internal + io : nullptr);
   if (tid == 0) inst_flags[io] = ok ? 1 : 0;
-}
-
-// Instances with more points than fit in shared memory (flag 2 from the kernel above): the same stage with the points,
-// the sort keys and the sorted copy in global memory.  One CTA per flagged instance; everything else exits at once.
-__global__ void __launch_bounds__(kPolyThreads)
-instance_polygons_large_kernel(const float4* __restrict__ rois, int layout, const int32_t* __restrict__ n_seeds, int Nmax,
-                               int H, int W, int cap, float2* __restrict__ poly_points,
-                               const int32_t* __restrict__ inst_start, const int32_t* __restrict__ inst_count,
-                               uint8_t* __restrict__ inst_flags, float2* __restrict__ inst_internal,
-                               unsigned long long* __restrict__ keys_ws, float2* __restrict__ tmp_ws) {
-  extern __shared__ __align__(16) unsigned char poly_smem_raw[];
-  PolySmem& s = *reinterpret_cast<PolySmem*>(poly_smem_raw);
-  const int b = blockIdx.y, inst = blockIdx.x;
-  const size_t io = (size_t)b * Nmax + inst;
-  if (inst >= min(n_seeds[b], Nmax) || inst_flags[io] != 2) return;
-  const int K = inst_count[io], start = inst_start[io];
-  float2* pts = poly_points + (size_t)b * cap + start;                       // raw row-major set, sorted in place
-  unsigned long long* keys = keys_ws + ((size_t)b * cap + start) * 2;        // room for the padded power of two
-  float2* tmp = tmp_ws + (size_t)b * cap + start;
-  const float2 centre = box_centre(rois[io], layout);
-  const int ok = finish_polygon<true>(s, pts, keys, tmp, pts, K, W, H, centre.x, centre.y,
-                                      inst_internal ? inst_internal + io : nullptr);
-  if (threadIdx.x == 0) inst_flags[io] = ok ? 1 : 0;
 }
 
 __global__ void zero_i32_kernel(int32_t* p, int n) {
@@ -467,19 +457,12 @@ extern "C" int isg_instance_polygons(const uint32_t* keepbits, const int32_t* la
   const size_t smem = sizeof(PolySmem);
   ISG_CUDA(cudaFuncSetAttribute(instance_polygons_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(Nmax, B);
+  unsigned long long* keys_ws = static_cast<unsigned long long*>(workspace);     // [B][2*cap]
+  float2* tmp_ws = workspace ? reinterpret_cast<float2*>(keys_ws + (size_t)B * cap * 2) : nullptr;   // [B][cap]
   instance_polygons_kernel<<<grid, kPolyThreads, smem, stream>>>(
       keepbits, label_map, reinterpret_cast<const float4*>(rois), layout, reinterpret_cast<const float4*>(ghost), n_seeds, Nmax, H, W,
       cdiv(W, 32), cap, obj_pixel_th, reinterpret_cast<float2*>(poly_points), inst_start, inst_count, inst_flags,
-      reinterpret_cast<float2*>(inst_internal), img_total, stats);
+      reinterpret_cast<float2*>(inst_internal), img_total, stats, keys_ws, tmp_ws);
   ISG_LAUNCH_CHECK();
-  if (workspace) {   // instances above the shared-memory capacity (flag 2) are finished from global memory
-    unsigned long long* keys_ws = static_cast<unsigned long long*>(workspace);
-    float2* tmp_ws = reinterpret_cast<float2*>(keys_ws + (size_t)B * cap * 2);
-    ISG_CUDA(cudaFuncSetAttribute(instance_polygons_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    instance_polygons_large_kernel<<<grid, kPolyThreads, smem, stream>>>(
-        reinterpret_cast<const float4*>(rois), layout, n_seeds, Nmax, H, W, cap, reinterpret_cast<float2*>(poly_points), inst_start,
-        inst_count, inst_flags, reinterpret_cast<float2*>(inst_internal), keys_ws, tmp_ws);
-    ISG_LAUNCH_CHECK();
-  }
   return ISG_OK;
 }

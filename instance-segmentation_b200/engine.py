@@ -161,7 +161,7 @@ class DecodePlan:
 
     def run_assign(self, kp: torch.Tensor, ae: torch.Tensor, rois: torch.Tensor, n_seeds: torch.Tensor,
                    layout: int = _lib.ISG_BOX_XYXY, time_main: bool = False, tail: str = "lists",
-                   obj_pixel_th: int = 0) -> None:
+                   obj_pixel_th: int = 0, seeds_ready: bool = False) -> None:
         """Stage 2: seeds -> assignment (dense or sparse) -> tail.  Needs self.thr_key.
         tail "lists": compaction + per-pixel labels + per-instance point sets (idx/label/flag/offsets/points);
         tail "polygons" (dense mode, XYXY rois): isg_instance_polygons straight from the label map
@@ -178,9 +178,10 @@ class DecodePlan:
         kp_stride = kp.stride(0) if B > 1 else H * W
         ae_img = ae.stride(0) if B > 1 else 4 * H * W
         ae_plane = ae.stride(1)
-        call("isg_build_seeds", ptr(rois), layout, ptr(n_seeds), B, N, ptr(self.ys), ptr(self.xs), H, W, self.ghost_k,
-             self.scale, ptr(self.seeds), ptr(self.ghost), s)
-        call("isg_stats_init", ptr(self.stats), B, N, s)
+        if not seeds_ready:   # the pipeline builds seeds / ghost / stats together with the detection tables
+            call("isg_build_seeds", ptr(rois), layout, ptr(n_seeds), B, N, ptr(self.ys), ptr(self.xs), H, W, self.ghost_k,
+                 self.scale, ptr(self.seeds), ptr(self.ghost), s)
+            call("isg_stats_init", ptr(self.stats), B, N, s)
         ev = None
         if time_main:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -256,7 +257,9 @@ class BoxPlan:
         self.ws, self.ws_ptr = aligned_workspace(self.ws_bytes, d)
 
     def run(self, anchors: torch.Tensor, regression: torch.Tensor, classification: torch.Tensor, cls_th: float,
-            iou_th: float) -> None:
+            iou_th: float, gather: bool = True) -> None:
+        """gather=False leaves the kept candidates in (keep, n_keep): the pipeline gathers them together with the seed
+        records of the decode (isg_gather_build_seeds)"""
         B, A, C = self.B, self.A, self.C
         assert anchors.numel() == A * 4 and regression.shape == (B, A, 4) and classification.shape == (B, A, C)
         assert anchors.is_contiguous() and regression.is_contiguous() and classification.is_contiguous()
@@ -267,8 +270,9 @@ class BoxPlan:
         call("isg_box_nms", ptr(self.cand_boxes), ptr(self.cand_scores), ptr(self.cand_cls), ptr(self.cand_anchor),
              ptr(self.cand_count), B, self.cap, float(iou_th), _lib.ISG_NMS_TV_GT, ptr(self.keep), ptr(self.n_keep),
              self.ws_ptr, self.ws_bytes, s)
-        call("isg_gather_kept", ptr(self.cand_boxes), ptr(self.cand_scores), ptr(self.cand_cls), ptr(self.keep),
-             ptr(self.n_keep), B, self.cap, self.N, ptr(self.rois), ptr(self.scores), ptr(self.cls), ptr(self.n_seeds), s)
+        if gather:
+            call("isg_gather_kept", ptr(self.cand_boxes), ptr(self.cand_scores), ptr(self.cand_cls), ptr(self.keep),
+                 ptr(self.n_keep), B, self.cap, self.N, ptr(self.rois), ptr(self.scores), ptr(self.cls), ptr(self.n_seeds), s)
 
 
 _plans = {}
@@ -313,9 +317,13 @@ class DecodePipeline:
         with torch.cuda.stream(self.side):
             self.dplan.run_topk(kp)
             self.join.record(self.side)
-        self.bplan.run(anchors, regression, classification, cls_th, iou_th)
+        bp, dp = self.bplan, self.dplan
+        bp.run(anchors, regression, classification, cls_th, iou_th, gather=False)
+        call("isg_gather_build_seeds", ptr(bp.cand_boxes), ptr(bp.cand_scores), ptr(bp.cand_cls), ptr(bp.keep), ptr(bp.n_keep),
+             bp.B, bp.cap, bp.N, ptr(dp.ys), ptr(dp.xs), dp.H, dp.W, dp.ghost_k, dp.scale, ptr(bp.rois), ptr(bp.scores),
+             ptr(bp.cls), ptr(bp.n_seeds), ptr(dp.seeds), ptr(dp.ghost), ptr(dp.stats), stream_ptr(self.device))
         main.wait_event(self.join)
-        self.dplan.run_assign(kp, ae, self.bplan.rois, self.bplan.n_seeds, _lib.ISG_BOX_XYXY, time_main, tail, obj_pixel_th)
+        dp.run_assign(kp, ae, bp.rois, bp.n_seeds, _lib.ISG_BOX_XYXY, time_main, tail, obj_pixel_th, seeds_ready=True)
 
 
 _pipes = {}
