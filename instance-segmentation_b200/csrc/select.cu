@@ -3,6 +3,7 @@
 // kp_mask.nonzero() (utils/decode.py:312).
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <algorithm>
 #include "keep.cuh"
 
 namespace cg = cooperative_groups;
@@ -180,6 +181,19 @@ __host__ __device__ inline TopkWs topk_ws_view(void* ws, int b, int npx, int k) 
   return v;
 }
 
+// ---- alternative fast path (ISG_TOPK_PATH=radix): two-level radix select with a 15-bit first digit ---------------
+// (1) topk_hist15_kernel: ONE pass over the batch builds, per image, the histogram of the top 15 key bits (sign,
+//     exponent, 6 mantissa bits) - per-CTA in shared memory (32768 x u32 = 128 KB), merged into global memory with one
+//     atomic per non-empty bin.  (2) topk_pick15_kernel finds the bin that holds the k-th largest key and the rank
+//     that is left inside it.  (3) topk_filter_kernel (bin mode) copies the keys of that one bin - a few thousand - to
+//     the candidate list.  (4) topk_select_kernel picks the exact key among them (bitonic sort in one CTA for up to
+//     4096 candidates, cluster radix select above; whole-image select if the bin overflowed the list).  Exact for any
+//     input; no sampling, no probabilistic bound.
+constexpr int kBins15 = 32768;
+constexpr int kH15Threads = 1024;
+constexpr int kH15Chunk = kH15Threads * 16;     // pixels per CTA iteration: 4 x float4 per thread
+__host__ __device__ inline size_t topk_hist15_bytes(int B) { return (size_t)B * kBins15 * sizeof(uint32_t); }
+
 constexpr int kSelCluster = 8;   // CTAs per image in the sample / select kernels (one thread-block cluster)
 
 // histogram increment aggregated with match.any: one shared-memory atomic per distinct bin per warp
@@ -289,7 +303,7 @@ topk_sample_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   uint32_t lower = 0u;                  // 0: every pixel is a candidate (step 3 then falls back if needed)
   if (rk < (long long)S)                // cluster-uniform
     lower = cluster_radix_select(cluster, sh_hist, S, (uint32_t)rk, [&](int i) { return skeys[i - lo]; });
-  if (r == 0 && t == 0) { *v.lower = lower; *v.ncand = 0u; }
+  if (r == 0 && t == 0) { *v.lower = lower; v.lower[3] = 0u; *v.ncand = 0u; }
 }
 
 // Single-CTA form of the sample step: at most kSample1Max samples per image, radix-selected with block barriers
@@ -336,7 +350,101 @@ topk_sample1_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, i
     }
     lower = prefix;
   }
-  if (t == 0) { *v.lower = lower; *v.ncand = 0u; }
+  if (t == 0) { *v.lower = lower; v.lower[3] = 0u; *v.ncand = 0u; }
+}
+
+__global__ void __launch_bounds__(kH15Threads, 1)
+topk_hist15_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int B, uint32_t* __restrict__ hist15, bool vec) {
+  extern __shared__ uint32_t sh15[];             // [kBins15]
+  const int t = threadIdx.x;
+  const int cpi = (npx + kH15Chunk - 1) / kH15Chunk;                 // chunks per image
+  const long long total = (long long)B * cpi;
+  const long long c_begin = total * blockIdx.x / gridDim.x, c_end = total * (blockIdx.x + 1) / gridDim.x;
+  int cur_b = -1;
+  auto flush = [&](int b) {
+    __syncthreads();
+    uint32_t* g = hist15 + (size_t)b * kBins15;
+    for (int i = t; i < kBins15; i += kH15Threads) { const uint32_t c = sh15[i]; if (c) atomicAdd(&g[i], c); }
+    __syncthreads();
+  };
+  auto add = [&](float x, bool in) {
+    const uint32_t d = float_key(x) >> 17;
+    // a warp whose pixels all fall into one bin (flat regions) adds once instead of serialising 32 ways
+    const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+    const unsigned inm = __ballot_sync(0xffffffffu, in);
+    if (__all_sync(0xffffffffu, !in || d == d0)) { if ((t & 31) == 0 && inm) atomicAdd(&sh15[d0], (uint32_t)__popc(inm)); }
+    else if (in) atomicAdd(&sh15[d], 1u);
+  };
+  for (long long c = c_begin; c < c_end; ++c) {
+    const int b = (int)(c / cpi);
+    if (b != cur_b) {
+      if (cur_b >= 0) flush(cur_b);
+      for (int i = t; i < kBins15; i += kH15Threads) sh15[i] = 0;
+      __syncthreads();
+      cur_b = b;
+    }
+    const float* img = kp + (int64_t)b * img_stride;
+    const int base = (int)(c - (long long)b * cpi) * kH15Chunk;
+    if (vec) {
+      float4 q[4];
+      bool in[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = base + u * kH15Threads * 4 + t * 4;
+        in[u] = p < npx;                                              // npx % 4 == 0 on this path
+        q[u] = in[u] ? ldg_stream4(img + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { add(q[u].x, in[u]); add(q[u].y, in[u]); add(q[u].z, in[u]); add(q[u].w, in[u]); }
+    } else {
+#pragma unroll 4
+      for (int u = 0; u < 16; ++u) {
+        const int p = base + u * kH15Threads + t;
+        const bool in = p < npx;
+        add(in ? __ldg(img + p) : 0.0f, in);
+      }
+    }
+  }
+  if (cur_b >= 0) flush(cur_b);
+}
+
+// one CTA per image: the 15-bit bin that holds the k-th largest key, and the rank left inside the bin
+__global__ void __launch_bounds__(1024)
+topk_pick15_kernel(const uint32_t* __restrict__ hist15, int npx, int k, void* ws) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t res[2];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint32_t* hist = hist15 + (size_t)b * kBins15;
+  uint32_t h[32];
+  uint32_t sum = 0;
+  const uint4* src = reinterpret_cast<const uint4*>(hist + t * 32);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const uint4 v = src[i]; h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w; }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) sum += h[i];
+  uint32_t suf = sum;                                       // inclusive suffix sum over threads (larger bins = larger keys)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += v; }
+  if (lane == 0) warp_tot[warp] = suf;
+  if (t == 0) { res[0] = 0; res[1] = 0; }
+  __syncthreads();
+  uint32_t above = 0;
+  for (int w = warp + 1; w < 32; ++w) above += warp_tot[w];
+  uint32_t cum = suf - sum + above;                         // keys in bins owned by higher threads
+  const uint32_t kk = (uint32_t)k;
+#pragma unroll
+  for (int i = 31; i >= 0; --i) {
+    if (cum < kk && kk <= cum + h[i]) { res[0] = (uint32_t)(t * 32 + i); res[1] = kk - cum; }
+    cum += h[i];
+  }
+  __syncthreads();
+  if (t == 0) {
+    TopkWs v = topk_ws_view(ws, b, npx, k);
+    v.lower[0] = res[0] << 17;      // smallest key of the bin
+    v.lower[2] = res[1];            // rank of the answer among the keys of the bin
+    v.lower[3] = 1u;                // bin mode (topk_filter_kernel / topk_select_kernel)
+    *v.ncand = 0u;
+  }
 }
 
 __global__ void __launch_bounds__(kFilterThreads)
@@ -346,6 +454,8 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   const int b = blockIdx.y, t = threadIdx.x, lane = t & 31;
   const TopkWs v = topk_ws_view(ws, b, npx, k);
   const uint32_t lower = *v.lower;
+  const bool bin_mode = v.lower[3] != 0u;      // candidates = the keys of ONE 15-bit bin (two-level radix select)
+  const uint32_t upper = bin_mode ? (lower | 0x1ffffu) : 0xffffffffu;
   const float* img = kp + (int64_t)b * img_stride;
   if (t == 0) s_count = 0;
   __syncthreads();
@@ -361,13 +471,13 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
       if (in) q = ldg_stream4(img + p);
       key[0] = float_key(q.x); key[1] = float_key(q.y); key[2] = float_key(q.z); key[3] = float_key(q.w);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { if (!in || key[i] < lower) key[i] = 0xffffffffu; else ++c; }
+      for (int i = 0; i < 4; ++i) { if (!in || key[i] < lower || key[i] > upper) key[i] = 0xffffffffu; else ++c; }
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int p = p0 + i * kFilterThreads + t;
         key[i] = 0xffffffffu;
-        if (p < end) { const uint32_t kk = float_key(__ldg(img + p)); if (kk >= lower) { key[i] = kk; ++c; } }
+        if (p < end) { const uint32_t kk = float_key(__ldg(img + p)); if (kk >= lower && kk <= upper) { key[i] = kk; ++c; } }
       }
     }
     // NOTE: 0xffffffff marks "not a candidate"; a real key of 0xffffffff (a NaN payload) is dropped, NaNs are
@@ -399,6 +509,8 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
     if ((size_t)g + i < capc) v.cand[g + i] = buf[i];
 }
 
+constexpr int kSmallSel = 4096;   // candidates sorted by one CTA in shared memory
+
 __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
 topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, void* ws,
                    uint32_t* __restrict__ thr_key) {
@@ -407,11 +519,35 @@ topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   const int b = blockIdx.y;
   const TopkWs v = topk_ws_view(ws, b, npx, k);
   const uint32_t nc = *v.ncand;
-  const bool use_cand = nc >= (uint32_t)k && (size_t)nc <= topk_cand_cap(npx, k);
+  const bool bin_mode = v.lower[3] != 0u;
+  const uint32_t rank = bin_mode ? v.lower[2] : (uint32_t)k;      // rank of the answer among the candidates
+  const bool use_cand = nc >= rank && rank >= 1u && (size_t)nc <= topk_cand_cap(npx, k);
   uint32_t key;
+  if (use_cand && nc <= (uint32_t)kSmallSel) {   // cluster-uniform: one CTA sorts the few candidates in shared memory
+    if (cluster.block_rank() != 0) return;
+    __shared__ uint32_t sk[kSmallSel];
+    const int t = threadIdx.x;
+    int P = 1;
+    while (P < (int)nc) P <<= 1;
+    for (int i = t; i < P; i += kSelThreads) sk[i] = i < (int)nc ? v.cand[i] : 0u;      // 0 sorts last (descending)
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = t; i < (P >> 1); i += kSelThreads) {
+          const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+          const bool desc = ((lo & size) == 0);
+          const uint32_t a = sk[lo], c = sk[hi];
+          if ((a < c) == desc) { sk[lo] = c; sk[hi] = a; }
+        }
+        __syncthreads();
+      }
+    }
+    if (t == 0) thr_key[b] = sk[rank - 1];
+    return;
+  }
   if (use_cand) {   // cluster-uniform
     const uint32_t* cand = v.cand;
-    key = cluster_radix_select(cluster, sh_hist, (int)nc, (uint32_t)k, [&](int i) { return cand[i]; });
+    key = cluster_radix_select(cluster, sh_hist, (int)nc, rank, [&](int i) { return cand[i]; });
   } else {
     const float* img = kp + (int64_t)b * img_stride;
     key = cluster_radix_select(cluster, sh_hist, npx, (uint32_t)k, [&](int i) { return float_key(__ldg(img + i)); });
@@ -628,7 +764,7 @@ using namespace isg;
 
 extern "C" size_t isg_topk_workspace_bytes(int B, int H, int W, int k) {
   if (B <= 0 || H <= 0 || W <= 0 || k < 0 || (int64_t)H * W > ((int64_t)1 << 30)) return 0;
-  return (size_t)B * topk_ws_per_image(H * W, k);
+  return (size_t)B * topk_ws_per_image(H * W, k) + topk_hist15_bytes(B);
 }
 
 extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t img_stride, int k,
@@ -661,16 +797,33 @@ extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t 
     return ISG_OK;
   }
   if (npx >= 65536) {
-    int stride = 64;
-    const char* samp_env = getenv("ISG_TOPK_SAMPLE");   // "cluster": the 8-CTA cluster form with a 4x larger sample (A/B)
-    if (samp_env && samp_env[0] == 'c') {
-      while (npx / stride > kSampleMax) stride *= 2;
-      const size_t smem = (size_t)cdiv(npx / stride, kSelCluster) * sizeof(uint32_t);
-      ISG_CUDA(cudaFuncSetAttribute(topk_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      topk_sample_kernel<<<dim3(kSelCluster, B), kSelThreads, smem, stream>>>(kp, img_stride, npx, k, stride, ws);
+    // default: sample -> filter -> select.  ISG_TOPK_PATH=radix selects the sampling-free two-level radix select
+    // (exact by construction, measured 82 us vs 71 us on the bench workload in round 1: every stage is latency-bound)
+    const char* path_env = getenv("ISG_TOPK_PATH");
+    if (!(path_env && path_env[0] == 'r')) {
+      int stride = 64;
+      const char* samp_env = getenv("ISG_TOPK_SAMPLE");   // "cluster": the 8-CTA cluster form with a 4x larger sample
+      if (samp_env && samp_env[0] == 'c') {
+        while (npx / stride > kSampleMax) stride *= 2;
+        const size_t smem = (size_t)cdiv(npx / stride, kSelCluster) * sizeof(uint32_t);
+        ISG_CUDA(cudaFuncSetAttribute(topk_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        topk_sample_kernel<<<dim3(kSelCluster, B), kSelThreads, smem, stream>>>(kp, img_stride, npx, k, stride, ws);
+      } else {
+        while (npx / stride > kSample1Max) stride *= 2;
+        topk_sample1_kernel<<<B, kSelThreads, 0, stream>>>(kp, img_stride, npx, k, stride, ws);
+      }
     } else {
-      while (npx / stride > kSample1Max) stride *= 2;
-      topk_sample1_kernel<<<B, kSelThreads, 0, stream>>>(kp, img_stride, npx, k, stride, ws);
+      uint32_t* hist15 = reinterpret_cast<uint32_t*>((char*)ws + (size_t)B * topk_ws_per_image(npx, k));
+      ISG_CUDA(cudaMemsetAsync(hist15, 0, topk_hist15_bytes(B), stream));
+      int dev = 0, sms = kSMs;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const long long chunks = (long long)B * cdiv(npx, kH15Chunk);
+      const int grid15 = (int)std::min<long long>(chunks, sms);
+      const size_t smem15 = (size_t)kBins15 * sizeof(uint32_t);
+      ISG_CUDA(cudaFuncSetAttribute(topk_hist15_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem15));
+      topk_hist15_kernel<<<grid15, kH15Threads, smem15, stream>>>(kp, img_stride, npx, B, hist15, vec);
+      topk_pick15_kernel<<<B, 1024, 0, stream>>>(hist15, npx, k, ws);
     }
     dim3 grid(cdiv(npx, kFilterPxPerBlock), B);
     topk_filter_kernel<<<grid, kFilterThreads, 0, stream>>>(kp, img_stride, npx, k, ws, vec);

@@ -85,10 +85,12 @@ def test_topk_count_property_full_size(mods):
 
 @pytest.mark.parametrize("shape,k,kind", [((1024, 2048), 1, "normal"), ((1024, 2048), 700000, "normal"), ((512, 1024), 20000, "flat"),
                                           ((512, 1024), 5000, "sorted"), ((300, 500), 149999, "normal"), ((256, 256), 65536, "flat")])
-def test_topk_threshold_paths(mods, shape, k, kind):
+@pytest.mark.parametrize("path", ["sample", "radix"])
+def test_topk_threshold_paths(mods, shape, k, kind, path, monkeypatch):
     """every host-selected path (sample/filter/select, legacy multi-CTA, single-CTA) and the in-kernel
     fallback (flat / sorted images defeat the sample bound) return the exact k-th largest value"""
     lib, eng = mods["lib"], mods["engine"]
+    monkeypatch.setenv("ISG_TOPK_PATH", path)      # read by libisg on every call: sample/filter/select or two-level radix
     H, W = shape
     g = torch.Generator(device="cpu").manual_seed(H + k)
     if kind == "normal":
