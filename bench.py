@@ -289,7 +289,7 @@ def run_ours(args, wl, rank, world, local_rank):
     roofline = None
     if kern_ms:
         achieved = ALGO_BYTES_PER_PIXEL * B * H * W / (kern_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "tile_lists_kernel + dense_v4_kernel (isg_assign_dense)" if args.mode == "dense" else "assign_sparse_kernel",
+        roofline = {"bound": "hbm", "kernel": "dense_v4_kernel (isg_assign_dense; its tile lists are prebuilt on the box branch)" if args.mode == "dense" else "assign_sparse_kernel",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                     "peak_source": peak_src, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL * B * H * W}
     cpu = None

@@ -144,13 +144,18 @@ int isg_assign_sparse(const float* ae, int64_t img_stride, int64_t plane_stride,
  * the launch completes, so the same workspace serves every later call.  The rest holds the per-tile seed lists
  * (rebuilt by every call).  One workspace per concurrently running call. */
 size_t isg_assign_dense_workspace_bytes(int B, int Nmax, int H, int W);
+/* Optional: build the per-tile seed lists of isg_assign_dense ahead of time (they depend on the seeds only, not on
+ * kp / ae / thr_key), e.g. on the box branch while the top-k threshold is still being computed on another stream.
+ * isg_assign_dense is then called with lists_prebuilt = 1 for the same seeds / workspace. */
+int isg_build_tile_lists(const uint32_t* seeds, const int32_t* n_seeds, int B, int Nmax, int H, int W,
+                         void* workspace, size_t workspace_bytes, isg_stream_t stream);
 int isg_assign_dense(const float* kp, int64_t kp_img_stride,
                      const float* ae, int64_t ae_img_stride, int64_t ae_plane_stride,
                      const uint32_t* thr_key,
                      const uint32_t* seeds, const float* ghost, const int32_t* n_seeds, int B, int Nmax,
                      int H, int W, const float* ys, const float* xs,
                      int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats,
-                     void* workspace, size_t workspace_bytes, isg_stream_t stream);
+                     void* workspace, size_t workspace_bytes, int lists_prebuilt, isg_stream_t stream);
 /* dense mode: labels / scores / ghost flags of the compacted keep pixels read back from the maps.
  * score_map nullable (then score is not written).  stats (nullable, pre-initialised by isg_stats_init): count /
  * bbox of the flagged pixels per instance - the same numbers isg_assign_dense accumulates when it is given a stats

@@ -698,12 +698,24 @@ extern "C" size_t isg_assign_dense_workspace_bytes(int B, int Nmax, int H, int W
   return dense_workspace_bytes(B, Nmax, H, W);
 }
 
+extern "C" int isg_build_tile_lists(const uint32_t* seeds, const int32_t* n_seeds, int B, int Nmax, int H, int W,
+                                    void* workspace, size_t workspace_bytes, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!seeds || !n_seeds || B <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
+  if (!aligned16(seeds)) return ISG_EINVAL;
+  if (!workspace || workspace_bytes < dense_workspace_bytes(B, Nmax, H, W) || !aligned16(workspace)) return ISG_EINVAL;
+  if (W % 4 != 0) return ISG_OK;      // the tensor-map kernel is not used for this width; nothing to prepare
+  const int rc = launch_dense_v4(nullptr, 0, nullptr, 0, 0, nullptr, seeds, nullptr, n_seeds, B, Nmax, H, W, nullptr, nullptr,
+                                 nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, 1, stream);
+  return rc == ISG_EUNSUPPORTED ? ISG_OK : rc;   // unsupported geometry: isg_assign_dense falls back and needs no lists
+}
+
 extern "C" int isg_assign_dense(const float* kp, int64_t kp_img_stride, const float* ae, int64_t ae_img_stride,
                                 int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds,
                                 const float* ghost, const int32_t* n_seeds, int B, int Nmax, int H, int W,
                                 const float* ys, const float* xs, int32_t* label_map, float* score_map,
                                 uint32_t* keepbits, int32_t* stats, void* workspace, size_t workspace_bytes,
-                                isg_stream_t stream_) {
+                                int lists_prebuilt, isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!kp || !ae || !thr_key || !seeds || !ghost || !n_seeds || !ys || !xs || !label_map || !keepbits) return ISG_EINVAL;
   if (B <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
@@ -719,7 +731,8 @@ extern "C" int isg_assign_dense(const float* kp, int64_t kp_img_stride, const fl
   const char* v2_env = getenv("ISG_DENSE_V2");
   if (vec && !(v1_env && v1_env[0] == '1') && !(v2_env && v2_env[0] == '1')) {
     const int rc = launch_dense_v4(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
-                                   Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, workspace, workspace_bytes, stream);
+                                   Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, workspace, workspace_bytes,
+                                   lists_prebuilt ? 2 : 0, stream);
     if (rc != ISG_EUNSUPPORTED) return rc;
   }
   if (vec && !(v1_env && v1_env[0] == '1')) {

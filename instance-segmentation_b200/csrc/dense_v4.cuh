@@ -52,7 +52,7 @@ struct D4Geom {
 // a 32-byte header followed by the first `cap` seed records overlapping the tile, in ascending seed index.
 struct __align__(16) TileHdr {
   int b, y0, x0, nhit;            // image, first row / column of the tile, seeds overlapping the tile (< 0: end marker)
-  uint32_t thr_key;               // selection threshold of image b
+  uint32_t thr_key;               // unused (the threshold comes from thr_key[b]: the lists do not depend on the top-k)
   int n_seeds;                    // seeds of image b
   int tile;                       // tile index (locates the overflow list when nhit > cap)
   int pad;
@@ -190,7 +190,7 @@ struct D4Smem {
 // only for the rare tiles with more than cap hits).
 __global__ void __launch_bounds__(256)
 tile_lists_kernel(const SeedRec* __restrict__ seeds, const int32_t* __restrict__ n_seeds,
-                  const uint32_t* __restrict__ thr_key, int Nmax, int B, int H, int W, int TH, int tilesX, int tilesY,
+                  int Nmax, int B, int H, int W, int TH, int tilesX, int tilesY,
                   int cap, unsigned char* __restrict__ lists, uint16_t* __restrict__ ovf) {
   // programmatic dependent launch: let the dense kernel's CTAs start (barrier init, first kp/ae loads) while this
   // grid is still running; its producer waits on the grid dependency before it touches a list
@@ -234,7 +234,7 @@ tile_lists_kernel(const SeedRec* __restrict__ seeds, const int32_t* __restrict__
   }
   if (lane == 0) {
     TileHdr h;
-    h.b = b; h.y0 = y0; h.x0 = x0; h.nhit = cnt; h.thr_key = thr_key[b]; h.n_seeds = n; h.tile = (int)t; h.pad = 0;
+    h.b = b; h.y0 = y0; h.x0 = x0; h.nhit = cnt; h.thr_key = 0u; h.n_seeds = n; h.tile = (int)t; h.pad = 0;
     *reinterpret_cast<TileHdr*>(out) = h;
   }
 }
@@ -242,7 +242,8 @@ tile_lists_kernel(const SeedRec* __restrict__ seeds, const int32_t* __restrict__
 template <int RW, int WG, int G, bool SCORE>
 __global__ void __launch_bounds__(32 * (WG * G + 1), 1)
 dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant__ CUtensorMap tm_ae,
-                const SeedRec* __restrict__ seeds, const float4* __restrict__ ghost, int Nmax, int B, int H, int W,
+                const uint32_t* __restrict__ thr_key, const SeedRec* __restrict__ seeds, const float4* __restrict__ ghost,
+                int Nmax, int B, int H, int W,
                 int Wwords, int tilesX, int tilesY, int nstages, int cap, const unsigned char* __restrict__ lists,
                 const uint16_t* __restrict__ ovf, const float* __restrict__ ys, const float* __restrict__ xs,
                 int32_t* __restrict__ label_map, float* __restrict__ score_map, uint32_t* __restrict__ keepbits,
@@ -336,8 +337,8 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
     const int b = h0.x;
     const int ybeg = h0.y + wl * RW;
     if (ybeg < H && !(dbg_flags & 1)) {                                     // warp-uniform (ragged bottom)
-      const int4 h1 = *reinterpret_cast<const int4*>(lst + 16);             // thr_key, n_seeds, tile, pad
-      const Thr thr = make_thr((uint32_t)h1.x);
+      const int4 h1 = *reinterpret_cast<const int4*>(lst + 16);             // -, n_seeds, tile, pad
+      const Thr thr = make_thr(__ldg(thr_key + b));                         // 32 bytes per batch: stays in L1
       const int x0 = h0.z + lane * 4;
       const bool colvalid = x0 < W;                                         // W % 4 == 0: a lane is all in or all out
       float xs4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -512,7 +513,8 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
                                int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds, const float* ghost,
                                const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys, const float* xs,
                                int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats, void* workspace,
-                               size_t workspace_bytes, int max_stages, cudaStream_t stream) {
+                               size_t workspace_bytes, int max_stages, int mode, cudaStream_t stream) {
+  // mode 0: tile lists + dense kernel; 1: tile lists only (isg_build_tile_lists); 2: dense kernel only (lists prebuilt)
   using Geo = D4Geom<RW, WG>;
   static_assert(Geo::TH >= kD4MinTileRows, "workspace is sized for tiles of at least kD4MinTileRows rows");
   if (Nmax > 65535) return ISG_EUNSUPPORTED;
@@ -529,6 +531,13 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   unsigned char* lists = ws + kDenseSchedBytes;
   const long long T_max = (long long)B * tilesX * cdiv(H, kD4MinTileRows);
   uint16_t* ovf = reinterpret_cast<uint16_t*>(lists + dense_lists_bytes(T_max, Nmax));
+  const SeedRec* srec = reinterpret_cast<const SeedRec*>(seeds);
+  if (mode != 2) {
+    tile_lists_kernel<<<(unsigned)cdiv64(T, 8), 256, 0, stream>>>(srec, n_seeds, Nmax, B, H, W, Geo::TH, tilesX, tilesY, cap, lists,
+                                                                  ovf);
+    ISG_LAUNCH_CHECK();
+    if (mode == 1) return ISG_OK;
+  }
   static isg_encode_tiled_fn encode = get_encode_tiled();
   if (!encode) return ISG_EUNSUPPORTED;
   CUtensorMap tm_kp, tm_ae;
@@ -562,28 +571,25 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   if (const char* e = getenv("ISG_DENSE_TAIL")) dyn_tail = std::max(0, atoi(e));
   int dbg_flags = 0;                                  // measurement aid: bit 0 = consumers release tiles without computing
   if (const char* e = getenv("ISG_DENSE_DEBUG")) dbg_flags = atoi(e);
-  const SeedRec* srec = reinterpret_cast<const SeedRec*>(seeds);
-  tile_lists_kernel<<<(unsigned)cdiv64(T, 8), 256, 0, stream>>>(srec, n_seeds, thr_key, Nmax, B, H, W, Geo::TH, tilesX, tilesY, cap,
-                                                                lists, ovf);
-  ISG_LAUNCH_CHECK();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   const char* pdl_env = getenv("ISG_DENSE_PDL");
-  cfg.attrs = attr; cfg.numAttrs = (pdl_env && pdl_env[0] == '0') ? 0 : 1;
+  // programmatic dependent launch only behind our own pre-pass (mode 0); with prebuilt lists the predecessor is unknown
+  cfg.attrs = attr; cfg.numAttrs = (mode != 0 || (pdl_env && pdl_env[0] == '0')) ? 0 : 1;
   const float4* ghost4 = reinterpret_cast<const float4*>(ghost);
   const unsigned char* clists = lists;
   const uint16_t* covf = ovf;
   if (score_map) {
     ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, true>, tm_kp, tm_ae, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
+    ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, true>, tm_kp, tm_ae, thr_key, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
                                 tilesY, nstages, cap, clists, covf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail,
                                 dbg_flags));
   } else {
     ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, false>, tm_kp, tm_ae, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
+    ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, false>, tm_kp, tm_ae, thr_key, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
                                 tilesY, nstages, cap, clists, covf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail,
                                 dbg_flags));
   }
@@ -596,7 +602,7 @@ inline int launch_dense_v4(const float* kp, int64_t kp_img_stride, const float* 
                            int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds, const float* ghost,
                            const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys, const float* xs,
                            int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats, void* workspace,
-                           size_t workspace_bytes, cudaStream_t stream) {
+                           size_t workspace_bytes, int mode, cudaStream_t stream) {
   int rw = 2, wg = 8, g = 2, st = kD4MaxStages;
   if (const char* e = getenv("ISG_DENSE_CFG")) {
     int a = 0, b_ = 0, c = 0, d = 0;
@@ -607,7 +613,7 @@ inline int launch_dense_v4(const float* kp, int64_t kp_img_stride, const float* 
 #define ISG_V4_CASE(RW_, WG_, G_)                                                                                      \
   if (rw == RW_ && wg == WG_ && g == G_)                                                                               \
     return launch_dense_v4_cfg<RW_, WG_, G_>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, \
-                                             n_seeds, B, Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, workspace, workspace_bytes, st, stream);
+                                             n_seeds, B, Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, workspace, workspace_bytes, st, mode, stream);
   ISG_V4_CASE(2, 8, 2)
   ISG_V4_CASE(4, 4, 3)
   ISG_V4_CASE(4, 4, 4)

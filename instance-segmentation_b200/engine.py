@@ -161,7 +161,7 @@ class DecodePlan:
 
     def run_assign(self, kp: torch.Tensor, ae: torch.Tensor, rois: torch.Tensor, n_seeds: torch.Tensor,
                    layout: int = _lib.ISG_BOX_XYXY, time_main: bool = False, tail: str = "lists",
-                   obj_pixel_th: int = 0, seeds_ready: bool = False) -> None:
+                   obj_pixel_th: int = 0, seeds_ready: bool = False, lists_ready: bool = False) -> None:
         """Stage 2: seeds -> assignment (dense or sparse) -> tail.  Needs self.thr_key.
         tail "lists": compaction + per-pixel labels + per-instance point sets (idx/label/flag/offsets/points);
         tail "polygons" (dense mode, XYXY rois): isg_instance_polygons straight from the label map
@@ -191,7 +191,7 @@ class DecodePlan:
             call("isg_assign_dense", ptr(kp), kp_stride, ptr(ae), ae_img, ae_plane, ptr(self.thr_key), ptr(self.seeds),
                  ptr(self.ghost), ptr(n_seeds), B, N, H, W, ptr(self.ys), ptr(self.xs), ptr(self.label_map),
                  ptr(self.score_map), ptr(self.keepbits), ptr(self.stats) if self.fused_stats else 0, ptr(self.dense_ws),
-                 self.dense_ws_bytes, s)
+                 self.dense_ws_bytes, 1 if lists_ready else 0, s)
             if ev:
                 ev[1].record()
             if tail == "polygons":
@@ -322,8 +322,13 @@ class DecodePipeline:
         call("isg_gather_build_seeds", ptr(bp.cand_boxes), ptr(bp.cand_scores), ptr(bp.cand_cls), ptr(bp.keep), ptr(bp.n_keep),
              bp.B, bp.cap, bp.N, ptr(dp.ys), ptr(dp.xs), dp.H, dp.W, dp.ghost_k, dp.scale, ptr(bp.rois), ptr(bp.scores),
              ptr(bp.cls), ptr(bp.n_seeds), ptr(dp.seeds), ptr(dp.ghost), ptr(dp.stats), stream_ptr(self.device))
+        dense = dp.mode == "dense"
+        if dense:   # the tile lists of the dense kernel only need the seeds: build them before joining the top-k branch
+            call("isg_build_tile_lists", ptr(dp.seeds), ptr(bp.n_seeds), dp.B, dp.N, dp.H, dp.W, ptr(dp.dense_ws),
+                 dp.dense_ws_bytes, stream_ptr(self.device))
         main.wait_event(self.join)
-        dp.run_assign(kp, ae, bp.rois, bp.n_seeds, _lib.ISG_BOX_XYXY, time_main, tail, obj_pixel_th, seeds_ready=True)
+        dp.run_assign(kp, ae, bp.rois, bp.n_seeds, _lib.ISG_BOX_XYXY, time_main, tail, obj_pixel_th, seeds_ready=True,
+                      lists_ready=dense)
 
 
 _pipes = {}
