@@ -262,7 +262,9 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
                          float2* __restrict__ tmp_ws) {
   extern __shared__ __align__(16) unsigned char poly_smem_raw[];
   PolySmem& s = *reinterpret_cast<PolySmem*>(poly_smem_raw);
-  const int b = blockIdx.y, inst = blockIdx.x;
+  // image index fastest: the CTAs of the real instances (inst < n_seeds) are contiguous in launch order and spread
+  // evenly over the SMs; the empty tail of the instance table comes last
+  const int b = blockIdx.x, inst = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t io = (size_t)b * Nmax + inst;
   const int n = min(n_seeds[b], Nmax);
@@ -456,7 +458,7 @@ extern "C" int isg_instance_polygons(const uint32_t* keepbits, const int32_t* la
   ISG_LAUNCH_CHECK();
   const size_t smem = sizeof(PolySmem);
   ISG_CUDA(cudaFuncSetAttribute(instance_polygons_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(Nmax, B);
+  dim3 grid(B, Nmax);
   unsigned long long* keys_ws = static_cast<unsigned long long*>(workspace);     // [B][2*cap]
   float2* tmp_ws = workspace ? reinterpret_cast<float2*>(keys_ws + (size_t)B * cap * 2) : nullptr;   // [B][cap]
   instance_polygons_kernel<<<grid, kPolyThreads, smem, stream>>>(

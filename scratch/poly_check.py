@@ -39,3 +39,9 @@ for b in range(B):
             assert p1.shape == p2.shape and np.array_equal(key(p1), key(p2))
             nd += 1
 print("polygons", nt, "identical", ne, "tie-order differences", nd)
+from isg_b200 import engine as _e
+for key, plan in _e._plans.items():
+    if key[0] == "d" and hasattr(plan, "inst_count"):
+        cnt = plan.inst_count.cpu().numpy().ravel()
+        fl = plan.inst_flags.cpu().numpy().ravel()
+        print("plan", key[1:6], "instances", int((cnt > 0).sum()), "K max", int(cnt.max()), "top10", sorted(cnt.tolist())[-10:], "mean", float(cnt[cnt > 0].mean()), "flags", np.bincount(fl, minlength=3).tolist())
