@@ -173,7 +173,7 @@ __device__ __forceinline__ void d4_tma_4d(void* dst, const CUtensorMap* tm, int 
 // shared-memory layout (byte offsets from the dynamic shared base)
 template <int RW, int WG>
 struct D4Smem {
-  int stage, list, list_stride, bars, total;
+  int stage, list, list_stride, bars, thr, total;
   __host__ __device__ D4Smem(int cap, int nstages) {
     using Geo = D4Geom<RW, WG>;
     int o = 0;
@@ -181,6 +181,7 @@ struct D4Smem {
     list_stride = (int)sizeof(TileHdr) + cap * (int)sizeof(SeedRec);
     list = o;  o += nstages * list_stride;
     bars = o;  o += 2 * kD4MaxStages * 8;
+    thr = o;   o += kD4MaxStages * 4;           // selection threshold key of the tile in each slot (written by the producer)
     total = o;
   }
 };
@@ -255,6 +256,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
   const D4Smem<RW, WG> L(cap, nstages);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);           // [kD4MaxStages]
   uint64_t* empty = full + kD4MaxStages;                                 // [kD4MaxStages]
+  uint32_t* s_thr = reinterpret_cast<uint32_t*>(smem + L.thr);           // [kD4MaxStages]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -293,6 +295,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
       // the slot must have been released by the consumers of its previous tile
       if (round >= 1) d4_wait_parked(&empty[slot], (uint32_t)((round - 1) & 1));
       unsigned char* st = smem + L.stage + (size_t)slot * Geo::kStage;
+      s_thr[slot] = __ldg(thr_key + b);          // ordinary store: released to the consumers by the arrive below
       mbar_expect_tx(&full[slot], Geo::kTx + list_bytes);
       bulk_g2s(smem + L.list + (size_t)slot * L.list_stride, lists + (size_t)t * list_bytes, list_bytes, &full[slot]);
       d4_tma_3d(st, &tm_kp, x0t - 4, y0t - 1, b, &full[slot]);
@@ -338,7 +341,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
     const int ybeg = h0.y + wl * RW;
     if (ybeg < H && !(dbg_flags & 1)) {                                     // warp-uniform (ragged bottom)
       const int4 h1 = *reinterpret_cast<const int4*>(lst + 16);             // -, n_seeds, tile, pad
-      const Thr thr = make_thr(__ldg(thr_key + b));                         // 32 bytes per batch: stays in L1
+      const Thr thr = make_thr(s_thr[slot]);
       const int x0 = h0.z + lane * 4;
       const bool colvalid = x0 < W;                                         // W % 4 == 0: a lane is all in or all out
       float xs4[4] = {0.f, 0.f, 0.f, 0.f};
