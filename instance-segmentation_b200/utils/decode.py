@@ -254,6 +254,16 @@ def draw_box(box_sizes, centers, trans_info, transforms):
     cv2.imwrite(r'{}/{}_{}.png'.format(base_dir, os.path.basename(trans_info.img_path), "box"), img)
 
 
+def draw_objs(img, kp_index, kp_mask, transforms, infos):
+    """:238-245 — draw, per column of the membership matrix kp_mask [L,C], the key points kp_index [L,2] it selects."""
+    l, c = kp_mask.shape
+    for i in range(c):
+        c_vec = kp_mask[:, i]
+        c_kps = to_numpy(kp_index[to_numpy(c_vec.nonzero()), :])
+        img = draw_kp(img, c_kps, transforms, i, infos, "objs")
+    return img
+
+
 def draw_candid(kps, lt, rb, img, color):
     import cv2
     if img is None:
