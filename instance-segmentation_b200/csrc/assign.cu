@@ -640,9 +640,6 @@ extern "C" int isg_gather_build_seeds(const float* cand_boxes, const float* cand
   if (B <= 0 || cap <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
   if (!aligned16(cand_boxes) || !aligned16(rois) || !aligned16(seeds) || !aligned16(ghost)) return ISG_EINVAL;
   dim3 grid(cdiv(Nmax, 128), B);
-  static const bool carve = (cudaFuncSetAttribute(gather_build_seeds_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                  (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess);
-  (void)carve;
   gather_build_seeds_kernel<<<grid, 128, 0, stream>>>(
       reinterpret_cast<const float4*>(cand_boxes), cand_scores, cand_cls, keep, n_keep, cap, Nmax, ys, xs, H, W, ghost_k, scale,
       reinterpret_cast<float4*>(rois), scores, cls, n_out, reinterpret_cast<SeedRec*>(seeds), reinterpret_cast<float4*>(ghost),

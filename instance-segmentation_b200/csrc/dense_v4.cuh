@@ -536,10 +536,6 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   uint16_t* ovf = reinterpret_cast<uint16_t*>(lists + dense_lists_bytes(T_max, Nmax));
   const SeedRec* srec = reinterpret_cast<const SeedRec*>(seeds);
   if (mode != 2) {
-    // same shared-memory carve-out as the dense kernel that follows: the SMs do not have to reconfigure in between
-    static const bool carve = (cudaFuncSetAttribute(tile_lists_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                    (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess);
-    (void)carve;
     tile_lists_kernel<<<(unsigned)cdiv64(T, 8), 256, 0, stream>>>(srec, n_seeds, Nmax, B, H, W, Geo::TH, tilesX, tilesY, cap, lists,
                                                                   ovf);
     ISG_LAUNCH_CHECK();

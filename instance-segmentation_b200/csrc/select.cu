@@ -833,9 +833,6 @@ extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t 
     for (int b = 0; b < B; ++b)
       ISG_CUDA(cudaMemsetAsync((char*)ws + (size_t)b * per + 3 * kHistBins * sizeof(uint32_t), 0, 64, stream));
   }
-  static const bool carve = (cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                  (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess);
-  (void)carve;
   topk_select_kernel<<<dim3(kSelCluster, B), kSelThreads, 0, stream>>>(kp, img_stride, npx, k, ws, thr_key);
   ISG_LAUNCH_CHECK();
   return ISG_OK;
