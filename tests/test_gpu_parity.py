@@ -468,6 +468,31 @@ def test_full_size_batch_properties(mods, oracle):
     assert np.array_equal(out["sparse"]["label"][0, :M], core["label"].numpy().astype(np.int32))
     np.testing.assert_allclose(out["sparse"]["score"][0, :M], core["score"].numpy(), rtol=RTOL, atol=ATOL)
     assert out["sparse"]["stats"][0, :, 0].sum() == out["sparse"]["flag"][0, :M].sum() == out["sparse"]["offsets"][0, N]
+    # device polygon tail at full size: every instance's polygon is a permutation of its point set from the list tail,
+    # its vertices come in non-decreasing polar angle about the internal point, and the statistics agree
+    dec = mods["decode"]
+    plan = eng.DecodePlan(B, H, W, N, 20000, DEV, "dense", want_score=False)
+    plan.run(kp, ae, rois, n, tail="polygons", obj_pixel_th=2)
+    torch.cuda.synchronize()
+    st, ct, fl = plan.inst_start.cpu().numpy(), plan.inst_count.cpu().numpy(), plan.inst_flags.cpu().numpy()
+    internal, pts = plan.inst_internal.cpu().numpy(), plan.poly_points.cpu().numpy()
+    assert np.array_equal(plan.stats.cpu().numpy(), out["dense"]["stats"])
+    key = lambda a: a[np.lexsort((a[:, 0], a[:, 1]))]
+    n_poly = 0
+    for b in range(B):
+        off = out["dense"]["offsets"][b]
+        assert int(plan.img_total[b].item()) == off[N]
+        for i in range(N):
+            want = out["dense"]["points"][b, off[i]:off[i + 1]]
+            got = pts[b, st[b, i]:st[b, i] + ct[b, i]]
+            assert ct[b, i] == want.shape[0] and np.array_equal(key(got), key(want)), (b, i)
+            if fl[b, i] == 1:
+                th = dec._polar_angles(got, np.repeat(internal[b, i][None], len(got), 0))
+                assert np.all(np.diff(th[~np.isnan(th)]) >= -1e-6), (b, i)      # numpy vs device arctan: <= 1-2 ulp
+                n_poly += 1
+            else:
+                assert fl[b, i] == 0
+    assert n_poly > N
 
 
 # ---------------------------------------------------------------------------------------------- transcendentals
