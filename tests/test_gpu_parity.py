@@ -133,7 +133,8 @@ def _run_plan(mods, img, kp_th, mode, want_score=True, fused_stats=False):
 
 
 @pytest.mark.parametrize("mode", ["sparse", "dense", "dense-fused-stats"])
-@pytest.mark.parametrize("shape,N,kp_th", [((256, 512), 20, 20000), ((96, 160), 5, 100), ((130, 257), 6, 3000)])
+@pytest.mark.parametrize("shape,N,kp_th", [((256, 512), 20, 20000), ((96, 160), 5, 100), ((130, 257), 6, 3000),
+                                          ((33, 64), 2, 500), ((70, 260), 4, 2000), ((48, 36), 2, 300)])
 def test_group_core_vs_oracle(mods, oracle, mode, shape, N, kp_th):
     rd, _ = oracle
     img = mods["synth"].make_image(77 + N, shape[0], shape[1], N)
