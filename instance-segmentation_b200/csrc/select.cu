@@ -194,7 +194,10 @@ constexpr int kH15Threads = 1024;
 constexpr int kH15Chunk = kH15Threads * 16;     // pixels per CTA iteration: 4 x float4 per thread
 __host__ __device__ inline size_t topk_hist15_bytes(int B) { return (size_t)B * kBins15 * sizeof(uint32_t); }
 
-constexpr int kSelCluster = 8;   // CTAs per image in the sample / select kernels (one thread-block cluster)
+#ifndef ISG_SEL_CLUSTER
+#define ISG_SEL_CLUSTER 8
+#endif
+constexpr int kSelCluster = ISG_SEL_CLUSTER;   // CTAs per image in the sample / select kernels (one thread-block cluster)
 
 // histogram increment aggregated with match.any: one shared-memory atomic per distinct bin per warp
 __device__ __forceinline__ void hist_add_match(uint32_t* sh, uint32_t bin, bool valid, int lane) {
@@ -249,7 +252,10 @@ __device__ void resolve_digit_cluster(cg::cluster_group& cluster, uint32_t* sh_h
 // cluster (1024 threads each) histograms a contiguous slice; the per-CTA histograms are summed through
 // DSMEM, so all CTAs resolve the same digit.  sh_hist: this CTA's 2048-bin histogram (shared memory).
 template <typename KeyAt>
-__device__ uint32_t cluster_radix_select(cg::cluster_group& cluster, uint32_t* sh_hist, int n, uint32_t rank, KeyAt key_at) {
+__device__ uint32_t cluster_radix_select(cg::cluster_group& cluster, uint32_t* sh_hist2, int n, uint32_t rank, KeyAt key_at) {
+  // sh_hist2: TWO 2048-bin histograms; pass p uses buffer p & 1, so a CTA may clear the buffer of the next pass while
+  // its peers still read the current one - one cluster barrier per pass instead of two, plus one before returning
+  // (a CTA must not exit while a peer can still read its shared memory).
   const int t = threadIdx.x, lane = t & 31;
   const int nb = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
   const int chunk = (n + nb - 1) / nb;
@@ -257,6 +263,7 @@ __device__ uint32_t cluster_radix_select(cg::cluster_group& cluster, uint32_t* s
   uint32_t prefix = 0, pmask = 0, krem = rank;
 #pragma unroll 1
   for (int pass = 0; pass < 3; ++pass) {
+    uint32_t* sh_hist = sh_hist2 + (pass & 1) * kHistBins;
     for (int i = t; i < kHistBins; i += kSelThreads) sh_hist[i] = 0;
     __syncthreads();
     for (int i0 = lo; i0 < hi; i0 += kSelThreads * 4) {   // warp-uniform trip count, 4 independent loads in flight
@@ -267,22 +274,22 @@ __device__ uint32_t cluster_radix_select(cg::cluster_group& cluster, uint32_t* s
 #pragma unroll
       for (int u = 0; u < 4; ++u) hist_add_match(sh_hist, digit_of(key[u], pass), in[u] && (key[u] & pmask) == prefix, lane);
     }
-    cluster.sync();   // every CTA's histogram is complete and visible
+    cluster.sync();   // every CTA's histogram of this pass is complete and visible
     uint32_t d, k2;
     resolve_digit_cluster(cluster, sh_hist, krem, &d, &k2);
     krem = k2;
     if (pass == 0) { prefix = d << 21; pmask = 0xffe00000u; }
     else if (pass == 1) { prefix |= d << 10; pmask = 0xfffffc00u; }
     else prefix |= d;
-    cluster.sync();   // nobody still reads this CTA's histogram when the next pass clears it
   }
+  cluster.sync();     // nobody still reads this CTA's histograms
   return prefix;
 }
 
 __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
 topk_sample_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, int stride, void* ws) {
   extern __shared__ uint32_t skeys[];   // this CTA's slice of the sample, [ceil(S / cluster)]
-  __shared__ uint32_t sh_hist[kHistBins];
+  __shared__ uint32_t sh_hist[2 * kHistBins];
   cg::cluster_group cluster = cg::this_cluster();
   const int b = blockIdx.y, t = threadIdx.x;
   const int r = (int)cluster.block_rank(), nb = (int)cluster.num_blocks();
@@ -514,7 +521,7 @@ constexpr int kSmallSel = 4096;   // candidates sorted by one CTA in shared memo
 __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
 topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, void* ws,
                    uint32_t* __restrict__ thr_key) {
-  __shared__ uint32_t sh_hist[kHistBins];
+  __shared__ uint32_t sh_hist[2 * kHistBins];
   cg::cluster_group cluster = cg::this_cluster();
   const int b = blockIdx.y;
   const TopkWs v = topk_ws_view(ws, b, npx, k);
