@@ -1,7 +1,7 @@
 """GPU sweep of the dense kernel geometries: time + equality against the v2 kernel (parity-green baseline)."""
 import os, sys, json
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this file lives in tools/)
 sys.path.insert(0, ROOT)
 import bench
 import isg_b200  # noqa
