@@ -201,3 +201,38 @@ def test_host_internal_points_equal_reference_search(dec):
         assert np.array_equal(internal[i], np.asarray(want, dtype=np.float32)), i
         n_fallback += not np.array_equal(want, c)
     assert n_fallback > 10
+
+
+def test_assembly_from_device_polygon_buffers(dec):
+    """decode_output's host side for the device polygon stage: slicing of the read-back buffers, box-order of the
+    instances, empty images, and the flag-2 path (an instance the device left unsorted is finished by aug_group)"""
+    from types import SimpleNamespace
+    B, N, cap = 3, 4, 64
+    ring = lambda cx, cy, r, n: np.stack([cx + r * np.cos(np.linspace(0, 2 * np.pi, n, endpoint=False)),
+                                          cy + r * np.sin(np.linspace(0, 2 * np.pi, n, endpoint=False))], 1).round().astype(np.float32)
+    p0, p1, p2 = ring(20, 20, 8, 12), ring(50, 30, 6, 10), ring(30, 30, 10, 16)
+    pts = np.zeros((B, cap, 2), np.float32)
+    # image 0: instance 1 allocated before instance 0 (blocks are handed out in completion order), instance 2 invalid
+    pts[0, 0:10], pts[0, 10:22] = p1, p0
+    rs = np.random.RandomState(0)
+    raw2 = p2[rs.permutation(len(p2))]                                 # image 2: one instance left unsorted (flag 2)
+    pts[2, 5:5 + len(raw2)] = raw2
+    plan = SimpleNamespace(
+        img_total=torch.tensor([22, 0, 21], dtype=torch.int32),
+        inst_start=torch.tensor([[10, 0, 22, 0], [0, 0, 0, 0], [5, 0, 0, 0]], dtype=torch.int32),
+        inst_count=torch.tensor([[12, 10, 1, 0], [0, 0, 0, 0], [16, 0, 0, 0]], dtype=torch.int32),
+        inst_flags=torch.tensor([[1, 1, 0, 0], [0, 0, 0, 0], [2, 0, 0, 0]], dtype=torch.uint8),
+        poly_points=torch.from_numpy(pts))
+    rois = np.zeros((B, N, 4), np.float32)
+    rois[0, 0], rois[0, 1], rois[0, 2] = (10, 10, 30, 30), (42, 22, 58, 38), (0, 0, 4, 4)
+    rois[2, 0] = (18, 18, 42, 42)
+    scores = np.linspace(0.9, 0.1, B * N, dtype=np.float32).reshape(B, N)
+    cls = np.arange(B * N, dtype=np.int32).reshape(B, N) % 5
+    dets = dec._dets_from_device_polygons(plan, B, np.array([3, 0, 1]), rois, scores, cls, DecodeCfg())
+    assert [len(d) for d in dets] == [2, 0, 1]
+    (c0, f0, k0, g0), (c1, f1, k1, g1) = dets[0]
+    assert np.array_equal(g0, p0) and np.array_equal(g1, p1) and (int(c0), int(c1)) == (0, 1)
+    assert f0 == scores[0, 0] and np.array_equal(k0, np.array([20, 20], np.float32)) and np.array_equal(k1, np.array([50, 30], np.float32))
+    # flag 2: same polygon as aug_group on the raw set (sorted by angle about the centre)
+    want = dec.aug_group(raw2.copy(), np.array([30, 30], np.float32))
+    assert want is not None and np.array_equal(dets[2][0][3], want)
