@@ -139,10 +139,9 @@ int isg_assign_sparse(const float* ae, int64_t img_stride, int64_t plane_stride,
  * top-k threshold and the 3x3 peak test, assigns every pixel, writes label_map [B,H,W] int32,
  * keepbits [B,H,ceil(W/32)], optional score_map [B,H,W] fp32 (nullable), and accumulates stats
  * for the keep pixels.  label_map[keep] equals isg_assign_sparse's label (rows are independent). */
-/* workspace: isg_assign_dense_workspace_bytes() bytes, 16-byte aligned.  Its first 256 bytes (the tile scheduler)
- * must be ZERO-FILLED by the caller once when the workspace is allocated; the kernel leaves them zero-filled when
- * the launch completes, so the same workspace serves every later call.  The rest holds the per-tile seed lists
- * (rebuilt by every call).  One workspace per concurrently running call. */
+/* workspace: isg_assign_dense_workspace_bytes() bytes, 16-byte aligned, uninitialised: the tile scheduler words and
+ * the per-tile seed lists in it are (re)written by every call (or by isg_build_tile_lists).  One workspace per
+ * concurrently running call. */
 size_t isg_assign_dense_workspace_bytes(int B, int Nmax, int H, int W);
 /* Optional: build the per-tile seed lists of isg_assign_dense ahead of time (they depend on the seeds only, not on
  * kp / ae / thr_key), e.g. on the box branch while the top-k threshold is still being computed on another stream.

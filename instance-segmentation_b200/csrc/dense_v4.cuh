@@ -274,8 +274,8 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
     int slot = 0, round = 0;
     // Tile order: the first n_static tiles of a CTA are c, c + P, c + 2P, ... (P = grid size; neighbouring CTAs work
     // on neighbouring tiles, no scheduling traffic); the last `dyn_tail` tiles per CTA (and the remainder of T / P)
-    // come from a global counter so that CTAs that finish early take over work from the slow ones.  The counter
-    // value is always requested one tile ahead: an atomic round trip under full memory load is ~2 us, a CTA that
+    // come from a global counter (zeroed by the host before the launch) so that CTAs that finish early take over work
+    // from the slow ones.  The counter value is always requested one tile ahead: an atomic round trip under full memory load is ~2 us, a CTA that
     // waited for it on every tile would be latency-bound.
     const unsigned P = gridDim.x;
     const unsigned n_static = (T / P > (unsigned)dyn_tail) ? (T / P - (unsigned)dyn_tail) : 0u;
@@ -315,7 +315,8 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
       mbar_arrive_plain(&full[slot]);
       if (++slot == nstages) { slot = 0; ++round; }
     }
-    // the last CTA to finish leaves the scheduler words zeroed for the next launch
+    // the last CTA to finish leaves the scheduler words zeroed, so a second lists_prebuilt launch on the same lists
+    // also starts from zero (the host additionally zeroes them whenever it rebuilds the lists)
     __threadfence();
     const unsigned done = atomicAdd(&sched[1], 1u);
     if (done == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
@@ -536,6 +537,9 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   uint16_t* ovf = reinterpret_cast<uint16_t*>(lists + dense_lists_bytes(T_max, Nmax));
   const SeedRec* srec = reinterpret_cast<const SeedRec*>(seeds);
   if (mode != 2) {
+    // the tile counter of the dynamic scheduler starts every launch at zero (reset here, together with the lists, so
+    // that a dense launch that follows on the same stream - this call or a later lists_prebuilt one - finds it clean)
+    ISG_CUDA(cudaMemsetAsync(sched, 0, kDenseSchedBytes, stream));
     tile_lists_kernel<<<(unsigned)cdiv64(T, 8), 256, 0, stream>>>(srec, n_seeds, Nmax, B, H, W, Geo::TH, tilesX, tilesY, cap, lists,
                                                                   ovf);
     ISG_LAUNCH_CHECK();

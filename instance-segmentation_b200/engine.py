@@ -133,9 +133,9 @@ class DecodePlan:
             self.poly_ws_bytes = int(_lib.lib().isg_instance_polygons_workspace_bytes(B, cap))
             self.poly_ws, self.poly_ws_ptr = aligned_workspace(self.poly_ws_bytes, d)
             self.label_map = torch.empty((B, H, W), dtype=i32, device=d)
-            # tile scheduler of the dense kernel: zero-filled once, the kernel leaves it zero-filled
+            # tile scheduler words + per-tile seed lists of the dense kernel
             self.dense_ws_bytes = int(_lib.lib().isg_assign_dense_workspace_bytes(B, N, H, W))
-            self.dense_ws = torch.zeros(self.dense_ws_bytes, dtype=torch.uint8, device=d)
+            self.dense_ws = torch.empty(self.dense_ws_bytes, dtype=torch.uint8, device=d)
             self.score_map = torch.empty((B, H, W), dtype=f32, device=d) if want_score else None
         else:
             self.label_map = self.score_map = None
