@@ -327,10 +327,22 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # rank 0 prints ONE JSON line on stdout: NCCL writes its version banner ("NCCL version ...", printed at
+        # NCCL_DEBUG=VERSION and above, which this image presets) to file descriptor 1 when the first communicator is
+        # created, so stdout points at stderr while the process group comes up and the first collective runs
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device=torch.device("cuda", local_rank))
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     try:
         run_ours(args, wl, rank, world, local_rank)
     finally:
