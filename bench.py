@@ -293,7 +293,7 @@ def run_ours(args, wl, rank, world, local_rank):
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                     "peak_source": peak_src, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL * B * H * W}
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # the CPU baseline is taken on rank 0 at N=1 only
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         n_img = max(1, min(args.cpu_images, B))
