@@ -276,6 +276,7 @@ nms_scan_kernel(const int32_t* __restrict__ count, int cap, void* ws, int32_t* _
 // shared memory.  The three-kernel path above remains for larger candidate sets.
 // ---------------------------------------------------------------------------------------------
 constexpr int kSmallMax = 1024;
+constexpr int kRankSortMax = 512;   // up to this many candidates: rank sort instead of the bitonic network
 
 __global__ void __launch_bounds__(kSortThreads)
 nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int32_t* __restrict__ cls,
@@ -289,7 +290,6 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
   uint32_t* val = reinterpret_cast<uint32_t*>(mask + (size_t)P * nwP);              // [P]
   int* scls = reinterpret_cast<int*>(val + P);                                      // [P]
   __shared__ unsigned long long remv[kSmallMax / 64];
-  __shared__ unsigned long long s_kept;
   const int b = blockIdx.x, t = threadIdx.x;
   const int n = min(max(count[b], 0), cap);
   int Pn = 1;
@@ -305,19 +305,32 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
     key[i] = k; val[i] = (uint32_t)i;
   }
   __syncthreads();
-  for (int size = 2; size <= Pn; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = t; i < (Pn >> 1); i += kSortThreads) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const unsigned long long a = key[lo], c = key[hi];
-        if ((a < c) == desc) {
-          key[lo] = c; key[hi] = a;
-          const uint32_t va = val[lo]; val[lo] = val[hi]; val[hi] = va;
+  if (n <= kRankSortMax) {
+    // few candidates: rank sort - every key counts the larger keys (broadcast reads, one barrier); the keys are distinct
+    // (they carry the tie-break index), so the ranks are a permutation
+    int rank = 0;
+    if (t < n) {
+      const unsigned long long mine = key[t];
+      for (int j = 0; j < n; ++j) rank += key[j] > mine;
+    }
+    __syncthreads();
+    if (t < n) val[rank] = (uint32_t)t;
+    __syncthreads();
+  } else {
+    for (int size = 2; size <= Pn; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = t; i < (Pn >> 1); i += kSortThreads) {
+          const int lo = 2 * i - (i & (stride - 1));
+          const int hi = lo + stride;
+          const bool desc = ((lo & size) == 0);
+          const unsigned long long a = key[lo], c = key[hi];
+          if ((a < c) == desc) {
+            key[lo] = c; key[hi] = a;
+            const uint32_t va = val[lo]; val[lo] = val[hi]; val[hi] = va;
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   for (int r = t; r < n; r += kSortThreads) {
@@ -365,53 +378,63 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
     }
   }
   __syncthreads();
-  for (int i = t; i < n; i += kSortThreads) {                   // one row per thread; its words are private to it
-    const float4 a = sbox[i];
-    const int ac = scls[i];
-    const int qend = bstart[(ac & 63) + 1];
-    int cur_w = -1;
-    unsigned long long bits = 0ull;
-    for (int q = posof[i] + 1; q < qend; ++q) {
-      const int c = memb[q];                                    // rank > i, ascending
-      if (scls[c] != ac) continue;                              // another class hashed into the same bucket
-      const bool sup = (convention == ISG_NMS_TV_GT) ? suppresses_tv(a, sbox[c], thr) : suppresses_plus1(a, sbox[c], thr_f);
-      if (!sup) continue;
-      const int w = c >> 6;
-      if (w != cur_w) { if (cur_w >= 0) mask[(size_t)i * nwP + cur_w] = bits; cur_w = w; bits = 0ull; }
-      bits |= 1ull << (c & 63);
+  {
+    // R threads per row share its successors (the rows are short, the block would otherwise be mostly idle)
+    const int R = n <= 256 ? 4 : (n <= 512 ? 2 : 1);
+    const int sub = t % R;
+    for (int i = t / R; i < n; i += kSortThreads / R) {
+      const float4 a = sbox[i];
+      const int ac = scls[i];
+      const int qend = bstart[(ac & 63) + 1];
+      int cur_w = -1;
+      unsigned long long bits = 0ull;
+      for (int q = posof[i] + 1 + sub; q < qend; q += R) {
+        const int c = memb[q];                                  // rank > i, ascending
+        if (scls[c] != ac) continue;                            // another class hashed into the same bucket
+        const bool sup = (convention == ISG_NMS_TV_GT) ? suppresses_tv(a, sbox[c], thr) : suppresses_plus1(a, sbox[c], thr_f);
+        if (!sup) continue;
+        const int w = c >> 6;
+        if (w != cur_w) { if (cur_w >= 0) atomicOr(&mask[(size_t)i * nwP + cur_w], bits); cur_w = w; bits = 0ull; }
+        bits |= 1ull << (c & 63);
+      }
+      if (cur_w >= 0) atomicOr(&mask[(size_t)i * nwP + cur_w], bits);
     }
-    if (cur_w >= 0) mask[(size_t)i * nwP + cur_w] = bits;
   }
   __syncthreads();
-  // greedy scan, 64-box chunks.  Inside a chunk only the KEPT boxes cost a (dependent) step: the next kept box
-  // is the lowest still-alive bit.  The kept rows are then OR-ed into the later words by (row, word) threads.
+  // greedy scan by warp 0, 64-box chunks, no block barriers.  Lane l holds the diagonal words of rows l and l + 32 of
+  // the chunk in registers; inside a chunk only the KEPT boxes cost a (dependent) step: the next kept box is the
+  // lowest still-alive bit and its word arrives by shuffle.  The kept rows are then OR-ed into the later words.
   int nk = 0;
+  if (warp != 0) return;
   int32_t* out = keep + (size_t)b * cap;
   for (int c = 0; c < nw; ++c) {
     const int base = c * 64;
     const int m = min(64, n - base);
-    if (t == 0) {
-      const unsigned long long valid = (m == 64) ? ~0ull : ((1ull << m) - 1ull);
-      unsigned long long alive = ~remv[c] & valid, kept = 0ull;
-      while (alive) {
-        const int q = __ffsll((long long)alive) - 1;
-        kept |= 1ull << q;
-        alive &= ~(mask[(size_t)(base + q) * nwP + c] | (1ull << q));
-      }
-      s_kept = kept;
+    const unsigned long long w_lo = (lane < m) ? mask[(size_t)(base + lane) * nwP + c] : 0ull;
+    const unsigned long long w_hi = (lane + 32 < m) ? mask[(size_t)(base + 32 + lane) * nwP + c] : 0ull;
+    const unsigned long long valid = (m == 64) ? ~0ull : ((1ull << m) - 1ull);
+    unsigned long long alive = ~remv[c] & valid, kept = 0ull;
+    while (alive) {                                               // warp-uniform
+      const int q = __ffsll((long long)alive) - 1;
+      const unsigned long long lo_w = __shfl_sync(0xffffffffu, w_lo, q & 31), hi_w = __shfl_sync(0xffffffffu, w_hi, q & 31);
+      kept |= 1ull << q;
+      alive &= ~((q < 32 ? lo_w : hi_w) | (1ull << q));
     }
-    __syncthreads();
-    const unsigned long long kept = s_kept;
-    if (t < m && ((kept >> t) & 1ull)) out[nk + __popcll(kept & ((1ull << t) - 1ull))] = (int32_t)val[base + t];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int bit = lane + 32 * h;
+      if (bit < m && ((kept >> bit) & 1ull)) out[nk + __popcll(kept & ((1ull << bit) - 1ull))] = (int32_t)val[base + bit];
+    }
     nk += __popcll(kept);
-    {
-      const int q = t & 63, w = c + 1 + (t >> 6);   // 1024 threads cover 64 rows x 16 words
-      if (w < nw && ((kept >> q) & 1ull)) {
-        const unsigned long long bits = mask[(size_t)(base + q) * nwP + w];
-        if (bits) atomicOr(&remv[w], bits);
-      }
+    for (int w = c + 1; w < nw; ++w) {
+      unsigned long long v = 0ull;
+      if ((kept >> lane) & 1ull) v |= mask[(size_t)(base + lane) * nwP + w];
+      if ((kept >> (lane + 32)) & 1ull) v |= mask[(size_t)(base + 32 + lane) * nwP + w];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) remv[w] |= v;
     }
-    __syncthreads();
+    __syncwarp();
   }
   if (t == 0) n_keep[b] = nk;
 }

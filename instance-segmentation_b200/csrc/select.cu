@@ -210,15 +210,27 @@ __device__ void resolve_digit_cluster(cg::cluster_group& cluster, uint32_t* sh_h
                                       uint32_t* out_krem) {
   __shared__ uint32_t warp_tot[kHistThreads / 32];
   __shared__ uint32_t res[2];
+  __shared__ __align__(16) uint32_t tot[kHistBins];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const bool own = t < kHistThreads;
+  // cluster-wide totals: all 1024 threads pull two bins each from every peer (independent remote loads in flight),
+  // instead of 256 threads pulling eight bins each - the remote-read latency was the larger part of a pass
+  static_assert(kSelThreads * 2 == kHistBins, "two bins per thread");
+  {
+    uint2 acc = make_uint2(0u, 0u);
+    uint2 v[kSelCluster];
+#pragma unroll
+    for (int r = 0; r < kSelCluster; ++r)
+      v[r] = (r < (int)cluster.num_blocks()) ? reinterpret_cast<const uint2*>(cluster.map_shared_rank(sh_hist, r))[t] : make_uint2(0u, 0u);
+#pragma unroll
+    for (int r = 0; r < kSelCluster; ++r) { acc.x += v[r].x; acc.y += v[r].y; }
+    reinterpret_cast<uint2*>(tot)[t] = acc;
+  }
+  __syncthreads();
   uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (own) {
-    for (unsigned r = 0; r < cluster.num_blocks(); ++r) {
-      const uint4* peer = reinterpret_cast<const uint4*>(cluster.map_shared_rank(sh_hist, r)) + t * 2;
-      const uint4 a = peer[0], c = peer[1];
-      h[0] += a.x; h[1] += a.y; h[2] += a.z; h[3] += a.w; h[4] += c.x; h[5] += c.y; h[6] += c.z; h[7] += c.w;
-    }
+    const uint4 a = reinterpret_cast<const uint4*>(tot)[t * 2], c = reinterpret_cast<const uint4*>(tot)[t * 2 + 1];
+    h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = c.x; h[5] = c.y; h[6] = c.z; h[7] = c.w;
   }
   uint32_t s = 0;
 #pragma unroll
@@ -271,8 +283,14 @@ __device__ uint32_t cluster_radix_select(cg::cluster_group& cluster, uint32_t* s
       bool in[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) { const int i = i0 + u * kSelThreads + t; in[u] = i < hi; key[u] = in[u] ? key_at(i) : 0u; }
+      // pass 0: the keys share a handful of leading digits -> aggregate per warp (match.any); later passes: the digits
+      // of the surviving keys are spread out, a plain atomic per key is cheaper than the match
 #pragma unroll
-      for (int u = 0; u < 4; ++u) hist_add_match(sh_hist, digit_of(key[u], pass), in[u] && (key[u] & pmask) == prefix, lane);
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = in[u] && (key[u] & pmask) == prefix;
+        if (pass == 0) hist_add_match(sh_hist, digit_of(key[u], pass), ok, lane);
+        else if (ok) atomicAdd(&sh_hist[digit_of(key[u], pass)], 1u);
+      }
     }
     cluster.sync();   // every CTA's histogram of this pass is complete and visible
     uint32_t d, k2;
