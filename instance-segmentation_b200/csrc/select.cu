@@ -342,9 +342,18 @@ topk_sample1_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, i
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
   const float* img = kp + (int64_t)b * img_stride;
   const int S = min(npx / stride, kSample1Max);   // sample i reads pixel i*stride + (i*37 % stride)
-  for (int i = t; i < S; i += kSelThreads) {
-    const int p = i * stride + (int)(((unsigned)i * 37u) % (unsigned)stride);
-    skeys[i] = float_key(__ldg(img + p));
+  {
+    // the sample loads are scattered (one DRAM sector each): issue all of a thread's loads before using any
+    constexpr int kPer = kSample1Max / kSelThreads;
+    float x[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int i = t + u * kSelThreads;
+      const int p = i * stride + (int)(((unsigned)i * 37u) % (unsigned)stride);
+      x[u] = (i < S) ? __ldg(img + p) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) { const int i = t + u * kSelThreads; if (i < S) skeys[i] = float_key(x[u]); }
   }
   __syncthreads();
   // same bound as topk_sample_kernel: sample rank of ~1.2k pixels plus 6 sigma and a constant
@@ -363,7 +372,8 @@ topk_sample1_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, i
         const uint32_t key = i < S ? skeys[i] : 0u;
         const bool valid = i < S && (key & pmask) == prefix;
         if (!__any_sync(0xffffffffu, valid)) continue;       // later passes: most warps hold no key of the prefix
-        hist_add_match(sh_hist, digit_of(key, pass), valid, lane);
+        if (pass == 0) hist_add_match(sh_hist, digit_of(key, pass), valid, lane);   // concentrated digits: aggregate
+        else if (valid) atomicAdd(&sh_hist[digit_of(key, pass)], 1u);               // spread digits: plain atomics
       }
       __syncthreads();
       uint32_t d, k2;
@@ -486,27 +496,8 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   __syncthreads();
   const int base = blockIdx.x * kFilterPxPerBlock;
   const int end = min(base + kFilterPxPerBlock, npx);
-  for (int p0 = base; p0 < end; p0 += kFilterThreads * 4) {   // warp-uniform trip count
-    uint32_t key[4];
-    int c = 0;
-    if (vec) {
-      const int p = p0 + t * 4;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      const bool in = p < end;
-      if (in) q = ldg_stream4(img + p);
-      key[0] = float_key(q.x); key[1] = float_key(q.y); key[2] = float_key(q.z); key[3] = float_key(q.w);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { if (!in || key[i] < lower || key[i] > upper) key[i] = 0xffffffffu; else ++c; }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int p = p0 + i * kFilterThreads + t;
-        key[i] = 0xffffffffu;
-        if (p < end) { const uint32_t kk = float_key(__ldg(img + p)); if (kk >= lower && kk <= upper) { key[i] = kk; ++c; } }
-      }
-    }
-    // NOTE: 0xffffffff marks "not a candidate"; a real key of 0xffffffff (a NaN payload) is dropped, NaNs are
-    // outside the contract.
+  // candidate keys of one 4-pixel group -> this block's shared-memory list (warp-aggregated append)
+  auto append4 = [&](uint32_t (&key)[4], int c) {
     if (__any_sync(0xffffffffu, c > 0)) {
       int inc = c;
 #pragma unroll
@@ -521,6 +512,41 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (key[i] != 0xffffffffu) buf[o2++] = key[i];
+    }
+  };
+  // NOTE: 0xffffffff marks "not a candidate"; a real key of 0xffffffff (a NaN payload) is dropped, NaNs are
+  // outside the contract.
+  if (vec) {
+    constexpr int kUnroll = 4;                                  // independent 128-bit loads in flight per thread
+    for (int p0 = base; p0 < end; p0 += kFilterThreads * 4 * kUnroll) {   // warp-uniform trip count
+      float4 q[kUnroll];
+      bool in[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int p = p0 + u * kFilterThreads * 4 + t * 4;
+        in[u] = p < end;
+        q[u] = in[u] ? ldg_stream4(img + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        uint32_t key[4] = {float_key(q[u].x), float_key(q[u].y), float_key(q[u].z), float_key(q[u].w)};
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { if (!in[u] || key[i] < lower || key[i] > upper) key[i] = 0xffffffffu; else ++c; }
+        append4(key, c);
+      }
+    }
+  } else {
+    for (int p0 = base; p0 < end; p0 += kFilterThreads * 4) {   // warp-uniform trip count
+      uint32_t key[4];
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int p = p0 + i * kFilterThreads + t;
+        key[i] = 0xffffffffu;
+        if (p < end) { const uint32_t kk = float_key(__ldg(img + p)); if (kk >= lower && kk <= upper) { key[i] = kk; ++c; } }
+      }
+      append4(key, c);
     }
   }
   __syncthreads();
