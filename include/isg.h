@@ -108,12 +108,13 @@ int isg_build_seeds(const float* rois, int layout, const int32_t* n_seeds, int B
 
 /* isg_gather_kept + isg_build_seeds (XYXY) + isg_stats_init in one launch, for the batched pipeline: the kept
  * candidates of isg_box_nms become the detection tables (rois / scores / cls / n_out, as isg_gather_kept) and, in the
- * same pass, the seed records, ghost bounds and (stats nullable) reset statistics of the decode. */
+ * same pass, the seed records, ghost bounds and (stats nullable) reset statistics of the decode.  img_total (nullable):
+ * the per-image point counters of isg_instance_polygons, zeroed here so that it can be called with totals_zeroed = 1. */
 int isg_gather_build_seeds(const float* cand_boxes, const float* cand_scores, const int32_t* cand_cls,
                            const int32_t* keep, const int32_t* n_keep, int B, int cap, int Nmax,
                            const float* ys, const float* xs, int H, int W, float ghost_k, float scale,
                            float* rois, float* scores, int32_t* cls, int32_t* n_out,
-                           uint32_t* seeds, float* ghost, int32_t* stats, isg_stream_t stream);
+                           uint32_t* seeds, float* ghost, int32_t* stats, int32_t* img_total, isg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1+K3 — embedding + Gaussian membership + assignment.  Replaces group_kp's arithmetic core
@@ -260,13 +261,14 @@ int isg_pairwise(const float* X, int M, const float* Y, int N, int D, int metric
  *   inst_internal [B,Nmax,2] fp32 (nullable): the internal point used;  img_total [B] int32: points per image
  *   stats (nullable, pre-initialised by isg_stats_init): count / bbox per instance
  *   workspace (nullable): isg_instance_polygons_workspace_bytes(B, cap) bytes, 256-byte aligned
+ *   totals_zeroed: 0 = img_total is zeroed by this call (one more small launch); 1 = the caller already zeroed it
  * ------------------------------------------------------------------------------------------ */
 size_t isg_instance_polygons_workspace_bytes(int B, int cap);
 int isg_instance_polygons(const uint32_t* keepbits, const int32_t* label_map, const float* rois, int layout, const float* ghost,
                           const int32_t* n_seeds, int B, int Nmax, int H, int W, int cap, int obj_pixel_th,
                           float* poly_points, int32_t* inst_start, int32_t* inst_count, uint8_t* inst_flags,
                           float* inst_internal, int32_t* img_total, int32_t* stats, void* workspace, size_t workspace_bytes,
-                          isg_stream_t stream);
+                          int totals_zeroed, isg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * HOST helpers of the polygon stage (aug_group / find_internal_point, utils/decode.py:51-68,167-204).

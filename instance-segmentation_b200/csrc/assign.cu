@@ -92,11 +92,12 @@ __global__ void gather_build_seeds_kernel(const float4* __restrict__ cand_boxes,
                                           float ghost_k, float scale, float4* __restrict__ rois,
                                           float* __restrict__ scores, int32_t* __restrict__ cls,
                                           int32_t* __restrict__ n_out, SeedRec* __restrict__ seeds,
-                                          float4* __restrict__ ghost, int32_t* __restrict__ stats) {
+                                          float4* __restrict__ ghost, int32_t* __restrict__ stats,
+                                          int32_t* __restrict__ img_total) {
   const int b = blockIdx.y;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = min(n_keep[b], Nmax);
-  if (r == 0) n_out[b] = n;
+  if (r == 0) { n_out[b] = n; if (img_total) img_total[b] = 0; }
   if (r >= Nmax) return;
   float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
   float sc = 0.f;
@@ -632,7 +633,7 @@ extern "C" int isg_gather_build_seeds(const float* cand_boxes, const float* cand
                                       const int32_t* keep, const int32_t* n_keep, int B, int cap, int Nmax, const float* ys,
                                       const float* xs, int H, int W, float ghost_k, float scale, float* rois, float* scores,
                                       int32_t* cls, int32_t* n_out, uint32_t* seeds, float* ghost, int32_t* stats,
-                                      isg_stream_t stream_) {
+                                      int32_t* img_total, isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!cand_boxes || !cand_scores || !cand_cls || !keep || !n_keep || !ys || !xs || !rois || !scores || !cls || !n_out ||
       !seeds || !ghost)
@@ -643,7 +644,7 @@ extern "C" int isg_gather_build_seeds(const float* cand_boxes, const float* cand
   gather_build_seeds_kernel<<<grid, 128, 0, stream>>>(
       reinterpret_cast<const float4*>(cand_boxes), cand_scores, cand_cls, keep, n_keep, cap, Nmax, ys, xs, H, W, ghost_k, scale,
       reinterpret_cast<float4*>(rois), scores, cls, n_out, reinterpret_cast<SeedRec*>(seeds), reinterpret_cast<float4*>(ghost),
-      stats);
+      stats, img_total);
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }

@@ -259,6 +259,9 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
   uint32_t* s_thr = reinterpret_cast<uint32_t*>(smem + L.thr);           // [kD4MaxStages]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // a kernel launched behind this one with programmatic stream serialisation (isg_instance_polygons) may be scheduled as
+  // soon as SMs free up at the tail; it waits for this grid's completion (griddepcontrol.wait) before reading anything
+  asm volatile("griddepcontrol.launch_dependents;");
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], WG); }
     mbar_fence_init();

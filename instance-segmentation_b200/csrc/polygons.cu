@@ -262,6 +262,9 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
                          float2* __restrict__ tmp_ws) {
   extern __shared__ __align__(16) unsigned char poly_smem_raw[];
   PolySmem& s = *reinterpret_cast<PolySmem*>(poly_smem_raw);
+  // launched with programmatic stream serialisation behind the dense kernel: nothing of its output is read before the
+  // whole preceding grid has completed (a no-op for an ordinary launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // image index fastest: the CTAs of the real instances (inst < n_seeds) are contiguous in launch order and spread
   // evenly over the SMs; the empty tail of the instance table comes last
   const int b = blockIdx.x, inst = blockIdx.y;
@@ -444,7 +447,7 @@ extern "C" int isg_instance_polygons(const uint32_t* keepbits, const int32_t* la
                                      int cap, int obj_pixel_th, float* poly_points, int32_t* inst_start,
                                      int32_t* inst_count, uint8_t* inst_flags, float* inst_internal,
                                      int32_t* img_total, int32_t* stats, void* workspace, size_t workspace_bytes,
-                                     isg_stream_t stream_) {
+                                     int totals_zeroed, isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!keepbits || !label_map || !rois || !ghost || !n_seeds || !poly_points || !inst_start || !inst_count || !inst_flags ||
       !img_total)
@@ -454,17 +457,27 @@ extern "C" int isg_instance_polygons(const uint32_t* keepbits, const int32_t* la
   if (((uintptr_t)rois & 15) || ((uintptr_t)ghost & 15) || ((uintptr_t)poly_points & 7)) return ISG_EINVAL;
   if (workspace && (workspace_bytes < isg_instance_polygons_workspace_bytes(B, cap) || ((uintptr_t)workspace & 255)))
     return ISG_EWORKSPACE;
-  zero_i32_kernel<<<cdiv(B, 256), 256, 0, stream>>>(img_total, B);
-  ISG_LAUNCH_CHECK();
+  if (!totals_zeroed) {
+    zero_i32_kernel<<<cdiv(B, 256), 256, 0, stream>>>(img_total, B);
+    ISG_LAUNCH_CHECK();
+  }
   const size_t smem = sizeof(PolySmem);
   ISG_CUDA(cudaFuncSetAttribute(instance_polygons_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(B, Nmax);
   unsigned long long* keys_ws = static_cast<unsigned long long*>(workspace);     // [B][2*cap]
   float2* tmp_ws = workspace ? reinterpret_cast<float2*>(keys_ws + (size_t)B * cap * 2) : nullptr;   // [B][cap]
-  instance_polygons_kernel<<<grid, kPolyThreads, smem, stream>>>(
-      keepbits, label_map, reinterpret_cast<const float4*>(rois), layout, reinterpret_cast<const float4*>(ghost), n_seeds, Nmax, H, W,
-      cdiv(W, 32), cap, obj_pixel_th, reinterpret_cast<float2*>(poly_points), inst_start, inst_count, inst_flags,
-      reinterpret_cast<float2*>(inst_internal), img_total, stats, keys_ws, tmp_ws);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kPolyThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = totals_zeroed ? 1 : 0;      // directly behind the dense kernel: overlap the launch
+  const float4* rois4 = reinterpret_cast<const float4*>(rois);
+  const float4* ghost4 = reinterpret_cast<const float4*>(ghost);
+  const int Wwords = cdiv(W, 32);
+  ISG_CUDA(cudaLaunchKernelEx(&cfg, instance_polygons_kernel, keepbits, label_map, rois4, layout, ghost4, n_seeds, Nmax, H, W, Wwords,
+                              cap, obj_pixel_th, reinterpret_cast<float2*>(poly_points), inst_start, inst_count, inst_flags,
+                              reinterpret_cast<float2*>(inst_internal), img_total, stats, keys_ws, tmp_ws));
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }

@@ -198,7 +198,8 @@ class DecodePlan:
                 call("isg_instance_polygons", ptr(self.keepbits), ptr(self.label_map), ptr(rois), layout, ptr(self.ghost), ptr(n_seeds),
                      B, N, H, W, cap, int(obj_pixel_th), ptr(self.poly_points), ptr(self.inst_start), ptr(self.inst_count),
                      ptr(self.inst_flags), ptr(self.inst_internal), ptr(self.img_total),
-                     0 if self.fused_stats else ptr(self.stats), self.poly_ws_ptr, self.poly_ws_bytes, s)
+                     0 if self.fused_stats else ptr(self.stats), self.poly_ws_ptr, self.poly_ws_bytes,
+                     1 if seeds_ready else 0, s)
                 if ev:
                     self.events.append(ev)
                 return
@@ -321,7 +322,8 @@ class DecodePipeline:
         bp.run(anchors, regression, classification, cls_th, iou_th, gather=False)
         call("isg_gather_build_seeds", ptr(bp.cand_boxes), ptr(bp.cand_scores), ptr(bp.cand_cls), ptr(bp.keep), ptr(bp.n_keep),
              bp.B, bp.cap, bp.N, ptr(dp.ys), ptr(dp.xs), dp.H, dp.W, dp.ghost_k, dp.scale, ptr(bp.rois), ptr(bp.scores),
-             ptr(bp.cls), ptr(bp.n_seeds), ptr(dp.seeds), ptr(dp.ghost), ptr(dp.stats), stream_ptr(self.device))
+             ptr(bp.cls), ptr(bp.n_seeds), ptr(dp.seeds), ptr(dp.ghost), ptr(dp.stats),
+             ptr(dp.img_total) if dp.mode == "dense" else 0, stream_ptr(self.device))
         dense = dp.mode == "dense"
         if dense:   # the tile lists of the dense kernel only need the seeds: build them before joining the top-k branch
             call("isg_build_tile_lists", ptr(dp.seeds), ptr(bp.n_seeds), dp.B, dp.N, dp.H, dp.W, ptr(dp.dense_ws),
