@@ -94,6 +94,8 @@ __global__ void gather_build_seeds_kernel(const float4* __restrict__ cand_boxes,
                                           int32_t* __restrict__ n_out, SeedRec* __restrict__ seeds,
                                           float4* __restrict__ ghost, int32_t* __restrict__ stats,
                                           int32_t* __restrict__ img_total) {
+  pdl_trigger();
+  pdl_wait();         // the keep list comes from the NMS kernel launched just before
   const int b = blockIdx.y;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = min(n_keep[b], Nmax);
@@ -641,10 +643,9 @@ extern "C" int isg_gather_build_seeds(const float* cand_boxes, const float* cand
   if (B <= 0 || cap <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
   if (!aligned16(cand_boxes) || !aligned16(rois) || !aligned16(seeds) || !aligned16(ghost)) return ISG_EINVAL;
   dim3 grid(cdiv(Nmax, 128), B);
-  gather_build_seeds_kernel<<<grid, 128, 0, stream>>>(
-      reinterpret_cast<const float4*>(cand_boxes), cand_scores, cand_cls, keep, n_keep, cap, Nmax, ys, xs, H, W, ghost_k, scale,
-      reinterpret_cast<float4*>(rois), scores, cls, n_out, reinterpret_cast<SeedRec*>(seeds), reinterpret_cast<float4*>(ghost),
-      stats, img_total);
+  ISG_CUDA(launch_pdl(gather_build_seeds_kernel, grid, dim3(128), 0, stream, reinterpret_cast<const float4*>(cand_boxes), cand_scores,
+                      cand_cls, keep, n_keep, cap, Nmax, ys, xs, H, W, ghost_k, scale, reinterpret_cast<float4*>(rois), scores, cls,
+                      n_out, reinterpret_cast<SeedRec*>(seeds), reinterpret_cast<float4*>(ghost), stats, img_total));
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }

@@ -19,6 +19,7 @@ decode_boxes_kernel(const float* __restrict__ anchors, const float* __restrict__
                     float thr, int cap, float4* __restrict__ cand_boxes, float* __restrict__ cand_scores,
                     int32_t* __restrict__ cand_cls, int32_t* __restrict__ cand_anchor,
                     int32_t* __restrict__ cand_count, bool vec) {
+  pdl_trigger();      // the NMS kernel behind this one may be scheduled early; it waits for this grid (common.cuh)
   const int b = blockIdx.y;
   const int a = blockIdx.x * kFrontThreads + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -290,6 +291,8 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
   uint32_t* val = reinterpret_cast<uint32_t*>(mask + (size_t)P * nwP);              // [P]
   int* scls = reinterpret_cast<int*>(val + P);                                      // [P]
   __shared__ unsigned long long remv[kSmallMax / 64];
+  pdl_trigger();
+  pdl_wait();         // candidates / counts come from the kernel launched just before
   const int b = blockIdx.x, t = threadIdx.x;
   const int n = min(max(count[b], 0), cap);
   int Pn = 1;
@@ -727,8 +730,8 @@ extern "C" int isg_box_nms(const float* boxes, const float* scores, const int32_
     const int nwP = P / 64 > 0 ? P / 64 : 1;
     const size_t smem = (size_t)P * (16 + 8 + 4 + 4) + (size_t)P * nwP * 8;
     ISG_CUDA(cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_small_kernel<<<B, kSortThreads, smem, stream>>>(reinterpret_cast<const float4*>(boxes), scores, cls, tiebreak, count,
-                                                        cap, P, thr, convention, keep, n_keep);
+    ISG_CUDA(launch_pdl(nms_small_kernel, dim3(B), dim3(kSortThreads), smem, stream, reinterpret_cast<const float4*>(boxes), scores,
+                        cls, tiebreak, count, cap, P, thr, convention, keep, n_keep));
     ISG_LAUNCH_CHECK();
     return ISG_OK;
   }

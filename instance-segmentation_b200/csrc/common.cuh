@@ -139,6 +139,26 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// Kernels of one stream that consume each other's output are launched with programmatic stream serialisation: the
+// consumer's CTAs may be scheduled while the producer grid is still draining (hides the launch latency, ~2 us per
+// kernel boundary), and the consumer calls pdl_wait() before it touches anything the producer wrote - the wait returns
+// when the whole preceding grid has completed and its writes are visible.  pdl_trigger() lets the next grid in.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -186,16 +186,22 @@ struct D4Smem {
   }
 };
 
+constexpr size_t kDenseSchedBytes = 256;     // scheduler words at the head of the dense workspace
+
 // Pre-pass: one warp per tile collects, in ascending seed index, the seeds of the tile's image whose boxes overlap
 // the tile.  lists: [T] x (TileHdr + cap records); ovf: [T][Nmax] seed indices of ALL hits (read by the dense kernel
 // only for the rare tiles with more than cap hits).
 __global__ void __launch_bounds__(256)
 tile_lists_kernel(const SeedRec* __restrict__ seeds, const int32_t* __restrict__ n_seeds,
                   int Nmax, int B, int H, int W, int TH, int tilesX, int tilesY,
-                  int cap, unsigned char* __restrict__ lists, uint16_t* __restrict__ ovf) {
+                  int cap, unsigned char* __restrict__ lists, uint16_t* __restrict__ ovf, unsigned int* __restrict__ sched) {
   // programmatic dependent launch: let the dense kernel's CTAs start (barrier init, first kp/ae loads) while this
   // grid is still running; its producer waits on the grid dependency before it touches a list
   asm volatile("griddepcontrol.launch_dependents;");
+  pdl_wait();         // the seed records come from the kernel launched just before (no-op for an ordinary launch)
+  // the tile counter of the dynamic scheduler starts every dense launch at zero: reset here, together with the lists
+  // (the dense kernel behind this grid reads it only after its own grid-dependency wait)
+  if (blockIdx.x == 0 && threadIdx.x < kDenseSchedBytes / 4) sched[threadIdx.x] = 0u;
   const int lane = threadIdx.x & 31;
   const long long T = (long long)B * tilesX * tilesY;
   const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -284,12 +290,13 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
     const unsigned n_static = (T / P > (unsigned)dyn_tail) ? (T / P - (unsigned)dyn_tail) : 0u;
     const unsigned T_s = n_static * P;
     unsigned i_static = 0;
+    // the tile lists and the zeroed counter come from the preceding grid (tile_lists_kernel): wait for it (no-op
+    // without PDL) before the first request
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     unsigned dyn = T_s + atomicAdd(&sched[0], 1u);
     unsigned t;
     if (n_static > 0) { t = blockIdx.x; i_static = 1; }
     else { t = dyn; dyn = (t < T) ? T_s + atomicAdd(&sched[0], 1u) : T; }
-    // the tile lists come from the preceding grid (tile_lists_kernel): wait for it (no-op without PDL)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     while (t < T) {
       const int b = (int)(t / (unsigned)tiles_per_img);
       const int rem = (int)t - b * tiles_per_img;
@@ -503,7 +510,6 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
 // ---- host side -------------------------------------------------------------------------------
 // Workspace: [0,256) scheduler words | tile lists [T_max] x (32 + cap*32) | overflow indices [T_max][Nmax] u16.
 // T_max is the tile count of the smallest compiled tile (8 rows), so that every geometry fits.
-constexpr size_t kDenseSchedBytes = 256;
 constexpr int kD4MinTileRows = 8;
 inline int dense_list_cap(int Nmax) { return Nmax <= 16 ? 16 : (Nmax <= 160 ? 16 : 32); }
 inline size_t dense_lists_bytes(long long T, int Nmax) {
@@ -540,11 +546,13 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   uint16_t* ovf = reinterpret_cast<uint16_t*>(lists + dense_lists_bytes(T_max, Nmax));
   const SeedRec* srec = reinterpret_cast<const SeedRec*>(seeds);
   if (mode != 2) {
-    // the tile counter of the dynamic scheduler starts every launch at zero (reset here, together with the lists, so
-    // that a dense launch that follows on the same stream - this call or a later lists_prebuilt one - finds it clean)
-    ISG_CUDA(cudaMemsetAsync(sched, 0, kDenseSchedBytes, stream));
-    tile_lists_kernel<<<(unsigned)cdiv64(T, 8), 256, 0, stream>>>(srec, n_seeds, Nmax, B, H, W, Geo::TH, tilesX, tilesY, cap, lists,
-                                                                  ovf);
+    if (mode == 1) {      // behind the seeds kernel of the pipeline: overlap the launch
+      ISG_CUDA(launch_pdl(tile_lists_kernel, dim3((unsigned)cdiv64(T, 8)), dim3(256), 0, stream, srec, n_seeds, Nmax, B, H, W,
+                          (int)Geo::TH, tilesX, tilesY, cap, lists, ovf, sched));
+    } else {
+      tile_lists_kernel<<<(unsigned)cdiv64(T, 8), 256, 0, stream>>>(srec, n_seeds, Nmax, B, H, W, Geo::TH, tilesX, tilesY, cap, lists,
+                                                                    ovf, sched);
+    }
     ISG_LAUNCH_CHECK();
     if (mode == 1) return ISG_OK;
   }

@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(kSelThreads)
 topk_sample1_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, int stride, void* ws) {
   __shared__ uint32_t skeys[kSample1Max];
   __shared__ uint32_t sh_hist[kHistBins];
+  pdl_trigger();                       // the filter kernel may be scheduled; it waits for this grid before reading `lower`
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
   const float* img = kp + (int64_t)b * img_stride;
   const int S = min(npx / stride, kSample1Max);   // sample i reads pixel i*stride + (i*37 % stride)
@@ -486,6 +487,8 @@ __global__ void __launch_bounds__(kFilterThreads)
 topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, void* ws, bool vec) {
   __shared__ uint32_t buf[kFilterPxPerBlock];
   __shared__ uint32_t s_count, s_base;
+  pdl_trigger();
+  pdl_wait();                          // `lower` / `ncand` come from the kernel launched just before
   const int b = blockIdx.y, t = threadIdx.x, lane = t & 31;
   const TopkWs v = topk_ws_view(ws, b, npx, k);
   const uint32_t lower = *v.lower;
@@ -567,6 +570,7 @@ topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
                    uint32_t* __restrict__ thr_key) {
   __shared__ uint32_t sh_hist[2 * kHistBins];
   cg::cluster_group cluster = cg::this_cluster();
+  pdl_wait();                          // the candidate list comes from the filter kernel
   const int b = blockIdx.y;
   const TopkWs v = topk_ws_view(ws, b, npx, k);
   const uint32_t nc = *v.ncand;
@@ -877,14 +881,14 @@ extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t 
       topk_pick15_kernel<<<B, 1024, 0, stream>>>(hist15, npx, k, ws);
     }
     dim3 grid(cdiv(npx, kFilterPxPerBlock), B);
-    topk_filter_kernel<<<grid, kFilterThreads, 0, stream>>>(kp, img_stride, npx, k, ws, vec);
+    ISG_CUDA(launch_pdl(topk_filter_kernel, grid, dim3(kFilterThreads), 0, stream, kp, img_stride, npx, k, ws, vec));
   } else {
     // small image: one CTA per image selects over all pixels directly (ncand = 0 -> full-image mode)
     const size_t per = topk_ws_per_image(npx, k);
     for (int b = 0; b < B; ++b)
       ISG_CUDA(cudaMemsetAsync((char*)ws + (size_t)b * per + 3 * kHistBins * sizeof(uint32_t), 0, 64, stream));
   }
-  topk_select_kernel<<<dim3(kSelCluster, B), kSelThreads, 0, stream>>>(kp, img_stride, npx, k, ws, thr_key);
+  ISG_CUDA(launch_pdl(topk_select_kernel, dim3(kSelCluster, B), dim3(kSelThreads), 0, stream, kp, img_stride, npx, k, ws, thr_key));
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }
