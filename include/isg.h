@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ISG_ABI_VERSION 2
+#define ISG_ABI_VERSION 3
 
 #define ISG_OK            0
 #define ISG_EINVAL       (-1)  /* bad argument (null pointer, negative extent, k > H*W ...) */
@@ -269,6 +269,29 @@ int isg_instance_polygons(const uint32_t* keepbits, const int32_t* label_map, co
                           float* poly_points, int32_t* inst_start, int32_t* inst_count, uint8_t* inst_flags,
                           float* inst_internal, int32_t* img_total, int32_t* stats, void* workspace, size_t workspace_bytes,
                           int totals_zeroed, isg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f2 - polygon rasteriser on the device.  Replaces poly_to_mask (utils/image.py:180-185 =
+ * cv2.fillPoly(zeros(img_size, int32), [poly.astype(int32)], 1)) as called per detection by the results writer
+ * (utils/eval_util.py:116), for n polygons per call, with bit-packed output.
+ *   points [*,2] fp32 (x,y), 8-byte aligned; polygon i = points[poly_start[i] .. poly_start[i] + poly_count[i])
+ *     (values are truncated to int32 like astype; every vertex must lie inside the H x W frame)
+ *   full_frame = 1: polygon i fills words[i*H*Wwords ..) as an [H, Wwords = ceil(W/32)] frame - the layout of
+ *     isg_mask_nms / isg_mask_pair_counts; full_frame = 0: polygon i gets rows x words_per_row words covering its
+ *     bounding box (word aligned in x), allocated from `words` in completion order
+ *   desc [n, ISG_FILL_DESC_WORDS] int32: {status, x0, y0, rows, words_per_row, offset_lo, offset_hi, n_vertices};
+ *     bit k of word w of row r = pixel (x0 + 32 w + k, y0 + r)
+ *   total: device scalar, zeroed by the call; words requested so far in compact mode (may exceed cap_words: the
+ *     polygons that did not fit have status ISG_FILL_OVERFLOW)
+ * ------------------------------------------------------------------------------------------ */
+#define ISG_FILL_DESC_WORDS 8
+#define ISG_FILL_OK       0
+#define ISG_FILL_EMPTY    1   /* no vertices: nothing written */
+#define ISG_FILL_OUTSIDE  2   /* a vertex lies outside the frame (OpenCV's edge clipping is not restated): nothing written */
+#define ISG_FILL_OVERFLOW 3   /* `words` too small: nothing written for this polygon */
+int isg_fill_polygons(const float* points, const int32_t* poly_start, const int32_t* poly_count, int n, int H, int W,
+                      int full_frame, uint32_t* words, size_t cap_words, int32_t* desc, unsigned long long* total,
+                      isg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * HOST helpers of the polygon stage (aug_group / find_internal_point, utils/decode.py:51-68,167-204).

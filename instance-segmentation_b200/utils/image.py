@@ -1,7 +1,8 @@
 """The four symbols of the reference's utils/image.py on the decode path:
 poly_to_mask (:180-185, host rasterisation via cv2 like the reference), compute_iou_for_mask (:188-191),
 compute_iou_for_poly (:194-202), is_cover (:205-207).  Mask statistics are popcounts on bit-packed masks
-computed by libisg.so."""
+computed by libisg.so.  `fill_polygons` / `polys_to_masks` are the batched device form of poly_to_mask
+(`isg_fill_polygons`): all polygons of a call are rasterised by one kernel launch."""
 from __future__ import annotations
 
 import numpy as np
@@ -69,3 +70,105 @@ def is_cover(mask1, mask2):
     c = mask_pair_counts(bits, [(0, 1), (0, 0), (1, 1)])
     inter, a, b = int(c[0, 0]), int(c[1, 0]), int(c[2, 0])
     return a == inter or b == inter
+
+
+FILL_OK, FILL_EMPTY, FILL_OUTSIDE, FILL_OVERFLOW = 0, 1, 2, 3
+_FILL_ERRORS = {FILL_OUTSIDE: "a vertex lies outside the %d x %d frame (the device rasteriser does not clip edges)",
+                FILL_OVERFLOW: "output capacity exceeded (frame %d x %d)"}
+
+
+class FilledPolygons:
+    """Bit-packed masks of n polygons on the device, as written by `isg_fill_polygons`.
+
+    words: int32 [cap] device buffer; desc: int32 [n,8] (host copy, see include/isg.h); in full-frame mode
+    `bits` is the [n,H,ceil(W/32)] view that `isg_mask_nms` / `mask_pair_counts` read."""
+
+    def __init__(self, words, desc, size, full_frame):
+        self.words, self.desc, self.size, self.full_frame = words, desc, (int(size[0]), int(size[1])), full_frame
+
+    def __len__(self):
+        return self.desc.shape[0]
+
+    @property
+    def bits(self) -> torch.Tensor:
+        if not self.full_frame:
+            raise ValueError("bits: only for full_frame=True")
+        H, W = self.size
+        return self.words[: len(self) * H * ((W + 31) // 32)].view(len(self), H, (W + 31) // 32)
+
+    def masks(self, dtype=np.int32):
+        """list of [H,W] 0/1 arrays equal to poly_to_mask(poly, size) (one D2H copy of the packed words)."""
+        H, W = self.size
+        host = self.words.cpu().numpy().view(np.uint32)
+        out = []
+        for st, x0, y0, rows, wpr, lo, hi, _k in self.desc.tolist():
+            m = np.zeros((H, W), dtype=dtype)
+            if st == FILL_OK:
+                off = (lo & 0xFFFFFFFF) | (hi << 32)
+                blk = host[off: off + rows * wpr].reshape(rows, wpr)
+                px = np.unpackbits(blk.view(np.uint8), axis=1, bitorder="little")       # [rows, 32*wpr]
+                x1 = min(W, x0 + 32 * wpr)
+                m[y0: y0 + rows, x0: x1] = px[:, : x1 - x0]
+            out.append(m)
+        return out
+
+
+def fill_polygons(polys, img_size, full_frame=False, dev=None) -> FilledPolygons:
+    """Rasterise polygons ([K_i,2] (x,y) arrays, or a device float32 [*,2] tensor with `(start, count)` given as
+    polys=(points, start, count)) into an H x W frame exactly like poly_to_mask, on the device.
+    Raises ValueError if a polygon has a vertex outside the frame."""
+    dev = dev or _dev()
+    H, W = int(img_size[0]), int(img_size[1])
+    if isinstance(polys, tuple) and torch.is_tensor(polys[0]):
+        pts, start, count = polys
+        pts = pts.to(dev, torch.float32).contiguous()
+        start = torch.as_tensor(start).to(dev, torch.int32).contiguous()
+        count = torch.as_tensor(count).to(dev, torch.int32).contiguous()
+        n = int(count.numel())
+        bound = None
+    else:
+        arrs = [np.asarray(p, dtype=np.float32).reshape(-1, 2) for p in polys]
+        n = len(arrs)
+        cnt = np.array([a.shape[0] for a in arrs], dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        if n:
+            st[1:] = np.cumsum(cnt)[:-1]
+        flat = np.concatenate(arrs) if n and cnt.sum() else np.zeros((1, 2), np.float32)
+        pts = torch.from_numpy(np.ascontiguousarray(flat)).to(dev)
+        start, count = torch.from_numpy(st).to(dev), torch.from_numpy(cnt).to(dev)
+        # exact output size of the compact layout: rows x words of every bounding box
+        bound = 0
+        for a in arrs:
+            if a.shape[0]:
+                ai = a.astype(np.int32)
+                bound += int(ai[:, 1].max() - ai[:, 1].min() + 1) * int((ai[:, 0].max() >> 5) - (ai[:, 0].min() >> 5) + 1)
+    if n == 0:
+        return FilledPolygons(torch.zeros(1, dtype=torch.int32, device=dev), np.zeros((0, 8), np.int32), (H, W), full_frame)
+    Ww = (W + 31) // 32
+    if full_frame:
+        cap = n * H * Ww
+    elif bound is not None:
+        cap = max(bound, 1)
+    else:
+        cap = n * H * Ww                                  # device-resident polygons: worst case
+    words = torch.empty(cap, dtype=torch.int32, device=dev)
+    desc = torch.empty((n, 8), dtype=torch.int32, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    call("isg_fill_polygons", ptr(pts), ptr(start), ptr(count), n, H, W, 1 if full_frame else 0, ptr(words), cap, ptr(desc),
+         ptr(total), stream_ptr(dev))
+    d = desc.cpu().numpy()
+    for code, msg in _FILL_ERRORS.items():
+        if (d[:, 0] == code).any():
+            raise ValueError("fill_polygons: polygon %d: " % int(np.nonzero(d[:, 0] == code)[0][0]) + msg % (H, W))
+    return FilledPolygons(words, d, (H, W), full_frame)
+
+
+def polys_to_masks(polys, img_size=None):
+    """[poly_to_mask(p, img_size) for p in polys] with one kernel launch and one D2H copy of bit-packed boxes.
+    img_size None: every mask is cropped to its own polygon's extent + 1 like poly_to_mask does."""
+    arrs = [np.asarray(p, dtype=np.float32).reshape(-1, 2) for p in polys]
+    if img_size is not None:
+        return fill_polygons(arrs, img_size).masks()
+    ext = [(a.astype(np.int32).max(0) + 1)[::-1] for a in arrs]                # per polygon (rows, cols)
+    H, W = max(int(e[0]) for e in ext), max(int(e[1]) for e in ext)
+    return [m[: e[0], : e[1]].copy() for m, e in zip(fill_polygons(arrs, (H, W)).masks(), ext)]

@@ -236,3 +236,16 @@ def test_assembly_from_device_polygon_buffers(dec):
     # flag 2: same polygon as aug_group on the raw set (sorted by angle about the centre)
     want = dec.aug_group(raw2.copy(), np.array([30, 30], np.float32))
     assert want is not None and np.array_equal(dets[2][0][3], want)
+
+
+def test_dets_json_round_trip(tmp_path):
+    """`{epoch}_dets.json` / `_infos.json` (reference utils/eval_util.py:23-32,65-70): numpy scalars and arrays
+    serialise to plain JSON and load back as lists."""
+    import importlib
+    eval_util = importlib.import_module("isg_b200.utils.eval_util")
+    dets = [[(np.int64(3), np.float32(0.75), np.array([4.0, 5.0], np.float32), np.array([[1, 2], [3, 4], [5, 1]], np.float32))], []]
+    infos = [("/a/b_leftImg8bit.png", (8, 16)), ("/a/c.png", (8, 16))]
+    eval_util.save_dets(dets, infos, str(tmp_path), 12)
+    d2, i2 = eval_util.load_dets(str(tmp_path), 12)
+    assert d2 == [[[3, 0.75, [4.0, 5.0], [[1.0, 2.0], [3.0, 4.0], [5.0, 1.0]]]], []]
+    assert i2 == [["/a/b_leftImg8bit.png", [8, 16]], ["/a/c.png", [8, 16]]]
