@@ -88,21 +88,35 @@ fill_polygons_kernel(const float2* __restrict__ pts, const int32_t* __restrict__
     const int lo = Y0 + ya, hi = lo + nr;                          // image rows [lo, hi) of this pass
     for (int k = tid; k < nr * Wb; k += kFillThreads) { togg[k] = 0u; cover[k] = 0u; }
     __syncthreads();
-    for (int e = tid; e < K; e += kFillThreads) {
-      const float2 pa = __ldg(v + (e == 0 ? K - 1 : e - 1)), pb = __ldg(v + e);
-      const int ax = (int)pa.x, ay = (int)pa.y, bx = (int)pb.x, by = (int)pb.y;
-      if (max(ay, by) < lo || min(ay, by) >= hi) continue;
-      {   // (1) the edge line, left end point first
-        int x = ax, y = ay, x1 = bx, y1 = by;
+    // Every loop below has a warp-uniform trip count (the maximum over the warp, lanes past their own end are
+    // predicated off): lanes with edges of different length would otherwise drift apart between the line loop and the
+    // crossing loop and the warp would execute them as many separate fragments.
+    for (int e0 = 0; e0 < K; e0 += kFillThreads) {
+      const int e = e0 + tid;
+      bool valid = e < K;
+      int ax = 0, ay = 0, bx = 0, by = 0;
+      if (valid) {
+        const float2 pa = __ldg(v + (e == 0 ? K - 1 : e - 1)), pb = __ldg(v + e);
+        ax = (int)pa.x; ay = (int)pa.y; bx = (int)pb.x; by = (int)pb.y;
+        valid = !(max(ay, by) < lo || min(ay, by) >= hi);
+      }
+      // (1) the edge line, left end point first
+      int x = ax, y = ay, sy = 1, major = -1, minor = 0, err = 0;
+      bool steep = false;
+      if (valid) {
+        int x1 = bx, y1 = by;
         if (x1 < x) { x = bx; y = by; x1 = ax; y1 = ay; }
         const int dx = x1 - x;
         int dy = y1 - y;
-        const int sy = dy < 0 ? -1 : 1;
+        sy = dy < 0 ? -1 : 1;
         dy = dy < 0 ? -dy : dy;
-        const bool steep = dy > dx;
-        const int major = steep ? dy : dx, minor = steep ? dx : dy;
-        int err = major - 2 * minor;
-        for (int s = 0; s <= major; ++s) {
+        steep = dy > dx;
+        major = steep ? dy : dx; minor = steep ? dx : dy;
+        err = major - 2 * minor;
+      }
+      const int n_line = __reduce_max_sync(0xffffffffu, major) + 1;
+      for (int s = 0; s < n_line; ++s) {
+        if (s <= major) {
           if (y >= lo && y < hi) atomicOr(&cover[(y - lo) * Wb + (x >> 5) - w_lo], 1u << (x & 31));
           const bool neg = err < 0;
           err += -2 * minor + (neg ? 2 * major : 0);
@@ -110,17 +124,25 @@ fill_polygons_kernel(const float2* __restrict__ pts, const int32_t* __restrict__
           else { x += 1; y += neg ? sy : 0; }
         }
       }
-      if (ay != by) {   // (2) scan-line crossings on rows [top, bottom)
-        const long long dxf = ((long long)(bx - ax) * 65536ll) / (long long)(by - ay);
+      // (2) scan-line crossings on rows [top, bottom) of the edge
+      int n_rows = 0, yc = 0;
+      long long X = 0, dxf = 0;
+      if (valid && ay != by) {
+        dxf = ((long long)(bx - ax) * 65536ll) / (long long)(by - ay);
         const int yt = min(ay, by), yb = max(ay, by);
-        const long long xt = (long long)(ay < by ? ax : bx) << 16;
-        for (int y = max(yt, lo); y < min(yb, hi); ++y) {
-          const long long X = xt + (long long)(y - yt) * dxf;
+        yc = max(yt, lo);
+        n_rows = max(0, min(yb, hi) - yc);
+        X = ((long long)(ay < by ? ax : bx) << 16) + (long long)(yc - yt) * dxf;
+      }
+      const int n_scan = __reduce_max_sync(0xffffffffu, n_rows);
+      for (int k = 0; k < n_scan; ++k) {
+        if (k < n_rows) {
           const int xi = (int)(X >> 16);
-          uint32_t* row_t = togg + (y - lo) * Wb;
-          if ((X & 0xffffll) == 0) atomicOr(&cover[(y - lo) * Wb + (xi >> 5) - w_lo], 1u << (xi & 31));
-          const int t = xi + 1, tw = (t >> 5) - w_lo;
-          if (tw < Wb) atomicXor(&row_t[tw], 1u << (t & 31));
+          const int rb = (yc + k - lo) * Wb - w_lo;
+          if ((X & 0xffffll) == 0) atomicOr(&cover[rb + (xi >> 5)], 1u << (xi & 31));
+          const int t = xi + 1;
+          if ((t >> 5) - w_lo < Wb) atomicXor(&togg[rb + (t >> 5)], 1u << (t & 31));
+          X += dxf;
         }
       }
     }

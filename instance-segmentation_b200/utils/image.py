@@ -83,8 +83,9 @@ class FilledPolygons:
     words: int32 [cap] device buffer; desc: int32 [n,8] (host copy, see include/isg.h); in full-frame mode
     `bits` is the [n,H,ceil(W/32)] view that `isg_mask_nms` / `mask_pair_counts` read."""
 
-    def __init__(self, words, desc, size, full_frame):
+    def __init__(self, words, desc, size, full_frame, used=None):
         self.words, self.desc, self.size, self.full_frame = words, desc, (int(size[0]), int(size[1])), full_frame
+        self.used = int(words.numel() if used is None else min(used, words.numel()))     # words actually written
 
     def __len__(self):
         return self.desc.shape[0]
@@ -99,7 +100,7 @@ class FilledPolygons:
     def masks(self, dtype=np.int32):
         """list of [H,W] 0/1 arrays equal to poly_to_mask(poly, size) (one D2H copy of the packed words)."""
         H, W = self.size
-        host = self.words.cpu().numpy().view(np.uint32)
+        host = self.words[: self.used].cpu().numpy().view(np.uint32)
         out = []
         for st, x0, y0, rows, wpr, lo, hi, _k in self.desc.tolist():
             m = np.zeros((H, W), dtype=dtype)
@@ -157,10 +158,22 @@ def fill_polygons(polys, img_size, full_frame=False, dev=None) -> FilledPolygons
     call("isg_fill_polygons", ptr(pts), ptr(start), ptr(count), n, H, W, 1 if full_frame else 0, ptr(words), cap, ptr(desc),
          ptr(total), stream_ptr(dev))
     d = desc.cpu().numpy()
+    used = n * H * Ww if full_frame else int(total.item())
     for code, msg in _FILL_ERRORS.items():
         if (d[:, 0] == code).any():
             raise ValueError("fill_polygons: polygon %d: " % int(np.nonzero(d[:, 0] == code)[0][0]) + msg % (H, W))
-    return FilledPolygons(words, d, (H, W), full_frame)
+    return FilledPolygons(words, d, (H, W), full_frame, used)
+
+
+def fill_instances(plan, full_frame=False) -> FilledPolygons:
+    """Masks of the polygons the device polygon stage left in a DecodePlan (`run_assign(..., tail="polygons")`),
+    without a host round trip: entry b * N + i is instance i of image b (status FILL_EMPTY where no polygon was
+    accepted).  Full-frame output is the [B*N, H, ceil(W/32)] input of `nms.mask_nms`."""
+    B, N, cap = plan.B, plan.N, plan.cap
+    base = torch.arange(B, device=plan.device, dtype=torch.int32)[:, None] * cap
+    start = (plan.inst_start + base).reshape(-1)
+    count = torch.where(plan.inst_flags == 1, plan.inst_count, torch.zeros_like(plan.inst_count)).reshape(-1)
+    return fill_polygons((plan.poly_points.view(-1, 2), start, count), (plan.H, plan.W), full_frame, plan.device)
 
 
 def polys_to_masks(polys, img_size=None):
