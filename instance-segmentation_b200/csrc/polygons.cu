@@ -104,6 +104,12 @@ __device__ __forceinline__ float2 box_centre(const float4 r4, int layout) {
 // LARGE = false: pts / keys are the CTA's shared-memory arrays (K <= kPolyMaxPoints).  LARGE = true: global memory,
 // tmp[0..K) is scratch for the permutation (the sequential-mean fall-back stages chunks through s.pts).
 // Returns 1 when the polygon is valid.  Must be called by the whole CTA.
+#ifdef ISG_POLY_DEBUG
+__device__ long long g_poly_dbg[4096 * 8];
+#define PSTAMP(k) do { const int cid__ = blockIdx.y * gridDim.x + blockIdx.x; if (threadIdx.x == 0 && cid__ < 4096) g_poly_dbg[cid__ * 8 + (k)] = clock64(); } while (0)
+#else
+#define PSTAMP(k) do {} while (0)
+#endif
 template <bool LARGE>
 __device__ int finish_polygon(PolySmem& s, float2* pts, unsigned long long* keys, float2* tmp, float2* out, int K, int W, int H,
                               float cx, float cy, float2* internal_out) {
@@ -167,6 +173,7 @@ __device__ int finish_polygon(PolySmem& s, float2* pts, unsigned long long* keys
     }
   }
   if (tid == 0 && internal_out) *internal_out = make_float2(ix, iy);
+  PSTAMP(4);
 
   // ---- polar angles + stable ascending sort (bitonic on (angle bits, index)) ----
   int Kp = 1;
@@ -185,6 +192,7 @@ __device__ int finish_polygon(PolySmem& s, float2* pts, unsigned long long* keys
     keys[i] = key;
   }
   __syncthreads();
+  PSTAMP(5);
   if (!LARGE && K <= kPolyRankSort) {
     // small sets: rank sort - every key counts the keys below it (broadcast reads, no barriers); keys are distinct
     // because they carry the index, so the ranks are a permutation
@@ -226,6 +234,7 @@ __device__ int finish_polygon(PolySmem& s, float2* pts, unsigned long long* keys
       }
     }
   }
+  PSTAMP(6);
   // sorted polygon -> global (and, for the shared-memory variant, a sorted copy in place for the final test)
   if (!LARGE) {
     float2 mine_pt[kPolyMaxPoints / kPolyThreads];
@@ -247,7 +256,9 @@ __device__ int finish_polygon(PolySmem& s, float2* pts, unsigned long long* keys
   }
   __syncthreads();
   // ---- centre strictly inside the sorted polygon (:201) ----
-  return pip_block(s, pts, K, cx, cy) > 0 ? 1 : 0;
+  const int ok__ = pip_block(s, pts, K, cx, cy) > 0 ? 1 : 0;
+  PSTAMP(7);
+  return ok__;
 }
 
 
@@ -269,6 +280,7 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
   // evenly over the SMs; the empty tail of the instance table comes last
   const int b = blockIdx.x, inst = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  PSTAMP(0);
   const size_t io = (size_t)b * Nmax + inst;
   const int n = min(n_seeds[b], Nmax);
   if (inst >= n) {
@@ -312,13 +324,35 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
     return base;
   };
 
+  // ---- stage the keep words of the range in shared memory: strided, independent loads (all in flight at once);
+  // the blocked passes below would otherwise pay one global round trip per word, one after the other ----
+  uint32_t* wcache = reinterpret_cast<uint32_t*>(s.pts);          // [2 * kPolyMaxPoints] words; free until the emit step
+  const bool cached = NW <= 2 * kPolyMaxPoints;
+  if (cached) {
+    for (int w = tid; w < NW; w += 4 * kPolyThreads) {
+      uint32_t m[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { int y, xb; m[u] = (w + u * kPolyThreads < NW) ? box_word(w + u * kPolyThreads, y, xb) : 0u; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (w + u * kPolyThreads < NW) wcache[w + u * kPolyThreads] = m[u];
+    }
+    __syncthreads();
+  }
+  auto range_word = [&](int w, int& y, int& xb) -> uint32_t {     // box_word through the staged copy
+    if (!cached) return box_word(w, y, xb);
+    const int r = w / Wb, c = w - r * Wb;
+    y = y_lo + r; xb = (w_lo + c) << 5;
+    return wcache[w];
+  };
   // ---- candidates: keep pixels inside the range, row-major (blocked word assignment keeps the order) ----
   const int q = (NW + kPolyThreads - 1) / kPolyThreads;
   const int w0 = min(tid * q, NW), w1 = min(w0 + q, NW);
   int ncand_mine = 0;
-  for (int w = w0; w < w1; ++w) { int y, xb; ncand_mine += __popc(box_word(w, y, xb)); }
+  if (cached) { for (int w = w0; w < w1; ++w) ncand_mine += __popc(wcache[w]); }
+  else { for (int w = w0; w < w1; ++w) { int y, xb; ncand_mine += __popc(box_word(w, y, xb)); } }
   int C = 0;
   const int cbase = block_scan(ncand_mine, C);
+  PSTAMP(1);
   uint32_t* cand = reinterpret_cast<uint32_t*>(s.keys);          // [kPolyMaxCand] packed (y << 16 | x), shares the sort buffer
   const bool listed = C <= kPolyMaxCand && H <= 65535 && W <= 65535;
   int K = 0, base = 0;
@@ -327,7 +361,7 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
       int pos = cbase;
       for (int w = w0; w < w1; ++w) {
         int y, xb;
-        uint32_t m = box_word(w, y, xb);
+        uint32_t m = range_word(w, y, xb);
         while (m) { const int bit = __ffs(m) - 1; m &= m - 1; cand[pos++] = ((uint32_t)y << 16) | (uint32_t)(xb + bit); }
       }
     }
@@ -354,6 +388,7 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
     base = block_scan(mine, K);
   }
 
+  PSTAMP(2);
   __shared__ int s_start;
   if (tid == 0) {
     s_start = (K > 0) ? atomicAdd(img_total + b, K) : 0;
@@ -403,6 +438,7 @@ instance_polygons_kernel(const uint32_t* __restrict__ keepbits, const int32_t* _
     if (tid == 0) st[0] = K;
   }
   __syncthreads();
+  PSTAMP(3);
   if (!fits) {
     // more points than the shared-memory arrays hold: the raw row-major set is in `out`; finish it in global memory
     // (sort keys / permutation scratch in the caller's workspace), or flag it for the caller when there is none
@@ -481,3 +517,9 @@ extern "C" int isg_instance_polygons(const uint32_t* keepbits, const int32_t* la
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }
+
+#ifdef ISG_POLY_DEBUG
+extern "C" int isg_debug_poly_stamps(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, isg::g_poly_dbg, sizeof(long long) * 4096 * 8);
+}
+#endif
