@@ -1,4 +1,6 @@
-"""Timings of the secondary entry points on the BASELINE.json parity configurations (not bench lines): the seeded k-means of
+"""(Run by hand: `python tests/aux_timings.py` on a B200; not collected by pytest.  Lives under tests/ because it times the
+CPU oracle next to the device.)
+Timings of the secondary entry points on the BASELINE.json parity configurations (not bench lines): the seeded k-means of
 config 4, mask NMS of config 5, py_cpu_nms and select_points — device (CUDA events) next to the CPU oracle (wall clock)."""
 import os, sys, time
 import numpy as np, torch
