@@ -495,6 +495,7 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   const bool bin_mode = v.lower[3] != 0u;      // candidates = the keys of ONE 15-bit bin (two-level radix select)
   const uint32_t upper = bin_mode ? (lower | 0x1ffffu) : 0xffffffffu;
   const float* img = kp + (int64_t)b * img_stride;
+  const float lower_f = float_from_ukey(lower);
   if (t == 0) s_count = 0;
   __syncthreads();
   const int base = blockIdx.x * kFilterPxPerBlock;
@@ -530,13 +531,19 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
         in[u] = p < end;
         q[u] = in[u] ? ldg_stream4(img + p) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      // Candidates are a few percent of the pixels: reject in the float domain first (x < lower_f as floats implies
+      // key(x) < lower; -0 / NaN / a NaN bound fail the strict compare and take the exact key test), and let the rare
+      // survivors append themselves one by one (the candidate list is an unordered set).
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        uint32_t key[4] = {float_key(q[u].x), float_key(q[u].y), float_key(q[u].z), float_key(q[u].w)};
-        int c = 0;
+        const float x4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { if (!in[u] || key[i] < lower || key[i] > upper) key[i] = 0xffffffffu; else ++c; }
-        append4(key, c);
+        for (int i = 0; i < 4; ++i) {
+          if (in[u] && !(x4[i] < lower_f)) {
+            const uint32_t kk = float_key(x4[i]);
+            if (kk >= lower && kk <= upper && kk != 0xffffffffu) buf[atomicAdd(&s_count, 1u)] = kk;
+          }
+        }
       }
     }
   } else {
