@@ -166,9 +166,9 @@ class DecodePlan:
         tail "lists": compaction + per-pixel labels + per-instance point sets (idx/label/flag/offsets/points);
         tail "polygons" (dense mode, XYXY rois): isg_instance_polygons straight from the label map
         (poly_points/inst_start/inst_count/inst_flags)."""
-        if tail not in ("lists", "polygons"):
-            raise ValueError("tail must be 'lists' or 'polygons'")
-        if tail == "polygons" and (self.mode != "dense" or self.ghost_k < 0):
+        if tail not in ("lists", "polygons", "defer"):
+            raise ValueError("tail must be 'lists', 'polygons' or 'defer' (the caller enqueues run_polygons itself)")
+        if tail in ("polygons", "defer") and (self.mode != "dense" or self.ghost_k < 0):
             raise ValueError("the device polygon stage needs dense mode and the device ghost filter")
         B, H, W, N, cap = self.B, self.H, self.W, self.N, self.cap
         kp = self._check(kp, ae)
@@ -194,12 +194,9 @@ class DecodePlan:
                  self.dense_ws_bytes, 1 if lists_ready else 0, s)
             if ev:
                 ev[1].record()
-            if tail == "polygons":
-                call("isg_instance_polygons", ptr(self.keepbits), ptr(self.label_map), ptr(rois), layout, ptr(self.ghost), ptr(n_seeds),
-                     B, N, H, W, cap, int(obj_pixel_th), ptr(self.poly_points), ptr(self.inst_start), ptr(self.inst_count),
-                     ptr(self.inst_flags), ptr(self.inst_internal), ptr(self.img_total),
-                     0 if self.fused_stats else ptr(self.stats), self.poly_ws_ptr, self.poly_ws_bytes,
-                     1 if seeds_ready else 0, s)
+            if tail in ("polygons", "defer"):
+                if tail == "polygons":
+                    self.run_polygons(rois, n_seeds, layout, obj_pixel_th, totals_zeroed=seeds_ready)
                 if ev:
                     self.events.append(ev)
                 return
@@ -221,6 +218,15 @@ class DecodePlan:
              B, N, ptr(self.offsets), ptr(self.points), s)
         if ev:
             self.events.append(ev)
+
+    def run_polygons(self, rois: torch.Tensor, n_seeds: torch.Tensor, layout: int = _lib.ISG_BOX_XYXY, obj_pixel_th: int = 0,
+                     totals_zeroed: bool = False) -> None:
+        """The polygon tail of a dense step (isg_instance_polygons) on the current stream."""
+        call("isg_instance_polygons", ptr(self.keepbits), ptr(self.label_map), ptr(rois), layout, ptr(self.ghost), ptr(n_seeds),
+             self.B, self.N, self.H, self.W, self.cap, int(obj_pixel_th), ptr(self.poly_points), ptr(self.inst_start),
+             ptr(self.inst_count), ptr(self.inst_flags), ptr(self.inst_internal), ptr(self.img_total),
+             0 if self.fused_stats else ptr(self.stats), self.poly_ws_ptr, self.poly_ws_bytes,
+             1 if totals_zeroed else 0, stream_ptr(self.device))
 
     def run(self, kp: torch.Tensor, ae: torch.Tensor, rois: torch.Tensor, n_seeds: torch.Tensor,
             layout: int = _lib.ISG_BOX_XYXY, time_main: bool = False, tail: str = "lists", obj_pixel_th: int = 0) -> None:
@@ -309,10 +315,45 @@ class DecodePipeline:
         self.side = torch.cuda.Stream(device=self.device)
         self.fork = torch.cuda.Event()
         self.join = torch.cuda.Event()
+        # pipelined steps: the polygon tail of step s runs on its own stream while step s+1's box head / NMS / top-k run
+        self.tail_stream = torch.cuda.Stream(device=self.device)
+        self.dense_done = torch.cuda.Event()
+        self.tail_done = torch.cuda.Event()
+        self.tail_pending = False
+        self.tail_deferred = None      # (obj_pixel_th,) of a pipelined step whose polygon tail is not enqueued yet
+
+    def _launch_tail(self) -> None:
+        """Enqueue the polygon tail of the last pipelined step on the tail stream (behind its dense kernel)."""
+        if self.tail_deferred is None:
+            return
+        (obj_pixel_th,) = self.tail_deferred
+        self.tail_deferred = None
+        bp, dp = self.bplan, self.dplan
+        self.tail_stream.wait_event(self.dense_done)
+        with torch.cuda.stream(self.tail_stream):
+            dp.run_polygons(bp.rois, bp.n_seeds, _lib.ISG_BOX_XYXY, obj_pixel_th, totals_zeroed=True)
+            self.tail_done.record(self.tail_stream)
+        self.tail_pending = True
+
+    def finish(self) -> None:
+        """Make the current stream wait for the polygon tail of the last pipelined step (no-op otherwise)."""
+        self._launch_tail()
+        if self.tail_pending:
+            torch.cuda.current_stream(self.device).wait_event(self.tail_done)
+            self.tail_pending = False
 
     def run(self, kp, ae, anchors, regression, classification, cls_th, iou_th, time_main: bool = False,
-            tail: str = "lists", obj_pixel_th: int = 0) -> None:
+            tail: str = "lists", obj_pixel_th: int = 0, pipelined: bool = False) -> None:
+        """One decode step on the current stream.  pipelined=True (dense mode, tail "polygons"): the polygon tail is
+        enqueued on a separate stream and the call returns without making the current stream wait for it, so that the
+        box head, NMS and top-k of the NEXT run() overlap it; the kernels of the next step that overwrite what the tail
+        reads (seeds, label map) wait for it.  Call finish() before reading the results on the current stream."""
         main = torch.cuda.current_stream(self.device)
+        pipelined = pipelined and tail == "polygons" and self.dplan.mode == "dense"
+        if not pipelined:
+            self.finish()
+        # the top-k of this step may start as soon as everything enqueued so far on `main` is done (in a pipelined
+        # sequence: the dense kernel of the previous step, which reads the previous threshold)
         self.fork.record(main)
         self.side.wait_event(self.fork)
         with torch.cuda.stream(self.side):
@@ -320,6 +361,13 @@ class DecodePipeline:
             self.join.record(self.side)
         bp, dp = self.bplan, self.dplan
         bp.run(anchors, regression, classification, cls_th, iou_th, gather=False)
+        # The previous step's polygon tail is enqueued only now, behind this step's box head in the hardware queues: the
+        # box head is a short bandwidth-bound grid, NMS occupies one CTA per image, and the tail (whose grid does not fit
+        # the GPU in one wave and would hold back every later grid until its last CTA is placed) fills the rest.
+        self._launch_tail()
+        if self.tail_pending:      # the seeds / label map about to be overwritten are still read by the previous tail
+            main.wait_event(self.tail_done)
+            self.tail_pending = False
         call("isg_gather_build_seeds", ptr(bp.cand_boxes), ptr(bp.cand_scores), ptr(bp.cand_cls), ptr(bp.keep), ptr(bp.n_keep),
              bp.B, bp.cap, bp.N, ptr(dp.ys), ptr(dp.xs), dp.H, dp.W, dp.ghost_k, dp.scale, ptr(bp.rois), ptr(bp.scores),
              ptr(bp.cls), ptr(bp.n_seeds), ptr(dp.seeds), ptr(dp.ghost), ptr(dp.stats),
@@ -329,8 +377,14 @@ class DecodePipeline:
             call("isg_build_tile_lists", ptr(dp.seeds), ptr(bp.n_seeds), dp.B, dp.N, dp.H, dp.W, ptr(dp.dense_ws),
                  dp.dense_ws_bytes, stream_ptr(self.device))
         main.wait_event(self.join)
-        dp.run_assign(kp, ae, bp.rois, bp.n_seeds, _lib.ISG_BOX_XYXY, time_main, tail, obj_pixel_th, seeds_ready=True,
-                      lists_ready=dense)
+        if not pipelined:
+            dp.run_assign(kp, ae, bp.rois, bp.n_seeds, _lib.ISG_BOX_XYXY, time_main, tail, obj_pixel_th, seeds_ready=True,
+                          lists_ready=dense)
+            return
+        dp.run_assign(kp, ae, bp.rois, bp.n_seeds, _lib.ISG_BOX_XYXY, time_main, "defer", obj_pixel_th, seeds_ready=True,
+                      lists_ready=True)
+        self.dense_done.record(main)
+        self.tail_deferred = (obj_pixel_th,)
 
 
 _pipes = {}

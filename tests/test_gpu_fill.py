@@ -144,3 +144,31 @@ def test_results_writer_matches_reference_files(image, tmp_path):
     eval_util.write_results(d2, i2, str(out2), names, ids)
     for f in os.listdir(str(tmp_path / "results")):
         assert open(str(tmp_path / "results" / f), "rb").read() == open(str(out2 / "results" / f), "rb").read()
+
+
+def test_fill_instances_from_device_polygons(image):
+    """Masks straight from the device polygon buffers of a DecodePlan (no host round trip of the polygons)."""
+    from isg_b200 import engine, synth
+    from isg_b200 import _lib
+    B, H, W, C = 2, 256, 512, 8
+    dev = torch.device(DEV)
+    anchors = synth.make_anchors(H, W)
+    scenes = [synth.make_scene(520 + b, H, W, [11, 7][b], C, anchors) for b in range(B)]
+    kp = torch.from_numpy(np.stack([s[0].kp for s in scenes])).to(dev); ae = torch.from_numpy(np.stack([s[0].ae for s in scenes])).to(dev)
+    reg = torch.from_numpy(np.stack([s[1] for s in scenes])).to(dev); cls = torch.from_numpy(np.stack([s[2] for s in scenes])).to(dev)
+    bplan = engine.BoxPlan(B, anchors.reshape(-1, 4).shape[0], C, H, W, dev, cap=1024, max_keep=64)
+    dplan = engine.DecodePlan(B, H, W, bplan.N, 3000, dev, "dense", want_score=False, wh_delta=0.1)
+    engine.DecodePipeline(bplan, dplan).run(kp, ae, torch.from_numpy(anchors).to(dev), reg, cls, 0.3, 0.2, tail="polygons", obj_pixel_th=2)
+    for full in (False, True):
+        filled = image.fill_instances(dplan, full_frame=full)
+        masks = filled.masks()
+        pts = dplan.poly_points.cpu().numpy(); st = dplan.inst_start.cpu().numpy(); ct = dplan.inst_count.cpu().numpy()
+        fl = dplan.inst_flags.cpu().numpy()
+        assert (fl == 1).sum() >= 10
+        for b in range(B):
+            for i in range(bplan.N):
+                m = masks[b * bplan.N + i]
+                if fl[b, i] == 1:
+                    assert np.array_equal(m, cv_mask(pts[b, st[b, i]: st[b, i] + ct[b, i]], (H, W)))
+                else:
+                    assert filled.desc[b * bplan.N + i, 0] == image.FILL_EMPTY and not m.any()

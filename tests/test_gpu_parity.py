@@ -608,3 +608,54 @@ def test_polygon_stage_large_instance(mods):
     for p_host, p_dev, ctr in zip(out["host"][3], out["device"][3], out["host"][2]):
         assert p_host.shape[0] > 2048
         assert_polygon_equivalent(dec, p_dev, p_host, ctr)
+
+
+def test_pipelined_steps_equal_isolated_steps(mods):
+    """engine.DecodePipeline.run(pipelined=True): the polygon tail of a step overlaps the head of the next one; the
+    results of every step must be those of the same step run on its own."""
+    synth, engine = mods["synth"], mods["engine"]
+    B, H, W, C = 3, 256, 512, 8
+    dev = torch.device(DEV)
+    anchors = synth.make_anchors(H, W)
+    anc = torch.from_numpy(anchors).to(dev)
+
+    def batch(seed, counts):
+        sc = [synth.make_scene(seed + b, H, W, counts[b], C, anchors) for b in range(B)]
+        return [torch.from_numpy(np.stack(x)).to(dev) for x in ([s[0].kp for s in sc], [s[0].ae for s in sc], [s[1] for s in sc], [s[2] for s in sc])]
+
+    batches = [batch(900, [12, 0, 20]), batch(940, [5, 17, 9])]
+    bplan = engine.BoxPlan(B, anchors.reshape(-1, 4).shape[0], C, H, W, dev, cap=1024, max_keep=64)
+    dplan = engine.DecodePlan(B, H, W, bplan.N, 3000, dev, "dense", want_score=False, wh_delta=0.1)
+    pipe = engine.DecodePipeline(bplan, dplan)
+
+    def snapshot():
+        torch.cuda.synchronize(dev)
+        out = {}
+        cnt = dplan.inst_count.cpu().numpy(); st = dplan.inst_start.cpu().numpy(); pts = dplan.poly_points.cpu().numpy()
+        n = bplan.n_seeds.cpu().numpy()
+        for b in range(B):
+            for i in range(int(n[b])):
+                out[(b, i)] = (int(dplan.inst_flags[b, i]), pts[b, st[b, i]: st[b, i] + cnt[b, i]].copy())
+        return n.copy(), out
+
+    def run(x, pipelined):
+        pipe.run(x[0], x[1], anc, x[2], x[3], 0.3, 0.2, tail="polygons", obj_pixel_th=2, pipelined=pipelined)
+
+    want = []
+    for x in batches:
+        run(x, False)
+        want.append(snapshot())
+    for seq in ([0, 1], [0, 1, 0], [1, 1, 0, 1, 0, 1, 0, 0, 1]):
+        for k in seq:
+            run(batches[k], True)
+        pipe.finish()
+        n, got = snapshot()
+        wn, wgot = want[seq[-1]]
+        assert np.array_equal(n, wn) and got.keys() == wgot.keys()
+        for key in got:
+            assert got[key][0] == wgot[key][0] and np.array_equal(got[key][1], wgot[key][1]), key
+    # a non-pipelined step behind a pipelined one waits for the pending tail by itself
+    run(batches[0], True)
+    run(batches[1], False)
+    n, got = snapshot()
+    assert np.array_equal(n, want[1][0]) and all(np.array_equal(got[k][1], want[1][1][k][1]) for k in got)
