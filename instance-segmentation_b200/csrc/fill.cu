@@ -24,6 +24,7 @@ namespace {
 constexpr int kFillThreads = 256;
 constexpr int kFillWarps = kFillThreads / 32;
 constexpr int kFillTileWords = 4096;          // words per bit plane held in shared memory (2 planes, 32 KB)
+constexpr int kFillThreadRowWords = 16;       // boxes up to this many words a row resolve with one thread per row
 
 __global__ void __launch_bounds__(kFillThreads)
 fill_polygons_kernel(const float2* __restrict__ pts, const int32_t* __restrict__ poly_start,
@@ -147,7 +148,21 @@ fill_polygons_kernel(const float2* __restrict__ pts, const int32_t* __restrict__
       }
     }
     __syncthreads();
-    // ---- toggles -> inside mask (prefix XOR along the row), one warp per row ----
+    // ---- toggles -> inside mask (prefix XOR along the row) ----
+    if (Wb <= kFillThreadRowWords) {
+      // narrow boxes (the usual case): one thread per row, the carry between words stays in a register
+      for (int r = tid; r < nr; r += kFillThreads) {
+        uint32_t carry = 0u;
+        for (int w = 0; w < Wb; ++w) {
+          uint32_t t = togg[r * Wb + w];
+          t ^= t << 1; t ^= t << 2; t ^= t << 4; t ^= t << 8; t ^= t << 16;
+          t ^= carry;
+          carry = (uint32_t)((int32_t)t >> 31);                        // all ones when the row is inside at the word's end
+          out[(size_t)(ya + r) * Wb + w] = t | cover[r * Wb + w];
+        }
+      }
+    } else
+    // wide boxes / full frames: one warp per row, 32 words at a time
     for (int r = warp; r < nr; r += kFillWarps) {
       uint32_t carry = 0u;
       for (int wb = 0; wb < Wb; wb += 32) {
