@@ -97,21 +97,27 @@ class FilledPolygons:
         H, W = self.size
         return self.words[: len(self) * H * ((W + 31) // 32)].view(len(self), H, (W + 31) // 32)
 
+    def _host_words(self):
+        if getattr(self, "_host", None) is None:
+            self._host = self.words[: self.used].cpu().numpy().view(np.uint32)     # one D2H copy of the packed words
+        return self._host
+
+    def mask(self, i, dtype=np.int32):
+        """[H,W] 0/1 array of polygon i, equal to poly_to_mask(poly_i, size)."""
+        H, W = self.size
+        st, x0, y0, rows, wpr, lo, hi, _k = (int(v) for v in self.desc[i])
+        m = np.zeros((H, W), dtype=dtype)
+        if st == FILL_OK:
+            off = (lo & 0xFFFFFFFF) | (hi << 32)
+            blk = self._host_words()[off: off + rows * wpr].reshape(rows, wpr)
+            px = np.unpackbits(blk.view(np.uint8), axis=1, bitorder="little")           # [rows, 32*wpr]
+            x1 = min(W, x0 + 32 * wpr)
+            m[y0: y0 + rows, x0: x1] = px[:, : x1 - x0]
+        return m
+
     def masks(self, dtype=np.int32):
         """list of [H,W] 0/1 arrays equal to poly_to_mask(poly, size) (one D2H copy of the packed words)."""
-        H, W = self.size
-        host = self.words[: self.used].cpu().numpy().view(np.uint32)
-        out = []
-        for st, x0, y0, rows, wpr, lo, hi, _k in self.desc.tolist():
-            m = np.zeros((H, W), dtype=dtype)
-            if st == FILL_OK:
-                off = (lo & 0xFFFFFFFF) | (hi << 32)
-                blk = host[off: off + rows * wpr].reshape(rows, wpr)
-                px = np.unpackbits(blk.view(np.uint8), axis=1, bitorder="little")       # [rows, 32*wpr]
-                x1 = min(W, x0 + 32 * wpr)
-                m[y0: y0 + rows, x0: x1] = px[:, : x1 - x0]
-            out.append(m)
-        return out
+        return [self.mask(i, dtype) for i in range(len(self))]
 
 
 def fill_polygons(polys, img_size, full_frame=False, dev=None) -> FilledPolygons:
@@ -151,14 +157,18 @@ def fill_polygons(polys, img_size, full_frame=False, dev=None) -> FilledPolygons
     elif bound is not None:
         cap = max(bound, 1)
     else:
-        cap = n * H * Ww                                  # device-resident polygons: worst case
-    words = torch.empty(cap, dtype=torch.int32, device=dev)
+        cap = min(n * H * Ww, 1 << 23)                    # device-resident polygons: 32 MB first, the exact size on overflow
     desc = torch.empty((n, 8), dtype=torch.int32, device=dev)
     total = torch.empty(1, dtype=torch.int64, device=dev)
-    call("isg_fill_polygons", ptr(pts), ptr(start), ptr(count), n, H, W, 1 if full_frame else 0, ptr(words), cap, ptr(desc),
-         ptr(total), stream_ptr(dev))
-    d = desc.cpu().numpy()
-    used = n * H * Ww if full_frame else int(total.item())
+    while True:
+        words = torch.empty(cap, dtype=torch.int32, device=dev)
+        call("isg_fill_polygons", ptr(pts), ptr(start), ptr(count), n, H, W, 1 if full_frame else 0, ptr(words), cap, ptr(desc),
+             ptr(total), stream_ptr(dev))
+        d = desc.cpu().numpy()
+        used = n * H * Ww if full_frame else int(total.item())
+        if full_frame or bound is not None or used <= cap:
+            break
+        cap = used                                        # the kernel reports the words it needed: run again with room for all
     for code, msg in _FILL_ERRORS.items():
         if (d[:, 0] == code).any():
             raise ValueError("fill_polygons: polygon %d: " % int(np.nonzero(d[:, 0] == code)[0][0]) + msg % (H, W))

@@ -172,3 +172,17 @@ def test_fill_instances_from_device_polygons(image):
                     assert np.array_equal(m, cv_mask(pts[b, st[b, i]: st[b, i] + ct[b, i]], (H, W)))
                 else:
                     assert filled.desc[b * bplan.N + i, 0] == image.FILL_EMPTY and not m.any()
+
+
+def test_fill_device_polygons_retry_on_overflow(image, monkeypatch):
+    """Device-resident polygons: the first output buffer is a guess; an overflow is answered with the exact size."""
+    rng = np.random.RandomState(4)
+    size = (1024, 2048)
+    polys = [np.stack([rng.randint(0, 2048, 5), rng.randint(0, 1024, 5)], 1).astype(np.float32) for _ in range(400)]
+    flat = torch.from_numpy(np.concatenate(polys)).to(DEV)
+    start = torch.arange(0, 5 * len(polys), 5, dtype=torch.int32)
+    count = torch.full((len(polys),), 5, dtype=torch.int32)
+    filled = image.fill_polygons((flat, start, count), size)          # 400 large boxes: more than the 32 MB first guess
+    assert filled.used > (1 << 23) and (filled.desc[:, 0] == image.FILL_OK).all()
+    for i in (0, 7, 399):
+        assert np.array_equal(filled.mask(i), cv_mask(polys[i], size))
