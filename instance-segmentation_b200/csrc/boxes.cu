@@ -381,9 +381,34 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
     }
   }
   __syncthreads();
-  {
+  if (n <= 256) {
+    // up to 256 candidates (4 suppression words a row): 4 threads per row collect their share of the row in registers,
+    // combine by shuffle and store the row once - no shared-memory atomics (64-bit ones are compare-and-swap loops)
+    const int sub = t & 3, i = t >> 2;                          // kSortThreads / 4 = 256 rows in one sweep
+    unsigned long long b0 = 0ull, b1 = 0ull, b2 = 0ull, b3 = 0ull;
+    if (i < n) {
+      const float4 a = sbox[i];
+      const int ac = scls[i];
+      const int qend = bstart[(ac & 63) + 1];
+      for (int q = posof[i] + 1 + sub; q < qend; q += 4) {
+        const int c = memb[q];                                  // rank > i, ascending
+        if (scls[c] != ac) continue;                            // another class hashed into the same bucket
+        const bool sup = (convention == ISG_NMS_TV_GT) ? suppresses_tv(a, sbox[c], thr) : suppresses_plus1(a, sbox[c], thr_f);
+        if (!sup) continue;
+        const unsigned long long bit = 1ull << (c & 63);
+        const int w = c >> 6;
+        if (w == 0) b0 |= bit; else if (w == 1) b1 |= bit; else if (w == 2) b2 |= bit; else b3 |= bit;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+      b0 |= __shfl_xor_sync(0xffffffffu, b0, o); b1 |= __shfl_xor_sync(0xffffffffu, b1, o);
+      b2 |= __shfl_xor_sync(0xffffffffu, b2, o); b3 |= __shfl_xor_sync(0xffffffffu, b3, o);
+    }
+    if (i < n && sub < nw) mask[(size_t)i * nwP + sub] = sub == 0 ? b0 : (sub == 1 ? b1 : (sub == 2 ? b2 : b3));
+  } else {
     // R threads per row share its successors (the rows are short, the block would otherwise be mostly idle)
-    const int R = n <= 256 ? 4 : (n <= 512 ? 2 : 1);
+    const int R = n <= 512 ? 2 : 1;
     const int sub = t % R;
     for (int i = t / R; i < n; i += kSortThreads / R) {
       const float4 a = sbox[i];
