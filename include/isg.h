@@ -232,10 +232,14 @@ int isg_mask_pair_counts(const uint32_t* masks, int n, int H, int Wwords, const 
 
 /* ------------------------------------------------------------------------------------------
  * K4 — seeded k-means with per-cluster allowed distance.  Replaces kmeans / pairwise_distance /
- * pairwise_cosine (utils/kmeans.py:16-130).  BLOCKING: iterates until center_shift^2 < tol
- * (utils/kmeans.py:90) or max_iter, synchronising `stream` to read the convergence flag.
- * X [M,D] fp32, centers [N,D] fp32 in/out, allow [N] fp32, labels [M] int32 out (N = outlier),
- * iters_host: host int* (nullable).  D <= 16.
+ * pairwise_cosine (utils/kmeans.py:16-130).  The whole Lloyd loop (assign + per-cluster sums, new
+ * centres, `center_shift^2 < tol` test of utils/kmeans.py:90) is ONE cooperative launch; the call is
+ * BLOCKING only at its end (it synchronises `stream` once to return the iteration count / status).
+ * X [M,D] fp32, centers [N,D] fp32 in/out, allow [N] fp32, labels [M] int32 out (N = outlier; labels of the
+ * LAST assignment, i.e. w.r.t. the pre-update centres, :93), iters_host: host int* (nullable).
+ * max_iter <= 0: no bound (like the reference).  D <= 16; N*(12*D + 8) + 128*(4*D + 4) bytes of shared memory <= 200 KB.
+ * The per-cluster mean is accumulated in fp64 in a fixed order (reproducible); the reference's fp32 mean
+ * differs by ~1e-7 relative.
  * ------------------------------------------------------------------------------------------ */
 size_t isg_kmeans_workspace_bytes(int M, int N, int D);
 int isg_kmeans(const float* X, int M, int D, float* centers, const float* allow, int N,

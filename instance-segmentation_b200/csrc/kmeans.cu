@@ -1,22 +1,34 @@
 // K4 — seeded k-means with per-cluster allowed distance.
 // Reference: kmeans / pairwise_distance / pairwise_cosine (utils/kmeans.py:16-130).
 //
-// One Lloyd iteration = assign (thread per point, centres in shared memory) + update (one warp per
-// cluster, fp64 shuffle reduction over the label list: deterministic, no atomics) + finish (centre
-// shift in cluster order, convergence flag).  Iterations are enqueued in batches; every kernel is a
-// no-op once the device-side `done` flag is set, so the host only reads the flag once per batch.
+// The whole Lloyd loop is ONE cooperative launch (kmeans_loop_kernel): the host never looks at the convergence flag
+// mid-run.  Per iteration:
+//   assign   thread per point against the centres staged in shared memory -> label (first index on ties, :57; outlier
+//            label N unless min distance < allow, :60-61), written to global and kept in a shared slab with the point;
+//   update   per CTA: walk the slab once in point order; the thread that owns cluster (label mod blockDim) adds the point
+//            to that cluster's fp64 accumulator in shared memory - exclusive ownership, so no atomics and a fixed
+//            order of additions.  The CTA's partial sums / counts go to the workspace;           O(M) work
+//   -- grid barrier --
+//   finish   warp per cluster: partials of all CTAs in CTA order (lane-strided + a fixed shuffle tree) -> mean ->
+//            new centre (unchanged when empty, :74) and its shift (:72);                           O(N * CTAs) work
+//   -- grid barrier --
+//   every CTA adds the shifts in cluster order in fp32 (:64,72) and takes the same `center_shift^2 < tol` decision (:90).
+// The additions of one cluster happen in ascending point order inside a CTA and in CTA order across CTAs: results are
+// reproducible run to run.  The mean is accumulated in fp64 (the reference's fp32 `mean` differs by ~1e-7 relative).
 #include <algorithm>
 #include "common.cuh"
 
 namespace isg {
 
 constexpr int kMaxD = 16;
+constexpr int kKmThreads = 128;      // power of two: cluster ownership is `label & (kKmThreads - 1)`
+constexpr int kKmMaxCtas = 2 * kSMs;
 
 struct KmeansState {   // lives in the workspace
+  unsigned int barrier;   // monotonic arrival counter of the grid barrier
   int done;
   int iters;
   float shift;
-  int pad;
 };
 
 template <int METRIC>
@@ -47,94 +59,160 @@ __device__ __forceinline__ float vec_norm(const float* v, int D) {
   return __fsqrt_rn(s);
 }
 
-template <int METRIC>
-__global__ void __launch_bounds__(256)
-kmeans_assign_kernel(const float* __restrict__ X, int M, int D, const float* __restrict__ centers,
-                     const float* __restrict__ allow, int N, int32_t* __restrict__ labels,
-                     const KmeansState* __restrict__ st) {
-  if (st->done) return;
-  extern __shared__ float sm[];
-  float* sc = sm;             // [N*D]
-  float* sn = sm + N * D;     // [N] centre norms (cosine)
-  for (int i = threadIdx.x; i < N * D; i += blockDim.x) sc[i] = centers[i];
+// all CTAs of a cooperative launch (co-resident by construction); `epoch` counts this CTA's barriers
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int ctas, unsigned int& epoch) {
   __syncthreads();
-  if (METRIC == ISG_KMEANS_COSINE) {
-    for (int i = threadIdx.x; i < N; i += blockDim.x) sn[i] = vec_norm(sc + i * D, D);
-    __syncthreads();
-  }
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  float x[kMaxD];
-  for (int d = 0; d < D; ++d) x[d] = X[(size_t)m * D + d];
-  const float xn = (METRIC == ISG_KMEANS_COSINE) ? vec_norm(x, D) : 0.0f;
-  float best = 0.0f;
-  int arg = 0;
-  for (int j = 0; j < N; ++j) {
-    const float dj = point_dist<METRIC>(x, sc + j * D, D, xn, (METRIC == ISG_KMEANS_COSINE) ? sn[j] : 0.0f);
-    if (j == 0 || dj < best) { best = dj; arg = j; }   // torch.min: first index on ties (:57)
-  }
-  // cluster id = num_clusters unless min distance < allowed distance (strict, :60-61)
-  labels[m] = (best < allow[arg]) ? arg : N;
-}
-
-constexpr int kUpdateWarps = 8;
-
-__global__ void __launch_bounds__(32 * kUpdateWarps)
-kmeans_update_kernel(const float* __restrict__ X, int M, int D, const float* __restrict__ centers, int N,
-                     const int32_t* __restrict__ labels, float* __restrict__ cnew, float* __restrict__ shift,
-                     int32_t* __restrict__ nonempty, const KmeansState* __restrict__ st) {
-  if (st->done) return;
-  const int k = blockIdx.x * kUpdateWarps + (threadIdx.x >> 5);
-  if (k >= N) return;
-  const int lane = threadIdx.x & 31;
-  double acc[kMaxD];
-  for (int d = 0; d < D; ++d) acc[d] = 0.0;
-  int cnt = 0;
-  for (int m = lane; m < M; m += 32) {
-    if (labels[m] == k) {
-      ++cnt;
-      for (int d = 0; d < D; ++d) acc[d] += (double)X[(size_t)m * D + d];
-    }
-  }
-  cnt = warp_sum(cnt);
-  for (int d = 0; d < D; ++d) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
-  }
-  if (lane == 0) {
-    float sh = 0.0f;
-    if (cnt > 0) {
-      // new centre = mean of the members (:70-72); shift = sqrt(sum((new - old)^2)) (:72)
-      float s = 0.0f;
-      for (int d = 0; d < D; ++d) {
-        const float nc = (float)(acc[d] / (double)cnt);
-        cnew[(size_t)k * D + d] = nc;
-        const float t = __fsub_rn(nc, centers[(size_t)k * D + d]);
-        s = (d == 0) ? __fmul_rn(t, t) : __fadd_rn(s, __fmul_rn(t, t));
-      }
-      sh = __fsqrt_rn(s);
-    } else {
-      for (int d = 0; d < D; ++d) cnew[(size_t)k * D + d] = centers[(size_t)k * D + d];   // unchanged (:74)
-    }
-    shift[k] = sh;
-    nonempty[k] = cnt > 0;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-kmeans_finish_kernel(float* __restrict__ centers, const float* __restrict__ cnew, int N, int D,
-                     const float* __restrict__ shift, const int32_t* __restrict__ nonempty, float tol,
-                     KmeansState* __restrict__ st) {
-  if (st->done) return;   // uniform: every thread reads the flag before thread 0 may set it (sync below)
-  __syncthreads();
-  for (int i = threadIdx.x; i < N * D; i += blockDim.x) centers[i] = cnew[i];
+  epoch += 1;
   if (threadIdx.x == 0) {
-    float cs = 0.0f;   // center_shift accumulates in cluster order, fp32 (:64,72)
-    for (int k = 0; k < N; ++k)
-      if (nonempty[k]) cs = __fadd_rn(cs, shift[k]);
-    st->shift = cs;
-    st->iters += 1;
-    if (__fmul_rn(cs, cs) < tol) st->done = 1;   // center_shift ** 2 < tol (:90)
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned int target = epoch * ctas;
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+// nearest centre of one point: (distance, index) with torch.min's first-index rule (:57)
+template <int METRIC, int DT>
+__device__ __forceinline__ void nearest(const float* x, const float* sc, const float* sn, int N, int D, float& best, int& arg) {
+  const int DD = DT > 0 ? DT : D;
+  if (METRIC == ISG_KMEANS_EUCLIDEAN) {
+    // sqrt is monotone: a centre whose SQUARED distance is not below the best one cannot win the strict `<` on the
+    // rounded square roots, so the square root is only taken for improving candidates
+    float best_s = 0.0f;
+    best = 0.0f; arg = 0;
+    for (int j = 0; j < N; ++j) {
+      const float* c = sc + j * DD;
+      float s = 0.0f;
+#pragma unroll
+      for (int d = 0; d < DD; ++d) {
+        const float t = __fsub_rn(x[d], c[d]);
+        const float q = __fmul_rn(t, t);
+        s = (d == 0) ? q : __fadd_rn(s, q);
+      }
+      if (j == 0 || s < best_s) {
+        const float r = __fsqrt_rn(s);
+        if (j == 0 || r < best) { best = r; arg = j; }
+        best_s = s;
+      }
+    }
+  } else {
+    const float xn = vec_norm(x, DD);
+    best = 0.0f; arg = 0;
+    for (int j = 0; j < N; ++j) {
+      const float dj = point_dist<METRIC>(x, sc + j * DD, DD, xn, sn[j]);
+      if (j == 0 || dj < best) { best = dj; arg = j; }
+    }
+  }
+}
+
+template <int METRIC, int DT>
+__global__ void __launch_bounds__(kKmThreads)
+kmeans_loop_kernel(const float* __restrict__ X, int M, int D, float* __restrict__ centers, const float* __restrict__ allow,
+                   int N, float tol, int max_iter, int32_t* __restrict__ labels, double* __restrict__ psum /*[G][N][D]*/,
+                   int32_t* __restrict__ pcnt /*[G][N]*/, float* __restrict__ shift /*[N], < 0 = empty*/,
+                   KmeansState* __restrict__ st) {
+  const int DD = DT > 0 ? DT : D;
+  extern __shared__ __align__(16) unsigned char km_smem[];
+  double* acc = reinterpret_cast<double*>(km_smem);                 // [N*DD] fp64 sums of this CTA's members
+  float* sc = reinterpret_cast<float*>(acc + (size_t)N * DD);       // [N*DD] centres
+  float* sn = sc + (size_t)N * DD;                                  // [N]    centre norms (cosine) / shifts (finish)
+  int32_t* cnt = reinterpret_cast<int32_t*>(sn + N);                // [N]
+  float* sx = reinterpret_cast<float*>(cnt + N);                    // [kKmThreads*DD] slab: points of the chunk
+  int32_t* sl = reinterpret_cast<int32_t*>(sx + kKmThreads * DD);   // [kKmThreads]    slab: their labels
+  __shared__ int s_done;
+  const int t = threadIdx.x, G = gridDim.x, cta = blockIdx.x;
+  const int lane = t & 31;
+  unsigned int epoch = 0;
+  int it = 0;
+  for (;;) {
+    for (int i = t; i < N * DD; i += kKmThreads) { sc[i] = centers[i]; acc[i] = 0.0; }
+    for (int i = t; i < N; i += kKmThreads) cnt[i] = 0;
+    __syncthreads();
+    if (METRIC == ISG_KMEANS_COSINE) {
+      for (int i = t; i < N; i += kKmThreads) sn[i] = vec_norm(sc + i * DD, DD);
+      __syncthreads();
+    }
+    for (int base = cta * kKmThreads; base < M; base += G * kKmThreads) {
+      const int m = base + t;
+      int lab = -1;
+      if (m < M) {
+        float x[DT > 0 ? DT : kMaxD];
+#pragma unroll
+        for (int d = 0; d < DD; ++d) { x[d] = X[(size_t)m * DD + d]; sx[t * DD + d] = x[d]; }
+        float best; int arg;
+        nearest<METRIC, DT>(x, sc, sn, N, D, best, arg);
+        lab = (best < allow[arg]) ? arg : N;       // strict (:60-61)
+        labels[m] = lab;
+      }
+      sl[t] = lab;
+      __syncthreads();
+      const int n_chunk = min(kKmThreads, M - base);
+      for (int i = 0; i < n_chunk; ++i) {          // ascending point order; thread (label mod blockDim) owns the cluster
+        const int l = sl[i];
+        if (l < N && (l & (kKmThreads - 1)) == t) {
+          cnt[l] += 1;
+#pragma unroll
+          for (int d = 0; d < DD; ++d) acc[l * DD + d] += (double)sx[i * DD + d];
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = t; i < N * DD; i += kKmThreads) psum[(size_t)cta * N * DD + i] = acc[i];
+    for (int i = t; i < N; i += kKmThreads) pcnt[(size_t)cta * N + i] = cnt[i];
+    grid_barrier(&st->barrier, G, epoch);
+
+    // finish: warp per cluster over the CTAs' partials
+    for (int k = cta * (kKmThreads / 32) + (t >> 5); k < N; k += G * (kKmThreads / 32)) {
+      double a[DT > 0 ? DT : kMaxD];
+#pragma unroll
+      for (int d = 0; d < DD; ++d) a[d] = 0.0;
+      int c = 0;
+      for (int g = lane; g < G; g += 32) {
+        c += pcnt[(size_t)g * N + k];
+#pragma unroll
+        for (int d = 0; d < DD; ++d) a[d] += psum[((size_t)g * N + k) * DD + d];
+      }
+      c = warp_sum(c);
+#pragma unroll
+      for (int d = 0; d < DD; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[d] += __shfl_xor_sync(0xffffffffu, a[d], o);
+      }
+      if (lane == 0) {
+        float sh = -1.0f;                           // empty cluster: centre unchanged, no shift term (:73-74)
+        if (c > 0) {
+          float s = 0.0f;
+#pragma unroll
+          for (int d = 0; d < DD; ++d) {
+            const float nc = (float)(a[d] / (double)c);                     // mean of the members (:70-71)
+            const float dlt = __fsub_rn(nc, sc[k * DD + d]);
+            s = (d == 0) ? __fmul_rn(dlt, dlt) : __fadd_rn(s, __fmul_rn(dlt, dlt));
+            centers[(size_t)k * DD + d] = nc;
+          }
+          sh = __fsqrt_rn(s);                                               // (:72)
+        }
+        shift[k] = sh;
+      }
+    }
+    grid_barrier(&st->barrier, G, epoch);
+
+    for (int i = t; i < N; i += kKmThreads) sn[i] = shift[i];
+    __syncthreads();
+    ++it;
+    if (t == 0) {
+      float cs = 0.0f;                              // center_shift accumulates in cluster order, fp32 (:64,72)
+      for (int k = 0; k < N; ++k)
+        if (sn[k] >= 0.0f) cs = __fadd_rn(cs, sn[k]);
+      const int done = __fmul_rn(cs, cs) < tol;     // center_shift ** 2 < tol (:90)
+      s_done = done;
+      if (cta == 0) { st->shift = cs; st->iters = it; st->done = done; }
+    }
+    __syncthreads();
+    if (s_done || (max_iter > 0 && it >= max_iter)) break;
   }
 }
 
@@ -157,9 +235,33 @@ using namespace isg;
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+static int km_max_ctas(int M) { return std::max(1, std::min(cdiv(M, kKmThreads), kKmMaxCtas)); }
+static size_t km_smem_bytes(int N, int D) {
+  return (size_t)N * D * 8 + (size_t)N * D * 4 + (size_t)N * 8 + (size_t)kKmThreads * D * 4 + kKmThreads * 4;
+}
+
 extern "C" size_t isg_kmeans_workspace_bytes(int M, int N, int D) {
   if (M < 0 || N <= 0 || D <= 0) return 0;
-  return align256(sizeof(KmeansState)) + align256((size_t)N * D * 4) + align256((size_t)N * 4) * 2;
+  const size_t G = (size_t)km_max_ctas(M);
+  return align256(sizeof(KmeansState)) + align256(G * N * D * 8) + align256(G * N * 4) + align256((size_t)N * 4);
+}
+
+template <int METRIC, int DT>
+static int km_launch(const float* X, int M, int D, float* centers, const float* allow, int N, float tol, int max_iter,
+                     int32_t* labels, double* psum, int32_t* pcnt, float* shift, KmeansState* st, cudaStream_t stream) {
+  auto kern = kmeans_loop_kernel<METRIC, DT>;
+  const size_t smem = km_smem_bytes(N, D);
+  ISG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0, per_sm = 0;
+  ISG_CUDA(cudaGetDevice(&dev));
+  ISG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  ISG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kKmThreads, smem));
+  if (per_sm < 1) return ISG_EUNSUPPORTED;
+  const int G = std::min(km_max_ctas(M), per_sm * sms);   // cooperative launch: every CTA resident
+  void* args[] = {(void*)&X, (void*)&M, (void*)&D, (void*)&centers, (void*)&allow, (void*)&N, (void*)&tol, (void*)&max_iter,
+                  (void*)&labels, (void*)&psum, (void*)&pcnt, (void*)&shift, (void*)&st};
+  ISG_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(G), dim3(kKmThreads), args, smem, stream));
+  return ISG_OK;
 }
 
 extern "C" int isg_kmeans(const float* X, int M, int D, float* centers, const float* allow, int N, float tol,
@@ -170,39 +272,26 @@ extern "C" int isg_kmeans(const float* X, int M, int D, float* centers, const fl
   if (D > kMaxD) return ISG_EUNSUPPORTED;
   if (metric != ISG_KMEANS_EUCLIDEAN && metric != ISG_KMEANS_COSINE) return ISG_EINVAL;
   if (!ws || ws_bytes < isg_kmeans_workspace_bytes(M, N, D) || ((uintptr_t)ws & 255)) return ISG_EWORKSPACE;
-  const size_t smem = ((size_t)N * D + N) * sizeof(float);
-  if (smem > 200 * 1024) return ISG_EUNSUPPORTED;
+  if (km_smem_bytes(N, D) > 200 * 1024) return ISG_EUNSUPPORTED;
+  const size_t G = (size_t)km_max_ctas(M);
   char* p = (char*)ws;
   KmeansState* st = (KmeansState*)p; p += align256(sizeof(KmeansState));
-  float* cnew = (float*)p;           p += align256((size_t)N * D * 4);
-  float* shift = (float*)p;          p += align256((size_t)N * 4);
-  int32_t* nonempty = (int32_t*)p;
+  double* psum = (double*)p;         p += align256(G * N * D * 8);
+  int32_t* pcnt = (int32_t*)p;       p += align256(G * N * 4);
+  float* shift = (float*)p;
   ISG_CUDA(cudaMemsetAsync(st, 0, sizeof(KmeansState), stream));
+  int rc;
   if (metric == ISG_KMEANS_EUCLIDEAN)
-    ISG_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<ISG_KMEANS_EUCLIDEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rc = (D == 2) ? km_launch<ISG_KMEANS_EUCLIDEAN, 2>(X, M, D, centers, allow, N, tol, max_iter, labels, psum, pcnt, shift, st, stream)
+                  : km_launch<ISG_KMEANS_EUCLIDEAN, 0>(X, M, D, centers, allow, N, tol, max_iter, labels, psum, pcnt, shift, st, stream);
   else
-    ISG_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<ISG_KMEANS_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int batch = 4;
-  int it = 0;
+    rc = (D == 2) ? km_launch<ISG_KMEANS_COSINE, 2>(X, M, D, centers, allow, N, tol, max_iter, labels, psum, pcnt, shift, st, stream)
+                  : km_launch<ISG_KMEANS_COSINE, 0>(X, M, D, centers, allow, N, tol, max_iter, labels, psum, pcnt, shift, st, stream);
+  if (rc != ISG_OK) return rc;
+  ISG_LAUNCH_CHECK();
   KmeansState h;
-  h.done = 0; h.iters = 0; h.shift = 0.f; h.pad = 0;
-  while (max_iter <= 0 || it < max_iter) {
-    const int nb = (max_iter > 0) ? std::min(batch, max_iter - it) : batch;
-    for (int r = 0; r < nb; ++r) {
-      if (metric == ISG_KMEANS_EUCLIDEAN)
-        kmeans_assign_kernel<ISG_KMEANS_EUCLIDEAN><<<cdiv(M, 256), 256, smem, stream>>>(X, M, D, centers, allow, N, labels, st);
-      else
-        kmeans_assign_kernel<ISG_KMEANS_COSINE><<<cdiv(M, 256), 256, smem, stream>>>(X, M, D, centers, allow, N, labels, st);
-      kmeans_update_kernel<<<cdiv(N, kUpdateWarps), 32 * kUpdateWarps, 0, stream>>>(X, M, D, centers, N, labels, cnew,
-                                                                                 shift, nonempty, st);
-      kmeans_finish_kernel<<<1, 256, 0, stream>>>(centers, cnew, N, D, shift, nonempty, tol, st);
-    }
-    ISG_LAUNCH_CHECK();
-    it += nb;
-    ISG_CUDA(cudaMemcpyAsync(&h, st, sizeof(KmeansState), cudaMemcpyDeviceToHost, stream));
-    ISG_CUDA(cudaStreamSynchronize(stream));
-    if (h.done) break;
-  }
+  ISG_CUDA(cudaMemcpyAsync(&h, st, sizeof(KmeansState), cudaMemcpyDeviceToHost, stream));
+  ISG_CUDA(cudaStreamSynchronize(stream));
   if (iters_host) *iters_host = h.iters;
   return h.done ? ISG_OK : ISG_ENOTCONVERGED;
 }

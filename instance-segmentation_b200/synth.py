@@ -321,3 +321,58 @@ def make_scene(seed: int, H: int, W: int, N: int, C: int = 8, anchors: np.ndarra
                                  dtype=np.float32)
         classification[a, classes[i]] = scores[i]
     return img, regression, classification, anchors
+
+
+# --------------------------------------------------------------------------------------------
+# seeded k-means (BASELINE config 4): embeddings around seed coordinates, label-stable by construction
+# --------------------------------------------------------------------------------------------
+def _kmeans_fp64(X, init, allow, tol):
+    """utils/kmeans.py:55-93 in fp64, recording every iteration's two smallest distances per point.
+    Returns (labels, centres, iterations, worst label margin per point, worst relative gap of shift^2 to tol)."""
+    X = X.astype(np.float64); c = init.astype(np.float64).copy(); allow = allow.astype(np.float64)
+    N = c.shape[0]
+    margin = np.full(X.shape[0], np.inf)
+    stop_gap = np.inf
+    it = 0
+    while True:
+        d = np.sqrt(((X[:, None, :] - c[None]) ** 2).sum(-1))                  # [M,N]
+        part = np.partition(d, 1, axis=1) if N > 1 else np.concatenate([d, np.full_like(d, np.inf)], axis=1)
+        best = d.argmin(1)
+        d1, d2 = part[:, 0], part[:, 1]
+        margin = np.minimum(margin, np.minimum(d2 - d1, np.abs(d1 - allow[best])))
+        lab = np.where(d1 < allow[best], best, N)
+        new = c.copy()
+        shift = 0.0
+        for k in np.unique(lab[lab < N]):
+            new[k] = X[lab == k].mean(0)
+            shift += np.sqrt(((new[k] - c[k]) ** 2).sum())
+        c = new
+        it += 1
+        stop_gap = min(stop_gap, abs(shift * shift - tol) / tol)
+        if shift * shift < tol or it > 500:
+            return lab, c, it, margin, stop_gap
+
+
+def make_kmeans_case(seed: int, M: int, N: int, noise: float = 0.004, allow: float = 0.05, tol: float = 1e-4,
+                     eps: float = 1e-5):
+    """X [M',2] fp32 (M' <= M), initial centres [N,2] fp32, allow [N] fp32 for utils/kmeans.py::kmeans, such that along
+    the whole Lloyd trajectory (followed in fp64) every point's nearest centre beats the runner-up by more than `eps`,
+    its distance stays more than `eps` away from the allowed distance, and center_shift^2 stays 1 % away from `tol`:
+    labels and the iteration count are then independent of fp32 rounding and of the order of the mean's additions
+    (centre perturbations ~1e-7).  Points that violate a margin are removed and the trajectory is re-certified."""
+    rs = np.random.RandomState(seed)
+    cen = np.stack([rs.uniform(0.05, 0.95, N), rs.uniform(0.05, 1.95, N)], axis=1).astype(np.float32)
+    X = (cen[rs.randint(0, N, size=M)] + rs.normal(0, noise, size=(M, 2))).astype(np.float32)
+    far = rs.rand(M) < 0.01                                                     # outliers beyond every allowed distance
+    X[far] += rs.choice([-1.0, 1.0], size=(int(far.sum()), 2)).astype(np.float32) * np.float32(3.0)
+    init = (cen + rs.normal(0, noise / 2, size=cen.shape)).astype(np.float32)
+    allow_v = np.full(N, allow, dtype=np.float32)
+    for _ in range(20):
+        lab, c, it, margin, gap = _kmeans_fp64(X, init, allow_v, tol)
+        bad = margin <= eps
+        if not bad.any():
+            if gap < 1e-2:
+                raise RuntimeError("kmeans case %d: center_shift^2 within 1%% of tol; pick another seed" % seed)
+            return X, init, allow_v, lab.astype(np.int64), c.astype(np.float32), it
+        X = X[~bad]
+    raise RuntimeError("kmeans case %d could not be certified" % seed)

@@ -515,14 +515,17 @@ def decode_single(kp_heat, ae_mat, boxes, info, transforms, decode_cfg, device):
 
 
 def decode_ct_hm(conf_mat, cls_mat, wh, num_classes, cls_th, transforms, info):
-    """:254-285 (dead code in the reference; the only caller of py_cpu_nms)."""
+    """:254-285 (dead code in the reference; the only caller of py_cpu_nms).  `cls_th` is the COUNT handed to
+    select_points (:256).  The peak selection (top-k + 3x3 maximum) and the per-class NMS run on the device; the values
+    at the <= k peaks are gathered on the host from the maps as the caller holds them."""
     cat, height, width = wh.size()
-    center_mask = select_points(conf_mat, cls_th).bool()
-    cls_mat, conf_mat, wh = cls_mat.to(center_mask.device), conf_mat.to(center_mask.device), wh.to(center_mask.device)
-    center_cls = to_numpy(cls_mat.masked_select(center_mask))
-    center_indexes = to_numpy(center_mask.nonzero())
-    center_confs = to_numpy(conf_mat.masked_select(center_mask)).astype(np.float32)
-    center_whs = to_numpy(wh.masked_select(center_mask)).reshape(cat, -1)
+    dev = _device_of(conf_mat)
+    center_mask = to_numpy(select_points(conf_mat, cls_th)).astype(bool)            # :256
+    ys, xs = np.nonzero(center_mask)                                                # row-major, like nonzero() at :258
+    center_indexes = np.stack((ys, xs), axis=1)
+    center_cls = to_numpy(cls_mat)[ys, xs]                                          # :257
+    center_confs = to_numpy(conf_mat)[ys, xs].astype(np.float32)                    # :259
+    center_whs = to_numpy(wh)[:, ys, xs].reshape(cat, -1)                           # :260
     keep_cls, keep_idx, keep_confs, keep_whs = [], [], [], []
     for c_i in range(0, num_classes):
         sel = center_cls == c_i
@@ -533,7 +536,7 @@ def decode_ct_hm(conf_mat, cls_mat, wh, num_classes, cls_th, transforms, info):
         swh = whs * compute_scale(info)
         boxes = np.array([[*(tc[j] - swh[:, j] / 2), *(tc[j] + swh[:, j] / 2), confs[j]] for j in range(tc.shape[0])],
                          dtype=np.float32)
-        keep = py_cpu_nms(boxes, thresh=0.5)
+        keep = py_cpu_nms(torch.from_numpy(boxes).to(dev), thresh=0.5)
         keep_cls.extend(cls[keep]); keep_idx.extend(centers[keep]); keep_confs.extend(confs[keep]); keep_whs.extend(whs[:, keep].T)
     return keep_cls, keep_idx, keep_confs, keep_whs
 

@@ -45,7 +45,7 @@ def kmeans(X, num_clusters, cluster_centers, allow_distances, distance='euclidea
     rc = lib.isg_kmeans(ptr(Xd), M, D, ptr(centers), ptr(allow), N, float(np.float32(tol)), _METRIC[distance],
                         int(max_iterations), ptr(labels), ctypes.addressof(iters), ws.data_ptr() + off, ws_bytes,
                         stream_ptr(dev))
-    _lib.launch_count += 3 * ((iters.value + 3) // 4) * 4
+    _lib.launch_count += 1          # the whole Lloyd loop is one cooperative launch
     if rc != 0:
         raise IsgError(rc, "isg_kmeans")
     kmeans.last_iterations = iters.value

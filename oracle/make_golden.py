@@ -114,6 +114,121 @@ def main():
         np.savez_compressed(os.path.join(OUT, "decode_single_%s.npz" % name), **d)
         print(name, "groups", len(captured), "dets", len(dets), "kept px", int(mask.sum()))
 
+    # ---- decode_single with rejections: an instance whose polygon does not contain its centre (aug_group -> None,
+    #      :201-204), an instance below obj_pixel_th (:355), and background pixels outside every box that land on
+    #      label 0 (:328) and are removed by the ghost filter (:351-352) ------------------------------------------------
+    seed, h, w, n, kp_th = 15, 128, 256, 8, 6000
+    img = synth.make_image(seed, h, w, n)
+    rs4 = np.random.RandomState(1500)
+    kp4 = img.kp[0].copy()
+    cx = (img.rois[:, 0] + img.rois[:, 2]) / 2
+    ww = img.rois[:, 2] - img.rois[:, 0]
+    yy, xx = np.nonzero(img.owner == 2)
+    cut = xx >= cx[2] - ww[2] / 4                                   # instance 2 keeps only the left quarter of its outline
+    kp4[yy[cut], xx[cut]] = rs4.normal(-6.0, 0.5, size=int(cut.sum())).astype(np.float32)
+    yy, xx = np.nonzero(img.owner == 5)
+    kp4[yy[1:], xx[1:]] = rs4.normal(-6.0, 0.5, size=yy.size - 1).astype(np.float32)   # instance 5 keeps one pixel
+    # stray peaks outside every box: all-zero membership row -> label 0 (:328); those outside instance 0's ghost band
+    # are removed by the filter (:351-352), the ones inside the band (0.5w..0.6w from its centre) stay
+    yy, xx = np.mgrid[0:h, 0:w]
+    covered = np.zeros((h, w), dtype=bool)
+    for x1, y1, x2, y2 in img.rois:
+        covered |= (xx >= x1 - 1) & (xx <= x2 + 1) & (yy >= y1 - 1) & (yy <= y2 + 1)
+    cy0, hh0 = (img.rois[0, 1] + img.rois[0, 3]) / 2, img.rois[0, 3] - img.rois[0, 1]
+    band = ~covered & (np.abs(xx - cx[0]) < 0.58 * ww[0]) & (np.abs(yy - cy0) < 0.58 * hh0)
+    far = ~covered & ((np.abs(xx - cx[0]) > 0.7 * ww[0]) | (np.abs(yy - cy0) > 0.7 * hh0))
+    for region, cnt in ((band, 3), (far, 12)):
+        ry, rx = np.nonzero(region)
+        pick = rs4.choice(ry.size, size=min(cnt, ry.size), replace=False)
+        kp4[ry[pick], rx[pick]] = rs4.uniform(4.0, 5.0, size=pick.size).astype(np.float32)
+    n_band, n_far = int(min(3, band.sum())), int(min(12, far.sum()))
+    kp4 = synth._distinct_float32(kp4)[None]
+    cfg.kp_th = kp_th
+    captured = []
+    orig = rdecode.aug_group
+
+    def spy4(pts, center_loc, _o=orig, _c=captured):
+        out = _o(pts, center_loc)
+        _c.append((np.array(pts, dtype=np.float32), np.array(center_loc, dtype=np.float32).reshape(-1), out is None))
+        return out
+    rdecode.aug_group = spy4
+    try:
+        boxes = {"rois": img.rois, "class_ids": img.class_ids, "scores": img.scores}
+        mask = rdecode.select_points(torch.from_numpy(kp4[0]), kp_th).numpy()
+        (dets,) = rdecode.decode_single(torch.from_numpy(kp4), torch.from_numpy(img.ae.copy()), boxes,
+                                        TransInfo("/nonexistent.png", (h, w)), tf, cfg, dev)
+    finally:
+        rdecode.aug_group = orig
+    d = dict(kp=kp4, ae=img.ae, rois=img.rois, class_ids=img.class_ids, scores=img.scores, kp_th=np.int64(kp_th), mask=mask,
+             n_groups=np.int64(len(captured)), n_dets=np.int64(len(dets)),
+             grp_rejected=np.array([c[2] for c in captured], dtype=bool))
+    for i, (pts, c, _) in enumerate(captured):
+        d["grp_pts_%d" % i] = pts
+        d["grp_ctr_%d" % i] = c
+    for i, (cls, conf, ctr, poly) in enumerate(dets):
+        d["det_cls_%d" % i] = np.int64(cls)
+        d["det_conf_%d" % i] = np.float32(conf)
+        d["det_ctr_%d" % i] = np.asarray(ctr, dtype=np.float32)
+        d["det_poly_%d" % i] = np.asarray(poly, dtype=np.float32)
+    assert len(dets) < len(captured) < n and n_band > 0 and n_far > 0, (len(dets), len(captured), n, n_band, n_far)
+    np.savez_compressed(os.path.join(OUT, "decode_single_s4.npz"), **d)
+    print("s4 boxes", n, "groups", len(captured), "dets", len(dets), "kept px", int(mask.sum()))
+
+    # ---- decode_single under a resize validation transform (utils/tranform.py:157-171) with decode.target_size = 2
+    #      (test.py:58): the network sees the half-size image, polygons come out in original-image pixels --------------
+    import json
+    import tempfile
+    trans = json.load(open(os.path.join(args.ref, "configs", "trans_cfg.json")))
+    trans["val_trans"] = {"trans_seq": ["resize"], "resize": {"target_size": 2}}
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(trans, f)
+    tf2 = CommonTransforms(Configer(configs=f.name), "val")
+    os.unlink(f.name)
+    seed, h, w, n, kp_th = 16, 96, 192, 5, 2500
+    img = synth.make_image(seed, h, w, n)
+    cfg.kp_th = kp_th
+    saved_ts = rdecode.target_size
+    rdecode.target_size = 2
+    captured = []
+
+    def spy5(pts, center_loc, _o=orig, _c=captured):
+        _c.append((np.array(pts, dtype=np.float32), np.array(center_loc, dtype=np.float32).reshape(-1)))
+        return _o(pts, center_loc)
+    rdecode.aug_group = spy5
+    try:
+        boxes = {"rois": img.rois, "class_ids": img.class_ids, "scores": img.scores}
+        (dets,) = rdecode.decode_single(torch.from_numpy(img.kp), torch.from_numpy(img.ae.copy()), boxes,
+                                        TransInfo("/nonexistent.png", (2 * h, 2 * w)), tf2, cfg, dev)
+    finally:
+        rdecode.aug_group = orig
+        rdecode.target_size = saved_ts
+    d = dict(kp=img.kp, ae=img.ae, rois=img.rois, class_ids=img.class_ids, scores=img.scores, kp_th=np.int64(kp_th),
+             img_size=np.array([2 * h, 2 * w], dtype=np.int64), target_size=np.int64(2),
+             n_groups=np.int64(len(captured)), n_dets=np.int64(len(dets)))
+    for i, (pts, c) in enumerate(captured):
+        d["grp_pts_%d" % i] = pts
+        d["grp_ctr_%d" % i] = c
+    for i, (cls, conf, ctr, poly) in enumerate(dets):
+        d["det_cls_%d" % i] = np.int64(cls)
+        d["det_conf_%d" % i] = np.float32(conf)
+        d["det_ctr_%d" % i] = np.asarray(ctr, dtype=np.float32)
+        d["det_poly_%d" % i] = np.asarray(poly, dtype=np.float32)
+    np.savez_compressed(os.path.join(OUT, "decode_single_resize.npz"), **d)
+    print("resize groups", len(captured), "dets", len(dets))
+
+    # ---- decode_ct_hm (:254-285): peaks of a centre heat map -> per-class boxes -> py_cpu_nms(0.5) --------------------
+    rs6 = np.random.RandomState(61)
+    h, w, ncls, k = 48, 80, 3, 60
+    conf = synth._distinct_float32(rs6.uniform(0.0, 1.0, size=(h, w)).astype(np.float32))
+    clsm = rs6.randint(0, ncls, size=(h, w)).astype(np.int64)
+    whm = rs6.uniform(6.0, 30.0, size=(2, h, w)).astype(np.float32)
+    out = rdecode.decode_ct_hm(torch.from_numpy(conf), torch.from_numpy(clsm), torch.from_numpy(whm), ncls, k, tf,
+                               TransInfo("/nonexistent.png", (h, w)))
+    np.savez_compressed(os.path.join(OUT, "decode_ct_hm.npz"), conf=conf, cls=clsm, wh=whm, num_classes=np.int64(ncls),
+                        k=np.int64(k), keep_cls=np.asarray(out[0], dtype=np.int64), keep_idx=np.asarray(out[1], dtype=np.int64).reshape(-1, 2),
+                        keep_conf=np.asarray(out[2], dtype=np.float32), keep_wh=np.asarray(out[3], dtype=np.float32).reshape(-1, 2))
+    print("decode_ct_hm kept", len(out[0]))
+
     # ---- decode_boxes ------------------------------------------------------------------------------
     H, W, C = 128, 256, 8
     anchors = synth.make_anchors(H, W)
@@ -144,6 +259,13 @@ def main():
                         labels_cos=labc.numpy(), centers_cos=ctrc.numpy(),
                         pd=pairwise_distance(torch.from_numpy(X[:40]), torch.from_numpy(init)).numpy(),
                         pc=pairwise_cosine(torch.from_numpy(X[:40] + 1.0), torch.from_numpy(init + 1.0)).numpy())
+
+    # BASELINE config 4 size: M ~ 20000 embeddings, N = 500 seeds, allow 0.05; margins certified by the generator
+    Xc, initc, allowc, _, _, _ = synth.make_kmeans_case(4, 20000, 500)
+    labc4, ctrc4 = rkmeans(torch.from_numpy(Xc), 500, torch.from_numpy(initc), allowc)
+    np.savez_compressed(os.path.join(OUT, "kmeans_crowd.npz"), X=Xc, init=initc, allow=allowc,
+                        labels=labc4.numpy().astype(np.int16), centers=ctrc4.numpy())
+    print("kmeans crowd", Xc.shape, "outliers", int((labc4 == 500).sum()))
 
     # ---- py_cpu_nms / boxes_nms -----------------------------------------------------------------------
     d = {}

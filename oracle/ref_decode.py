@@ -131,18 +131,41 @@ def dense_labels(hm_ae: torch.Tensor, rois: np.ndarray, rows_per_chunk: int = 16
 # ----------------------------------------------------------------------------------------------
 # a6 — per-instance point sets with the ghost filter
 # ----------------------------------------------------------------------------------------------
+def detransform_pixel(pixels: np.ndarray, img_size, resize_target=None) -> np.ndarray:
+    """CommonTransforms.detransform_pixel (utils/tranform.py:157-171): (y,x) -> (x,y), then — when the validation
+    transform resized the image by 1/resize_target — the inverse affine map back to the original img_size (h,w),
+    clipped to the frame (utils/image.py:48-82)."""
+    import cv2
+    rev = pixels.reshape(-1, 2)[:, ::-1]
+    if resize_target is None:
+        return rev
+    height, width = img_size
+    out_size = (int(round(width * (1 / resize_target))), int(round(height * (1 / resize_target))))   # :166-167
+    in_size = tuple(img_size)[::-1]
+    src = np.array([[0, 0], [0, in_size[1] - 1], [in_size[0] - 1, in_size[1] - 1]], dtype=np.float32)    # image.py:56
+    dst = np.array([[0, 0], [0, out_size[1] - 1], [out_size[0] - 1, out_size[1] - 1]], dtype=np.float32)
+    t = cv2.getAffineTransform(dst, src).astype(np.float32)                                              # inv=True, :63,78
+    pts_h = np.hstack((rev, np.ones((rev.shape[0], 1), dtype=np.float32)))
+    out = np.dot(t, pts_h.T).T
+    out[:, 0] = out[:, 0].clip(min=0, max=in_size[0] - 1)
+    out[:, 1] = out[:, 1].clip(min=0, max=in_size[1] - 1)
+    return out[:, :2]
+
+
 def instance_points(idx: torch.Tensor, label: torch.Tensor, centres: np.ndarray, whs: np.ndarray, wh_delta: float,
-                    scale=1):
-    """utils/decode.py:337-353 with the identity val transform (detransform_pixel = (y,x)->(x,y) flip,
-    utils/tranform.py:157-159).  Returns list over instances of (points f32 [K,2] (x,y), centre f32 [2] (x,y))."""
+                    scale=1, img_size=None, resize_target=None):
+    """utils/decode.py:337-353.  With resize_target None the val transform is the identity (detransform_pixel =
+    (y,x)->(x,y) flip, utils/tranform.py:157-159); otherwise pixels and centres go through the inverse resize and
+    `scale` (= decode.target_size, :34-35) multiplies the box sizes.
+    Returns list over instances of (points f32 [K,2] (x,y), centre f32 [2] (x,y))."""
     out = []
     idx_np = idx.numpy()
     lab_np = label.numpy()
     for i in range(centres.shape[0]):
         h, w = tuple(whs[i] * scale)                                             # :339
         sel = np.nonzero(lab_np == i)[0]                                         # :342
-        true_pixels = idx_np[sel].astype(np.float32)[:, ::-1]                    # :343-345
-        center_loc = centres[i].reshape(-1, 2)[:, ::-1][0]                       # :347-348
+        true_pixels = detransform_pixel(idx_np[sel].astype(np.float32), img_size, resize_target)   # :343-345
+        center_loc = detransform_pixel(centres[i], img_size, resize_target)[0]   # :347-348
         x, y = center_loc[0], center_loc[1]
         xm = (x - (0.5 + wh_delta) * w < true_pixels[:, 0]) * (true_pixels[:, 0] < x + (0.5 + wh_delta) * w)  # :351
         ym = (y - (0.5 + wh_delta) * h < true_pixels[:, 1]) * (true_pixels[:, 1] < y + (0.5 + wh_delta) * h)  # :352
@@ -208,8 +231,9 @@ def aug_group(pts: np.ndarray, center_loc: np.ndarray):
     return None
 
 
-def group_kp(hm_kp, hm_ae, rois, class_ids, scores, kp_th=20000, wh_delta=0.1, obj_pixel_th=2):
-    """group_kp (utils/decode.py:288-374) with draw_flag False and the identity val transform."""
+def group_kp(hm_kp, hm_ae, rois, class_ids, scores, kp_th=20000, wh_delta=0.1, obj_pixel_th=2, scale=1, img_size=None,
+             resize_target=None):
+    """group_kp (utils/decode.py:288-374) with draw_flag False; identity val transform unless resize_target is given."""
     n = len(rois)
     if n == 0:
         return [], [], [], []
@@ -217,7 +241,8 @@ def group_kp(hm_kp, hm_ae, rois, class_ids, scores, kp_th=20000, wh_delta=0.1, o
     if core["idx"].shape[0] == 0:                                                # :300
         return [], [], [], []
     clss, confs, centers, polys = [], [], [], []
-    for i, (pts, center_loc) in enumerate(instance_points(core["idx"], core["label"], core["centres"], core["whs"], wh_delta)):
+    for i, (pts, center_loc) in enumerate(instance_points(core["idx"], core["label"], core["centres"], core["whs"], wh_delta,
+                                                           scale, img_size, resize_target)):
         if pts.shape[0] < obj_pixel_th:                                          # :355
             continue
         poly = aug_group(pts, center_loc)
@@ -226,13 +251,40 @@ def group_kp(hm_kp, hm_ae, rois, class_ids, scores, kp_th=20000, wh_delta=0.1, o
     return clss, confs, centers, polys
 
 
-def decode_single(kp_heat, ae_mat, boxes, kp_th=20000, wh_delta=0.1, obj_pixel_th=2):
+def decode_single(kp_heat, ae_mat, boxes, kp_th=20000, wh_delta=0.1, obj_pixel_th=2, scale=1, img_size=None,
+                  resize_target=None):
     """utils/decode.py:422-441."""
     if boxes["class_ids"].shape[0] == 0:
         return ([],)
     c, f, ctr, g = group_kp(kp_heat[0], ae_mat, boxes["rois"], boxes["class_ids"], boxes["scores"], kp_th, wh_delta,
-                            obj_pixel_th)
+                            obj_pixel_th, scale, img_size, resize_target)
     return ([e for e in zip(c, f, ctr, g)],)
+
+
+def decode_ct_hm(conf_mat: torch.Tensor, cls_mat: torch.Tensor, wh: torch.Tensor, num_classes: int, k: int):
+    """utils/decode.py:254-285 with the identity val transform and target_size 1: the `k` (= cls_th, a COUNT) best
+    3x3 peaks of conf_mat -> per class boxes [c - wh/2, c + wh/2, conf] in (x,y) order -> py_cpu_nms(0.5).
+    Returns (classes i64 [n], centre indexes i64 [n,2] (y,x), confidences f32 [n], sizes f32 [n,2])."""
+    from .ref_kmeans_nms import py_cpu_nms
+    cat = wh.shape[0]
+    mask = select_points(conf_mat, k).bool()                                     # :256
+    center_cls = cls_mat[mask].numpy()                                           # :257
+    center_indexes = mask.nonzero().numpy()                                      # :258
+    center_confs = conf_mat[mask].numpy().astype(np.float32)                     # :259
+    center_whs = wh[:, mask].numpy().reshape(cat, -1)                            # :260
+    kc, ki, kf, kw = [], [], [], []
+    for c_i in range(num_classes):                                               # :266
+        sel = center_cls == c_i
+        if sel.sum() == 0:
+            continue
+        cls, confs, whs, centers = center_cls[sel], center_confs[sel], center_whs[:, sel], center_indexes[sel, :]
+        tc = detransform_pixel(centers, None)[:, ::-1]                           # :274 (flip twice: back to (y,x))
+        boxes = np.array([[*(tc[j] - whs[:, j] / 2), *(tc[j] + whs[:, j] / 2), confs[j]] for j in range(tc.shape[0])],
+                         dtype=np.float32)                                       # :276
+        keep = py_cpu_nms(boxes, 0.5)                                            # :277
+        kc.extend(cls[keep]); ki.extend(centers[keep]); kf.extend(confs[keep]); kw.extend(whs[:, keep].T)
+    return (np.asarray(kc, dtype=np.int64), np.asarray(ki, dtype=np.int64).reshape(-1, 2), np.asarray(kf, dtype=np.float32),
+            np.asarray(kw, dtype=np.float32).reshape(-1, 2))
 
 
 # ----------------------------------------------------------------------------------------------

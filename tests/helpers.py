@@ -22,6 +22,31 @@ class IdentityTransforms:
         return pixels.reshape(-1, 2)[:, ::-1]
 
 
+class _ResizeConfiger:
+    def __init__(self, scale):
+        self.scale = scale
+
+    def get(self, *key):
+        if key == ('val_trans', 'trans_seq'):
+            return ['resize']
+        if key == ('val_trans', 'resize'):
+            return {'target_size': self.scale}
+        raise KeyError(key)
+
+
+class ResizeTransforms:
+    """detransform_pixel of CommonTransforms with val_trans.trans_seq = ['resize'], resize.target_size = scale
+    (utils/tranform.py:157-171): flip to (x,y), then the inverse affine map to the original image size."""
+
+    def __init__(self, scale):
+        self.scale = scale
+        self.configer = _ResizeConfiger(scale)
+
+    def detransform_pixel(self, pixels, info):
+        from oracle.ref_decode import detransform_pixel
+        return detransform_pixel(np.asarray(pixels), info.img_size, self.scale)
+
+
 class DecodeCfg:
     def __init__(self, **kw):
         self.cls_th, self.iou_th, self.kp_th = 0.3, 0.2, 20000

@@ -200,10 +200,11 @@ def _all_memberships(rd, img):
     return P.numpy()
 
 
-@pytest.mark.parametrize("name", ["s0", "s1", "s2", "s3"])
+@pytest.mark.parametrize("name", ["s0", "s1", "s2", "s3", "s4"])
 @pytest.mark.parametrize("mode", ["sparse", "dense", "dense-host-polygons"])
 def test_decode_single_golden(mods, golden, name, mode):
-    """the drop-in decode_single against polygons produced by the reference itself"""
+    """the drop-in decode_single against polygons produced by the reference itself (s4: one polygon rejected by the
+    centre-inside test, one instance below obj_pixel_th, label-0 strays removed by the ghost filter)"""
     g = golden("decode_single_" + name)
     dec = mods["decode"]
     saved = dec.decode_mode, dec.device_polygon_stage
@@ -225,6 +226,53 @@ def test_decode_single_golden(mods, golden, name, mode):
             assert_polygon_equivalent(dec, poly, g["det_poly_%d" % i], ctr)
         else:
             assert np.array_equal(poly, g["det_poly_%d" % i])
+
+
+@pytest.mark.parametrize("mode", ["sparse", "dense"])
+@pytest.mark.parametrize("draw", [False, True])
+def test_decode_single_resize_transform_golden(mods, golden, mode, draw, tmp_path):
+    """non-identity validation transform (resize, utils/tranform.py:157-171) with decode.target_size = 2 (test.py:58):
+    the ghost filter and the polygon stage run on the host in original-image pixels; draw=True is the stock
+    configs/decode_cfg.yaml setting (drawing itself is skipped when the reference's utils.visualize is absent)"""
+    import cv2
+    import warnings
+    from helpers import ResizeTransforms
+    g = golden("decode_single_resize")
+    dec = mods["decode"]
+    ts, size = int(g["target_size"]), tuple(int(v) for v in g["img_size"])
+    img_path = str(tmp_path / "frame.png")
+    cv2.imwrite(img_path, np.zeros(size + (3,), np.uint8))
+    saved = dec.decode_mode, dec.target_size, dec.base_dir
+    dec.decode_mode, dec.target_size, dec.base_dir = mode, ts, str(tmp_path)
+    try:
+        boxes = {"rois": g["rois"], "class_ids": g["class_ids"], "scores": g["scores"]}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            (dets,) = dec.decode_single(torch.from_numpy(g["kp"]).to(DEV), torch.from_numpy(g["ae"]).to(DEV), boxes,
+                                        TransInfo(img_path, size), ResizeTransforms(ts),
+                                        DecodeCfg(kp_th=int(g["kp_th"]), draw_flag=draw), torch.device(DEV))
+    finally:
+        dec.decode_mode, dec.target_size, dec.base_dir = saved
+    assert len(dets) == int(g["n_dets"]) > 0
+    for i, (cls, conf, ctr, poly) in enumerate(dets):
+        assert int(cls) == int(g["det_cls_%d" % i]) and np.float32(conf) == g["det_conf_%d" % i]
+        assert np.array_equal(ctr, g["det_ctr_%d" % i])
+        assert np.array_equal(poly, g["det_poly_%d" % i])
+
+
+def test_decode_ct_hm_golden(mods, golden):
+    """decode_ct_hm (utils/decode.py:254-285) against the reference's own output"""
+    g = golden("decode_ct_hm")
+    h, w = g["conf"].shape
+    mods["decode"].device = torch.device(DEV)          # what test.py:134 / evaluate.py:40 set
+    for where in ("cpu", DEV):           # the reference's callers hand CPU tensors; device tensors work too
+        out = mods["decode"].decode_ct_hm(torch.from_numpy(g["conf"]).to(where), torch.from_numpy(g["cls"]).to(where),
+                                          torch.from_numpy(g["wh"]).to(where), int(g["num_classes"]), int(g["k"]),
+                                          IdentityTransforms(), TransInfo("/nonexistent.png", (h, w)))
+        assert np.array_equal(np.asarray(out[0], dtype=np.int64), g["keep_cls"])
+        assert np.array_equal(np.asarray(out[1], dtype=np.int64).reshape(-1, 2), g["keep_idx"])
+        assert np.array_equal(np.asarray(out[2], dtype=np.float32), g["keep_conf"])
+        assert np.array_equal(np.asarray(out[3], dtype=np.float32).reshape(-1, 2), g["keep_wh"])
 
 
 def test_decode_single_no_boxes(mods):
@@ -395,21 +443,40 @@ def test_kmeans_golden(mods, golden):
         km.kmeans(torch.zeros(4, 2), 2, torch.zeros(2, 2), np.ones(2, np.float32), distance="manhattan")
 
 
-def test_kmeans_dense_crowd_vs_oracle(mods, oracle):
-    """BASELINE config 4 shape: M = 20000 embeddings, N = 500 seeds, allow = 0.05"""
+def test_kmeans_crowd_golden(mods, golden):
+    """BASELINE config 4 shape (M ~ 20000 embeddings, N = 500 seeds, allow 0.05): labels of the REFERENCE, bit for bit.
+    The generator certified every point's label margin along the whole trajectory (synth.make_kmeans_case)."""
+    g = golden("kmeans_crowd")
+    km = mods["kmeans"]
+    lab, ctr = km.kmeans(torch.from_numpy(g["X"]), 500, torch.from_numpy(g["init"]), g["allow"], device=torch.device(DEV))
+    assert np.array_equal(lab.cpu().numpy(), g["labels"].astype(np.int64))
+    np.testing.assert_allclose(ctr.cpu().numpy(), g["centers"], rtol=1e-6, atol=1e-7)
+    again, ctr2 = km.kmeans(torch.from_numpy(g["X"]), 500, torch.from_numpy(g["init"]), g["allow"], device=torch.device(DEV))
+    assert torch.equal(again, lab) and torch.equal(ctr2, ctr)                 # fixed order of additions: reproducible
+
+
+@pytest.mark.parametrize("M,N,seed", [(6000, 200, 7), (3000, 33, 8), (100, 500, 9)])
+def test_kmeans_vs_oracle_exact(mods, oracle, M, N, seed):
+    """labels and iteration count bit-exact against the oracle on margin-certified cases (incl. more clusters than points)"""
     _, rk = oracle
-    rs = np.random.RandomState(4)
-    N, M = 500, 20000
-    cen = np.stack([rs.uniform(0.05, 0.95, N), rs.uniform(0.05, 1.95, N)], axis=1).astype(np.float32)
-    X = (cen[rs.randint(0, N, size=M)] + rs.normal(0, 0.004, size=(M, 2))).astype(np.float32)
-    init = (cen + rs.normal(0, 0.002, size=cen.shape)).astype(np.float32)
-    allow = np.full(N, 0.05, dtype=np.float32)
+    X, init, allow, _, _, _ = mods["synth"].make_kmeans_case(seed, M, N)
     lab_w, ctr_w, it_w = rk.kmeans(torch.from_numpy(X), N, torch.from_numpy(init), allow)
     lab, ctr = mods["kmeans"].kmeans(torch.from_numpy(X), N, torch.from_numpy(init), allow, device=torch.device(DEV))
-    # labels are exact except where two centres are equidistant within fp32 rounding (not present in this draw)
-    assert (lab.cpu().numpy() != lab_w.numpy()).mean() < 1e-3
-    np.testing.assert_allclose(ctr.cpu().numpy(), ctr_w.numpy(), rtol=RTOL, atol=1e-6)
-    assert abs(mods["kmeans"].kmeans.last_iterations - it_w) <= 1
+    assert np.array_equal(lab.cpu().numpy(), lab_w.numpy())
+    assert mods["kmeans"].kmeans.last_iterations == it_w
+    np.testing.assert_allclose(ctr.cpu().numpy(), ctr_w.numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_kmeans_max_iterations_is_an_error(mods):
+    km = mods["kmeans"]
+    saved = km.max_iterations
+    km.max_iterations = 1
+    try:
+        with pytest.raises(mods["lib"].IsgError):
+            km.kmeans(torch.tensor([[0.0, 0.0], [1.0, 1.0], [4.0, 4.0]]), 1, torch.tensor([[3.0, 3.0]]), np.array([100.0], np.float32),
+                      device=torch.device(DEV))
+    finally:
+        km.max_iterations = saved
 
 
 # ---------------------------------------------------------------------------------------------- K6

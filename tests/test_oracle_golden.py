@@ -49,6 +49,55 @@ def test_decode_single_matches_reference(golden, name):
         assert np.array_equal(poly, g["det_poly_%d" % i])
 
 
+def test_decode_single_with_rejections_matches_reference(golden):
+    """s4: one polygon rejected by the centre-inside test (aug_group -> None), one instance below obj_pixel_th, and
+    label-0 background pixels removed by the ghost filter — all decided by the reference itself"""
+    g = golden("decode_single_s4")
+    kp, ae = torch.from_numpy(g["kp"]), torch.from_numpy(g["ae"])
+    kp_th, n = int(g["kp_th"]), len(g["rois"])
+    assert np.array_equal(rd.select_points(kp[0], kp_th).numpy(), g["mask"])
+    core = rd.group_core(kp[0], ae, g["rois"], kp_th)
+    inst = rd.instance_points(core["idx"], core["label"], core["centres"], core["whs"], 0.1)
+    assert int((core["label"] == 0).sum()) > inst[0][0].shape[0] > 0            # the ghost filter removed label-0 pixels
+    groups = [(p, c) for p, c in inst if p.shape[0] >= 2]
+    assert len(groups) == int(g["n_groups"]) == n - 1                             # one instance below obj_pixel_th
+    rejected = []
+    for i, (pts, ctr) in enumerate(groups):
+        assert np.array_equal(pts, g["grp_pts_%d" % i])
+        assert np.array_equal(ctr, g["grp_ctr_%d" % i])
+        rejected.append(rd.aug_group(pts, ctr) is None)
+    assert rejected == g["grp_rejected"].tolist() and sum(rejected) == 1
+    boxes = {"rois": g["rois"], "class_ids": g["class_ids"], "scores": g["scores"]}
+    (dets,) = rd.decode_single(kp, ae, boxes, kp_th)
+    assert len(dets) == int(g["n_dets"]) == n - 2
+    for i, (cls, conf, ctr, poly) in enumerate(dets):
+        assert int(cls) == int(g["det_cls_%d" % i]) and np.float32(conf) == g["det_conf_%d" % i]
+        assert np.array_equal(ctr, g["det_ctr_%d" % i]) and np.array_equal(poly, g["det_poly_%d" % i])
+
+
+def test_decode_single_resize_transform_matches_reference(golden):
+    """val_trans = resize(target_size 2) + decode.target_size = 2 (utils/tranform.py:157-171, test.py:58)"""
+    g = golden("decode_single_resize")
+    kp, ae = torch.from_numpy(g["kp"]), torch.from_numpy(g["ae"])
+    boxes = {"rois": g["rois"], "class_ids": g["class_ids"], "scores": g["scores"]}
+    ts, size = int(g["target_size"]), tuple(int(v) for v in g["img_size"])
+    (dets,) = rd.decode_single(kp, ae, boxes, int(g["kp_th"]), scale=ts, img_size=size, resize_target=ts)
+    assert len(dets) == int(g["n_dets"]) > 0
+    for i, (cls, conf, ctr, poly) in enumerate(dets):
+        assert int(cls) == int(g["det_cls_%d" % i]) and np.float32(conf) == g["det_conf_%d" % i]
+        assert np.array_equal(ctr, g["det_ctr_%d" % i]) and np.array_equal(poly, g["det_poly_%d" % i])
+    assert max(float(g["det_poly_%d" % i][:, 0].max()) for i in range(len(dets))) > kp.shape[-1]   # original-image pixels
+
+
+def test_decode_ct_hm_matches_reference(golden):
+    g = golden("decode_ct_hm")
+    cls, idx, conf, wh = rd.decode_ct_hm(torch.from_numpy(g["conf"]), torch.from_numpy(g["cls"]), torch.from_numpy(g["wh"]),
+                                         int(g["num_classes"]), int(g["k"]))
+    assert len(cls) > 0 and len(cls) < int(g["k"])
+    assert np.array_equal(cls, g["keep_cls"]) and np.array_equal(idx, g["keep_idx"])
+    assert np.array_equal(conf, g["keep_conf"]) and np.array_equal(wh, g["keep_wh"])
+
+
 def test_dense_labels_agree_with_sparse(golden):
     g = golden("decode_single_s1")
     kp, ae = torch.from_numpy(g["kp"]), torch.from_numpy(g["ae"])
@@ -82,6 +131,14 @@ def test_kmeans_matches_reference(golden):
     np.testing.assert_allclose(ctr.numpy(), g["centers_cos"], rtol=1e-5, atol=1e-7)
     assert np.array_equal(rk.pairwise_distance(torch.from_numpy(g["X"][:40]), torch.from_numpy(g["init"])).numpy(), g["pd"])
     assert np.array_equal(rk.pairwise_cosine(torch.from_numpy(g["X"][:40] + 1.0), torch.from_numpy(g["init"] + 1.0)).numpy(), g["pc"])
+
+
+def test_kmeans_crowd_matches_reference(golden):
+    """BASELINE config 4 size (M ~ 20000, N = 500): labels of the reference itself, bit for bit"""
+    g = golden("kmeans_crowd")
+    lab, ctr, _ = rk.kmeans(torch.from_numpy(g["X"]), 500, torch.from_numpy(g["init"]), g["allow"])
+    assert np.array_equal(lab.numpy(), g["labels"].astype(np.int64))
+    np.testing.assert_allclose(ctr.numpy(), g["centers"], rtol=1e-6, atol=1e-7)
 
 
 def test_py_cpu_nms_matches_reference(golden):
