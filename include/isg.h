@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ISG_ABI_VERSION 3
+#define ISG_ABI_VERSION 4
 
 #define ISG_OK            0
 #define ISG_EINVAL       (-1)  /* bad argument (null pointer, negative extent, k > H*W ...) */
@@ -201,6 +201,14 @@ int isg_box_nms(const float* boxes, const float* scores, const int32_t* cls, con
  * also applies ClipBoxes (utils/utils.py:349-363) for an H x W image. */
 int isg_bbox_transform(const float* anchors, const float* regression, int B, int A, int clip, int H, int W,
                        float* boxes, isg_stream_t stream);
+/* Anchors.forward (utils/utils.py:366-450): the multi-level anchor table [A,4] (y1,x1,y2,x2), bit-identical to the
+ * reference's numpy-float64-then-astype construction.  strides [n_levels] HOST ints (the reference's 2**level);
+ * half_sizes [n_levels][per_cell][2] HOST doubles = (anchor_size_x_2, anchor_size_y_2) of utils/utils.py:424-425 in
+ * itertools.product(scales, ratios) order; n_levels <= 8, per_cell <= 16.  half_precision != 0 writes fp16 (the
+ * reference's dtype == torch.float16 branch, :413-414).  isg_anchor_count is a host query (no GPU): A, or -1. */
+int64_t isg_anchor_count(int H, int W, const int* strides, int n_levels, int per_cell);
+int isg_generate_anchors(int H, int W, const int* strides, int n_levels, const double* half_sizes, int per_cell,
+                         int half_precision, void* out /*[A,4]*/, isg_stream_t stream);
 /* ClipBoxes.forward in place on n boxes (x1,y1,x2,y2) (utils/utils.py:357-361) */
 int isg_clip_boxes(float* boxes, int64_t n, int H, int W, isg_stream_t stream);
 

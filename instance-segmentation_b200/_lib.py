@@ -38,6 +38,8 @@ PROTOTYPES = {
     "isg_decode_boxes": (I, [P, P, P, I, I, I, I, I, F, I, P, P, P, P, P, P]),
     "isg_bbox_transform": (I, [P, P, I, I, I, I, I, P, P]),
     "isg_clip_boxes": (I, [P, I64, I, I, P]),
+    "isg_anchor_count": (I64, [I, I, P, I, I]),
+    "isg_generate_anchors": (I, [I, I, P, I, P, I, I, P, P]),
     "isg_pack_masks": (I, [P, I, I, I, P, P]),
     "isg_gather_kept": (I, [P, P, P, P, P, I, I, I, P, P, P, P, P]),
     "isg_box_nms_workspace_bytes": (SZ, [I, I]),
@@ -107,7 +109,7 @@ _LAUNCHES = {
     "isg_compact_points": 1, "isg_build_seeds": 1, "isg_stats_init": 1, "isg_assign_sparse": 1,
     "isg_gather_build_seeds": 1, "isg_build_tile_lists": 1, "isg_assign_dense": lambda a: 1 if a[21] else 2, "isg_gather_labels": 1, "isg_instance_polygons": lambda a: 1 if a[21] else 2, "isg_decode_boxes": 1,
     "isg_gather_kept": 1, "isg_mask_nms": 5, "isg_mask_pair_counts": 1, "isg_pairwise": 1,
-    "isg_bbox_transform": 1, "isg_clip_boxes": 1, "isg_pack_masks": 1, "isg_fill_polygons": 1,
+    "isg_bbox_transform": 1, "isg_clip_boxes": 1, "isg_generate_anchors": 1, "isg_pack_masks": 1, "isg_fill_polygons": 1,
     # (idx,label,flag,count,cap,n_seeds,B,Nmax,...): one multisplit kernel unless the seed table is huge
     "isg_group_points": lambda a: 1 if (16 * a[7] + a[7] + 1 + a[4]) * 4 <= 200 * 1024 else 3,
     # (boxes,scores,cls,tiebreak,count,B,cap,...): fused single-CTA kernel for cap <= 1024

@@ -4,6 +4,7 @@
 // (utils/utils.py:318-363), py_cpu_nms (utils/nms.py:11-39), torchvision batched_nms semantics at
 // utils/decode.py:400, mask IoU formula (utils/image.py:188-191).
 #include <algorithm>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace isg {
@@ -705,6 +706,89 @@ extern "C" int isg_clip_boxes(float* boxes, int64_t n, int H, int W, isg_stream_
   if (!boxes || n <= 0 || !aligned16(boxes)) return ISG_EINVAL;
   clip_boxes_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, stream>>>(reinterpret_cast<float4*>(boxes), n, (float)(W - 1),
                                                                  (float)(H - 1));
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+// ---- anchor generation (Anchors.forward, utils/utils.py:366-450) ------------------------------------------------
+// The reference builds the table in numpy float64 and casts it once (`astype`, :441): every coordinate here is the same
+// fp64 expression (cell centre stride/2 + i*stride, exact; minus/plus the fp64 half size computed by the host exactly as
+// :423-425 do) followed by ONE round-to-nearest conversion, so the table is bit-identical.
+namespace isg {
+constexpr int kAnchorLevels = 8, kAnchorsPerCell = 16;
+struct AnchorParams {
+  int n_levels, per_cell, H, W;
+  int stride[kAnchorLevels], nx[kAnchorLevels], ny[kAnchorLevels];
+  long long first[kAnchorLevels + 1];                       // first anchor index of each level
+  double half_x[kAnchorLevels][kAnchorsPerCell], half_y[kAnchorLevels][kAnchorsPerCell];
+};
+
+template <typename T> struct AnchorOut;
+template <> struct AnchorOut<float> {
+  static __device__ __forceinline__ void store(float* out, long long a, double y1, double x1, double y2, double x2) {
+    reinterpret_cast<float4*>(out)[a] = make_float4(__double2float_rn(y1), __double2float_rn(x1), __double2float_rn(y2),
+                                                    __double2float_rn(x2));
+  }
+};
+template <> struct AnchorOut<__half> {
+  static __device__ __forceinline__ void store(__half* out, long long a, double y1, double x1, double y2, double x2) {
+    out[4 * a + 0] = __double2half(y1); out[4 * a + 1] = __double2half(x1);
+    out[4 * a + 2] = __double2half(y2); out[4 * a + 3] = __double2half(x2);
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) anchors_kernel(const __grid_constant__ AnchorParams p, T* __restrict__ out) {
+  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= p.first[p.n_levels]) return;
+  int l = 0;
+  while (l + 1 < p.n_levels && a >= p.first[l + 1]) ++l;
+  const long long r = a - p.first[l];
+  const int k = (int)(r % p.per_cell);                      // (scale, ratio) pair in itertools.product order (:420)
+  const long long cell = r / p.per_cell;                    // meshgrid(x, y).reshape(-1): row-major over (y, x) (:429-431)
+  const int ix = (int)(cell % p.nx[l]), iy = (int)(cell / p.nx[l]);
+  const double s = (double)p.stride[l];
+  const double xc = s / 2 + ix * s, yc = s / 2 + iy * s;    // np.arange(stride / 2, size, stride) (:427-428)
+  AnchorOut<T>::store(out, a, yc - p.half_y[l][k], xc - p.half_x[l][k], yc + p.half_y[l][k], xc + p.half_x[l][k]);   // :434-435
+}
+}  // namespace isg
+
+extern "C" int64_t isg_anchor_count(int H, int W, const int* strides, int n_levels, int per_cell) {
+  if (H <= 0 || W <= 0 || !strides || n_levels <= 0 || n_levels > isg::kAnchorLevels || per_cell <= 0 || per_cell > isg::kAnchorsPerCell)
+    return -1;
+  int64_t n = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const int s = strides[l];
+    if (s <= 0) return -1;
+    // len(np.arange(s/2, size, s)) = ceil((size - s/2) / s)
+    const int64_t nx = (2LL * W - s + 2LL * s - 1) / (2LL * s), ny = (2LL * H - s + 2LL * s - 1) / (2LL * s);
+    n += (nx > 0 ? nx : 0) * (ny > 0 ? ny : 0) * per_cell;
+  }
+  return n;
+}
+
+extern "C" int isg_generate_anchors(int H, int W, const int* strides, int n_levels, const double* half_sizes, int per_cell,
+                                    int half_precision, void* out, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!out || !half_sizes || isg_anchor_count(H, W, strides, n_levels, per_cell) <= 0) return ISG_EINVAL;
+  if (!half_precision && !aligned16(out)) return ISG_EINVAL;
+  isg::AnchorParams p = {};
+  p.n_levels = n_levels; p.per_cell = per_cell; p.H = H; p.W = W;
+  p.first[0] = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const int s = strides[l];
+    p.stride[l] = s;
+    p.nx[l] = (int)std::max<int64_t>(0, (2LL * W - s + 2LL * s - 1) / (2LL * s));
+    p.ny[l] = (int)std::max<int64_t>(0, (2LL * H - s + 2LL * s - 1) / (2LL * s));
+    p.first[l + 1] = p.first[l] + (long long)p.nx[l] * p.ny[l] * per_cell;
+    for (int k = 0; k < per_cell; ++k) {
+      p.half_x[l][k] = half_sizes[((size_t)l * per_cell + k) * 2 + 0];
+      p.half_y[l][k] = half_sizes[((size_t)l * per_cell + k) * 2 + 1];
+    }
+  }
+  const unsigned blocks = (unsigned)cdiv64(p.first[n_levels], 256);
+  if (half_precision) isg::anchors_kernel<__half><<<blocks, 256, 0, stream>>>(p, reinterpret_cast<__half*>(out));
+  else isg::anchors_kernel<float><<<blocks, 256, 0, stream>>>(p, reinterpret_cast<float*>(out));
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }

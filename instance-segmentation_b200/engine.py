@@ -86,7 +86,8 @@ class DecodePlan:
     """select -> assign (dense or sparse) -> compact -> group for a batch of B images of HxW."""
 
     def __init__(self, B: int, H: int, W: int, max_seeds: int, kp_th: int, device, mode: str = "sparse",
-                 want_score: bool = True, wh_delta: float = 0.1, scale: float = 1.0, fused_stats: bool = False):
+                 want_score: bool = True, wh_delta: float = 0.1, scale: float = 1.0, fused_stats: bool = False,
+                 min_cap: int = 0):
         if mode not in ("dense", "sparse"):
             raise ValueError("mode must be 'dense' or 'sparse'")
         self.device = require_cuda(device)
@@ -95,7 +96,9 @@ class DecodePlan:
         self.kp_th = int(kp_th)
         if self.kp_th > H * W:
             raise RuntimeError("selected index k out of range")   # torch.topk, utils/decode.py:81
-        self.cap = max(min(self.kp_th, H * W), 1)
+        # room for the keep pixels of one image: k, unless the caller saw more (ties at the k-th value select every tied
+        # pixel, so a plateau can exceed k; the drop-in re-plans with the reported count, see utils/decode.py)
+        self.cap = min(max(min(self.kp_th, H * W), int(min_cap), 1), H * W)
         self.mode, self.want_score = mode, bool(want_score)
         # dense mode: per-instance count/bbox either inside the fused kernel (one atomic set per keep pixel in the hot
         # loop) or in the gather pass over the compacted keep pixels (default: same numbers, cheaper)
@@ -285,13 +288,13 @@ class BoxPlan:
 _plans = {}
 
 
-def get_decode_plan(B, H, W, max_seeds, kp_th, device, mode, want_score=True, wh_delta=0.1, scale=1.0) -> DecodePlan:
+def get_decode_plan(B, H, W, max_seeds, kp_th, device, mode, want_score=True, wh_delta=0.1, scale=1.0, min_cap=0) -> DecodePlan:
     device = require_cuda(device)
-    key = ("d", B, H, W, max_seeds, kp_th, device.index, mode, want_score, wh_delta, float(scale))
+    key = ("d", B, H, W, max_seeds, kp_th, device.index, mode, want_score, wh_delta, float(scale), int(min_cap))
     if key not in _plans:
         if len(_plans) > 8:
             _plans.clear()
-        _plans[key] = DecodePlan(B, H, W, max_seeds, kp_th, device, mode, want_score, wh_delta, scale)
+        _plans[key] = DecodePlan(B, H, W, max_seeds, kp_th, device, mode, want_score, wh_delta, scale, min_cap=min_cap)
     return _plans[key]
 
 

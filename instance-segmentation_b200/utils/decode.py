@@ -269,7 +269,9 @@ def draw_candid(kps, lt, rb, img, color):
     if img is None:
         return img
     cv2.rectangle(img, lt, rb, color)
-    return cv2.drawKeypoints(img, cv2.KeyPoint_convert(kps.reshape((-1, 1, 2))), None, color=color)
+    # :251 reshapes to (-1, 1, 2), which OpenCV >= 4.5 no longer parses as points2f; (-1, 2) is the same point list
+    return cv2.drawKeypoints(img, cv2.KeyPoint_convert(np.ascontiguousarray(kps, dtype=np.float32).reshape((-1, 2))), None,
+                             color=color)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -389,13 +391,21 @@ def _polygons_for_image_fast(points, offsets, n, centres_yx, center_cls, center_
     return n_clss, n_confs, n_centers, kps
 
 
-def _run_plan(kp, ae, boxes_dev, n_dev, layout, decode_cfg, transforms, dev, max_seeds):
+def _overflow(plan, device_polygons) -> int:
+    """Keep pixels the plan had no room for: 0, or the per-image capacity a re-run needs.  Ties at the k-th value
+    select every tied pixel, so plateaus of the heat map can push an image beyond k = decode_cfg.kp_th; the kernels
+    keep counting past the capacity (img_total / count) without storing."""
+    seen = int((plan.img_total if device_polygons else plan.count).max().item())
+    return seen if seen > plan.cap else 0
+
+
+def _run_plan(kp, ae, boxes_dev, n_dev, layout, decode_cfg, transforms, dev, max_seeds, min_cap=0):
     """Enqueue select/assign/group for a batch; returns (plan, identity)."""
     B, H, W = kp.shape[0], kp.shape[-2], kp.shape[-1]
     identity = _identity_transform(transforms)
     plan = engine.get_decode_plan(B, H, W, max_seeds, int(decode_cfg.kp_th), dev, decode_mode, want_score=False,
                                   wh_delta=float(decode_cfg.wh_delta) if identity else None,
-                                  scale=float(compute_scale(None)))
+                                  scale=float(compute_scale(None)), min_cap=min_cap)
     device_polygons = identity and not decode_cfg.draw_flag and decode_mode == "dense" and device_polygon_stage
     plan.run(kp, ae, boxes_dev, n_dev, layout, tail="polygons" if device_polygons else "lists",
              obj_pixel_th=int(decode_cfg.obj_pixel_th))
@@ -416,6 +426,10 @@ def group_kp(hm_kp, hm_ae, transforms, center_whs, center_indexes, center_cls, c
     boxes = torch.from_numpy(np.ascontiguousarray(np.concatenate([centres, whs], axis=1))[None]).to(dev)
     n_dev = torch.tensor([objs_num], dtype=torch.int32, device=dev)
     plan, identity, device_polygons = _run_plan(kp, ae, boxes, n_dev, _lib.ISG_BOX_CYCXHW, decode_cfg, transforms, dev, objs_num)
+    need = _overflow(plan, device_polygons)
+    if need:                      # a plateau at the k-th value selected more pixels than k: decode again with room for them
+        plan, identity, device_polygons = _run_plan(kp, ae, boxes, n_dev, _lib.ISG_BOX_CYCXHW, decode_cfg, transforms, dev,
+                                                    objs_num, min_cap=need)
     if device_polygons:
         tot = int(plan.img_total[0].item())
         if tot == 0:                                                 # :300
@@ -628,7 +642,7 @@ def _decode_output_batch(inputs, outs, infos, transforms, decode_cfg, device):
     ae = engine.as_f32_planes(kp_out[1], dev)
     B, H, W = kp.shape[0], kp.shape[-2], kp.shape[-1]
     height, width = inputs.shape[2], inputs.shape[3]
-    cap, max_keep = 1024, 256
+    cap, max_keep, min_cap = 1024, 256, 0
     reg = engine.as_f32_planes(regression, dev).contiguous()
     cls_t = engine.as_f32_planes(classification, dev).contiguous()
     anc = engine.as_f32_planes(anchors, dev).contiguous()
@@ -638,7 +652,7 @@ def _decode_output_batch(inputs, outs, infos, transforms, decode_cfg, device):
         bplan = engine.get_box_plan(B, A, C, height, width, dev, cap, max_keep)
         plan = engine.get_decode_plan(B, H, W, bplan.N, int(decode_cfg.kp_th), dev, decode_mode, want_score=False,
                                       wh_delta=float(decode_cfg.wh_delta) if identity else None,
-                                      scale=float(compute_scale(None)))
+                                      scale=float(compute_scale(None)), min_cap=min_cap)
         # identity val-transform without drawing: the whole per-instance stage (point sets, internal point, angular
         # sort, centre test) runs on the device; otherwise the device emits the point sets and the host finishes
         device_polygons = identity and not decode_cfg.draw_flag and decode_mode == "dense" and device_polygon_stage
@@ -656,6 +670,9 @@ def _decode_output_batch(inputs, outs, infos, transforms, decode_cfg, device):
             cap = min(cap * 4, _lib.ISG_NMS_MAX_BOXES); continue
         if n_keep.max(initial=0) > bplan.N:
             max_keep = min(max(max_keep * 4, int(n_keep.max())), bplan.cap); continue
+        need = int(_host(plan.img_total if device_polygons else plan.count).max(initial=0))
+        if need > plan.cap:       # a plateau at the k-th value selected more pixels than k: decode again with room for them
+            min_cap = need; continue
         break
     import time as _time
     _t0 = _time.perf_counter()

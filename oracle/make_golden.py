@@ -246,6 +246,26 @@ def main():
         print("decode_boxes img", b, "kept", len(det["class_ids"]))
     np.savez_compressed(os.path.join(OUT, "decode_boxes.npz"), **d)
 
+    # ---- Anchors.forward (utils/utils.py:366-450): full table at a small shape, digests + samples at the bench shapes
+    import hashlib
+    from utils.utils import Anchors as RAnchors
+    d = {}
+    small = RAnchors()(torch.zeros(1, 3, 128, 256)).numpy()
+    d["a_128x256"] = small
+    d["a_half_128x256"] = RAnchors()(torch.zeros(1, 3, 128, 256), dtype=torch.float16).numpy()
+    d["a_custom_96x160"] = RAnchors(anchor_scale=3., pyramid_levels=[2, 3, 4], scales=[1.0, 1.5], ratios=[(1.0, 1.0), (2.0, 0.5)])(
+        torch.zeros(2, 3, 96, 160)).numpy()                      # H % 16 == 0 is not required by the reference, only W (:416)
+    d["a_ragged_100x64"] = RAnchors(pyramid_levels=[3, 4])(torch.zeros(1, 3, 100, 64)).numpy()   # H not divisible by the stride
+    for (h, w) in ((1024, 2048), (512, 1024)):
+        a = RAnchors()(torch.zeros(1, 3, h, w)).numpy()
+        d["sha_%dx%d" % (h, w)] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+        d["count_%dx%d" % (h, w)] = np.int64(a.shape[1])
+        pick = np.random.RandomState(h).randint(0, a.shape[1], size=64)
+        d["rows_%dx%d" % (h, w)] = pick
+        d["vals_%dx%d" % (h, w)] = a[0, pick]
+    np.savez_compressed(os.path.join(OUT, "anchors.npz"), **d)
+    print("anchors", small.shape, int(d["count_1024x2048"]))
+
     # ---- kmeans / pairwise ---------------------------------------------------------------------------
     rs = np.random.RandomState(21)
     cen = rs.uniform(0, 1, size=(10, 2)).astype(np.float32)

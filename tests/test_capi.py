@@ -37,7 +37,7 @@ def test_library_exports_every_header_symbol(built):
 def test_binding_table_matches_header(built):
     assert sorted(built.PROTOTYPES) == header_symbols()
     lib = built.lib()
-    assert lib.isg_abi_version() == 3
+    assert lib.isg_abi_version() == 4
     assert lib.isg_strerror(0) == b"ok" and lib.isg_strerror(-1) == b"invalid argument"
 
 
@@ -49,6 +49,12 @@ def test_host_side_queries_need_no_gpu(built):
     assert lib.isg_box_nms_workspace_bytes(2, 1000) > 2 * 1000 * 16 * 8
     assert lib.isg_kmeans_workspace_bytes(100, 10, 2) > 0
     assert lib.isg_mask_nms_workspace_bytes(100) > 0
+    import ctypes
+    strides = (ctypes.c_int * 5)(8, 16, 32, 64, 128)
+    assert lib.isg_anchor_count(1024, 2048, strides, 5, 9) == 392832      # A at 1024x2048
+    assert lib.isg_anchor_count(512, 1024, strides, 5, 9) == 98208
+    assert lib.isg_anchor_count(100, 64, strides, 2, 9) == 9 * (12 * 8 + 6 * 4)   # ragged height: ceil((H - s/2) / s) rows
+    assert lib.isg_anchor_count(64, 64, strides, 9, 9) == -1
 
 
 def test_bad_arguments_are_rejected_without_touching_the_device(built):

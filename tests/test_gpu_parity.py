@@ -258,6 +258,7 @@ def test_decode_single_resize_transform_golden(mods, golden, mode, draw, tmp_pat
         assert int(cls) == int(g["det_cls_%d" % i]) and np.float32(conf) == g["det_conf_%d" % i]
         assert np.array_equal(ctr, g["det_ctr_%d" % i])
         assert np.array_equal(poly, g["det_poly_%d" % i])
+    assert (tmp_path / "frame.png_candid.png").exists() == draw          # the debug image of :370-372
 
 
 def test_decode_ct_hm_golden(mods, golden):
@@ -301,6 +302,33 @@ def test_decode_boxes_golden(mods, golden):
         assert np.array_equal(det["scores"], g["scores_%d" % b])
         np.testing.assert_allclose(det["rois"], g["rois_%d" % b].reshape(det["rois"].shape), rtol=1e-6, atol=1e-4)
     assert dets[2]["rois"].shape == (0,)
+
+
+def test_anchors_golden(mods, golden):
+    """device anchor generation (isg_generate_anchors behind the Anchors module) is bit-identical to the reference's
+    Anchors.forward (utils/utils.py:366-450), incl. the fp16 branch, custom levels/scales/ratios and a ragged height"""
+    import hashlib
+    g = golden("anchors")
+    Anchors = mods["utils"].Anchors
+    img = lambda b, h, w: torch.empty((b, 3, h, w), device=DEV)
+    a = Anchors()(img(1, 128, 256))
+    assert a.dtype == torch.float32 and a.device.type == "cuda" and np.array_equal(a.cpu().numpy(), g["a_128x256"])
+    assert np.array_equal(Anchors()(img(1, 128, 256), dtype=torch.float16).cpu().numpy(), g["a_half_128x256"])
+    custom = Anchors(anchor_scale=3., pyramid_levels=[2, 3, 4], scales=[1.0, 1.5], ratios=[(1.0, 1.0), (2.0, 0.5)])
+    assert np.array_equal(custom(img(2, 96, 160)).cpu().numpy(), g["a_custom_96x160"])
+    assert np.array_equal(Anchors(pyramid_levels=[3, 4])(img(1, 100, 64)).cpu().numpy(), g["a_ragged_100x64"])
+    for h, w in ((1024, 2048), (512, 1024)):
+        mod = Anchors()
+        t = mod(img(1, h, w))
+        assert mod(img(1, h, w)) is t                                  # cached per (shape, device), :401-402
+        arr = t.cpu().numpy()
+        assert arr.shape == (1, int(g["count_%dx%d" % (h, w)]), 4)
+        assert np.array_equal(np.frombuffer(hashlib.sha256(arr.tobytes()).digest(), dtype=np.uint8), g["sha_%dx%d" % (h, w)])
+        assert np.array_equal(arr[0, g["rows_%dx%d" % (h, w)]], g["vals_%dx%d" % (h, w)])
+    with pytest.raises(ValueError):
+        Anchors()(img(1, 128, 200))                                    # W not divisible by the stride, :416-417
+    with pytest.raises(RuntimeError):
+        Anchors()(torch.empty((1, 3, 128, 256)))                       # no CPU path
 
 
 def test_bbox_transform_and_clip_vs_oracle(mods, oracle, golden):
@@ -393,6 +421,38 @@ def test_decode_output_vs_oracle(mods, oracle, mode):
             assert int(c1) == int(c2) and np.float32(f1) == np.float32(f2)
             assert np.array_equal(ctr1, ctr2)
             assert_polygon_equivalent(dec, p1, p2, ctr2)
+
+
+@pytest.mark.parametrize("mode", ["sparse", "dense", "dense-host-polygons"])
+def test_decode_output_plateau_overflow_is_not_silent(mods, mode):
+    """A plateau at the k-th value: every tied pixel is selected, so an image keeps more pixels than k.  The drop-in must
+    notice (the kernels keep counting past the plan's capacity) and decode again with room - never return fewer
+    detections silently.  Checked against the same decode with k = H*W, where nothing can overflow."""
+    synth, dec = mods["synth"], mods["decode"]
+    H, W, B = 64, 128, 2
+    anchors = synth.make_anchors(H, W)
+    scenes = [synth.make_scene(700 + b, H, W, 3, 8, anchors) for b in range(B)]
+    kp = torch.zeros((B, 1, H, W)); kp[1] = 0.5                      # flat heat maps: all H*W pixels tie and are 3x3 maxima
+    ae = torch.from_numpy(np.stack([s[0].ae for s in scenes]))
+    reg = torch.from_numpy(np.stack([s[1] for s in scenes])); cls = torch.from_numpy(np.stack([s[2] for s in scenes]))
+    outs = ((kp.to(DEV), ae.to(DEV), None), reg.to(DEV), cls.to(DEV), torch.from_numpy(anchors).to(DEV))
+    infos = [TransInfo("/nonexistent.png", (H, W))] * B
+    saved = dec.decode_mode, dec.device_polygon_stage
+    dec.decode_mode, dec.device_polygon_stage = mode.split("-")[0], not mode.endswith("host-polygons")
+    try:
+        got = dec.decode_output(torch.zeros((B, 3, H, W)), outs, infos, IdentityTransforms(), DecodeCfg(kp_th=100), torch.device(DEV))
+        want = dec.decode_output(torch.zeros((B, 3, H, W)), outs, infos, IdentityTransforms(), DecodeCfg(kp_th=H * W), torch.device(DEV))
+        boxes = dec.decode_boxes(torch.zeros((B, 3, H, W)), outs[3], outs[1], outs[2], 0.3, 0.2)
+        (single,) = dec.decode_single(outs[0][0][0], outs[0][1][0], boxes[0], infos[0], IdentityTransforms(), DecodeCfg(kp_th=100),
+                                      torch.device(DEV))
+    finally:
+        dec.decode_mode, dec.device_polygon_stage = saved
+    assert sum(len(g) for g in got) > 0
+    for res, ref in ((got[0], want[0]), (got[1], want[1]), (single, want[0])):
+        assert len(res) == len(ref)
+        for (c1, f1, ctr1, p1), (c2, f2, ctr2, p2) in zip(res, ref):
+            assert int(c1) == int(c2) and np.float32(f1) == np.float32(f2) and np.array_equal(ctr1, ctr2)
+            assert p1.shape[0] > 100 and np.array_equal(p1, p2)      # more points than k in ONE instance
 
 
 def assert_polygon_equivalent(dec, got, want, centre_xy):

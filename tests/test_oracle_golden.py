@@ -161,3 +161,16 @@ def test_mask_iou_matches_reference(golden):
             assert rk.is_cover(dense[i], dense[j]) == bool(g["cover"][i, j])
             inter = rk.popcount(masks[i] & masks[j]); uni = rk.popcount(masks[i] | masks[j])
             assert float(inter + 1) / float(uni + 1) == g["iou"][i, j]
+
+
+def test_anchor_restatement_matches_reference(golden):
+    """synth.make_anchors (the generator every box-head test uses) against the reference's Anchors.forward"""
+    import hashlib
+    from isg_b200 import synth
+    g = golden("anchors")
+    assert np.array_equal(synth.make_anchors(128, 256), g["a_128x256"])
+    for h, w in ((1024, 2048), (512, 1024)):
+        a = synth.make_anchors(h, w)
+        assert a.shape[1] == int(g["count_%dx%d" % (h, w)])
+        assert np.array_equal(np.frombuffer(hashlib.sha256(a.tobytes()).digest(), dtype=np.uint8), g["sha_%dx%d" % (h, w)])
+        assert np.array_equal(a[0, g["rows_%dx%d" % (h, w)]], g["vals_%dx%d" % (h, w)])
