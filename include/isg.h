@@ -57,6 +57,9 @@ typedef void* isg_stream_t;    /* cudaStream_t */
 
 int         isg_abi_version(void);
 const char* isg_strerror(int code);
+/* Experiment hook (tests, tools/sweep_dense.py): the ISG_* tuning variables are read from the environment once, at the
+ * first call into the library; this re-reads them.  Not for production use; not thread-safe against running calls. */
+void        isg_debug_reload_tuning(void);
 /* host query: 1 if `device` is a compute-capability 10.x part this library was built for, else 0 */
 int         isg_device_supported(int device);
 

@@ -19,6 +19,7 @@ PROTOTYPES = {
     "isg_abi_version": (I, []),
     "isg_strerror": (C.c_char_p, [I]),
     "isg_device_supported": (I, [I]),
+    "isg_debug_reload_tuning": (None, []),
     "isg_topk_workspace_bytes": (SZ, [I, I, I, I]),
     "isg_topk_threshold": (I, [P, I, I, I, I64, I, P, P, SZ, P]),
     "isg_keep_points": (I, [P, I, I, I, I64, P, P, P, P]),

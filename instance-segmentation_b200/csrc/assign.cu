@@ -601,7 +601,6 @@ group_split_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ 
 
 }  // namespace isg
 
-#include "dense_tma.cuh"
 #include "dense_v4.cuh"
 
 using namespace isg;
@@ -727,23 +726,16 @@ extern "C" int isg_assign_dense(const float* kp, int64_t kp_img_stride, const fl
   if ((size_t)Nmax * sizeof(SeedRec) * 2 > 200 * 1024) return ISG_EUNSUPPORTED;
   const bool vec = (W % 4 == 0) && (kp_img_stride % 4 == 0) && (ae_img_stride % 4 == 0) && (ae_plane_stride % 4 == 0) &&
                    aligned16(kp) && aligned16(ae) && aligned16(label_map) && (!score_map || aligned16(score_map));
-  // v4 (persistent, TMA-fed, dynamic scheduler) whenever the layout allows tensor maps; ISG_DENSE_V2 / ISG_DENSE_V1
-  // select the older kernels for A/B measurements; v1 also serves the layouts TMA cannot describe (W % 4 != 0)
-  const char* v1_env = getenv("ISG_DENSE_V1");
-  const char* v2_env = getenv("ISG_DENSE_V2");
-  if (vec && !(v1_env && v1_env[0] == '1') && !(v2_env && v2_env[0] == '1')) {
+  // v4 (persistent, TMA-fed, dynamic scheduler) whenever the layout allows tensor maps; the plain-LDG kernel serves the
+  // layouts TMA cannot describe (W % 4 != 0) and, with ISG_DENSE_V1=1, A/B measurements
+  const Tuning& tn = tuning();
+  if (vec && !tn.dense_v1) {
     const int rc = launch_dense_v4(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
                                    Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, workspace, workspace_bytes,
                                    lists_prebuilt ? 2 : 0, stream);
     if (rc != ISG_EUNSUPPORTED) return rc;
   }
-  if (vec && !(v1_env && v1_env[0] == '1')) {
-    const int rc = launch_dense_tma(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
-                                    Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, stream);
-    if (rc != ISG_EUNSUPPORTED) return rc;
-  }
-  const char* rw_env = getenv("ISG_DENSE_RW");   // v1 tuning knob (rows per warp); default 4
-  const int rw = rw_env ? atoi(rw_env) : 4;
+  const int rw = tn.dense_v1_rw;
   if (rw == 2)
     return launch_dense<2>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, n_seeds, B,
                            Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, vec, stream);

@@ -159,6 +159,21 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Tuning knobs for experiments.  Read from the environment ONCE (first use) - never on the launch path; the only way to
+// change them afterwards is isg_debug_reload_tuning() (tests and tools/sweep_dense.py).  Defaults are the shipped path.
+struct Tuning {
+  int dense_rw = 2, dense_wg = 8, dense_g = 2, dense_stages = 0;   // ISG_DENSE_CFG = "<RW>x<WG>x<G>[:stages]"
+  int dense_tail = 4;        // ISG_DENSE_TAIL: tiles per CTA left to the dynamic scheduler
+  int dense_debug = 0;       // ISG_DENSE_DEBUG: bit 0 = consumers release tiles without computing (loads-only ceiling)
+  int dense_pdl = 1;         // ISG_DENSE_PDL=0: no programmatic dependent launch behind the pre-pass
+  int dense_v1 = 0;          // ISG_DENSE_V1=1: plain-LDG kernel (also serves W % 4 != 0)
+  int dense_v1_rw = 4;       // ISG_DENSE_RW: rows per warp of the v1 kernel
+  int dense_spare = 0;       // ISG_DENSE_SPARE: SMs the persistent dense kernel leaves to concurrently running kernels
+  int topk_radix = 0;        // ISG_TOPK_PATH=radix: sampling-free two-level radix select
+  int topk_cluster_sample = 0;   // ISG_TOPK_SAMPLE=cluster
+};
+const Tuning& tuning();      // api.cu
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

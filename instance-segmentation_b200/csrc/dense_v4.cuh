@@ -1,4 +1,4 @@
-// Fused dense kernel, v4: persistent CTAs, dynamic tile scheduler, producer-side seed culling.
+// Fused dense kernel (dense_v4_kernel + tile_lists_kernel): embedding + membership + assignment + 3x3 peak test.
 //
 // What one launch does for every pixel of the batch (reference: select_points / nms_hm, utils/decode.py:42-48,71-85,
 // and the core of group_kp, :303-328):
@@ -6,20 +6,23 @@
 //   embedding = tanh(ae[0:2]) + grid, sigma = exp(ae[2:4]),
 //   label     = first seed (in index order) with the largest membership exp(-q) among the seeds whose box
 //               contains the pixel, q = (e_y-c_y)^2*s_y + (e_x-c_x)^2*s_x; 0 when no membership is > 0,
-//   per-instance count / bbox of the keep pixels that pass the ghost filter.
+//   optionally the per-instance count / bbox of the keep pixels that pass the ghost filter.
 // Every input pixel is read from HBM once (kp halo rows/columns are re-read from L2), the label is written once.
 //
 // Structure
-//   * one CTA per SM.  The last warp is the PRODUCER: it takes tile indices from a global counter (dynamic
-//     scheduling, in image order), stages the seed table of the tile's image in shared memory (1-D bulk copy, two
-//     buffers), culls it against the tile (ordered, so that the first-index tie rule survives), writes a small
-//     header + hit list next to the stage and issues the two TMA box loads of the tile (kp with a 1-pixel halo,
-//     out-of-image elements NaN-filled = the reference's -inf padding because fmax ignores NaN; the four ae
-//     planes as one 4-D box);
+//   * PRE-PASS (tile_lists_kernel, one warp per tile): the ordered list (ascending seed index, so that the first-index
+//     tie rule survives) of the seed records whose boxes overlap the tile, as a 32-byte header + the first `cap`
+//     records in the workspace; all hit indices also go to an overflow array read only by tiles with more hits.  The
+//     lists depend on the seeds only: the engine builds them on the box branch while the top-k threshold is computed.
+//   * MAIN KERNEL: persistent, one CTA per SM (minus Tuning::dense_spare).  The last warp's lane 0 is the PRODUCER: per
+//     tile it issues three async copies into a shared-memory ring on one mbarrier - the kp box with a 1-pixel halo
+//     (out-of-image elements NaN-filled = the reference's -inf padding because fmax ignores NaN), the four ae planes
+//     as one 4-D box, and the tile's list (1-D bulk copy).  Tiles are assigned statically (t = cta, cta + grid, ...)
+//     except the last `dyn_tail` per CTA, which come from a global counter so that early finishers absorb imbalance;
 //   * the other warps are CONSUMERS in G groups of WG warps; group g takes the stages k = g (mod G).  Inside a
-//     tile a warp owns RW consecutive rows and walks down them two at a time with a rolling window of the
-//     separable 3x3 maximum; a lane owns 4 consecutive pixels of each row;
-//   * consumers are stateless with respect to images: everything they need is in the stage header;
+//     tile a warp owns RW consecutive rows and walks down them with a rolling window of the separable 3x3 maximum; a
+//     lane owns 4 consecutive pixels of each row;
+//   * consumers are stateless with respect to images: everything they need is in the stage (header + list);
 //   * the membership loop tracks the SMALLEST exponent q instead of the largest exp(-q): exp is monotone, so the
 //     winner is the same seed whenever two memberships differ as fp32 numbers, and the transcendental per
 //     (pixel, seed) pair disappears.  q >= ln(2^150) is where exp(-q) rounds to 0 in fp32 (label stays 0).
@@ -35,6 +38,22 @@ constexpr int kD4TileW = 128;
 constexpr int kD4KpW = kD4TileW + 8;          // 4 columns of padding on each side keep the box 16-byte granular
 constexpr int kD4MaxStages = 8;
 constexpr float kQZero = 103.97207708f;       // ln(2^150): exp(-q) == 0 in fp32 (round to nearest, subnormals kept)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
+typedef CUresult (*isg_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline isg_encode_tiled_fn get_encode_tiled() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+  if (q != cudaDriverEntryPointSuccess) return nullptr;
+  return reinterpret_cast<isg_encode_tiled_fn>(fn);
+}
 
 template <int RW, int WG>
 struct D4Geom {
@@ -581,22 +600,21 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   int dev = 0, sms = kSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = (int)std::min<long long>(T, sms);
+  const Tuning& tn = tuning();
+  // one CTA per SM; `dense_spare` SMs stay free for the small kernels of neighbouring pipeline steps (engine.py)
+  const int grid = (int)std::min<long long>(T, std::max(1, sms - tn.dense_spare));
   const size_t smem = (size_t)D4Smem<RW, WG>(cap, nstages).total;
   const int Wwords = cdiv(W, 32);
   const int threads = 32 * (WG * G + 1);
-  int dyn_tail = 4;                                   // tiles per CTA left to the dynamic scheduler
-  if (const char* e = getenv("ISG_DENSE_TAIL")) dyn_tail = std::max(0, atoi(e));
-  int dbg_flags = 0;                                  // measurement aid: bit 0 = consumers release tiles without computing
-  if (const char* e = getenv("ISG_DENSE_DEBUG")) dbg_flags = atoi(e);
+  const int dyn_tail = tn.dense_tail;                 // tiles per CTA left to the dynamic scheduler
+  const int dbg_flags = tn.dense_debug;               // measurement aid: bit 0 = consumers release tiles without computing
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  const char* pdl_env = getenv("ISG_DENSE_PDL");
   // programmatic dependent launch only behind our own pre-pass (mode 0); with prebuilt lists the predecessor is unknown
-  cfg.attrs = attr; cfg.numAttrs = (mode != 0 || (pdl_env && pdl_env[0] == '0')) ? 0 : 1;
+  cfg.attrs = attr; cfg.numAttrs = (mode != 0 || !tn.dense_pdl) ? 0 : 1;
   const float4* ghost4 = reinterpret_cast<const float4*>(ghost);
   const unsigned char* clists = lists;
   const uint16_t* covf = ovf;
@@ -621,13 +639,8 @@ inline int launch_dense_v4(const float* kp, int64_t kp_img_stride, const float* 
                            const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys, const float* xs,
                            int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats, void* workspace,
                            size_t workspace_bytes, int mode, cudaStream_t stream) {
-  int rw = 2, wg = 8, g = 2, st = kD4MaxStages;
-  if (const char* e = getenv("ISG_DENSE_CFG")) {
-    int a = 0, b_ = 0, c = 0, d = 0;
-    const int got = sscanf(e, "%dx%dx%d:%d", &a, &b_, &c, &d);
-    if (got >= 3) { rw = a; wg = b_; g = c; }
-    if (got >= 4 && d > 0) st = d;
-  }
+  const Tuning& tn = tuning();
+  const int rw = tn.dense_rw, wg = tn.dense_wg, g = tn.dense_g, st = tn.dense_stages > 0 ? tn.dense_stages : kD4MaxStages;
 #define ISG_V4_CASE(RW_, WG_, G_)                                                                                      \
   if (rw == RW_ && wg == WG_ && g == G_)                                                                               \
     return launch_dense_v4_cfg<RW_, WG_, G_>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, \

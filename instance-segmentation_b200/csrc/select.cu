@@ -861,11 +861,9 @@ extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t 
   if (npx >= 65536) {
     // default: sample -> filter -> select.  ISG_TOPK_PATH=radix selects the sampling-free two-level radix select
     // (exact by construction, measured 82 us vs 71 us on the bench workload in round 1: every stage is latency-bound)
-    const char* path_env = getenv("ISG_TOPK_PATH");
-    if (!(path_env && path_env[0] == 'r')) {
+    if (!tuning().topk_radix) {
       int stride = 64;
-      const char* samp_env = getenv("ISG_TOPK_SAMPLE");   // "cluster": the 8-CTA cluster form with a 4x larger sample
-      if (samp_env && samp_env[0] == 'c') {
+      if (tuning().topk_cluster_sample) {   // ISG_TOPK_SAMPLE=cluster: the 8-CTA cluster form with a 4x larger sample
         while (npx / stride > kSampleMax) stride *= 2;
         const size_t smem = (size_t)cdiv(npx / stride, kSelCluster) * sizeof(uint32_t);
         ISG_CUDA(cudaFuncSetAttribute(topk_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -90,7 +90,9 @@ def test_topk_threshold_paths(mods, shape, k, kind, path, monkeypatch):
     """every host-selected path (sample/filter/select, legacy multi-CTA, single-CTA) and the in-kernel
     fallback (flat / sorted images defeat the sample bound) return the exact k-th largest value"""
     lib, eng = mods["lib"], mods["engine"]
-    monkeypatch.setenv("ISG_TOPK_PATH", path)      # read by libisg on every call: sample/filter/select or two-level radix
+    # sample/filter/select or two-level radix; libisg reads its tuning variables once, the debug hook re-reads them
+    monkeypatch.setenv("ISG_TOPK_PATH", path)
+    lib.lib().isg_debug_reload_tuning()
     H, W = shape
     g = torch.Generator(device="cpu").manual_seed(H + k)
     if kind == "normal":
@@ -107,6 +109,8 @@ def test_topk_threshold_paths(mods, shape, k, kind, path, monkeypatch):
     kth = torch.topk(kp[0].reshape(-1), k).values[-1].item()
     u = np.array([thr[0].item()], dtype=np.int32).view(np.uint32)[0]
     f = np.array([u & 0x7FFFFFFF if u & 0x80000000 else ~u], dtype=np.uint32).view(np.float32)[0]
+    monkeypatch.delenv("ISG_TOPK_PATH")
+    lib.lib().isg_debug_reload_tuning()
     assert f == np.float32(kth)
 
 
@@ -429,7 +433,7 @@ def test_decode_output_plateau_overflow_is_not_silent(mods, mode):
     notice (the kernels keep counting past the plan's capacity) and decode again with room - never return fewer
     detections silently.  Checked against the same decode with k = H*W, where nothing can overflow."""
     synth, dec = mods["synth"], mods["decode"]
-    H, W, B = 64, 128, 2
+    H, W, B = 128, 256, 2
     anchors = synth.make_anchors(H, W)
     scenes = [synth.make_scene(700 + b, H, W, 3, 8, anchors) for b in range(B)]
     kp = torch.zeros((B, 1, H, W)); kp[1] = 0.5                      # flat heat maps: all H*W pixels tie and are 3x3 maxima

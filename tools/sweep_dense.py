@@ -1,4 +1,4 @@
-"""GPU sweep of the dense kernel geometries: time + equality against the v2 kernel (parity-green baseline)."""
+"""GPU sweep of the dense kernel geometries: time + equality against the first configuration (v1 = the plain-LDG kernel)."""
 import os, sys, json
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this file lives in tools/)
@@ -9,7 +9,7 @@ from isg_b200 import _lib, engine
 
 def main():
     wlname = sys.argv[1] if len(sys.argv) > 1 else "cityscapes_1024x2048_b8_n100"
-    cfgs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["v2", "2x8x2", "4x4x3", "4x4x4", "4x2x6", "2x4x4", "2x4x6", "2x8x3"]
+    cfgs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["v1", "2x8x2", "4x4x3", "4x4x4", "4x2x6", "2x4x4", "2x4x6", "2x8x3"]
     wl = bench.WORKLOADS[wlname]
     dev = torch.device("cuda", 0)
     B, H, W, N = wl["B"], wl["H"], wl["W"], wl["N"]
@@ -22,17 +22,20 @@ def main():
     pipe = engine.DecodePipeline(bplan, dplan)
     ref = None
     for cfg in cfgs:
-        os.environ.pop("ISG_DENSE_V2", None); os.environ.pop("ISG_DENSE_CFG", None)
-        os.environ.pop("ISG_DENSE_TAIL", None)
-        if cfg == "v2": os.environ["ISG_DENSE_V2"] = "1"
+        os.environ.pop("ISG_DENSE_V1", None); os.environ.pop("ISG_DENSE_CFG", None)
+        os.environ.pop("ISG_DENSE_TAIL", None); os.environ.pop("ISG_DENSE_SPARE", None)
+        if cfg == "v1": os.environ["ISG_DENSE_V1"] = "1"
         else:
             c = cfg
+            if "-" in c:
+                c, spare = c.split("-"); os.environ["ISG_DENSE_SPARE"] = spare
             os.environ.pop("ISG_DENSE_DEBUG", None)
             if "!" in c:
                 c, dbg = c.split("!"); os.environ["ISG_DENSE_DEBUG"] = dbg
             if "@" in c:
                 c, tail = c.split("@"); os.environ["ISG_DENSE_TAIL"] = tail
             os.environ["ISG_DENSE_CFG"] = c
+        _lib.lib().isg_debug_reload_tuning()
         dplan.label_map.fill_(-7); dplan.keepbits.fill_(0)
         try:
             for _ in range(3):
