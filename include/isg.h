@@ -60,6 +60,11 @@ const char* isg_strerror(int code);
 /* Experiment hook (tests, tools/sweep_dense.py): the ISG_* tuning variables are read from the environment once, at the
  * first call into the library; this re-reads them.  Not for production use; not thread-safe against running calls. */
 void        isg_debug_reload_tuning(void);
+/* host helper: the device address of page-locked, mapped HOST memory (cudaHostAlloc / torch pin_memory()), for the
+ * entry points that accept such a pointer in place of a device pointer (documented per parameter: the `ae` of
+ * isg_assign_sparse and the `regression` of isg_decode_boxes are only read at the selected pixels / candidate anchors,
+ * so they can stay in host memory and be gathered over PCIe).  Returns a cudaError_t (> 0) if the memory is not mapped. */
+int         isg_host_device_pointer(const void* host_ptr, void** device_ptr);
 /* host query: 1 if `device` is a compute-capability 10.x part this library was built for, else 0 */
 int         isg_device_supported(int device);
 
@@ -139,6 +144,11 @@ int isg_assign_sparse(const float* ae, int64_t img_stride, int64_t plane_stride,
                       const uint32_t* seeds, const float* ghost, const int32_t* n_seeds, int B, int Nmax,
                       int H, int W, const float* ys, const float* xs,
                       int32_t* label, float* score, uint8_t* flag, int32_t* stats, isg_stream_t stream);
+/* label_map[b, idx[b,m]] = label[b,m] for the compacted keep pixels (m < min(count[b], cap)); every other element of
+ * label_map is left untouched.  Lets the consumers of the dense label map (isg_instance_polygons, which looks labels up
+ * at keep pixels only) run behind isg_assign_sparse. */
+int isg_scatter_labels(const int32_t* idx, const int32_t* count, int cap, const int32_t* label, int B, int H, int W,
+                       int32_t* label_map, isg_stream_t stream);
 /* dense fused: every pixel.  Reads kp (+1-pixel halo) and the 4 ae planes once, applies the
  * top-k threshold and the 3x3 peak test, assigns every pixel, writes label_map [B,H,W] int32,
  * keepbits [B,H,ceil(W/32)], optional score_map [B,H,W] fp32 (nullable), and accumulates stats
@@ -284,6 +294,50 @@ int isg_instance_polygons(const uint32_t* keepbits, const int32_t* label_map, co
                           float* poly_points, int32_t* inst_start, int32_t* inst_count, uint8_t* inst_flags,
                           float* inst_internal, int32_t* img_total, int32_t* stats, void* workspace, size_t workspace_bytes,
                           int totals_zeroed, isg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One whole decode step = decode_output (utils/decode.py:444-461) for a batch already visible to the device,
+ * enqueued by a single host call: isg_decode_boxes -> isg_box_nms -> isg_gather_build_seeds (-> isg_build_tile_lists)
+ * on `main`; isg_topk_threshold (ISG_ASSIGN_SPARSE: + isg_keep_points + isg_compact_points) on `side`, forked from and
+ * joined back into `main` with the two caller-owned events; then the assignment and (polygons != 0)
+ * isg_instance_polygons on `main`.  Every pointer has the meaning documented at the entry point that consumes it.
+ *   ISG_ASSIGN_DENSE : isg_assign_dense (label for every pixel; needs label_map, keepbits, dense_ws).
+ *   ISG_ASSIGN_SPARSE: isg_assign_sparse + isg_scatter_labels (keep pixels only; needs idx, count, label too).  In this
+ *                      mode `ae` and `regression` may be DEVICE ADDRESSES OF MAPPED HOST MEMORY (isg_host_device_pointer):
+ *                      they are only read at the keep pixels / candidate anchors, so the planes never cross PCIe.
+ * time_begin / time_end (nullable): events recorded on `main` around the assignment launches.
+ * Nothing is synchronised; results are read by the caller after `main` has drained.  struct_bytes = sizeof(struct).
+ * ------------------------------------------------------------------------------------------ */
+#define ISG_ASSIGN_DENSE  0
+#define ISG_ASSIGN_SPARSE 1
+typedef struct isg_decode_step {
+  int struct_bytes;
+  int assign, polygons;
+  int B, H, W, img_h, img_w, A, C, Nmax, cand_cap, cap, kp_th, obj_pixel_th;
+  float cls_th, ghost_k, scale;
+  double iou_th;
+  /* model outputs */
+  const float* kp; int64_t kp_img_stride;
+  const float* ae; int64_t ae_img_stride, ae_plane_stride;
+  const float* anchors; const float* regression; const float* classification;
+  const float* ys; const float* xs;
+  /* box head */
+  float* cand_boxes; float* cand_scores; int32_t* cand_cls; int32_t* cand_anchor; int32_t* cand_count;
+  int32_t* keep; int32_t* n_keep; void* nms_ws; size_t nms_ws_bytes;
+  float* rois; float* scores; int32_t* cls; int32_t* n_seeds;
+  /* selection + assignment */
+  uint32_t* thr_key; void* topk_ws; size_t topk_ws_bytes;
+  uint32_t* seeds; float* ghost; int32_t* stats;
+  uint32_t* keepbits; int32_t* label_map; void* dense_ws; size_t dense_ws_bytes;
+  int32_t* idx; int32_t* count; int32_t* label;
+  /* per-instance polygons */
+  float* poly_points; int32_t* inst_start; int32_t* inst_count; uint8_t* inst_flags; float* inst_internal;
+  int32_t* img_total; void* poly_ws; size_t poly_ws_bytes;
+  /* streams (cudaStream_t) and events (cudaEvent_t) */
+  isg_stream_t main; isg_stream_t side; void* fork_event; void* join_event; void* time_begin; void* time_end;
+} isg_decode_step_t;
+int isg_decode_step(const isg_decode_step_t* step);
+size_t isg_decode_step_bytes(void);   /* host query: sizeof(isg_decode_step_t) as compiled into the library */
 
 /* ------------------------------------------------------------------------------------------
  * f2 - polygon rasteriser on the device.  Replaces poly_to_mask (utils/image.py:180-185 =

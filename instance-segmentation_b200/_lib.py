@@ -14,6 +14,32 @@ F = C.c_float
 D = C.c_double
 SZ = C.c_size_t
 
+
+
+class DecodeStep(C.Structure):
+    """isg_decode_step_t (include/isg.h), field for field"""
+    _fields_ = [
+        ("struct_bytes", I), ("assign", I), ("polygons", I),
+        ("B", I), ("H", I), ("W", I), ("img_h", I), ("img_w", I), ("A", I), ("C", I), ("Nmax", I), ("cand_cap", I), ("cap", I),
+        ("kp_th", I), ("obj_pixel_th", I),
+        ("cls_th", F), ("ghost_k", F), ("scale", F), ("iou_th", D),
+        ("kp", P), ("kp_img_stride", I64), ("ae", P), ("ae_img_stride", I64), ("ae_plane_stride", I64),
+        ("anchors", P), ("regression", P), ("classification", P), ("ys", P), ("xs", P),
+        ("cand_boxes", P), ("cand_scores", P), ("cand_cls", P), ("cand_anchor", P), ("cand_count", P),
+        ("keep", P), ("n_keep", P), ("nms_ws", P), ("nms_ws_bytes", SZ),
+        ("rois", P), ("scores", P), ("cls", P), ("n_seeds", P),
+        ("thr_key", P), ("topk_ws", P), ("topk_ws_bytes", SZ),
+        ("seeds", P), ("ghost", P), ("stats", P),
+        ("keepbits", P), ("label_map", P), ("dense_ws", P), ("dense_ws_bytes", SZ),
+        ("idx", P), ("count", P), ("label", P),
+        ("poly_points", P), ("inst_start", P), ("inst_count", P), ("inst_flags", P), ("inst_internal", P),
+        ("img_total", P), ("poly_ws", P), ("poly_ws_bytes", SZ),
+        ("main", P), ("side", P), ("fork_event", P), ("join_event", P), ("time_begin", P), ("time_end", P),
+    ]
+
+
+ISG_ASSIGN_DENSE, ISG_ASSIGN_SPARSE = 0, 1
+
 # name -> (restype, argtypes); mirrors include/isg.h one to one
 PROTOTYPES = {
     "isg_abi_version": (I, []),
@@ -31,6 +57,8 @@ PROTOTYPES = {
     "isg_stats_init": (I, [P, I, I, P]),
     "isg_gather_build_seeds": (I, [P, P, P, P, P, I, I, I, P, P, I, I, F, F, P, P, P, P, P, P, P, P, P]),
     "isg_assign_sparse": (I, [P, I64, I64, P, P, I, P, P, P, I, I, I, I, P, P, P, P, P, P, P]),
+    "isg_scatter_labels": (I, [P, P, I, P, I, I, I, P, P]),
+    "isg_host_device_pointer": (I, [P, P]),
     "isg_assign_dense_workspace_bytes": (SZ, [I, I, I, I]),
     "isg_build_tile_lists": (I, [P, P, I, I, I, I, P, SZ, P]),
     "isg_assign_dense": (I, [P, I64, P, I64, I64, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P, SZ, I, P]),
@@ -54,6 +82,8 @@ PROTOTYPES = {
     "isg_instance_polygons_workspace_bytes": (SZ, [I, I]),
     "isg_instance_polygons": (I, [P, P, P, I, P, P, I, I, I, I, I, I, P, P, P, P, P, P, P, P, SZ, I, P]),
     "isg_fill_polygons": (I, [P, P, P, I, I, I, I, P, SZ, P, P, P]),
+    "isg_decode_step": (I, [P]),
+    "isg_decode_step_bytes": (SZ, []),
     "isg_host_point_in_polygon": (I, [P, I, F, F]),
     "isg_host_internal_points": (I, [P, P, I, P, I, P]),
     "isg_host_centres_inside": (I, [P, P, I, P, P]),
@@ -108,7 +138,7 @@ launch_count = 0
 _LAUNCHES = {
     "isg_topk_threshold": 3, "isg_keep_points": 1, "isg_select_points": 4, "isg_nms_hm": 1,
     "isg_compact_points": 1, "isg_build_seeds": 1, "isg_stats_init": 1, "isg_assign_sparse": 1,
-    "isg_gather_build_seeds": 1, "isg_build_tile_lists": 1, "isg_assign_dense": lambda a: 1 if a[21] else 2, "isg_gather_labels": 1, "isg_instance_polygons": lambda a: 1 if a[21] else 2, "isg_decode_boxes": 1,
+    "isg_gather_build_seeds": 1, "isg_scatter_labels": 1, "isg_build_tile_lists": 1, "isg_assign_dense": lambda a: 1 if a[21] else 2, "isg_gather_labels": 1, "isg_instance_polygons": lambda a: 1 if a[21] else 2, "isg_decode_boxes": 1,
     "isg_gather_kept": 1, "isg_mask_nms": 5, "isg_mask_pair_counts": 1, "isg_pairwise": 1,
     "isg_bbox_transform": 1, "isg_clip_boxes": 1, "isg_generate_anchors": 1, "isg_pack_masks": 1, "isg_fill_polygons": 1,
     # (idx,label,flag,count,cap,n_seeds,B,Nmax,...): one multisplit kernel unless the seed table is huge

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libisg.so")
-SOURCES = ["api.cu", "select.cu", "assign.cu", "boxes.cu", "kmeans.cu", "polygons.cu", "fill.cu", "host_polygon.cpp"]
+SOURCES = ["api.cu", "select.cu", "assign.cu", "boxes.cu", "kmeans.cu", "polygons.cu", "fill.cu", "host_polygon.cpp", "step.cpp"]
 HEADERS = ["common.cuh", "keep.cuh", "dense_v4.cuh", os.path.join("..", "..", "include", "isg.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared"]

@@ -61,3 +61,12 @@ extern "C" int isg_device_supported(int device) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0;
   return prop.major == 10 ? 1 : 0;
 }
+
+extern "C" int isg_host_device_pointer(const void* host_ptr, void** device_ptr) {
+  if (!host_ptr || !device_ptr) return ISG_EINVAL;
+  void* d = nullptr;
+  const cudaError_t e = cudaHostGetDevicePointer(&d, const_cast<void*>(host_ptr), 0);
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  *device_ptr = d;
+  return ISG_OK;
+}

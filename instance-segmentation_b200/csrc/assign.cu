@@ -746,6 +746,28 @@ extern "C" int isg_assign_dense(const float* kp, int64_t kp_img_stride, const fl
                          Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, vec, stream);
 }
 
+namespace isg {
+__global__ void __launch_bounds__(256)
+scatter_labels_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ count, int cap,
+                      const int32_t* __restrict__ label, int H, int W, int32_t* __restrict__ label_map) {
+  const int b = blockIdx.y;
+  const int m = blockIdx.x * 256 + threadIdx.x;
+  if (m >= min(count[b], cap)) return;
+  const size_t o = (size_t)b * cap + m;
+  const int y = idx[o * 2], x = idx[o * 2 + 1];
+  label_map[((size_t)b * H + y) * W + x] = label[o];
+}
+}  // namespace isg
+
+extern "C" int isg_scatter_labels(const int32_t* idx, const int32_t* count, int cap, const int32_t* label, int B, int H,
+                                  int W, int32_t* label_map, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!idx || !count || !label || !label_map || B <= 0 || cap <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
+  isg::scatter_labels_kernel<<<dim3(cdiv(cap, 256), B), 256, 0, stream>>>(idx, count, cap, label, H, W, label_map);
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
 extern "C" int isg_gather_labels(const int32_t* label_map, const float* score_map, const int32_t* idx,
                                  const int32_t* count, int cap, const float* ghost, int B, int Nmax, int H, int W,
                                  int32_t* label, float* score, uint8_t* flag, int32_t* stats, isg_stream_t stream_) {

@@ -46,6 +46,21 @@ def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+def device_address(t: torch.Tensor) -> int:
+    """Address a kernel can dereference: the data pointer of a CUDA tensor, or the mapped device address of a PINNED
+    host tensor (isg_host_device_pointer).  Pageable host memory raises."""
+    if t.is_cuda:
+        return t.data_ptr()
+    if not t.is_pinned():
+        raise RuntimeError("a host tensor handed to a kernel must be pinned (page-locked, mapped)")
+    import ctypes
+    out = ctypes.c_void_p()
+    rc = _lib.lib().isg_host_device_pointer(t.data_ptr(), ctypes.byref(out))
+    if rc != 0:
+        raise _lib.IsgError(rc, "isg_host_device_pointer")
+    return int(out.value)
+
+
 _tables = {}
 
 
@@ -82,12 +97,48 @@ def aligned_workspace(nbytes: int, device: torch.device):
     return t, t.data_ptr() + ((-t.data_ptr()) % 256)
 
 
+class Arena:
+    """One device buffer + a pinned host mirror for everything the host reads back after a step (counts, detection
+    tables, per-instance polygon tables and points): the read-back is ONE device->host copy and one wait instead of a
+    blocking `.cpu()` per buffer.  Plans take their host-visible outputs from an arena when they are given one."""
+
+    def __init__(self, nbytes: int, device):
+        self.device = require_cuda(device)
+        self.nbytes = (int(nbytes) + 255) // 256 * 256
+        self.dev = torch.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+        self.host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
+        self.used = 0
+        self.ready = torch.cuda.Event()
+
+    def alloc(self, shape, dtype):
+        """(device tensor, host mirror tensor) of `shape`/`dtype` carved from the arena (256-byte aligned)"""
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        off = (self.used + 255) // 256 * 256
+        if off + n > self.nbytes:
+            raise RuntimeError("arena too small: %d + %d > %d" % (off, n, self.nbytes))
+        self.used = off + n
+        return (self.dev[off:off + n].view(dtype).view(shape), self.host[off:off + n].view(dtype).view(shape))
+
+    def fetch_async(self) -> None:
+        """enqueue the device->host copy of the used part on the current stream"""
+        self.host[:self.used].copy_(self.dev[:self.used], non_blocking=True)
+        self.ready.record(torch.cuda.current_stream(self.device))
+
+    def wait(self) -> int:
+        self.ready.synchronize()
+        return self.used
+
+    @staticmethod
+    def bytes_for(B: int, N: int, cap: int) -> int:
+        return B * (cap * 8 + N * 64) + 64 * 256
+
+
 class DecodePlan:
     """select -> assign (dense or sparse) -> compact -> group for a batch of B images of HxW."""
 
     def __init__(self, B: int, H: int, W: int, max_seeds: int, kp_th: int, device, mode: str = "sparse",
                  want_score: bool = True, wh_delta: float = 0.1, scale: float = 1.0, fused_stats: bool = False,
-                 min_cap: int = 0):
+                 min_cap: int = 0, arena: Arena | None = None):
         if mode not in ("dense", "sparse"):
             raise ValueError("mode must be 'dense' or 'sparse'")
         self.device = require_cuda(device)
@@ -110,11 +161,20 @@ class DecodePlan:
         self.events = []
         d, i32, f32 = self.device, torch.int32, torch.float32
         B, N, cap = self.B, self.N, self.cap
+        self.arena, self.host = arena, {}
+
+        def out(name, shape, dtype):
+            """a buffer the host reads back: from the arena (with a pinned mirror in self.host) when there is one"""
+            if arena is None:
+                return torch.empty(shape, dtype=dtype, device=d)
+            t, h = arena.alloc(shape, dtype)
+            self.host[name] = h
+            return t
         self.ys, self.xs = coordinate_tables(H, W, d)
         self.thr_key = torch.empty(B, dtype=i32, device=d)
         self.keepbits = torch.empty((B, H, self.Ww), dtype=i32, device=d)
         self.idx = torch.empty((B, cap, 2), dtype=i32, device=d)
-        self.count = torch.empty(B, dtype=i32, device=d)
+        self.count = out("count", (B,), i32)
         self.label = torch.empty((B, cap), dtype=i32, device=d)
         self.score = torch.empty((B, cap), dtype=f32, device=d) if want_score else None
         self.flag = torch.empty((B, cap), dtype=torch.uint8, device=d)
@@ -127,12 +187,12 @@ class DecodePlan:
         self.ws, self.ws_ptr = aligned_workspace(self.ws_bytes, d)
         if mode == "dense":
             # device polygon stage (isg_instance_polygons)
-            self.poly_points = torch.empty((B, cap, 2), dtype=f32, device=d)
-            self.inst_start = torch.empty((B, N), dtype=i32, device=d)
-            self.inst_count = torch.empty((B, N), dtype=i32, device=d)
-            self.inst_flags = torch.empty((B, N), dtype=torch.uint8, device=d)
+            self.img_total = out("img_total", (B,), i32)
+            self.inst_start = out("inst_start", (B, N), i32)
+            self.inst_count = out("inst_count", (B, N), i32)
+            self.inst_flags = out("inst_flags", (B, N), torch.uint8)
+            self.poly_points = out("poly_points", (B, cap, 2), f32)
             self.inst_internal = torch.empty((B, N, 2), dtype=f32, device=d)
-            self.img_total = torch.empty(B, dtype=i32, device=d)
             self.poly_ws_bytes = int(_lib.lib().isg_instance_polygons_workspace_bytes(B, cap))
             self.poly_ws, self.poly_ws_ptr = aligned_workspace(self.poly_ws_bytes, d)
             self.label_map = torch.empty((B, H, W), dtype=i32, device=d)
@@ -244,7 +304,8 @@ class DecodePlan:
 class BoxPlan:
     """decode_boxes on the device: front-end -> class-aware NMS -> per-image detection tables."""
 
-    def __init__(self, B: int, A: int, C: int, H: int, W: int, device, cap: int = 4096, max_keep: int = 1024):
+    def __init__(self, B: int, A: int, C: int, H: int, W: int, device, cap: int = 4096, max_keep: int = 1024,
+                 arena: Arena | None = None):
         self.device = require_cuda(device)
         check_device(self.device)
         self.B, self.A, self.C, self.H, self.W = int(B), int(A), int(C), int(H), int(W)
@@ -252,16 +313,24 @@ class BoxPlan:
         self.N = int(min(max_keep, self.cap))
         d, i32, f32 = self.device, torch.int32, torch.float32
         B, cap, N = self.B, self.cap, self.N
+        self.arena, self.host = arena, {}
+
+        def out(name, shape, dtype):
+            if arena is None:
+                return torch.empty(shape, dtype=dtype, device=d)
+            t, h = arena.alloc(shape, dtype)
+            self.host[name] = h
+            return t
         self.cand_boxes = torch.empty((B, cap, 4), dtype=f32, device=d)
         self.cand_scores = torch.empty((B, cap), dtype=f32, device=d)
         self.cand_cls = torch.empty((B, cap), dtype=i32, device=d)
         self.cand_anchor = torch.empty((B, cap), dtype=i32, device=d)
-        self.cand_count = torch.empty(B, dtype=i32, device=d)
+        self.cand_count = out("cand_count", (B,), i32)
         self.keep = torch.empty((B, cap), dtype=i32, device=d)
-        self.n_keep = torch.empty(B, dtype=i32, device=d)
-        self.rois = torch.empty((B, N, 4), dtype=f32, device=d)
-        self.scores = torch.empty((B, N), dtype=f32, device=d)
-        self.cls = torch.empty((B, N), dtype=i32, device=d)
+        self.n_keep = out("n_keep", (B,), i32)
+        self.rois = out("rois", (B, N, 4), f32)
+        self.scores = out("scores", (B, N), f32)
+        self.cls = out("cls", (B, N), i32)
         self.n_seeds = torch.empty(B, dtype=i32, device=d)
         self.ws_bytes = int(_lib.lib().isg_box_nms_workspace_bytes(B, cap))
         self.ws, self.ws_ptr = aligned_workspace(self.ws_bytes, d)
@@ -324,6 +393,79 @@ class DecodePipeline:
         self.tail_done = torch.cuda.Event()
         self.tail_pending = False
         self.tail_deferred = None      # (obj_pixel_th,) of a pipelined step whose polygon tail is not enqueued yet
+        self._step = None              # isg_decode_step_t with every plan pointer filled in (run_native)
+        self.time_events = None        # (begin, end) CUDA events around the assignment of the last timed native step
+
+    def _native_step(self) -> "_lib.DecodeStep":
+        if self._step is not None:
+            return self._step
+        bp, dp = self.bplan, self.dplan
+        if dp.mode != "dense" or dp.ghost_k < 0:
+            raise ValueError("the native step needs a dense-mode plan with the device ghost filter")
+        st = _lib.DecodeStep()
+        st.struct_bytes = int(_lib.lib().isg_decode_step_bytes())
+        st.B, st.H, st.W, st.img_h, st.img_w, st.A, st.C = dp.B, dp.H, dp.W, bp.H, bp.W, bp.A, bp.C
+        st.Nmax, st.cand_cap, st.cap, st.kp_th = dp.N, bp.cap, dp.cap, dp.kp_th
+        st.ghost_k, st.scale = dp.ghost_k, dp.scale
+        st.ys, st.xs = ptr(dp.ys), ptr(dp.xs)
+        for name in ("cand_boxes", "cand_scores", "cand_cls", "cand_anchor", "cand_count", "keep", "n_keep", "rois", "scores",
+                     "cls", "n_seeds"):
+            setattr(st, name, ptr(getattr(bp, name)))
+        st.nms_ws, st.nms_ws_bytes = bp.ws_ptr, bp.ws_bytes
+        for name in ("thr_key", "seeds", "ghost", "stats", "keepbits", "label_map", "idx", "count", "label", "poly_points",
+                     "inst_start", "inst_count", "inst_flags", "inst_internal", "img_total"):
+            setattr(st, name, ptr(getattr(dp, name)))
+        st.topk_ws, st.topk_ws_bytes = dp.ws_ptr, dp.ws_bytes
+        st.dense_ws, st.dense_ws_bytes = ptr(dp.dense_ws), dp.dense_ws_bytes
+        st.poly_ws, st.poly_ws_bytes = dp.poly_ws_ptr, dp.poly_ws_bytes
+        # torch creates the cudaEvent_t lazily: record once so that the handles exist
+        cur = torch.cuda.current_stream(self.device)
+        self._t0, self._t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for ev in (self.fork, self.join, self._t0, self._t1):
+            ev.record(cur)
+        st.side, st.fork_event, st.join_event = self.side.cuda_stream, self.fork.cuda_event, self.join.cuda_event
+        self._step = st
+        return st
+
+    def run_native(self, kp, ae, anchors, regression, classification, cls_th, iou_th, obj_pixel_th: int = 0,
+                   assign: str = "dense", polygons: bool = True, time_main: bool = False) -> None:
+        """One whole step through isg_decode_step (a single host call) on the current stream + the side stream.
+        assign "sparse": only the keep pixels are assigned (isg_assign_sparse + isg_scatter_labels); `ae` and `regression`
+        may then be PINNED HOST tensors - they are gathered over PCIe at the keep pixels / candidate anchors instead of
+        being uploaded.  Results as for run(tail="polygons")."""
+        st = self._native_step()
+        dp, bp = self.dplan, self.bplan
+        B, H, W = dp.B, dp.H, dp.W
+        if kp.dim() == 4:
+            kp = kp[:, 0]
+        assert kp.shape == (B, H, W) and kp.dtype == torch.float32 and _rows_contiguous(kp) and kp.is_cuda
+        assert ae.shape == (B, 4, H, W) and ae.dtype == torch.float32 and _rows_contiguous(ae)
+        assert regression.shape == (B, bp.A, 4) and classification.shape == (B, bp.A, bp.C) and anchors.numel() == bp.A * 4
+        assert regression.is_contiguous() and classification.is_contiguous() and anchors.is_contiguous() and classification.is_cuda
+        sparse = assign == "sparse"
+        if not sparse and not (ae.is_cuda and regression.is_cuda):
+            raise ValueError("host-resident ae / regression need assign='sparse'")
+        st.assign = _lib.ISG_ASSIGN_SPARSE if sparse else _lib.ISG_ASSIGN_DENSE
+        st.polygons, st.obj_pixel_th = 1 if polygons else 0, int(obj_pixel_th)
+        st.cls_th, st.iou_th = float(np.float32(cls_th)), float(iou_th)
+        st.kp, st.kp_img_stride = ptr(kp), kp.stride(0) if B > 1 else H * W
+        st.ae, st.ae_img_stride, st.ae_plane_stride = device_address(ae), ae.stride(0) if B > 1 else 4 * H * W, ae.stride(1)
+        st.anchors, st.regression, st.classification = ptr(anchors), device_address(regression), ptr(classification)
+        st.main = stream_ptr(self.device)
+        if time_main:
+            st.time_begin, st.time_end = self._t0.cuda_event, self._t1.cuda_event
+        else:
+            st.time_begin = st.time_end = None
+        import ctypes
+        rc = _lib.lib().isg_decode_step(ctypes.byref(st))
+        if rc != 0:
+            raise _lib.IsgError(rc, "isg_decode_step")
+        _lib.launch_count += (8 if sparse else 8) + (1 if polygons else 0) + (2 if sparse else 0)
+        if time_main:
+            ev = (self._t0, self._t1)
+            self._t0, self._t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self._t0.record(torch.cuda.current_stream(self.device)); self._t1.record(torch.cuda.current_stream(self.device))
+            dp.events.append(ev)
 
     def _launch_tail(self) -> None:
         """Enqueue the polygon tail of the last pipelined step on the tail stream (behind its dense kernel)."""
@@ -388,6 +530,55 @@ class DecodePipeline:
                       lists_ready=True)
         self.dense_done.record(main)
         self.tail_deferred = (obj_pixel_th,)
+
+
+class DecodeRing:
+    """n independent pipelines (own plans, arenas and streams) used round-robin.  Steps submitted back to back overlap:
+    the box head / NMS / top-k of the next steps and the polygon stage of the previous ones fill the machine around
+    each step's dense kernel, which runs one CTA per SM.  Every step still executes all of its kernels
+    on its own inputs; results of slot i are valid after wait(i)."""
+
+    def __init__(self, make_pipeline, n: int = 4):
+        self.pipes = [make_pipeline() for _ in range(n)]
+        self.device = self.pipes[0].device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n)]
+        self.done = [torch.cuda.Event() for _ in range(n)]
+        self.ready = torch.cuda.Event()
+        self.next = 0
+
+    def submit(self, *args, fetch: bool = False, **kw) -> int:
+        """run_native(*args, **kw) on the next slot's stream, ordered behind the caller's current stream (the inputs).
+        fetch=True also enqueues the read-back of the slot's arena.  Returns the slot."""
+        i = self.next
+        self.next = (i + 1) % len(self.pipes)
+        s = self.streams[i]
+        self.ready.record(torch.cuda.current_stream(self.device))
+        s.wait_event(self.ready)
+        with torch.cuda.stream(s):
+            self.pipes[i].run_native(*args, **kw)
+            if fetch:
+                self.pipes[i].bplan.arena.fetch_async()
+            self.done[i].record(s)
+        return i
+
+    def wait(self, i: int | None = None) -> None:
+        """make the caller's current stream wait for slot i (default: every slot)"""
+        cur = torch.cuda.current_stream(self.device)
+        for j in (range(len(self.pipes)) if i is None else (i,)):
+            cur.wait_event(self.done[j])
+
+
+def make_pipeline(B, A, C, H, W, img_h, img_w, kp_th, device, cand_cap=1024, max_keep=256, min_cap=0, wh_delta=0.1,
+                  scale=1.0) -> "DecodePipeline":
+    """box plan + dense-mode decode plan + pipeline sharing one read-back arena"""
+    device = require_cuda(device)
+    N = int(min(max_keep, min(cand_cap, _lib.ISG_NMS_MAX_BOXES, A)))
+    cap = min(max(min(int(kp_th), H * W), int(min_cap), 1), H * W)
+    arena = Arena(Arena.bytes_for(B, N, cap), device)
+    bplan = BoxPlan(B, A, C, img_h, img_w, device, cand_cap, max_keep, arena=arena)
+    dplan = DecodePlan(B, H, W, bplan.N, kp_th, device, "dense", want_score=False, wh_delta=wh_delta, scale=scale,
+                       min_cap=min_cap, arena=arena)
+    return DecodePipeline(bplan, dplan)
 
 
 _pipes = {}

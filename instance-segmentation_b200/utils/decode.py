@@ -561,38 +561,95 @@ def _host(t):
     return t.cpu().numpy()
 
 
-def _dets_from_device_polygons(plan, B, n_keep, rois, scores, cls, decode_cfg):
-    """Assemble decode_output's result from isg_instance_polygons' buffers (one read-back per buffer)."""
-    totals = _host(plan.img_total)
-    tot = int(totals.max(initial=0))
-    starts = _host(plan.inst_start); cnts = _host(plan.inst_count); flags = _host(plan.inst_flags)
-    pts = _host(plan.poly_points[:, :max(tot, 1)])
+def _dets_from_polygon_tables(B, n_keep, rois, scores, cls, totals, starts, cnts, flags, pts):
+    """decode_output's result lists from the tables of isg_instance_polygons (numpy views, e.g. of an arena's pinned
+    mirror).  Per image: one copy of the image's points, polygons are slices of it; no per-instance device traffic."""
     dets = []
     for b in range(B):
         n = int(n_keep[b])
-        if n == 0 or totals[b] == 0:                                # :426-427, :300
+        tot = int(totals[b])
+        if n == 0 or tot == 0:                                      # :426-427, :300
             dets.append([]); continue
+        fl = flags[b, :n]
+        sel = np.flatnonzero(fl == 1)
         r = rois[b, :n]
         centres_xy = (r[:, :2] + r[:, 2:]) / 2                       # :428-432 + detransform_pixel flip -> (x,y)
-        fl, st, ct = flags[b, :n].tolist(), starts[b, :n].tolist(), cnts[b, :n].tolist()
-        cls_b, sc_b, pb = cls[b, :n].astype(np.int64), scores[b, :n], pts[b]
-        out = []
+        pb = pts[b, :tot].copy()
+        st = starts[b, :n]
+        en = st + cnts[b, :n]
+        cls_b = cls[b, :n].astype(np.int64)
+        sc_b = scores[b, :n].copy()
+        if sel.size == n or not (fl == 2).any():
+            stl, enl = st[sel].tolist(), en[sel].tolist()
+            polys = [pb[a:e] for a, e in zip(stl, enl)]
+            dets.append(list(zip(cls_b[sel], sc_b[sel], centres_xy[sel], polys)))
+            continue
+        out = []                                                    # rare: instances beyond the device stage's capacity
         for i in range(n):
-            f = fl[i]
-            if f == 1:
-                out.append((cls_b[i], sc_b[i], centres_xy[i], pb[st[i]:st[i] + ct[i]].copy()))
-            elif f == 2:                                            # more points than the device stage handles
-                poly = aug_group(pb[st[i]:st[i] + ct[i]].copy(), centres_xy[i])
+            if fl[i] == 1:
+                out.append((cls_b[i], sc_b[i], centres_xy[i], pb[st[i]:en[i]]))
+            elif fl[i] == 2:
+                poly = aug_group(pb[st[i]:en[i]].copy(), centres_xy[i])
                 if poly is not None:
                     out.append((cls_b[i], sc_b[i], centres_xy[i], poly))
         dets.append(out)
     return dets
 
 
-# host-resident model outputs are uploaded and decoded in chunks of this many images, the upload of chunk k+1
-# overlapping the kernels / read-back / list assembly of chunk k (0 disables the chunking)
+def _dets_from_device_polygons(plan, B, n_keep, rois, scores, cls, decode_cfg):
+    """Assemble decode_output's result from isg_instance_polygons' buffers (one read-back per buffer)."""
+    totals = _host(plan.img_total)
+    tot = int(totals.max(initial=0))
+    starts = _host(plan.inst_start); cnts = _host(plan.inst_count); flags = _host(plan.inst_flags)
+    pts = _host(plan.poly_points[:, :max(tot, 1)])
+    return _dets_from_polygon_tables(B, n_keep, rois, scores, cls, totals, starts, cnts, flags, pts)
+
+
+def _dets_from_arena(pipe, B):
+    """the same from the pinned mirror of the pipeline's arena (after arena.wait())"""
+    hb, hd = pipe.bplan.host, pipe.dplan.host
+    return _dets_from_polygon_tables(B, hb["n_keep"].numpy(), hb["rois"].numpy(), hb["scores"].numpy(), hb["cls"].numpy(),
+                                     hd["img_total"].numpy(), hd["inst_start"].numpy(), hd["inst_count"].numpy(),
+                                     hd["inst_flags"].numpy(), hd["poly_points"].numpy())
+
+
+# host-resident model outputs are uploaded and decoded in chunks of this many images, the upload of the later chunks
+# overlapping the kernels / read-back / list assembly of the earlier ones (0 disables the chunking)
 host_chunk_images = int(os.environ.get("ISG_HOST_CHUNK", "2"))
+# pinned host outputs: upload only kp and classification; the kernels gather `ae` at the keep pixels and `regression` at
+# the candidate anchors straight from the pinned buffers (the reference's own amount of work, :312-315,:395-398)
+host_zero_copy = os.environ.get("ISG_HOST_ZERO_COPY", "1") != "0"
 _copy_streams = {}
+_rings = {}
+
+
+def _get_ring(n_slots, B, A, C, H, W, height, width, kp_th, dev, cand_cap, max_keep, min_cap, wh_delta, scale):
+    key = (n_slots, B, A, C, H, W, height, width, kp_th, dev.index, cand_cap, max_keep, min_cap, wh_delta, scale)
+    if key not in _rings:
+        if len(_rings) > 6:
+            _rings.clear()
+        _rings[key] = engine.DecodeRing(lambda: engine.make_pipeline(B, A, C, H, W, height, width, kp_th, dev, cand_cap, max_keep,
+                                                                     min_cap, wh_delta, scale), n_slots)
+    return _rings[key]
+
+
+def _plan_overflow(pipe, sparse=False):
+    """(cand_cap, max_keep, min_cap) a re-run needs, or None when everything fitted (after arena.wait())"""
+    bp, dp = pipe.bplan, pipe.dplan
+    n_cand = int(bp.host["cand_count"].max()); n_keep = int(bp.host["n_keep"].max()); tot = int(dp.host["img_total"].max())
+    if sparse:                     # the compaction stores at most `cap` keep pixels per image and keeps counting
+        tot = max(tot, int(dp.host["count"].max()))
+    if n_cand <= bp.cap and n_keep <= bp.N and tot <= dp.cap:
+        return None
+    if n_cand > bp.cap and bp.cap >= min(_lib.ISG_NMS_MAX_BOXES, bp.A):
+        raise RuntimeError("decode_output: %d candidates above cls_th exceed the supported %d per image" % (n_cand, bp.cap))
+    cand_cap = min(max(bp.cap * 4, n_cand), _lib.ISG_NMS_MAX_BOXES) if n_cand > bp.cap else bp.cap
+    return cand_cap, (min(max(bp.N * 4, n_keep), cand_cap) if n_keep > bp.N else bp.N), (tot if tot > dp.cap else 0)
+
+
+def _fast_path(transforms, decode_cfg) -> bool:
+    """identity val-transform without drawing, dense mode: the whole per-instance stage runs on the device"""
+    return _identity_transform(transforms) and not decode_cfg.draw_flag and decode_mode == "dense" and device_polygon_stage
 
 
 def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
@@ -611,6 +668,11 @@ def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
     cs = _copy_streams[dev.index]
     main = torch.cuda.current_stream(dev)
     anc = engine.as_f32_planes(anchors, dev).contiguous()
+    zero_copy = (host_zero_copy and _fast_path(transforms, decode_cfg) and
+                 all(t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous() for t in (kp_out[0], kp_out[1], regression, classification)))
+    if zero_copy:
+        return _decode_output_zero_copy(inputs, kp_out[0], kp_out[1], regression, classification, anc, infos, transforms,
+                                        decode_cfg, dev, cb, cs, main)
 
     def upload(b0):
         b1 = min(b0 + cb, B)
@@ -634,6 +696,63 @@ def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
     return dets
 
 
+def _decode_output_zero_copy(inputs, kp_h, ae_h, reg_h, cls_h, anc, infos, transforms, decode_cfg, dev, cb, cs, main):
+    """decode_output for PINNED host outputs.  Only kp and classification are uploaded (every element of them is
+    needed: top-k / 3x3 maxima and the class maximum); `ae` is gathered at the ~k keep pixels and `regression` at the
+    candidate anchors by the kernels themselves, out of the pinned buffers.  All uploads are enqueued up front on the copy
+    stream; chunk c is decoded by slot c mod 2 of a two-slot ring (isg_decode_step, sparse assignment + device polygon
+    stage), so the kernels of a chunk overlap the read-back and list assembly of the previous one."""
+    import time as _time
+    B, H, W = kp_h.shape[0], kp_h.shape[-2], kp_h.shape[-1]
+    height, width = inputs.shape[2], inputs.shape[3]
+    A, C = cls_h.shape[1], cls_h.shape[2]
+    ring = _get_ring(2, cb, A, C, H, W, height, width, int(decode_cfg.kp_th), dev, 1024, 256, 0, float(decode_cfg.wh_delta),
+                     float(compute_scale(None)))
+    chunks = []
+    with torch.cuda.stream(cs):
+        for b0 in range(0, B - B % cb, cb):
+            kp_d = kp_h[b0:b0 + cb].to(dev, non_blocking=True)
+            cls_d = cls_h[b0:b0 + cb].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            chunks.append((b0, kp_d, cls_d, ev))
+    dets, pending, host_s, d2h = [], [], 0.0, 0
+
+    def finish(slot, b0):
+        nonlocal host_s, d2h
+        pipe = ring.pipes[slot]
+        d2h += pipe.bplan.arena.wait()
+        t0 = _time.perf_counter()
+        over = _plan_overflow(pipe, sparse=True)
+        if over is not None:       # rare: more candidates / kept boxes / keep pixels than planned - decode the chunk on its own
+            sl = slice(b0, b0 + cb)
+            sub_inputs = inputs[sl] if inputs.shape[0] == B else inputs
+            out = _decode_output_batch(sub_inputs, ((kp_h[sl], ae_h[sl], None), reg_h[sl], cls_h[sl], anc), infos[sl], transforms,
+                                       decode_cfg, dev)
+        else:
+            out = _dets_from_arena(pipe, cb)
+        host_s += _time.perf_counter() - t0
+        return out
+
+    for b0, kp_d, cls_d, ev in chunks:
+        if len(pending) == len(ring.pipes):
+            dets += finish(*pending.pop(0))
+        main.wait_event(ev)
+        slot = ring.submit(kp_d, ae_h[b0:b0 + cb], anc, reg_h[b0:b0 + cb], cls_d, decode_cfg.cls_th, decode_cfg.iou_th,
+                           obj_pixel_th=int(decode_cfg.obj_pixel_th), assign="sparse", fetch=True)
+        pending.append((slot, b0))
+    while pending:
+        dets += finish(*pending.pop(0))
+    if B % cb:                     # ragged last chunk: the ring's plans are sized for `cb` images
+        sl = slice(B - B % cb, B)
+        dets += _decode_output_batch(inputs[sl] if inputs.shape[0] == B else inputs, ((kp_h[sl], ae_h[sl], None), reg_h[sl], cls_h[sl], anc),
+                                     infos[sl], transforms, decode_cfg, dev)
+        d2h += int(last_timing.get("d2h_bytes", 0))
+    last_timing.update(d2h_bytes=d2h, readback_s=0.0, host_polygons_s=host_s,
+                       h2d_bytes=sum(c[1].numel() * 4 + c[2].numel() * 4 for c in chunks))
+    return dets
+
+
 def _decode_output_batch(inputs, outs, infos, transforms, decode_cfg, device):
     """decode_output for one device-sized batch"""
     kp_out, regression, classification, anchors = outs
@@ -648,16 +767,32 @@ def _decode_output_batch(inputs, outs, infos, transforms, decode_cfg, device):
     anc = engine.as_f32_planes(anchors, dev).contiguous()
     A, C = cls_t.shape[1], cls_t.shape[2]
     identity = _identity_transform(transforms)
+    import time as _time
+    if _fast_path(transforms, decode_cfg):
+        # one host call per step (isg_decode_step) and one read-back (the pipeline's arena)
+        while True:
+            ring = _get_ring(1, B, A, C, H, W, height, width, int(decode_cfg.kp_th), dev, cap, max_keep, min_cap,
+                             float(decode_cfg.wh_delta), float(compute_scale(None)))
+            slot = ring.submit(kp, ae, anc, reg, cls_t, decode_cfg.cls_th, decode_cfg.iou_th,
+                               obj_pixel_th=int(decode_cfg.obj_pixel_th), assign="dense", fetch=True)
+            pipe = ring.pipes[slot]
+            last_timing["d2h_bytes"] = pipe.bplan.arena.wait()
+            over = _plan_overflow(pipe)
+            if over is None:
+                break
+            cap, max_keep, min_cap = over
+        _t0 = _time.perf_counter()
+        dets = _dets_from_arena(pipe, B)
+        last_timing.update(readback_s=0.0, host_polygons_s=_time.perf_counter() - _t0)
+        return dets
     while True:
         bplan = engine.get_box_plan(B, A, C, height, width, dev, cap, max_keep)
         plan = engine.get_decode_plan(B, H, W, bplan.N, int(decode_cfg.kp_th), dev, decode_mode, want_score=False,
                                       wh_delta=float(decode_cfg.wh_delta) if identity else None,
                                       scale=float(compute_scale(None)), min_cap=min_cap)
-        # identity val-transform without drawing: the whole per-instance stage (point sets, internal point, angular
-        # sort, centre test) runs on the device; otherwise the device emits the point sets and the host finishes
-        device_polygons = identity and not decode_cfg.draw_flag and decode_mode == "dense" and device_polygon_stage
-        engine.get_pipeline(bplan, plan).run(kp, ae, anc, reg, cls_t, decode_cfg.cls_th, decode_cfg.iou_th,
-                                             tail="polygons" if device_polygons else "lists",
+        # the device emits the per-instance point sets, the host runs the polygon stage (non-identity val transform,
+        # drawing, sparse mode or ISG_DEVICE_POLYGONS=0)
+        engine.get_pipeline(bplan, plan).run(kp, ae, anc, reg, cls_t, decode_cfg.cls_th, decode_cfg.iou_th, tail="lists",
                                              obj_pixel_th=int(decode_cfg.obj_pixel_th))
         # one read-back for the whole batch
         last_timing["d2h_bytes"] = 0
@@ -670,17 +805,12 @@ def _decode_output_batch(inputs, outs, infos, transforms, decode_cfg, device):
             cap = min(cap * 4, _lib.ISG_NMS_MAX_BOXES); continue
         if n_keep.max(initial=0) > bplan.N:
             max_keep = min(max(max_keep * 4, int(n_keep.max())), bplan.cap); continue
-        need = int(_host(plan.img_total if device_polygons else plan.count).max(initial=0))
+        need = int(_host(plan.count).max(initial=0))
         if need > plan.cap:       # a plateau at the k-th value selected more pixels than k: decode again with room for them
             min_cap = need; continue
         break
-    import time as _time
     _t0 = _time.perf_counter()
     rois = _host(bplan.rois); scores = _host(bplan.scores); cls = _host(bplan.cls)
-    if device_polygons:
-        dets = _dets_from_device_polygons(plan, B, n_keep, rois, scores, cls, decode_cfg)
-        last_timing.update(readback_s=0.0, host_polygons_s=_time.perf_counter() - _t0)
-        return dets
     counts = _host(plan.count)
     offsets = _host(plan.offsets)
     tot = int(offsets[np.arange(B), np.minimum(n_keep, bplan.N)].max(initial=0))

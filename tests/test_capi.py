@@ -43,13 +43,15 @@ def test_binding_table_matches_header(built):
 
 def test_host_side_queries_need_no_gpu(built):
     lib = built.lib()
+    assert lib.isg_decode_step_bytes() == ctypes.sizeof(built.DecodeStep)      # the ctypes mirror of isg_decode_step_t
+    step = built.DecodeStep()
+    assert lib.isg_decode_step(ctypes.byref(step)) == -1                         # struct_bytes not set
     assert lib.isg_topk_workspace_bytes(8, 1024, 2048, 20000) >= 8 * (3 * 2048 * 4 + 8 * 20000 * 4)
     assert lib.isg_topk_workspace_bytes(1, 0, 4, 1) == 0
     assert lib.isg_select_points_workspace_bytes(1, 64, 64, 10) >= lib.isg_topk_workspace_bytes(1, 64, 64, 10) + 4
     assert lib.isg_box_nms_workspace_bytes(2, 1000) > 2 * 1000 * 16 * 8
     assert lib.isg_kmeans_workspace_bytes(100, 10, 2) > 0
     assert lib.isg_mask_nms_workspace_bytes(100) > 0
-    import ctypes
     strides = (ctypes.c_int * 5)(8, 16, 32, 64, 128)
     assert lib.isg_anchor_count(1024, 2048, strides, 5, 9) == 392832      # A at 1024x2048
     assert lib.isg_anchor_count(512, 1024, strides, 5, 9) == 98208

@@ -716,6 +716,107 @@ def test_decode_output_host_chunks_equal_device_batch(mods):
             assert int(c1) == int(c2) and f1 == f2 and np.array_equal(k1, k2) and np.array_equal(p1, p2)
 
 
+@pytest.mark.parametrize("B", [4, 5])
+def test_decode_output_zero_copy_equals_device_batch(mods, B):
+    """pinned host outputs: only kp / classification are uploaded, ae and regression are gathered by the kernels out of
+    the pinned buffers (isg_decode_step, sparse assignment); the detections are those of the dense device-resident decode"""
+    synth, dec = mods["synth"], mods["decode"]
+    H, W, C = 256, 512, 8
+    anchors = synth.make_anchors(H, W)
+    scenes = [synth.make_scene(760 + b, H, W, [14, 0, 9, 22, 5][b], C, anchors) for b in range(B)]
+    kp = torch.from_numpy(np.stack([s[0].kp for s in scenes])); ae = torch.from_numpy(np.stack([s[0].ae for s in scenes]))
+    reg = torch.from_numpy(np.stack([s[1] for s in scenes])); cls = torch.from_numpy(np.stack([s[2] for s in scenes]))
+    anc = torch.from_numpy(anchors)
+    infos = [TransInfo("/nonexistent.png", (H, W))] * B
+    cfg, tf, inputs = DecodeCfg(kp_th=3000), IdentityTransforms(), torch.zeros((B, 3, H, W))
+    pinned = ((kp.pin_memory(), ae.pin_memory(), None), reg.pin_memory(), cls.pin_memory(), anc)
+    ae_before = pinned[0][1].clone()
+    saved = dec.decode_mode, dec.host_chunk_images, dec.host_zero_copy
+    dec.decode_mode, dec.host_chunk_images = "dense", 2
+    try:
+        dec.host_zero_copy = True
+        got = dec.decode_output(inputs, pinned, infos, tf, cfg, torch.device(DEV))
+        h2d = dec.last_timing["h2d_bytes"]
+        again = dec.decode_output(inputs, pinned, infos, tf, cfg, torch.device(DEV))
+        dec.host_zero_copy = False
+        uploaded = dec.decode_output(inputs, pinned, infos, tf, cfg, torch.device(DEV))
+        want = dec.decode_output(inputs, ((kp.to(DEV), ae.to(DEV), None), reg.to(DEV), cls.to(DEV), anc.to(DEV)), infos, tf,
+                                 cfg, torch.device(DEV))
+    finally:
+        dec.decode_mode, dec.host_chunk_images, dec.host_zero_copy = saved
+    assert h2d == (B - B % 2) * (kp[0].numel() + cls[0].numel()) * 4         # kp + classification only
+    assert torch.equal(pinned[0][1], ae_before)                              # inputs are not modified
+    assert len(got) == len(want) == B and len(got[1]) == 0 and sum(len(g) for g in got) > 20
+    for res in (got, again, uploaded):
+        for g, w in zip(res, want):
+            assert len(g) == len(w)
+            for (c1, f1, k1, p1), (c2, f2, k2, p2) in zip(g, w):
+                assert int(c1) == int(c2) and f1 == f2 and np.array_equal(k1, k2) and np.array_equal(p1, p2)
+
+
+def test_decode_ring_overlapped_steps_equal_isolated_steps(mods):
+    """engine.DecodeRing: steps submitted back to back run concurrently on independent pipelines (isg_decode_step, one host
+    call per step); every slot must hold exactly the result of its own batch, for the dense and the sparse assignment."""
+    synth, engine = mods["synth"], mods["engine"]
+    B, H, W, C = 2, 256, 512, 8
+    dev = torch.device(DEV)
+    anchors = synth.make_anchors(H, W)
+    anc = torch.from_numpy(anchors).to(dev)
+    A = anchors.reshape(-1, 4).shape[0]
+
+    def batch(seed, counts):
+        sc = [synth.make_scene(seed + b, H, W, counts[b], C, anchors) for b in range(B)]
+        return [torch.from_numpy(np.stack(x)).to(dev) for x in ([s[0].kp for s in sc], [s[0].ae for s in sc], [s[1] for s in sc], [s[2] for s in sc])]
+
+    batches = [batch(1200, [12, 3]), batch(1210, [0, 25]), batch(1220, [7, 7])]
+    make = lambda: engine.make_pipeline(B, A, C, H, W, H, W, 3000, dev, cand_cap=1024, max_keep=64)
+
+    def tables(pipe):
+        pipe.bplan.arena.wait()
+        h = {**pipe.bplan.host, **pipe.dplan.host}
+        n = h["n_keep"].numpy().copy()
+        out = {}
+        for b in range(B):
+            for i in range(int(n[b])):
+                s0, c0 = int(h["inst_start"][b, i]), int(h["inst_count"][b, i])
+                out[(b, i)] = (int(h["inst_flags"][b, i]), h["poly_points"][b, s0:s0 + c0].numpy().copy())
+        return n, h["rois"].numpy().copy(), out
+
+    # reference results: the Python multi-call pipeline, one batch at a time
+    ref_pipe = engine.DecodePipeline(engine.BoxPlan(B, A, C, H, W, dev, cap=1024, max_keep=64),
+                                     engine.DecodePlan(B, H, W, 64, 3000, dev, "dense", want_score=False, wh_delta=0.1))
+    want = []
+    for x in batches:
+        ref_pipe.run(x[0], x[1], anc, x[2], x[3], 0.3, 0.2, tail="polygons", obj_pixel_th=2)
+        torch.cuda.synchronize(dev)
+        bp, dp = ref_pipe.bplan, ref_pipe.dplan
+        n = bp.n_keep.cpu().numpy()
+        st, ct, fl, pts = dp.inst_start.cpu().numpy(), dp.inst_count.cpu().numpy(), dp.inst_flags.cpu().numpy(), dp.poly_points.cpu().numpy()
+        want.append((n, bp.rois.cpu().numpy(), {(b, i): (int(fl[b, i]), pts[b, st[b, i]:st[b, i] + ct[b, i]].copy())
+                                                for b in range(B) for i in range(int(n[b]))}))
+    for assign in ("dense", "sparse"):
+        ring = engine.DecodeRing(make, 3)
+        for seq in ([0, 1, 2], [2, 2, 0, 1, 1, 0, 2, 1, 0]):
+            slots = []
+            for k in seq:
+                x = batches[k]
+                slots.append((ring.submit(x[0], x[1], anc, x[2], x[3], 0.3, 0.2, obj_pixel_th=2, assign=assign, fetch=True), k))
+                if len(slots) == 3:               # a slot is read before it is reused
+                    slot, kk = slots.pop(0)
+                    n, rois, got = tables(ring.pipes[slot])
+                    wn, wrois, wgot = want[kk]
+                    assert np.array_equal(n, wn) and got.keys() == wgot.keys()
+                    assert all(np.array_equal(rois[b, :n[b]], wrois[b, :n[b]]) for b in range(B))
+                    for key in got:
+                        assert got[key][0] == wgot[key][0] and np.array_equal(got[key][1], wgot[key][1]), (assign, key)
+            for slot, kk in slots:
+                n, rois, got = tables(ring.pipes[slot])
+                wn, wrois, wgot = want[kk]
+                assert np.array_equal(n, wn) and got.keys() == wgot.keys()
+                for key in got:
+                    assert got[key][0] == wgot[key][0] and np.array_equal(got[key][1], wgot[key][1]), (assign, key)
+
+
 def test_polygon_stage_large_instance(mods):
     """an instance with more boundary points than fit in shared memory (2048) is finished by the global-memory variant
     of the device stage: same polygon as the all-host path (up to the order of equal-angle points)"""
