@@ -149,6 +149,11 @@ int isg_assign_sparse(const float* ae, int64_t img_stride, int64_t plane_stride,
  * at keep pixels only) run behind isg_assign_sparse. */
 int isg_scatter_labels(const int32_t* idx, const int32_t* count, int cap, const int32_t* label, int B, int H, int W,
                        int32_t* label_map, isg_stream_t stream);
+/* emb[b,m] = (e_y, e_x) = tanh(ae[0:2]) + grid at the compacted keep pixels (utils/decode.py:305,313-314): the points
+ * the seeded k-means refinement of BASELINE config 4 clusters (X = e[M,2] for isg_kmeans).  emb: [B,cap,2] fp32. */
+int isg_gather_embeddings(const float* ae, int64_t img_stride, int64_t plane_stride, const int32_t* idx,
+                          const int32_t* count, int cap, int B, int H, int W, const float* ys, const float* xs,
+                          float* emb, isg_stream_t stream);
 /* dense fused: every pixel.  Reads kp (+1-pixel halo) and the 4 ae planes once, applies the
  * top-k threshold and the 3x3 peak test, assigns every pixel, writes label_map [B,H,W] int32,
  * keepbits [B,H,ceil(W/32)], optional score_map [B,H,W] fp32 (nullable), and accumulates stats

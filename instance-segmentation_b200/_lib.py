@@ -58,6 +58,7 @@ PROTOTYPES = {
     "isg_gather_build_seeds": (I, [P, P, P, P, P, I, I, I, P, P, I, I, F, F, P, P, P, P, P, P, P, P, P]),
     "isg_assign_sparse": (I, [P, I64, I64, P, P, I, P, P, P, I, I, I, I, P, P, P, P, P, P, P]),
     "isg_scatter_labels": (I, [P, P, I, P, I, I, I, P, P]),
+    "isg_gather_embeddings": (I, [P, I64, I64, P, P, I, I, I, I, P, P, P, P]),
     "isg_host_device_pointer": (I, [P, P]),
     "isg_assign_dense_workspace_bytes": (SZ, [I, I, I, I]),
     "isg_build_tile_lists": (I, [P, P, I, I, I, I, P, SZ, P]),
@@ -138,7 +139,7 @@ launch_count = 0
 _LAUNCHES = {
     "isg_topk_threshold": 3, "isg_keep_points": 1, "isg_select_points": 4, "isg_nms_hm": 1,
     "isg_compact_points": 1, "isg_build_seeds": 1, "isg_stats_init": 1, "isg_assign_sparse": 1,
-    "isg_gather_build_seeds": 1, "isg_scatter_labels": 1, "isg_build_tile_lists": 1, "isg_assign_dense": lambda a: 1 if a[21] else 2, "isg_gather_labels": 1, "isg_instance_polygons": lambda a: 1 if a[21] else 2, "isg_decode_boxes": 1,
+    "isg_gather_build_seeds": 1, "isg_scatter_labels": 1, "isg_gather_embeddings": 1, "isg_build_tile_lists": 1, "isg_assign_dense": lambda a: 1 if a[21] else 2, "isg_gather_labels": 1, "isg_instance_polygons": lambda a: 1 if a[21] else 2, "isg_decode_boxes": 1,
     "isg_gather_kept": 1, "isg_mask_nms": 5, "isg_mask_pair_counts": 1, "isg_pairwise": 1,
     "isg_bbox_transform": 1, "isg_clip_boxes": 1, "isg_generate_anchors": 1, "isg_pack_masks": 1, "isg_fill_polygons": 1,
     # (idx,label,flag,count,cap,n_seeds,B,Nmax,...): one multisplit kernel unless the seed table is huge

@@ -759,6 +759,34 @@ scatter_labels_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict
 }
 }  // namespace isg
 
+namespace isg {
+__global__ void __launch_bounds__(256)
+gather_embeddings_kernel(const float* __restrict__ ae, int64_t img_stride, int64_t plane_stride, const int32_t* __restrict__ idx,
+                         const int32_t* __restrict__ count, int cap, int W, const float* __restrict__ ys,
+                         const float* __restrict__ xs, float2* __restrict__ emb) {
+  const int b = blockIdx.y;
+  const int m = blockIdx.x * 256 + threadIdx.x;
+  if (m >= min(count[b], cap)) return;
+  const size_t o = (size_t)b * cap + m;
+  const int y = idx[o * 2], x = idx[o * 2 + 1];
+  const float* p = ae + (int64_t)b * img_stride + (int64_t)y * W + x;
+  // e = tanh(ae[0:2]) + xym (utils/decode.py:305), the same arithmetic as the assignment kernels
+  emb[o] = make_float2(__fadd_rn(tanh_fast(__ldg(p)), ys[y]), __fadd_rn(tanh_fast(__ldg(p + plane_stride)), xs[x]));
+}
+}  // namespace isg
+
+extern "C" int isg_gather_embeddings(const float* ae, int64_t img_stride, int64_t plane_stride, const int32_t* idx,
+                                     const int32_t* count, int cap, int B, int H, int W, const float* ys, const float* xs,
+                                     float* emb, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!ae || !idx || !count || !ys || !xs || !emb || B <= 0 || cap <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
+  if (((uintptr_t)emb & 7) != 0) return ISG_EINVAL;
+  isg::gather_embeddings_kernel<<<dim3(cdiv(cap, 256), B), 256, 0, stream>>>(ae, img_stride, plane_stride, idx, count, cap, W, ys,
+                                                                              xs, reinterpret_cast<float2*>(emb));
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
 extern "C" int isg_scatter_labels(const int32_t* idx, const int32_t* count, int cap, const int32_t* label, int B, int H,
                                   int W, int32_t* label_map, isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -20,6 +20,11 @@ def is_dist() -> bool:
     return dist.is_available() and dist.is_initialized()
 
 
+def barrier() -> None:
+    if is_dist():
+        dist.barrier()
+
+
 def reduce_max(value: float, device=None) -> float:
     """max over ranks of a host scalar (step time: the job is as slow as its slowest rank)"""
     if not is_dist():

@@ -91,6 +91,12 @@ def as_f32_planes(t: torch.Tensor, device: torch.device) -> torch.Tensor:
     return t
 
 
+def popcount_rows(bits: torch.Tensor):
+    """number of set bits per leading index of a bit-packed tensor (host side; diagnostics only)"""
+    a = bits.detach().cpu().numpy()
+    return np.unpackbits(a.reshape(a.shape[0], -1).view(np.uint8), axis=1).sum(axis=1)
+
+
 def aligned_workspace(nbytes: int, device: torch.device):
     """(tensor, 256-byte aligned device pointer) of at least `nbytes`"""
     t = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
