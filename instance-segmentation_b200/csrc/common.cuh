@@ -125,11 +125,16 @@ __device__ __forceinline__ float tanh_poly(float x) {
   p = fmaf(p, u, -0.3333333134651184f);
   return fmaf(x * u, p, x);
 }
+// |x| >= 0.55: 1 - 2/(e^{2|x|} + 1) with e^{2|x|} = ex2.approx(2|x| log2 e).  A relative error d of the exponential moves
+// the result by 2e/(e+1)^2 * d <= 0.38 d here, so neither the compensated argument of exp_fast nor an exact division
+// is needed: ex2.approx (2 ulp) + the rounding of the argument + rcp.approx stay below 1 ulp of the result (measured:
+// tests/test_gpu_parity.py::test_fast_tanh_exp_accuracy).  Overflow: e = +inf -> 2/inf = 0 -> 1.
 __device__ __forceinline__ float tanh_large(float x) {
   const float a = fabsf(x);
-  const float e = exp_fast(2.0f * fminf(a, 44.0f));
-  const float r = 1.0f - __fdividef(2.0f, e + 1.0f);
-  return copysignf(r, x);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * 2.88539008177792681472f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return copysignf(fmaf(-2.0f, r, 1.0f), x);
 }
 __device__ __forceinline__ float tanh_fast(float x) { return fabsf(x) < 0.55f ? tanh_poly(x) : tanh_large(x); }
 

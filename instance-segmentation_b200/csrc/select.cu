@@ -521,7 +521,7 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   // NOTE: 0xffffffff marks "not a candidate"; a real key of 0xffffffff (a NaN payload) is dropped, NaNs are
   // outside the contract.
   if (vec) {
-    constexpr int kUnroll = 4;                                  // independent 128-bit loads in flight per thread
+    constexpr int kUnroll = 8;                                  // independent 128-bit loads in flight per thread (the block in one go)
     for (int p0 = base; p0 < end; p0 += kFilterThreads * 4 * kUnroll) {   // warp-uniform trip count
       float4 q[kUnroll];
       bool in[kUnroll];

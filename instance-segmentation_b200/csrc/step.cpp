@@ -21,7 +21,8 @@ extern "C" size_t isg_decode_step_bytes(void) { return sizeof(isg_decode_step_t)
 
 extern "C" int isg_decode_step(const isg_decode_step_t* s) {
   if (!s || s->struct_bytes != (int)sizeof(isg_decode_step_t)) return ISG_EINVAL;
-  if (!s->main || !s->side || !s->fork_event || !s->join_event || s->main == s->side) return ISG_EINVAL;
+  // `main` may be the default stream (a null handle); `side` must be a different stream
+  if (!s->side || !s->fork_event || !s->join_event || s->main == s->side) return ISG_EINVAL;
   if (s->assign != ISG_ASSIGN_DENSE && s->assign != ISG_ASSIGN_SPARSE) return ISG_EINVAL;
   cudaStream_t main = (cudaStream_t)s->main, side = (cudaStream_t)s->side;
   cudaEvent_t fork = (cudaEvent_t)s->fork_event, join = (cudaEvent_t)s->join_event;

@@ -50,3 +50,29 @@ def gather_ints(values, device=None):
     out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
     dist.all_gather(out, t)
     return [o.tolist() for o in out]
+
+
+def decode_output_sharded(inputs, outs, infos, transforms, decode_cfg, device, decode_fn=None):
+    """decode_output (utils/decode.py:444-461) of a GLOBAL batch over all ranks: every rank is handed the same global
+    arguments (host tensors, e.g. pinned), decodes its contiguous shard of the images (shard_range; images are
+    independent, utils/parell_util.py:5-8 - no collective on the data path) and the variable-length per-image results
+    are gathered to rank 0 (gather_object).  Returns the full list (global image order) on rank 0, None elsewhere.
+    `decode_fn` defaults to the drop-in utils.decode.decode_output."""
+    if decode_fn is None:
+        from .utils.decode import decode_output as decode_fn
+    kp_out, regression, classification, anchors = outs
+    n = kp_out[0].shape[0]
+    rank, world = (dist.get_rank(), dist.get_world_size()) if is_dist() else (0, 1)
+    lo, hi = shard_range(n, rank, world)
+    mine = []
+    if hi > lo:
+        sub = (tuple(None if t is None else t[lo:hi] for t in kp_out), regression[lo:hi], classification[lo:hi], anchors)
+        sub_inputs = inputs[lo:hi] if inputs.shape[0] == n else inputs
+        mine = decode_fn(sub_inputs, sub, infos[lo:hi], transforms, decode_cfg, device)
+    if world == 1:
+        return mine
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    if rank != 0:
+        return None
+    return [d for part in parts for d in part]

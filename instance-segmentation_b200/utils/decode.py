@@ -696,6 +696,9 @@ def decode_output(inputs, outs, infos, transforms, decode_cfg, device):
     return dets
 
 
+_learned_sizes = {}    # (A, C, H, W, kp_th) -> (cand_cap, max_keep, min_cap) that the last batch of this shape needed
+
+
 def _decode_output_zero_copy(inputs, kp_h, ae_h, reg_h, cls_h, anc, infos, transforms, decode_cfg, dev, cb, cs, main):
     """decode_output for PINNED host outputs.  Only kp and classification are uploaded (every element of them is
     needed: top-k / 3x3 maxima and the class maximum); `ae` is gathered at the ~k keep pixels and `regression` at the
@@ -706,8 +709,13 @@ def _decode_output_zero_copy(inputs, kp_h, ae_h, reg_h, cls_h, anc, infos, trans
     B, H, W = kp_h.shape[0], kp_h.shape[-2], kp_h.shape[-1]
     height, width = inputs.shape[2], inputs.shape[3]
     A, C = cls_h.shape[1], cls_h.shape[2]
-    ring = _get_ring(2, cb, A, C, H, W, height, width, int(decode_cfg.kp_th), dev, 1024, 256, 0, float(decode_cfg.wh_delta),
-                     float(compute_scale(None)))
+    size_key = (A, C, H, W, int(decode_cfg.kp_th))
+    sizes = _learned_sizes.get(size_key, (1024, 256, 0))
+
+    def get_ring():
+        return _get_ring(2, cb, A, C, H, W, height, width, int(decode_cfg.kp_th), dev, sizes[0], sizes[1], sizes[2],
+                         float(decode_cfg.wh_delta), float(compute_scale(None)))
+    ring = get_ring()
     chunks = []
     with torch.cuda.stream(cs):
         for b0 in range(0, B - B % cb, cb):
@@ -718,29 +726,34 @@ def _decode_output_zero_copy(inputs, kp_h, ae_h, reg_h, cls_h, anc, infos, trans
             chunks.append((b0, kp_d, cls_d, ev))
     dets, pending, host_s, d2h = [], [], 0.0, 0
 
-    def finish(slot, b0):
-        nonlocal host_s, d2h
-        pipe = ring.pipes[slot]
+    def submit(r, b0, kp_d, cls_d):
+        return r.submit(kp_d, ae_h[b0:b0 + cb], anc, reg_h[b0:b0 + cb], cls_d, decode_cfg.cls_th, decode_cfg.iou_th,
+                        obj_pixel_th=int(decode_cfg.obj_pixel_th), assign="sparse", fetch=True)
+
+    def finish(r, slot, b0, kp_d, cls_d):
+        nonlocal host_s, d2h, sizes, ring
+        pipe = r.pipes[slot]
         d2h += pipe.bplan.arena.wait()
-        t0 = _time.perf_counter()
         over = _plan_overflow(pipe, sparse=True)
-        if over is not None:       # rare: more candidates / kept boxes / keep pixels than planned - decode the chunk on its own
-            sl = slice(b0, b0 + cb)
-            sub_inputs = inputs[sl] if inputs.shape[0] == B else inputs
-            out = _decode_output_batch(sub_inputs, ((kp_h[sl], ae_h[sl], None), reg_h[sl], cls_h[sl], anc), infos[sl], transforms,
-                                       decode_cfg, dev)
-        else:
-            out = _dets_from_arena(pipe, cb)
+        while over is not None:     # more candidates / kept boxes / keep pixels than planned: larger plans from here on
+            sizes = (max(sizes[0], over[0]), max(sizes[1], over[1]), max(sizes[2], over[2]))
+            _learned_sizes[size_key] = sizes
+            ring = get_ring()
+            r = ring
+            slot = submit(r, b0, kp_d, cls_d)
+            pipe = r.pipes[slot]
+            d2h += pipe.bplan.arena.wait()
+            over = _plan_overflow(pipe, sparse=True)
+        t0 = _time.perf_counter()
+        out = _dets_from_arena(pipe, cb)
         host_s += _time.perf_counter() - t0
         return out
 
     for b0, kp_d, cls_d, ev in chunks:
-        if len(pending) == len(ring.pipes):
+        if len(pending) == len(ring.pipes) or (pending and pending[0][0] is not ring):
             dets += finish(*pending.pop(0))
         main.wait_event(ev)
-        slot = ring.submit(kp_d, ae_h[b0:b0 + cb], anc, reg_h[b0:b0 + cb], cls_d, decode_cfg.cls_th, decode_cfg.iou_th,
-                           obj_pixel_th=int(decode_cfg.obj_pixel_th), assign="sparse", fetch=True)
-        pending.append((slot, b0))
+        pending.append((ring, submit(ring, b0, kp_d, cls_d), b0, kp_d, cls_d))
     while pending:
         dets += finish(*pending.pop(0))
     if B % cb:                     # ragged last chunk: the ring's plans are sized for `cb` images

@@ -18,7 +18,17 @@ def _worker(rank, world, port, q):
         t = idist.reduce_max(1.0 + rank)             # slowest rank defines the step time
         s = idist.reduce_sum(hi - lo)
         g = idist.gather_ints([rank, hi - lo])
-        q.put((rank, lo, hi, t, s, g))
+        # sharded decode of a global batch of 5 "images": every rank decodes its shard, rank 0 gets all results in order
+        kp = torch.arange(5, dtype=torch.float32).view(5, 1, 1, 1)
+        outs = ((kp, kp.repeat(1, 4, 1, 1), None), torch.zeros(5, 3, 4), torch.zeros(5, 3, 2), torch.zeros(1, 3, 4))
+        seen = []
+
+        def fake_decode(inputs, o, infos, transforms, cfg, device):
+            seen.append((inputs.shape[0], o[0][0].shape[0], o[1].shape[0], o[2].shape[0], o[3].shape[0], len(infos)))
+            return [[("img", int(v), info)] * int(v) for v, info in zip(o[0][0].flatten().tolist(), infos)]   # ragged
+        full = idist.decode_output_sharded(torch.zeros(5, 3, 1, 1), outs, ["i%d" % i for i in range(5)], None, None, "cpu",
+                                           decode_fn=fake_decode)
+        q.put((rank, lo, hi, t, s, g, full, seen))
     finally:
         dist.destroy_process_group()
 
@@ -40,6 +50,8 @@ def test_two_rank_sharding_and_reduction():
     assert [(r[1], r[2]) for r in res] == [(0, 32), (32, 64)]
     assert all(r[3] == 2.0 and r[4] == 64.0 for r in res)
     assert res[0][5] == [[0, 32], [1, 32]]
+    assert res[1][6] is None and res[0][6] == [[("img", v, "i%d" % v)] * v for v in range(5)]
+    assert res[0][7] == [(3, 3, 3, 3, 1, 3)] and res[1][7] == [(2, 2, 2, 2, 1, 2)]
 
 
 def test_shard_range_covers_everything():
@@ -54,3 +66,4 @@ def test_shard_range_covers_everything():
     with pytest.raises(ValueError):
         idist.shard_range(4, 2, 2)
     assert idist.reduce_max(3.5) == 3.5 and idist.gather_ints([1, 2]) == [[1, 2]]
+    idist.barrier()                                                           # no process group: a no-op

@@ -1,0 +1,162 @@
+"""GPU parity at the BASELINE.json configuration sizes: the drop-in decode_output against the oracle's
+decode_output on the same seeded inputs — class / confidence / centre bit-exact, polygons bit-exact up to the order of
+equal-angle vertices AND with identical rasterised masks (what the evaluator consumes, utils/eval_util.py:100-125);
+mask NMS keep list bit-exact at 1000 masks of 800x1333; plus the reference's caller shape driven through install_dropin()."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import DecodeCfg, IdentityTransforms, TransInfo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import isg_b200
+    from isg_b200 import _lib, engine, synth
+    from isg_b200.utils import decode, image, nms
+    from oracle import ref_decode, ref_kmeans_nms
+    _lib.lib()
+    return dict(isg=isg_b200, lib=_lib, engine=engine, synth=synth, decode=decode, image=image, nms=nms, rd=ref_decode, rk=ref_kmeans_nms)
+
+
+def _fill(poly, shape):
+    import cv2
+    return cv2.fillPoly(np.zeros(shape, np.uint8), [np.asarray(poly).astype(np.int32)], 1)
+
+
+def _same_detections(dec, got, want, shape, min_total):
+    from test_gpu_parity import assert_polygon_equivalent
+    assert len(got) == len(want)
+    total = 0
+    for g, w in zip(got, want):
+        assert len(g) == len(w)
+        for (c1, f1, ctr1, p1), (c2, f2, ctr2, p2) in zip(g, w):
+            assert int(c1) == int(c2) and np.float32(f1) == np.float32(f2) and np.array_equal(ctr1, ctr2)
+            assert_polygon_equivalent(dec, p1, p2, ctr2)
+            if not np.array_equal(p1, p2):         # equal-angle vertices in another order: the mask must not change
+                lo = np.floor(p2.min(0)).astype(int)
+                box = tuple((np.ceil(p2.max(0)).astype(int) - lo + 1)[::-1])
+                assert np.array_equal(_fill(p1 - lo, box), _fill(p2 - lo, box))
+            total += 1
+    assert total >= min_total, total
+
+
+def _scene_batch(synth, seeds, H, W, N, C=8, n_dup=2):
+    anchors = synth.make_anchors(H, W)
+    sc = [synth.make_scene(s, H, W, N, C, anchors, n_dup) for s in seeds]
+    return (torch.from_numpy(np.stack([s[0].kp for s in sc])), torch.from_numpy(np.stack([s[0].ae for s in sc])),
+            torch.from_numpy(np.stack([s[1] for s in sc])), torch.from_numpy(np.stack([s[2] for s in sc])), torch.from_numpy(anchors))
+
+
+_cases = {}
+
+
+@pytest.mark.parametrize("name,H,W,B,N,n_dup,min_total", [
+    ("config2_batch8_512x1024_n50", 512, 1024, 8, 50, 2, 300),
+    ("config3_share_1024x2048_n100", 1024, 2048, 2, 100, 2, 150),
+    ("config4_crowd_1024x2048_n500", 1024, 2048, 1, 500, 1, 300),
+])
+@pytest.mark.parametrize("where", ["device", "pinned-host"])
+def test_decode_output_at_config_size(mods, name, H, W, B, N, n_dup, min_total, where):
+    synth, dec, rd = mods["synth"], mods["decode"], mods["rd"]
+    if name not in _cases:                  # inputs + the oracle's answer, shared by the two parametrisations
+        batch = _scene_batch(synth, [5000 + 17 * b + N for b in range(B)], H, W, N, n_dup=n_dup)
+        _cases[name] = (batch, rd.decode_output(H, W, ((batch[0], batch[1], None), batch[2], batch[3], batch[4]), kp_th=20000))
+    (kp, ae, reg, cls, anc), want = _cases[name]
+    infos = [TransInfo("/nonexistent.png", (H, W))] * B
+    if where == "device":
+        outs = ((kp.to(DEV), ae.to(DEV), None), reg.to(DEV), cls.to(DEV), anc.to(DEV))
+    else:                                   # the zero-copy path: ae / regression stay in pinned host memory
+        outs = ((kp.pin_memory(), ae.pin_memory(), None), reg.pin_memory(), cls.pin_memory(), anc)
+    saved = dec.decode_mode, dec.host_chunk_images
+    dec.decode_mode, dec.host_chunk_images = "dense", (2 if B > 2 else 1)
+    try:
+        got = dec.decode_output(torch.empty((B, 3, H, W), device="meta"), outs, infos, IdentityTransforms(), DecodeCfg(), torch.device(DEV))
+    finally:
+        dec.decode_mode, dec.host_chunk_images = saved
+    _same_detections(dec, got, want, (H, W), min_total)
+
+
+def test_mask_nms_at_config5_size(mods):
+    """BASELINE config 5: 1000 candidate masks at 800x1333, 80 classes: keep list bit-exact against the oracle's greedy loop"""
+    synth, nms, rk = mods["synth"], mods["nms"], mods["rk"]
+    masks, boxes, scores, cls = synth.make_masks(5, 1000, 800, 1333, 80)
+    want = rk.mask_nms(masks, scores, cls, 0.5)
+    got = nms.mask_nms(torch.from_numpy(masks.view(np.int32)).to(DEV), scores, cls, 0.5)
+    assert np.array_equal(np.asarray(got, dtype=np.int64), np.asarray(want, dtype=np.int64)) and 100 < len(got) < 1000
+    got_bb = nms.mask_nms(masks, scores, cls, 0.5, bboxes=boxes)          # caller-supplied tight boxes: same answer
+    assert np.array_equal(np.asarray(got_bb, dtype=np.int64), np.asarray(want, dtype=np.int64))
+
+
+def test_install_dropin_drives_the_reference_caller_shape(mods, tmp_path):
+    """install_dropin() + the loop of the reference's utils/eval_util.py:35-71 (eval_outputs) and test.py:110-117: a stub
+    `utils` package whose eval_util imports `from utils import decode` exactly like the reference, a stand-in model that
+    returns the network outputs, a loader yielding (inputs, targets, infos).  The detections must be the oracle's and
+    survive the reference's JSON encoder (NpEncoder, utils/eval_util.py:23-32)."""
+    synth, rd = mods["synth"], mods["rd"]
+    pkg = tmp_path / "utils"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text("")
+    (pkg / "eval_util.py").write_text(
+        "import json\n"
+        "import numpy as np\n"
+        "import torch\n"
+        "from utils import decode\n"                                            # utils/eval_util.py:14
+        "class NpEncoder(json.JSONEncoder):\n"                                  # :23-32
+        "    def default(self, obj):\n"
+        "        if isinstance(obj, np.integer): return int(obj)\n"
+        "        if isinstance(obj, np.floating): return float(obj)\n"
+        "        if isinstance(obj, np.ndarray): return obj.tolist()\n"
+        "        return super(NpEncoder, self).default(obj)\n"
+        "def eval_outputs(eval_dataloader, transforms, model, decode_cfg, device):\n"   # :35-71 without the file i/o
+        "    decode.device = device\n"
+        "    dets_list, info_list = [], []\n"
+        "    for iter_id, eval_data in enumerate(eval_dataloader):\n"
+        "        inputs, targets, infos = eval_data\n"
+        "        inputs = inputs.to(device)\n"
+        "        with torch.no_grad():\n"
+        "            outputs = model(inputs)\n"
+        "            dets = decode.decode_output(inputs, outputs, infos, transforms, decode_cfg, device)\n"
+        "        dets_list.extend(dets)\n"
+        "        info_list.extend(infos)\n"
+        "    return dets_list, json.dumps(dets_list, cls=NpEncoder), json.dumps(info_list, cls=NpEncoder)\n")
+    saved_modules = {k: v for k, v in sys.modules.items() if k == "utils" or k.startswith("utils.")}
+    for k in saved_modules:
+        del sys.modules[k]
+    sys.path.insert(0, str(tmp_path))
+    try:
+        import utils                                                           # the stub package (the reference's name)
+        decode, kmeans, nms = mods["isg"].install_dropin()
+        from utils import eval_util
+        assert eval_util.decode is decode and sys.modules["utils.kmeans"] is kmeans and utils.nms is nms
+        H, W, B = 256, 512, 2
+        batches = [_scene_batch(synth, [8100 + 10 * i + b for b in range(B)], H, W, 9) for i in range(2)]
+        loader = [(torch.zeros((B, 3, H, W)), None, [TransInfo("/nonexistent_%d_%d.png" % (i, b), (H, W)) for b in range(B)])
+                  for i in range(2)]
+        calls = iter(batches)
+
+        def model(inputs):                                                     # EfficientSeg.forward's return structure
+            kp, ae, reg, cls, anc = next(calls)
+            d = inputs.device
+            return (kp.to(d), ae.to(d), torch.zeros((B, 2, H, W), device=d)), reg.to(d), cls.to(d), anc.to(d)
+        dets, dets_json, infos_json = eval_util.eval_outputs(loader, IdentityTransforms(), model, DecodeCfg(kp_th=3000), torch.device(DEV))
+        want = []
+        for kp, ae, reg, cls, anc in batches:
+            want += rd.decode_output(H, W, ((kp, ae, None), reg, cls, anc), kp_th=3000)
+        _same_detections(decode, dets, want, (H, W), 20)
+        import json
+        back = json.loads(dets_json)
+        assert len(back) == 4 and len(back[0][0]) == 4 and isinstance(back[0][0][0], int) and isinstance(back[0][0][3][0][0], float)
+        assert json.loads(infos_json)[3][0] == "/nonexistent_1_1.png"
+    finally:
+        sys.path.remove(str(tmp_path))
+        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            del sys.modules[k]
+        sys.modules.update(saved_modules)
