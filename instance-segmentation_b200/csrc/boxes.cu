@@ -225,9 +225,14 @@ nms_mask_kernel(const int32_t* __restrict__ count, int cap, double thr, int conv
 // ---------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256;   // >= nw for cap <= 16384
 
-// `rows` (dynamic shared memory, [64][nwc] words or absent): the suppression rows of the current chunk, words
-// c .. nchunk-1 only, staged by all threads before the chunk is resolved - the greedy step and the propagation then
-// read shared memory instead of paying one global round trip per kept box (199 us -> the mask NMS of 1000 candidates).
+// Shared-memory staging of the suppression rows (dynamic shared memory), chosen by the launcher:
+//   staged 2: the WHOLE matrix [n][nw] is loaded once (fits for up to ~1400 candidates) - no global round trip inside
+//             the chunk loop at all;
+//   staged 1: the rows of the current chunk, words c .. nchunk-1 only, are loaded by all threads before the chunk is
+//             resolved;
+//   staged 0: rows are read from global memory (very large candidate sets).
+// The 64 dependent steps of a chunk run in one thread on registers (fully unrolled: test bit q, OR row q's diagonal
+// word); the propagation of the kept rows into the later words is one independent load per row and thread.
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const int32_t* __restrict__ count, int cap, void* ws, int32_t* __restrict__ keep,
                 int32_t* __restrict__ n_keep, int staged) {
@@ -243,26 +248,38 @@ nms_scan_kernel(const int32_t* __restrict__ count, int cap, void* ws, int32_t* _
   remv[t] = 0ull;
   int nk = 0;
   int32_t* out = keep + (size_t)b * cap;
+  if (staged == 2) {
+    const uint4* src = reinterpret_cast<const uint4*>(v.mask);          // rows are 8-byte words; n * nw of them
+    const int n2 = (n * nw) >> 1;
+    for (int e = t; e < n2; e += kScanThreads) reinterpret_cast<uint4*>(scan_rows)[e] = src[e];
+    if (t == 0 && ((n * nw) & 1)) scan_rows[n * nw - 1] = v.mask[(size_t)n * nw - 1];
+  }
   __syncthreads();
   for (int c = 0; c < nchunk; ++c) {
     const int base = c * 64;
     const int m = min(64, n - base);
-    const int nwc = nchunk - c;                 // words c .. nchunk-1 of each row matter from here on
-    if (staged) {
+    const int nwc = nchunk - c;                 // staged 1: words c .. nchunk-1 of each row
+    const unsigned long long* rows;
+    int rstride, woff;
+    if (staged == 2) { rows = scan_rows + (size_t)base * nw; rstride = nw; woff = 0; }
+    else if (staged == 1) {
       for (int e = t; e < m * nwc; e += kScanThreads) {
         const int q = e / nwc, w = e - q * nwc;
         scan_rows[q * nwc + w] = v.mask[(size_t)(base + q) * nw + c + w];
       }
       __syncthreads();
-      if (t < m) diag[t] = scan_rows[t * nwc];
-    } else {
-      if (t < m) diag[t] = v.mask[(size_t)(base + t) * nw + c];
-    }
-    __syncthreads();
+      rows = scan_rows; rstride = nwc; woff = -c;
+    } else { rows = v.mask + (size_t)base * nw; rstride = nw; woff = 0; }
     if (t == 0) {
+      unsigned long long dq[64];
+#pragma unroll
+      for (int q = 0; q < 64; ++q) dq[q] = q < m ? rows[(size_t)q * rstride + c + woff] : 0ull;
       unsigned long long word = remv[c], kept = 0ull;
-      for (int q = 0; q < m; ++q) {
-        if (!((word >> q) & 1ull)) { kept |= 1ull << q; word |= diag[q]; }
+#pragma unroll
+      for (int q = 0; q < 64; ++q) {
+        const bool take = q < m && !((word >> q) & 1ull);
+        kept |= take ? (1ull << q) : 0ull;
+        word |= take ? dq[q] : 0ull;
       }
       s_kept = kept;
     }
@@ -271,15 +288,13 @@ nms_scan_kernel(const int32_t* __restrict__ count, int cap, void* ws, int32_t* _
     if (t < m && ((kept >> t) & 1ull))
       out[nk + __popcll(kept & ((1ull << t) - 1ull))] = v.order[base + t];
     nk += __popcll(kept);
-    // propagate the kept rows of this chunk to the later words
+    // propagate the kept rows of this chunk to the later words (independent loads, no dependent bit scan)
     const int w = t;
     if (w > c && w < nchunk) {
-      unsigned long long acc = 0ull, kk = kept;
-      while (kk) {
-        const int q = __ffsll((long long)kk) - 1;
-        kk &= kk - 1;
-        acc |= staged ? scan_rows[q * nwc + (w - c)] : v.mask[(size_t)(base + q) * nw + w];
-      }
+      unsigned long long acc = 0ull;
+#pragma unroll 8
+      for (int q = 0; q < 64; ++q)
+        if ((kept >> q) & 1ull) acc |= rows[(size_t)q * rstride + w + woff];
       remv[w] |= acc;
     }
     __syncthreads();
@@ -287,16 +302,18 @@ nms_scan_kernel(const int32_t* __restrict__ count, int cap, void* ws, int32_t* _
   if (t == 0) n_keep[b] = nk;
 }
 
-// launch helper: stage the rows when 64 rows of the (possibly shorter) live width fit in shared memory
+// launch helper: picks the staging mode by what fits in shared memory
 static inline cudaError_t launch_nms_scan(const int32_t* count, int B, int cap, void* ws, int32_t* keep, int32_t* n_keep,
                                           cudaStream_t stream) {
-  const size_t smem = (size_t)64 * ((cap + 63) / 64) * sizeof(unsigned long long);
-  const int staged = smem <= 160 * 1024 ? 1 : 0;
+  const size_t nw = (size_t)(cap + 63) / 64;
+  const size_t all = (size_t)cap * nw * sizeof(unsigned long long), chunk = 64 * nw * sizeof(unsigned long long);
+  const int staged = all <= 200 * 1024 ? 2 : (chunk <= 160 * 1024 ? 1 : 0);
+  const size_t smem = staged == 2 ? all : (staged == 1 ? chunk : 0);
   if (staged) {
     const cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  nms_scan_kernel<<<B, kScanThreads, staged ? smem : 0, stream>>>(count, cap, ws, keep, n_keep, staged);
+  nms_scan_kernel<<<B, kScanThreads, smem, stream>>>(count, cap, ws, keep, n_keep, staged);
   return cudaGetLastError();
 }
 

@@ -467,9 +467,12 @@ def assert_polygon_equivalent(dec, got, want, centre_xy):
     assert got.shape == want.shape and got.dtype == want.dtype
     key = lambda a: a[np.lexsort((a[:, 0], a[:, 1]))]
     assert np.array_equal(key(got), key(want)), "different point sets"
-    internal = np.asarray(dec.find_internal_point(want, np.asarray(centre_xy, dtype=np.float32)), dtype=np.float32)
+    # the internal point is found on the UNSORTED point set (row-major pixel order, utils/decode.py:342-359): its
+    # crossing test depends on the vertex order, so it must not be recomputed from the sorted polygon
+    internal = np.asarray(dec.find_internal_point(key(want), np.asarray(centre_xy, dtype=np.float32)), dtype=np.float32)
     th_g = dec._polar_angles(got, np.repeat(internal[None], len(got), 0))
     th_w = dec._polar_angles(want, np.repeat(internal[None], len(want), 0))
+    assert np.all(np.diff(th_w[~np.isnan(th_w)]) >= 0), "the expected polygon is not sorted about this internal point"
     assert np.array_equal(th_g, th_w, equal_nan=True), "polygons differ beyond the order of equal-angle points"
 
 
