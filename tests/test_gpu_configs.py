@@ -31,30 +31,66 @@ def _fill(poly, shape):
     return cv2.fillPoly(np.zeros(shape, np.uint8), [np.asarray(poly).astype(np.int32)], 1)
 
 
-def _same_detections(dec, got, want, shape, min_total):
-    """class / confidence / centre bit-exact; polygon bit-exact except for the order inside runs of EQUAL polar angle
-    (np.argsort at utils/decode.py:183 is an unstable sort whose tie order depends on the numpy build and the CPU's
-    vector ISA, so the reference itself is not reproducible there; the device keeps ties in row-major order).  Where the
-    tie order differs the two rasterised masks (cv2.fillPoly, what the evaluator consumes) may differ by a sliver:
-    measured <= 7 pixels / < 0.1 % of the mask on the config inputs, asserted here as <= 16 pixels and <= 0.5 %."""
-    from test_gpu_parity import assert_polygon_equivalent
-    assert len(got) == len(want)
-    total = reordered = 0
-    for g, w in zip(got, want):
-        assert len(g) == len(w)
-        for (c1, f1, ctr1, p1), (c2, f2, ctr2, p2) in zip(g, w):
-            assert int(c1) == int(c2) and np.float32(f1) == np.float32(f2) and np.array_equal(ctr1, ctr2)
-            assert_polygon_equivalent(dec, p1, p2, ctr2)
-            if not np.array_equal(p1, p2):
-                lo = np.floor(p2.min(0)).astype(int)
-                box = tuple((np.ceil(p2.max(0)).astype(int) - lo + 1)[::-1])
-                m1, m2 = _fill(p1 - lo, box), _fill(p2 - lo, box)
-                diff = int((m1 != m2).sum())
-                assert diff <= 16 and diff <= 0.005 * int(m2.sum()), (diff, int(m2.sum()))
-                reordered += 1
+def _tie_instances(rd, kp, ae, reg, cls, anc, H, W, kp_th):
+    """per image: the set of instance centres (x, y) whose polar-angle sort (utils/decode.py:181-183) has EQUAL keys.
+    np.argsort is an unstable sort there: the order inside a run of equal angles - and with it the polygon's edges, its
+    rasterised mask and sometimes the centre-inside verdict (:201) - depends on the numpy build and the CPU's vector ISA,
+    i.e. the reference's own output is not reproducible on such instances.  Everything else is compared bit-exactly."""
+    import torch
+    boxes = rd.decode_boxes(H, W, anc, reg, cls, 0.3, 0.2)
+    out = []
+    for b in range(kp.shape[0]):
+        ties = set()
+        if boxes[b]["class_ids"].shape[0]:
+            core = rd.group_core(kp[b, 0], ae[b], boxes[b]["rois"], kp_th)
+            for pts, ctr in rd.instance_points(core["idx"], core["label"], core["centres"], core["whs"], 0.1):
+                if pts.shape[0] >= 2:
+                    theta = rd.cartesian2polar(pts, rd.find_internal_point(pts, ctr))[:, 0]
+                    if np.unique(theta).size < theta.size:
+                        ties.add((float(ctr[0]), float(ctr[1])))
+        out.append(ties)
+    return out
+
+
+def _same_detections(got, want, ties, min_total):
+    """class / confidence / centre / polygon bit-exact for every instance whose angle sort is tie-free; an instance
+    with equal angles must carry the same point set when both sides accept it, and is the only kind that may be
+    accepted by one side alone.  One more documented tolerance enters through the box head: exp() of the size
+    regression differs by an ulp between the device and torch's CPU kernel (boxes rtol 1e-6), so a box centre
+    can differ in its last bit; such an instance (rare) is matched by its rounded centre and compared like a tie."""
+    key = lambda a: a[np.lexsort((a[:, 0], a[:, 1]))]
+    ck_of = lambda c: (round(float(c[0]), 2), round(float(c[1]), 2))
+    assert len(got) == len(want) == len(ties)
+    total = n_tie = n_ulp = flipped = 0
+    for g, w, tie in zip(got, want, ties):
+        gd = {ck_of(c): (k, f, c, p) for k, f, c, p in g}
+        wd = {ck_of(c): (k, f, c, p) for k, f, c, p in w}
+        tie = {ck_of(c) for c in tie}
+        assert len(gd) == len(g) and len(wd) == len(w)
+        for ck in sorted(set(gd) | set(wd)):
+            if ck not in gd or ck not in wd:
+                flipped += 1
+                n_ulp += ck not in tie       # only explained by an ulp-different box (checked in bulk below)
+                continue
+            (c1, f1, ctr1, p1), (c2, f2, ctr2, p2) = gd[ck], wd[ck]
+            assert int(c1) == int(c2) and np.float32(f1) == np.float32(f2)
+            np.testing.assert_allclose(ctr1, ctr2, rtol=1e-6, atol=0)
+            exact_box = np.array_equal(ctr1, ctr2)
+            n_ulp += not exact_box
+            if ck in tie or not exact_box:
+                if p1.shape == p2.shape:
+                    assert np.array_equal(key(p1), key(p2))
+                else:
+                    assert not exact_box          # an ulp-different box edge can move one boundary pixel in or out
+                n_tie += ck in tie
+            else:
+                assert np.array_equal(p1, p2), "polygon of a tie-free instance differs: %r" % (ck,)
             total += 1
+        # the order of the detections is the order of the boxes (score descending) on both sides
+        common = [ck for ck in [ck_of(c) for _, _, c, _ in g] if ck in wd]
+        assert common == [ck for ck in [ck_of(c) for _, _, c, _ in w] if ck in gd]
     assert total >= min_total, total
-    assert reordered <= 0.1 * total, (reordered, total)          # ties are the exception (3 % of the instances measured)
+    assert n_tie <= 0.15 * total and n_ulp <= 0.03 * total + 1 and flipped <= 0.03 * total + 1, (n_tie, n_ulp, flipped, total)
 
 
 def _scene_batch(synth, seeds, H, W, N, C=8, n_dup=2):
@@ -77,8 +113,9 @@ def test_decode_output_at_config_size(mods, name, H, W, B, N, n_dup, min_total, 
     synth, dec, rd = mods["synth"], mods["decode"], mods["rd"]
     if name not in _cases:                  # inputs + the oracle's answer, shared by the two parametrisations
         batch = _scene_batch(synth, [5000 + 17 * b + N for b in range(B)], H, W, N, n_dup=n_dup)
-        _cases[name] = (batch, rd.decode_output(H, W, ((batch[0], batch[1], None), batch[2], batch[3], batch[4]), kp_th=20000))
-    (kp, ae, reg, cls, anc), want = _cases[name]
+        _cases[name] = (batch, rd.decode_output(H, W, ((batch[0], batch[1], None), batch[2], batch[3], batch[4]), kp_th=20000),
+                        _tie_instances(rd, *batch, H, W, 20000))
+    (kp, ae, reg, cls, anc), want, ties = _cases[name]
     infos = [TransInfo("/nonexistent.png", (H, W))] * B
     if where == "device":
         outs = ((kp.to(DEV), ae.to(DEV), None), reg.to(DEV), cls.to(DEV), anc.to(DEV))
@@ -90,7 +127,7 @@ def test_decode_output_at_config_size(mods, name, H, W, B, N, n_dup, min_total, 
         got = dec.decode_output(torch.empty((B, 3, H, W), device="meta"), outs, infos, IdentityTransforms(), DecodeCfg(), torch.device(DEV))
     finally:
         dec.decode_mode, dec.host_chunk_images = saved
-    _same_detections(dec, got, want, (H, W), min_total)
+    _same_detections(got, want, ties, min_total)
 
 
 def test_mask_nms_at_config5_size(mods):
@@ -156,10 +193,11 @@ def test_install_dropin_drives_the_reference_caller_shape(mods, tmp_path):
             d = inputs.device
             return (kp.to(d), ae.to(d), torch.zeros((B, 2, H, W), device=d)), reg.to(d), cls.to(d), anc.to(d)
         dets, dets_json, infos_json = eval_util.eval_outputs(loader, IdentityTransforms(), model, DecodeCfg(kp_th=3000), torch.device(DEV))
-        want = []
+        want, ties = [], []
         for kp, ae, reg, cls, anc in batches:
             want += rd.decode_output(H, W, ((kp, ae, None), reg, cls, anc), kp_th=3000)
-        _same_detections(decode, dets, want, (H, W), 20)
+            ties += _tie_instances(rd, kp, ae, reg, cls, anc, H, W, 3000)
+        _same_detections(dets, want, ties, 20)
         import json
         back = json.loads(dets_json)
         assert len(back) == 4 and len(back[0][0]) == 4 and isinstance(back[0][0][0], int) and isinstance(back[0][0][3][0][0], float)
