@@ -619,6 +619,7 @@ host_chunk_images = int(os.environ.get("ISG_HOST_CHUNK", "2"))
 # pinned host outputs: upload only kp and classification; the kernels gather `ae` at the keep pixels and `regression` at
 # the candidate anchors straight from the pinned buffers (the reference's own amount of work, :312-315,:395-398)
 host_zero_copy = os.environ.get("ISG_HOST_ZERO_COPY", "1") != "0"
+e2e_trace = os.environ.get("ISG_E2E_TRACE", "0") == "1"       # host timeline of the zero-copy path in last_timing["trace_ms"]
 _copy_streams = {}
 _rings = {}
 
@@ -703,8 +704,9 @@ def _decode_output_zero_copy(inputs, kp_h, ae_h, reg_h, cls_h, anc, infos, trans
     """decode_output for PINNED host outputs.  Only kp and classification are uploaded (every element of them is
     needed: top-k / 3x3 maxima and the class maximum); `ae` is gathered at the ~k keep pixels and `regression` at the
     candidate anchors by the kernels themselves, out of the pinned buffers.  All uploads are enqueued up front on the copy
-    stream; chunk c is decoded by slot c mod 2 of a two-slot ring (isg_decode_step, sparse assignment + device polygon
-    stage), so the kernels of a chunk overlap the read-back and list assembly of the previous one."""
+    stream; the chunks go through two-slot rings (isg_decode_step, sparse assignment + device polygon stage), so the
+    kernels of a chunk overlap the read-back and list assembly of the previous one.  The last chunk is decoded image by
+    image: what follows the end of the upload (kernel chain, read-back, assembly of the last piece) is the exposed tail."""
     import time as _time
     B, H, W = kp_h.shape[0], kp_h.shape[-2], kp_h.shape[-1]
     height, width = inputs.shape[2], inputs.shape[3]
@@ -712,57 +714,71 @@ def _decode_output_zero_copy(inputs, kp_h, ae_h, reg_h, cls_h, anc, infos, trans
     size_key = (A, C, H, W, int(decode_cfg.kp_th))
     sizes = _learned_sizes.get(size_key, (1024, 256, 0))
 
-    def get_ring():
-        return _get_ring(2, cb, A, C, H, W, height, width, int(decode_cfg.kp_th), dev, sizes[0], sizes[1], sizes[2],
+    spans = [(b0, min(cb, B - b0)) for b0 in range(0, B, cb)]
+    if spans[-1][1] > 1:                                            # shorter tail: the last chunk image by image
+        b0, nb = spans.pop()
+        spans += [(b, 1) for b in range(b0, b0 + nb)]
+    # one ring slot per chunk (up to 4 per chunk size): every chunk is submitted right away - its kernels wait for its
+    # upload on the device - and the host only ever blocks on results
+    n_slots = {nb: min(4, sum(1 for _, m in spans if m == nb)) for _, nb in spans}
+
+    def get_ring(nb):
+        return _get_ring(n_slots[nb], nb, A, C, H, W, height, width, int(decode_cfg.kp_th), dev, sizes[0], sizes[1], sizes[2],
                          float(decode_cfg.wh_delta), float(compute_scale(None)))
-    ring = get_ring()
+    trace = [] if e2e_trace else None
+    _t_start = _time.perf_counter()
     chunks = []
     with torch.cuda.stream(cs):
-        for b0 in range(0, B - B % cb, cb):
-            kp_d = kp_h[b0:b0 + cb].to(dev, non_blocking=True)
-            cls_d = cls_h[b0:b0 + cb].to(dev, non_blocking=True)
+        for b0, nb in spans:
+            kp_d = kp_h[b0:b0 + nb].to(dev, non_blocking=True)
+            cls_d = cls_h[b0:b0 + nb].to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(cs)
-            chunks.append((b0, kp_d, cls_d, ev))
+            chunks.append((b0, nb, kp_d, cls_d, ev))
     dets, pending, host_s, d2h = [], [], 0.0, 0
 
-    def submit(r, b0, kp_d, cls_d):
-        return r.submit(kp_d, ae_h[b0:b0 + cb], anc, reg_h[b0:b0 + cb], cls_d, decode_cfg.cls_th, decode_cfg.iou_th,
-                        obj_pixel_th=int(decode_cfg.obj_pixel_th), assign="sparse", fetch=True)
+    def submit(b0, nb, kp_d, cls_d):
+        r = get_ring(nb)
+        return r, r.submit(kp_d, ae_h[b0:b0 + nb], anc, reg_h[b0:b0 + nb], cls_d, decode_cfg.cls_th, decode_cfg.iou_th,
+                           obj_pixel_th=int(decode_cfg.obj_pixel_th), assign="sparse", fetch=True)
 
-    def finish(r, slot, b0, kp_d, cls_d):
-        nonlocal host_s, d2h, sizes, ring
+    def finish(r, slot, b0, nb, kp_d, cls_d):
+        nonlocal host_s, d2h, sizes
         pipe = r.pipes[slot]
         d2h += pipe.bplan.arena.wait()
+        if trace is not None:
+            trace.append(("images %d-%d on host" % (b0, b0 + nb - 1), _time.perf_counter() - _t_start))
         over = _plan_overflow(pipe, sparse=True)
         while over is not None:     # more candidates / kept boxes / keep pixels than planned: larger plans from here on
             sizes = (max(sizes[0], over[0]), max(sizes[1], over[1]), max(sizes[2], over[2]))
             _learned_sizes[size_key] = sizes
-            ring = get_ring()
-            r = ring
-            slot = submit(r, b0, kp_d, cls_d)
+            r, slot = submit(b0, nb, kp_d, cls_d)
             pipe = r.pipes[slot]
             d2h += pipe.bplan.arena.wait()
             over = _plan_overflow(pipe, sparse=True)
         t0 = _time.perf_counter()
-        out = _dets_from_arena(pipe, cb)
+        out = _dets_from_arena(pipe, nb)
         host_s += _time.perf_counter() - t0
         return out
 
-    for b0, kp_d, cls_d, ev in chunks:
-        if len(pending) == len(ring.pipes) or (pending and pending[0][0] is not ring):
+    if trace is not None:
+        trace.append(("uploads enqueued", _time.perf_counter() - _t_start))
+    for b0, nb, kp_d, cls_d, ev in chunks:
+        r = get_ring(nb)
+        while sum(1 for p in pending if p[0] is r) >= len(r.pipes):   # a ring slot (round-robin) is read before it is reused
             dets += finish(*pending.pop(0))
         main.wait_event(ev)
-        pending.append((ring, submit(ring, b0, kp_d, cls_d), b0, kp_d, cls_d))
+        r, slot = submit(b0, nb, kp_d, cls_d)
+        pending.append((r, slot, b0, nb, kp_d, cls_d))
+        if trace is not None:
+            trace.append(("images %d-%d submitted" % (b0, b0 + nb - 1), _time.perf_counter() - _t_start))
     while pending:
         dets += finish(*pending.pop(0))
-    if B % cb:                     # ragged last chunk: the ring's plans are sized for `cb` images
-        sl = slice(B - B % cb, B)
-        dets += _decode_output_batch(inputs[sl] if inputs.shape[0] == B else inputs, ((kp_h[sl], ae_h[sl], None), reg_h[sl], cls_h[sl], anc),
-                                     infos[sl], transforms, decode_cfg, dev)
-        d2h += int(last_timing.get("d2h_bytes", 0))
+    if trace is not None:
+        trace.append(("all lists assembled", _time.perf_counter() - _t_start))
+        last_timing["trace_ms"] = [(n, round(1e3 * t, 3)) for n, t in trace]
     last_timing.update(d2h_bytes=d2h, readback_s=0.0, host_polygons_s=host_s,
-                       h2d_bytes=sum(c[1].numel() * 4 + c[2].numel() * 4 for c in chunks))
+                       h2d_bytes=sum(c[2].numel() * 4 + c[3].numel() * 4 for c in chunks))
     return dets
 
 

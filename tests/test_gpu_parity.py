@@ -747,7 +747,7 @@ def test_decode_output_zero_copy_equals_device_batch(mods, B):
                                  cfg, torch.device(DEV))
     finally:
         dec.decode_mode, dec.host_chunk_images, dec.host_zero_copy = saved
-    assert h2d == (B - B % 2) * (kp[0].numel() + cls[0].numel()) * 4         # kp + classification only
+    assert h2d == B * (kp[0].numel() + cls[0].numel()) * 4                   # kp + classification only
     assert torch.equal(pinned[0][1], ae_before)                              # inputs are not modified
     assert len(got) == len(want) == B and len(got[1]) == 0 and sum(len(g) for g in got) > 20
     for res in (got, again, uploaded):
