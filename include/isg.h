@@ -263,7 +263,7 @@ int isg_mask_pair_counts(const uint32_t* masks, int n, int H, int Wwords, const 
  * BLOCKING only at its end (it synchronises `stream` once to return the iteration count / status).
  * X [M,D] fp32, centers [N,D] fp32 in/out, allow [N] fp32, labels [M] int32 out (N = outlier; labels of the
  * LAST assignment, i.e. w.r.t. the pre-update centres, :93), iters_host: host int* (nullable).
- * max_iter <= 0: no bound (like the reference).  D <= 16; N*(12*D + 8) + 128*(4*D + 4) bytes of shared memory <= 200 KB.
+ * max_iter <= 0: no bound (like the reference).  D <= 16; N*(12*D + 8) bytes of shared memory <= 200 KB.
  * The per-cluster mean is accumulated in fp64 in a fixed order (reproducible); the reference's fp32 mean
  * differs by ~1e-7 relative.
  * ------------------------------------------------------------------------------------------ */

@@ -174,6 +174,7 @@ struct Tuning {
   int dense_v1 = 0;          // ISG_DENSE_V1=1: plain-LDG kernel (also serves W % 4 != 0)
   int dense_v1_rw = 4;       // ISG_DENSE_RW: rows per warp of the v1 kernel
   int dense_spare = 0;       // ISG_DENSE_SPARE: SMs the persistent dense kernel leaves to concurrently running kernels
+  int dense_skip_ae = 1;     // ISG_DENSE_SKIP_AE=0: load the ae planes of tiles no seed box overlaps too (A/B measurements)
   int topk_radix = 0;        // ISG_TOPK_PATH=radix: sampling-free two-level radix select
   int topk_cluster_sample = 0;   // ISG_TOPK_SAMPLE=cluster
 };

@@ -273,7 +273,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
                 int Wwords, int tilesX, int tilesY, int nstages, int cap, const unsigned char* __restrict__ lists,
                 const uint16_t* __restrict__ ovf, const float* __restrict__ ys, const float* __restrict__ xs,
                 int32_t* __restrict__ label_map, float* __restrict__ score_map, uint32_t* __restrict__ keepbits,
-                int32_t* __restrict__ stats, unsigned int* __restrict__ sched, int dyn_tail, int dbg_flags) {
+                int32_t* __restrict__ stats, unsigned int* __restrict__ sched, int dyn_tail, int dbg_flags, int skip_ae) {
   static_assert(RW % 2 == 0, "rows are processed in pairs");
   using Geo = D4Geom<RW, WG>;
   constexpr int kConsumers = WG * G;
@@ -316,6 +316,14 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
     unsigned t;
     if (n_static > 0) { t = blockIdx.x; i_static = 1; }
     else { t = dyn; dyn = (t < T) ? T_s + atomicAdd(&sched[0], 1u) : T; }
+    // Seeds overlapping the tile (header word 3 of its list), fetched one tile ahead so that the load is in flight
+    // while the producer waits for a free slot.  A tile that no seed box overlaps needs no embedding at all - every
+    // pixel outside all boxes gets label 0 (utils/decode.py:325-328) - so its four ae planes (3/4 of a tile's bytes)
+    // are not loaded.
+    auto nhit_of = [&](unsigned tt) -> int {
+      return tt < T ? __ldg(reinterpret_cast<const int*>(lists + (size_t)tt * list_bytes) + 3) : 0;
+    };
+    int nh = nhit_of(t);
     while (t < T) {
       const int b = (int)(t / (unsigned)tiles_per_img);
       const int rem = (int)t - b * tiles_per_img;
@@ -325,10 +333,11 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
       if (round >= 1) d4_wait_parked(&empty[slot], (uint32_t)((round - 1) & 1));
       unsigned char* st = smem + L.stage + (size_t)slot * Geo::kStage;
       s_thr[slot] = __ldg(thr_key + b);          // ordinary store: released to the consumers by the arrive below
-      mbar_expect_tx(&full[slot], Geo::kTx + list_bytes);
+      const bool with_ae = nh > 0 || skip_ae == 0;
+      mbar_expect_tx(&full[slot], (with_ae ? Geo::kTx : (uint32_t)Geo::kKpBytes) + list_bytes);
       bulk_g2s(smem + L.list + (size_t)slot * L.list_stride, lists + (size_t)t * list_bytes, list_bytes, &full[slot]);
       d4_tma_3d(st, &tm_kp, x0t - 4, y0t - 1, b, &full[slot]);
-      d4_tma_4d(st + Geo::kKpStage, &tm_ae, x0t, y0t, 0, b, &full[slot]);
+      if (with_ae) d4_tma_4d(st + Geo::kKpStage, &tm_ae, x0t, y0t, 0, b, &full[slot]);
       if (++slot == nstages) { slot = 0; ++round; }
       if (i_static < n_static) {
         t = blockIdx.x + (i_static++) * P;
@@ -336,6 +345,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
         t = dyn;
         dyn = (t < T) ? T_s + atomicAdd(&sched[0], 1u) : T;
       }
+      nh = nhit_of(t);
     }
     // one end marker per consumer group (the next G stages cover every group once)
     for (int g = 0; g < G; ++g) {
@@ -408,6 +418,13 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
           }
         }
 
+        float bq[2][4];
+        int lab[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { bq[r][i] = kQZero; lab[r][i] = 0; }
+        if (nhit > 0 || skip_ae == 0) {                                      // tile-uniform
         // --- embedding of the lane's 2 x 4 pixels ---
         float ey[2][4], ex[2][4], sy[2][4], sx[2][4];
         {
@@ -447,12 +464,6 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
         }
 
         // --- membership: smallest exponent among the seeds whose box contains the pixel, ascending seed index ---
-        float bq[2][4];
-        int lab[2][4];
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { bq[r][i] = kQZero; lab[r][i] = 0; }
         auto visit = [&](const int4 bx, const int4 cw) {                      // y0,y1,x0,x1 | cy,cx,id,pad (warp-uniform)
           const bool in0 = (y >= bx.x) && (y <= bx.y), in1 = (y + 1 >= bx.x) && (y + 1 <= bx.y);
           if (!(in0 || in1)) return;                                           // row test
@@ -487,6 +498,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
           const int4* g = reinterpret_cast<const int4*>(seeds + (size_t)b * Nmax + id);
           visit(__ldg(g), __ldg(g + 1));
         }
+        }   // nhit > 0
 
         // --- stores + statistics of the keep pixels ---
         if (colvalid) {
@@ -608,6 +620,7 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   const int threads = 32 * (WG * G + 1);
   const int dyn_tail = tn.dense_tail;                 // tiles per CTA left to the dynamic scheduler
   const int dbg_flags = tn.dense_debug;               // measurement aid: bit 0 = consumers release tiles without computing
+  const int skip_ae = tn.dense_skip_ae;               // seedless tiles: label 0 without loading the ae planes
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -622,12 +635,12 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
     ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, true>, tm_kp, tm_ae, thr_key, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
                                 tilesY, nstages, cap, clists, covf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail,
-                                dbg_flags));
+                                dbg_flags, skip_ae));
   } else {
     ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, false>, tm_kp, tm_ae, thr_key, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
                                 tilesY, nstages, cap, clists, covf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail,
-                                dbg_flags));
+                                dbg_flags, skip_ae));
   }
   ISG_LAUNCH_CHECK();
   return ISG_OK;

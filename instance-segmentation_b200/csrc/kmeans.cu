@@ -3,25 +3,28 @@
 //
 // The whole Lloyd loop is ONE cooperative launch (kmeans_loop_kernel): the host never looks at the convergence flag
 // mid-run.  Per iteration:
-//   assign   thread per point against the centres staged in shared memory -> label (first index on ties, :57; outlier
-//            label N unless min distance < allow, :60-61), written to global and kept in a shared slab with the point;
-//   update   per CTA: walk the slab once in point order; the thread that owns cluster (label mod blockDim) adds the point
-//            to that cluster's fp64 accumulator in shared memory - exclusive ownership, so no atomics and a fixed
-//            order of additions.  The CTA's partial sums / counts go to the workspace;           O(M) work
+//   assign   four threads per point, each against a quarter of the centres staged in shared memory, merged in index
+//            order -> label (first index on ties, :57; outlier label N unless min distance < allow, :60-61);
+//   update   per CTA, without atomics and in a fixed order: inside a warp the lowest lane of every label group
+//            (match.any) adds its members in lane order, then the point warps add their groups to the CTA's fp64
+//            accumulators in shared memory one warp after the other.  The CTA's partial sums / counts go to the
+//            workspace;                                                                           O(M) work
 //   -- grid barrier --
 //   finish   warp per cluster: partials of all CTAs in CTA order (lane-strided + a fixed shuffle tree) -> mean ->
 //            new centre (unchanged when empty, :74) and its shift (:72);                           O(N * CTAs) work
 //   -- grid barrier --
 //   every CTA adds the shifts in cluster order in fp32 (:64,72) and takes the same `center_shift^2 < tol` decision (:90).
-// The additions of one cluster happen in ascending point order inside a CTA and in CTA order across CTAs: results are
-// reproducible run to run.  The mean is accumulated in fp64 (the reference's fp32 `mean` differs by ~1e-7 relative).
+// The additions of one cluster happen in a fixed order (lane order inside a warp, warp order inside a CTA, CTA order
+// across CTAs): results are reproducible run to run.  The mean is accumulated in fp64 (the reference's fp32 `mean` differs by ~1e-7 relative).
 #include <algorithm>
 #include "common.cuh"
 
 namespace isg {
 
 constexpr int kMaxD = 16;
-constexpr int kKmThreads = 128;      // power of two: cluster ownership is `label & (kKmThreads - 1)`
+constexpr int kKmPoints = 128;       // points per CTA chunk
+constexpr int kKmSlices = 4;         // threads per point: each scans a quarter of the centres
+constexpr int kKmThreads = kKmPoints * kKmSlices;
 constexpr int kKmMaxCtas = 2 * kSMs;
 
 struct KmeansState {   // lives in the workspace
@@ -75,16 +78,18 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-// nearest centre of one point: (distance, index) with torch.min's first-index rule (:57)
+// nearest centre of one point among the centres [j0, j1): (distance, index) with torch.min's first-index rule (:57);
+// an empty range returns (+inf, N)
 template <int METRIC, int DT>
-__device__ __forceinline__ void nearest(const float* x, const float* sc, const float* sn, int N, int D, float& best, int& arg) {
+__device__ __forceinline__ void nearest(const float* x, const float* sc, const float* sn, int j0, int j1, int N, int D,
+                                        float& best, int& arg) {
   const int DD = DT > 0 ? DT : D;
+  best = INFINITY; arg = N;
   if (METRIC == ISG_KMEANS_EUCLIDEAN) {
     // sqrt is monotone: a centre whose SQUARED distance is not below the best one cannot win the strict `<` on the
     // rounded square roots, so the square root is only taken for improving candidates
-    float best_s = 0.0f;
-    best = 0.0f; arg = 0;
-    for (int j = 0; j < N; ++j) {
+    float best_s = INFINITY;
+    for (int j = j0; j < j1; ++j) {
       const float* c = sc + j * DD;
       float s = 0.0f;
 #pragma unroll
@@ -93,22 +98,25 @@ __device__ __forceinline__ void nearest(const float* x, const float* sc, const f
         const float q = __fmul_rn(t, t);
         s = (d == 0) ? q : __fadd_rn(s, q);
       }
-      if (j == 0 || s < best_s) {
+      if (j == j0 || s < best_s) {
         const float r = __fsqrt_rn(s);
-        if (j == 0 || r < best) { best = r; arg = j; }
+        if (j == j0 || r < best) { best = r; arg = j; }
         best_s = s;
       }
     }
   } else {
     const float xn = vec_norm(x, DD);
-    best = 0.0f; arg = 0;
-    for (int j = 0; j < N; ++j) {
+    for (int j = j0; j < j1; ++j) {
       const float dj = point_dist<METRIC>(x, sc + j * DD, DD, xn, sn[j]);
-      if (j == 0 || dj < best) { best = dj; arg = j; }
+      if (j == j0 || dj < best) { best = dj; arg = j; }
     }
   }
 }
 
+// A CTA works on chunks of kKmPoints points with kKmSlices threads per point: thread (slice s, point p) = s * kKmPoints
+// + p scans the contiguous centre range of its slice (all lanes of a warp read the same centre: broadcast), the slices
+// are merged in ascending order with a strict `<` (first index on ties).  More warps per SM hide the latency of the
+// dependent compare chain; the loop itself is too short to fill the machine with one thread per point.
 template <int METRIC, int DT>
 __global__ void __launch_bounds__(kKmThreads)
 kmeans_loop_kernel(const float* __restrict__ X, int M, int D, float* __restrict__ centers, const float* __restrict__ allow,
@@ -121,11 +129,14 @@ kmeans_loop_kernel(const float* __restrict__ X, int M, int D, float* __restrict_
   float* sc = reinterpret_cast<float*>(acc + (size_t)N * DD);       // [N*DD] centres
   float* sn = sc + (size_t)N * DD;                                  // [N]    centre norms (cosine) / shifts (finish)
   int32_t* cnt = reinterpret_cast<int32_t*>(sn + N);                // [N]
-  float* sx = reinterpret_cast<float*>(cnt + N);                    // [kKmThreads*DD] slab: points of the chunk
-  int32_t* sl = reinterpret_cast<int32_t*>(sx + kKmThreads * DD);   // [kKmThreads]    slab: their labels
+  __shared__ float s_best[kKmSlices][kKmPoints];
+  __shared__ int s_arg[kKmSlices][kKmPoints];
   __shared__ int s_done;
   const int t = threadIdx.x, G = gridDim.x, cta = blockIdx.x;
-  const int lane = t & 31;
+  const int lane = t & 31, warp = t >> 5;
+  const int slice = t / kKmPoints, p = t - slice * kKmPoints;
+  const int per = (N + kKmSlices - 1) / kKmSlices;
+  const int j0 = min(slice * per, N), j1 = min(j0 + per, N);
   unsigned int epoch = 0;
   int it = 0;
   for (;;) {
@@ -136,27 +147,52 @@ kmeans_loop_kernel(const float* __restrict__ X, int M, int D, float* __restrict_
       for (int i = t; i < N; i += kKmThreads) sn[i] = vec_norm(sc + i * DD, DD);
       __syncthreads();
     }
-    for (int base = cta * kKmThreads; base < M; base += G * kKmThreads) {
-      const int m = base + t;
-      int lab = -1;
+    for (int base = cta * kKmPoints; base < M; base += G * kKmPoints) {
+      const int m = base + p;
+      float x[DT > 0 ? DT : kMaxD];
+      float best = INFINITY;
+      int arg = N;
       if (m < M) {
-        float x[DT > 0 ? DT : kMaxD];
 #pragma unroll
-        for (int d = 0; d < DD; ++d) { x[d] = X[(size_t)m * DD + d]; sx[t * DD + d] = x[d]; }
-        float best; int arg;
-        nearest<METRIC, DT>(x, sc, sn, N, D, best, arg);
-        lab = (best < allow[arg]) ? arg : N;       // strict (:60-61)
+        for (int d = 0; d < DD; ++d) x[d] = X[(size_t)m * DD + d];
+        nearest<METRIC, DT>(x, sc, sn, j0, j1, N, D, best, arg);
+      }
+      s_best[slice][p] = best; s_arg[slice][p] = arg;
+      __syncthreads();
+      int lab = -1;
+      if (slice == 0 && m < M) {
+#pragma unroll
+        for (int s2 = 1; s2 < kKmSlices; ++s2) {
+          const float b2 = s_best[s2][p];
+          if (b2 < best) { best = b2; arg = s_arg[s2][p]; }       // strict: the earlier slice (lower indices) keeps ties
+        }
+        lab = (best < allow[arg]) ? arg : N;                       // strict (:60-61)
         labels[m] = lab;
       }
-      sl[t] = lab;
-      __syncthreads();
-      const int n_chunk = min(kKmThreads, M - base);
-      for (int i = 0; i < n_chunk; ++i) {          // ascending point order; thread (label mod blockDim) owns the cluster
-        const int l = sl[i];
-        if (l < N && (l & (kKmThreads - 1)) == t) {
-          cnt[l] += 1;
+      // per-cluster sums of the chunk, deterministic and without atomics: inside a warp the lowest lane of every label
+      // group adds its members in lane order (shuffles); the point warps then update the CTA's accumulators one after
+      // the other (leaders of one warp hold distinct labels)
+      if (slice == 0) {
+        const bool valid = lab >= 0 && lab < N;
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? lab : -1 - lane);
+        const bool leader = valid && lane == __ffs(peers) - 1;
+        double a[DT > 0 ? DT : kMaxD];
 #pragma unroll
-          for (int d = 0; d < DD; ++d) acc[l * DD + d] += (double)sx[i * DD + d];
+        for (int d = 0; d < DD; ++d) a[d] = 0.0;
+        for (int src = 0; src < 32; ++src) {
+#pragma unroll
+          for (int d = 0; d < DD; ++d) {
+            const float xv = __shfl_sync(0xffffffffu, (m < M) ? x[d] : 0.0f, src);
+            if (leader && ((peers >> src) & 1u)) a[d] += (double)xv;
+          }
+        }
+        for (int w = 0; w < kKmPoints / 32; ++w) {
+          if (warp == w && leader) {
+            cnt[lab] += __popc(peers);
+#pragma unroll
+            for (int d = 0; d < DD; ++d) acc[lab * DD + d] += a[d];
+          }
+          asm volatile("bar.sync 1, %0;" :: "n"(kKmPoints) : "memory");   // the point warps only
         }
       }
       __syncthreads();
@@ -166,7 +202,7 @@ kmeans_loop_kernel(const float* __restrict__ X, int M, int D, float* __restrict_
     grid_barrier(&st->barrier, G, epoch);
 
     // finish: warp per cluster over the CTAs' partials
-    for (int k = cta * (kKmThreads / 32) + (t >> 5); k < N; k += G * (kKmThreads / 32)) {
+    for (int k = cta * (kKmThreads / 32) + warp; k < N; k += G * (kKmThreads / 32)) {
       double a[DT > 0 ? DT : kMaxD];
 #pragma unroll
       for (int d = 0; d < DD; ++d) a[d] = 0.0;
@@ -235,9 +271,9 @@ using namespace isg;
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static int km_max_ctas(int M) { return std::max(1, std::min(cdiv(M, kKmThreads), kKmMaxCtas)); }
+static int km_max_ctas(int M) { return std::max(1, std::min(cdiv(M, kKmPoints), kKmMaxCtas)); }
 static size_t km_smem_bytes(int N, int D) {
-  return (size_t)N * D * 8 + (size_t)N * D * 4 + (size_t)N * 8 + (size_t)kKmThreads * D * 4 + kKmThreads * 4;
+  return (size_t)N * D * 8 + (size_t)N * D * 4 + (size_t)N * 8;
 }
 
 extern "C" size_t isg_kmeans_workspace_bytes(int M, int N, int D) {
