@@ -115,6 +115,15 @@ __device__ __forceinline__ float exp_fast_ftz(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
   return fmaf(r * 0.693147182464599609375f, e, r);
 }
+// Bare ex2.approx.ftz(x * log2 e): the rounding of the product adds |x| * log2e * 2^-24 * ln2 (3e-7 relative at
+// |x| = 5.3, the sigma of a 200-unit-per-px^2 Gaussian) to the unit's 2 ulp.  Used for the per-pixel sigma of the DENSE
+// kernel only, where sigma scales the exponent q whose ORDER decides the label: a relative error d of sigma moves
+// exp(-q) by q*d - inside the 1e-5 membership tolerance up to q ~ 30, where the membership itself is below 1e-13.
+__device__ __forceinline__ float exp_bare_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.44269502162933349609375f));
+  return r;
+}
 // tanh: |x| < 0.55 -> x + x^3 * P(x^2) (degree-4 minimax fit, < 1 ulp); otherwise 1 - 2/(1 + e^{2|x|})
 __device__ __forceinline__ float tanh_poly(float x) {
   const float u = x * x;

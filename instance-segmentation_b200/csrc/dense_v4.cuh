@@ -32,6 +32,13 @@
 #include <cstdlib>
 #include "keep.cuh"
 
+// sigma = exp(ae[2:4]) of the dense kernel: the compensated form (<= 2 ulp) unless ISG_D4_BARE_SIGMA is defined
+#ifdef ISG_D4_BARE_SIGMA
+#define D4_SIGMA_EXP exp_bare_ftz
+#else
+#define D4_SIGMA_EXP exp_fast_ftz
+#endif
+
 namespace isg {
 
 constexpr int kD4TileW = 128;
@@ -438,8 +445,8 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
             const float4 a3 = *reinterpret_cast<const float4*>(ar + 3 * Geo::kAePlane);
             t0[r][0] = a0.x; t0[r][1] = a0.y; t0[r][2] = a0.z; t0[r][3] = a0.w;
             t1[r][0] = a1.x; t1[r][1] = a1.y; t1[r][2] = a1.z; t1[r][3] = a1.w;
-            sy[r][0] = exp_fast_ftz(a2.x); sy[r][1] = exp_fast_ftz(a2.y); sy[r][2] = exp_fast_ftz(a2.z); sy[r][3] = exp_fast_ftz(a2.w);
-            sx[r][0] = exp_fast_ftz(a3.x); sx[r][1] = exp_fast_ftz(a3.y); sx[r][2] = exp_fast_ftz(a3.z); sx[r][3] = exp_fast_ftz(a3.w);
+            sy[r][0] = D4_SIGMA_EXP(a2.x); sy[r][1] = D4_SIGMA_EXP(a2.y); sy[r][2] = D4_SIGMA_EXP(a2.z); sy[r][3] = D4_SIGMA_EXP(a2.w);
+            sx[r][0] = D4_SIGMA_EXP(a3.x); sx[r][1] = D4_SIGMA_EXP(a3.y); sx[r][2] = D4_SIGMA_EXP(a3.z); sx[r][3] = D4_SIGMA_EXP(a3.w);
           }
           float amax = 0.0f;
 #pragma unroll
