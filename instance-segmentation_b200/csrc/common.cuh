@@ -147,6 +147,48 @@ __device__ __forceinline__ float tanh_large(float x) {
 }
 __device__ __forceinline__ float tanh_fast(float x) { return fabsf(x) < 0.55f ? tanh_poly(x) : tanh_large(x); }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2) -----------------------------------------------------
+// Two IEEE round-to-nearest fp32 operations per issued instruction; every component is rounded exactly like the scalar
+// __fadd_rn / __fmul_rn / fmaf.  NOTE: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (unlike the scalar .rn
+// forms), so wherever the reference needs a separately rounded product and sum the final addition is done with scalar
+// __fadd_rn on the unpacked halves.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// tanh_poly on two values (the same operations as the scalar form, component by component)
+__device__ __forceinline__ f32x2 tanh_poly2(f32x2 x) {
+  const f32x2 u = mul2(x, x);
+  f32x2 p = pack2(-0.00661575747653842f, -0.00661575747653842f);
+  p = fma2(p, u, pack2(0.02131274715065956f, 0.02131274715065956f));
+  p = fma2(p, u, pack2(-0.053910065442323685f, -0.053910065442323685f));
+  p = fma2(p, u, pack2(0.13333117961883545f, 0.13333117961883545f));
+  p = fma2(p, u, pack2(-0.3333333134651184f, -0.3333333134651184f));
+  return fma2(mul2(x, u), p, x);
+}
+// exp_fast_ftz on two values
+__device__ __forceinline__ f32x2 exp_fast_ftz2(f32x2 x) {
+  const f32x2 hi = pack2(1.44269502162933349609375f, 1.44269502162933349609375f);
+  const f32x2 t = mul2(x, hi);
+  f32x2 e = fma2(x, hi, t ^ 0x8000000080000000ull);                       // x * L2E_HI - t (exact residual)
+  e = fma2(x, pack2(1.925963033500011e-8f, 1.925963033500011e-8f), e);
+  float t0, t1, r0, r1;
+  unpack2(t, t0, t1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1));
+  const f32x2 r = pack2(r0, r1);
+  return fma2(mul2(r, pack2(0.693147182464599609375f, 0.693147182464599609375f)), e, r);
+}
+
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

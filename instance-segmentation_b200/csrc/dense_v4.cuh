@@ -432,6 +432,73 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 4; ++i) { bq[r][i] = kQZero; lab[r][i] = 0; }
         if (nhit > 0 || skip_ae == 0) {                                      // tile-uniform
+#ifndef ISG_D4_SCALAR
+        // --- embedding of the lane's 2 x 4 pixels, two pixels per instruction (FADD2 / FMUL2 / FFMA2, common.cuh) ---
+        f32x2 ey[2][2], ex[2][2], sy[2][2], sx[2][2];
+        {
+          float4 a0[2], a1[2];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const float* ar = arow + (rp + r) * kD4TileW;
+            a0[r] = *reinterpret_cast<const float4*>(ar);
+            a1[r] = *reinterpret_cast<const float4*>(ar + Geo::kAePlane);
+            const float4 a2 = *reinterpret_cast<const float4*>(ar + 2 * Geo::kAePlane);
+            const float4 a3 = *reinterpret_cast<const float4*>(ar + 3 * Geo::kAePlane);
+            sy[r][0] = exp_fast_ftz2(pack2(a2.x, a2.y)); sy[r][1] = exp_fast_ftz2(pack2(a2.z, a2.w));
+            sx[r][0] = exp_fast_ftz2(pack2(a3.x, a3.y)); sx[r][1] = exp_fast_ftz2(pack2(a3.z, a3.w));
+          }
+          float amax = 0.0f;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a0[r].x), fabsf(a0[r].y)), fmaxf(fabsf(a0[r].z), fabsf(a0[r].w))));
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a1[r].x), fabsf(a1[r].y)), fmaxf(fabsf(a1[r].z), fabsf(a1[r].w))));
+          }
+          const bool small = __all_sync(0xffffffffu, amax < 0.55f);       // warp-uniform: polynomial branch only
+          const float yv[2] = {__ldg(ys + y), __ldg(ys + min(y + 1, H - 1))};
+          const f32x2 xs01 = pack2(xs4[0], xs4[1]), xs23 = pack2(xs4[2], xs4[3]);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const f32x2 yy = pack2(yv[r], yv[r]);
+            if (small) {
+              ey[r][0] = add2(tanh_poly2(pack2(a0[r].x, a0[r].y)), yy); ey[r][1] = add2(tanh_poly2(pack2(a0[r].z, a0[r].w)), yy);
+              ex[r][0] = add2(tanh_poly2(pack2(a1[r].x, a1[r].y)), xs01); ex[r][1] = add2(tanh_poly2(pack2(a1[r].z, a1[r].w)), xs23);
+            } else {
+              ey[r][0] = add2(pack2(tanh_fast(a0[r].x), tanh_fast(a0[r].y)), yy); ey[r][1] = add2(pack2(tanh_fast(a0[r].z), tanh_fast(a0[r].w)), yy);
+              ex[r][0] = add2(pack2(tanh_fast(a1[r].x), tanh_fast(a1[r].y)), xs01); ex[r][1] = add2(pack2(tanh_fast(a1[r].z), tanh_fast(a1[r].w)), xs23);
+            }
+          }
+        }
+
+        // --- membership: smallest exponent among the seeds whose box contains the pixel, ascending seed index ---
+        auto visit = [&](const int4 bx, const int4 cw) {                      // y0,y1,x0,x1 | cy,cx,id,pad (warp-uniform)
+          const bool in0 = (y >= bx.x) && (y <= bx.y), in1 = (y + 1 >= bx.x) && (y + 1 <= bx.y);
+          if (!(in0 || in1)) return;                                           // row test
+          const float cy = __int_as_float(cw.x), cx = __int_as_float(cw.y);
+          const f32x2 cy2 = pack2(cy, cy), cx2 = pack2(cx, cx);
+          const int id = cw.z;
+          const int lo = bx.z - x0, hi = bx.w - x0;                            // pixel i is inside iff lo <= i <= hi
+          bool pin[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pin[i] = (lo <= i) && (hi >= i);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (r == 0 ? in0 : in1) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                // (e - c)^2 * sigma per axis with separately rounded operations (:326-327); the two products are added
+                // with scalar FADDs (ptxas would contract a packed multiply + add into FFMA2)
+                const f32x2 dy = sub2(ey[r][h], cy2), dx = sub2(ex[r][h], cx2);
+                const f32x2 ty = mul2(mul2(dy, dy), sy[r][h]), tx = mul2(mul2(dx, dx), sx[r][h]);
+                float ty0, ty1, tx0, tx1;
+                unpack2(ty, ty0, ty1); unpack2(tx, tx0, tx1);
+                const float q0 = __fadd_rn(ty0, tx0), q1 = __fadd_rn(ty1, tx1);
+                if (pin[2 * h] && q0 < bq[r][2 * h]) { bq[r][2 * h] = q0; lab[r][2 * h] = id; }   // strict: first index wins ties (:328)
+                if (pin[2 * h + 1] && q1 < bq[r][2 * h + 1]) { bq[r][2 * h + 1] = q1; lab[r][2 * h + 1] = id; }
+              }
+            }
+          }
+        };
+#else
         // --- embedding of the lane's 2 x 4 pixels ---
         float ey[2][4], ex[2][4], sy[2][4], sx[2][4];
         {
@@ -497,6 +564,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
             }
           }
         };
+#endif
         for (int q = 0; q < nsm; ++q)
           visit(*reinterpret_cast<const int4*>(recs + q * (int)sizeof(SeedRec)),
                 *reinterpret_cast<const int4*>(recs + q * (int)sizeof(SeedRec) + 16));

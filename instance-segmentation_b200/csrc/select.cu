@@ -536,10 +536,14 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
       // survivors append themselves one by one (the candidate list is an unordered set).
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
+        // one test per 128-bit group first: its maximum below the bound rejects all four pixels (3 FMNMX + 1 compare
+        // instead of four compare-and-branch pairs; fmaxf drops NaN operands, and NaNs are outside the contract)
+        const float m4 = fmaxf(fmaxf(q[u].x, q[u].y), fmaxf(q[u].z, q[u].w));
+        if (!in[u] || m4 < lower_f) continue;
         const float x4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (in[u] && !(x4[i] < lower_f)) {
+          if (!(x4[i] < lower_f)) {
             const uint32_t kk = float_key(x4[i]);
             if (kk >= lower && kk <= upper && kk != 0xffffffffu) buf[atomicAdd(&s_count, 1u)] = kk;
           }
