@@ -34,4 +34,7 @@ full kmeans kmeans_loop 2 python bench.py --workload crowd_1024x2048_b4_n500_kme
 full mask_area mask_area 2 python bench.py --workload coco_800x1333_c80_n1000 --steps 2 --warmup 3 --no-e2e --no-cpu
 full mask_pair mask_pair 2 python bench.py --workload coco_800x1333_c80_n1000 --steps 2 --warmup 3 --no-e2e --no-cpu
 full nms_scan nms_scan 2 python bench.py --workload coco_800x1333_c80_n1000 --steps 2 --warmup 3 --no-e2e --no-cpu
+full fill_polygons fill_polygons 1 python tools/bench_fill.py
+python tools/bench_fill.py > $O/r2ev_fill_polygons.txt 2>&1
+python tools/overlap_experiment.py > $O/r2ev_overlap.txt 2>&1
 ls -la $O/r2ev_*.ncu-rep

@@ -74,6 +74,11 @@ if traffic.get("ncu:dense_wide"):
 if all(traffic.get("ncu:" + k) for k in ("mask_area", "mask_pair", "nms_scan")):
     traffic["coco_800x1333_c80_n1000"] = sum(traffic["ncu:" + k] for k in ("mask_area", "mask_pair", "nms_scan"))
 json.dump(traffic, open(os.path.join(P, "dense_traffic.json"), "w"), indent=1)
+for src, dst, head in (("_fill_polygons.txt", "r2_fill_polygons.txt", "# python tools/bench_fill.py on a B200\n"),
+                       ("_overlap.txt", "r2_overlap_ablation.txt", "# python tools/overlap_experiment.py on a B200 (ring = independent pipelines used round-robin; spare = SMs the dense\n# kernel leaves free, ISG_DENSE_SPARE; 200 steps per point, best of 2)\n")):
+    path = os.path.join(G, PREFIX + src)
+    if os.path.exists(path):
+        open(os.path.join(P, dst), "w").write(head + open(path).read())
 aux = os.path.join(G, PREFIX + "_aux_timings.txt")
 if os.path.exists(aux):
     open(os.path.join(P, "r2_aux_timings.txt"), "w").write("# python tests/aux_timings.py on a B200 (device time through the drop-in call incl. its read-back; CPU oracle on the box's host)\n" + open(aux).read())
