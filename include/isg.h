@@ -301,6 +301,18 @@ int isg_instance_polygons(const uint32_t* keepbits, const int32_t* label_map, co
                           int totals_zeroed, isg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f4 - the producer side: the 1x1 heads of EfficientDecoder at inference (models/efficient.py:508-510,536-541; heads
+ * {"kp": 1, "ae": 4, "tan": 2}, :608).  Computes the five channels the decode reads (`tan` is ignored by decode_output,
+ * utils/decode.py:447) in one pass over the decoder's last feature map x [B,Cin,H,W] (planar fp32, Cin <= 64, H*W % 4 == 0)
+ * and writes them in the decode's own layout: kp [B,1,H,W], ae [B,4,H,W].
+ * w_kp [1,Cin], b_kp [1], w_ae [4,Cin], b_ae [4]: HOST pointers (nn.Conv2d.weight / .bias of the kp and ae heads).
+ * out[c] = bias[c] + sum_k w[c][k] * x[k] with fp32 FMAs in channel order (cuDNN / oneDNN order the sum differently:
+ * equal to ~1e-6 relative, not bit for bit).
+ * ------------------------------------------------------------------------------------------ */
+int isg_decode_heads(const float* x, int B, int Cin, int H, int W, const float* w_kp, const float* b_kp,
+                     const float* w_ae, const float* b_ae, float* kp, float* ae, isg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * One whole decode step = decode_output (utils/decode.py:444-461) for a batch already visible to the device,
  * enqueued by a single host call: isg_decode_boxes -> isg_box_nms -> isg_gather_build_seeds (-> isg_build_tile_lists)
  * on `main`; isg_topk_threshold (ISG_ASSIGN_SPARSE: + isg_keep_points + isg_compact_points) on `side`, forked from and

@@ -83,6 +83,7 @@ PROTOTYPES = {
     "isg_instance_polygons_workspace_bytes": (SZ, [I, I]),
     "isg_instance_polygons": (I, [P, P, P, I, P, P, I, I, I, I, I, I, P, P, P, P, P, P, P, P, SZ, I, P]),
     "isg_fill_polygons": (I, [P, P, P, I, I, I, I, P, SZ, P, P, P]),
+    "isg_decode_heads": (I, [P, I, I, I, I, P, P, P, P, P, P, P]),
     "isg_decode_step": (I, [P]),
     "isg_decode_step_bytes": (SZ, []),
     "isg_host_point_in_polygon": (I, [P, I, F, F]),
@@ -141,7 +142,7 @@ _LAUNCHES = {
     "isg_compact_points": 1, "isg_build_seeds": 1, "isg_stats_init": 1, "isg_assign_sparse": 1,
     "isg_gather_build_seeds": 1, "isg_scatter_labels": 1, "isg_gather_embeddings": 1, "isg_build_tile_lists": 1, "isg_assign_dense": lambda a: 1 if a[21] else 2, "isg_gather_labels": 1, "isg_instance_polygons": lambda a: 1 if a[21] else 2, "isg_decode_boxes": 1,
     "isg_gather_kept": 1, "isg_mask_nms": 5, "isg_mask_pair_counts": 1, "isg_pairwise": 1,
-    "isg_bbox_transform": 1, "isg_clip_boxes": 1, "isg_generate_anchors": 1, "isg_pack_masks": 1, "isg_fill_polygons": 1,
+    "isg_bbox_transform": 1, "isg_clip_boxes": 1, "isg_generate_anchors": 1, "isg_decode_heads": 1, "isg_pack_masks": 1, "isg_fill_polygons": 1,
     # (idx,label,flag,count,cap,n_seeds,B,Nmax,...): one multisplit kernel unless the seed table is huge
     "isg_group_points": lambda a: 1 if (16 * a[7] + a[7] + 1 + a[4]) * 4 <= 200 * 1024 else 3,
     # (boxes,scores,cls,tiebreak,count,B,cap,...): fused single-CTA kernel for cap <= 1024

@@ -474,25 +474,30 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
     }
   }
   __syncthreads();
-  // greedy scan by warp 0, 64-box chunks, no block barriers.  Lane l holds the diagonal words of rows l and l + 32 of
-  // the chunk in registers; inside a chunk only the KEPT boxes cost a (dependent) step: the next kept box is the
-  // lowest still-alive bit and its word arrives by shuffle.  The kept rows are then OR-ed into the later words.
+  // greedy scan by warp 0, 64-box chunks, no block barriers.  The 64 dependent steps of a chunk run in ONE lane on
+  // registers (fully unrolled: test bit q of the running word, OR row q's diagonal word): ~12 cycles a step whether the
+  // box is kept or not, instead of a shuffle round trip (~180 cycles) per kept box.  The kept rows are then OR-ed into
+  // the later words by all lanes.
   int nk = 0;
   if (warp != 0) return;
   int32_t* out = keep + (size_t)b * cap;
   for (int c = 0; c < nw; ++c) {
     const int base = c * 64;
     const int m = min(64, n - base);
-    const unsigned long long w_lo = (lane < m) ? mask[(size_t)(base + lane) * nwP + c] : 0ull;
-    const unsigned long long w_hi = (lane + 32 < m) ? mask[(size_t)(base + 32 + lane) * nwP + c] : 0ull;
-    const unsigned long long valid = (m == 64) ? ~0ull : ((1ull << m) - 1ull);
-    unsigned long long alive = ~remv[c] & valid, kept = 0ull;
-    while (alive) {                                               // warp-uniform
-      const int q = __ffsll((long long)alive) - 1;
-      const unsigned long long lo_w = __shfl_sync(0xffffffffu, w_lo, q & 31), hi_w = __shfl_sync(0xffffffffu, w_hi, q & 31);
-      kept |= 1ull << q;
-      alive &= ~((q < 32 ? lo_w : hi_w) | (1ull << q));
+    unsigned long long kept = 0ull;
+    if (lane == 0) {
+      unsigned long long dq[64];
+#pragma unroll
+      for (int q = 0; q < 64; ++q) dq[q] = q < m ? mask[(size_t)(base + q) * nwP + c] : 0ull;
+      unsigned long long word = remv[c];
+#pragma unroll
+      for (int q = 0; q < 64; ++q) {
+        const bool take = q < m && !((word >> q) & 1ull);
+        kept |= take ? (1ull << q) : 0ull;
+        word |= take ? dq[q] : 0ull;
+      }
     }
+    kept = __shfl_sync(0xffffffffu, kept, 0);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int bit = lane + 32 * h;
@@ -877,6 +882,60 @@ extern "C" int isg_generate_anchors(int H, int W, const int* strides, int n_leve
   const unsigned blocks = (unsigned)cdiv64(p.first[n_levels], 256);
   if (half_precision) isg::anchors_kernel<__half><<<blocks, 256, 0, stream>>>(p, reinterpret_cast<__half*>(out));
   else isg::anchors_kernel<float><<<blocks, 256, 0, stream>>>(p, reinterpret_cast<float*>(out));
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
+}
+
+// ---- f4: the inference-time heads of EfficientDecoder (models/efficient.py:508-510,536-541) ---------------------------
+// The reference applies three 1x1 convolutions (kp: 1, ae: 4, tan: 2 channels) to the decoder's last feature map and the
+// decode then ignores `tan` (utils/decode.py:447).  This kernel computes only the five channels the decode reads, in
+// ONE pass over the feature map, straight into the planar fp32 layout isg_assign_dense / isg_topk_threshold consume:
+// out[c] = bias[c] + sum_k w[c][k] * x[k], accumulated in channel order with FMAs.  HBM-bound: 4*Cin B/px read, 20 B/px written.
+namespace isg {
+constexpr int kHeadMaxCin = 64;
+struct HeadParams { float w[5][kHeadMaxCin]; float b[5]; };
+
+__global__ void __launch_bounds__(256)
+decode_heads_kernel(const float* __restrict__ x, int Cin, long long plane, const __grid_constant__ HeadParams p,
+                    float* __restrict__ kp, float* __restrict__ ae) {
+  const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;      // first of 4 consecutive pixels
+  const int b = blockIdx.y;
+  if (q >= plane) return;
+  float4 acc[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) acc[c] = make_float4(p.b[c], p.b[c], p.b[c], p.b[c]);
+  const float* xb = x + (long long)b * Cin * plane + q;
+  for (int k = 0; k < Cin; ++k) {
+    const float4 v = ldg_stream4(xb + (long long)k * plane);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      const float w = p.w[c][k];
+      acc[c].x = fmaf(w, v.x, acc[c].x); acc[c].y = fmaf(w, v.y, acc[c].y);
+      acc[c].z = fmaf(w, v.z, acc[c].z); acc[c].w = fmaf(w, v.w, acc[c].w);
+    }
+  }
+  *reinterpret_cast<float4*>(kp + (long long)b * plane + q) = acc[0];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(ae + ((long long)b * 4 + c) * plane + q) = acc[1 + c];
+}
+}  // namespace isg
+
+extern "C" int isg_decode_heads(const float* x, int B, int Cin, int H, int W, const float* w_kp, const float* b_kp,
+                                const float* w_ae, const float* b_ae, float* kp, float* ae, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!x || !w_kp || !b_kp || !w_ae || !b_ae || !kp || !ae || B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
+  if (Cin > isg::kHeadMaxCin) return ISG_EUNSUPPORTED;
+  const long long plane = (long long)H * W;
+  if (plane % 4 != 0 || !aligned16(x) || !aligned16(kp) || !aligned16(ae)) return ISG_EUNSUPPORTED;
+  isg::HeadParams p = {};
+  for (int k = 0; k < Cin; ++k) {
+    p.w[0][k] = w_kp[k];
+    for (int c = 0; c < 4; ++c) p.w[1 + c][k] = w_ae[c * Cin + k];
+  }
+  p.b[0] = b_kp[0];
+  for (int c = 0; c < 4; ++c) p.b[1 + c] = b_ae[c];
+  dim3 grid((unsigned)cdiv64(plane / 4, 256), B);
+  isg::decode_heads_kernel<<<grid, 256, 0, stream>>>(x, Cin, plane, p, kp, ae);
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }

@@ -266,6 +266,18 @@ def main():
     np.savez_compressed(os.path.join(OUT, "anchors.npz"), **d)
     print("anchors", small.shape, int(d["count_1024x2048"]))
 
+    # ---- f4: the 1x1 heads of the reference's EfficientDecoder (models/efficient.py:508-510,536-541) -------------------------
+    from models.efficient import EfficientDecoder
+    torch.manual_seed(4)
+    dec_mod = EfficientDecoder([320, 112, 40, 24, 16], {"kp": 1, "ae": 4, "tan": 2}).eval()
+    xf = torch.randn(2, 16, 24, 40)
+    with torch.no_grad():
+        heads = [dec_mod.__getattr__(h)(xf) for h in dec_mod.headers.keys()]      # the loop at :537-539
+    np.savez_compressed(os.path.join(OUT, "heads.npz"), x=xf.numpy(), kp=heads[0].numpy(), ae=heads[1].numpy(),
+                        w_kp=dec_mod.kp.weight.detach().numpy(), b_kp=dec_mod.kp.bias.detach().numpy(),
+                        w_ae=dec_mod.ae.weight.detach().numpy(), b_ae=dec_mod.ae.bias.detach().numpy())
+    print("heads", [tuple(h.shape) for h in heads])
+
     # ---- kmeans / pairwise ---------------------------------------------------------------------------
     rs = np.random.RandomState(21)
     cen = rs.uniform(0, 1, size=(10, 2)).astype(np.float32)

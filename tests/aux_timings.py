@@ -55,5 +55,16 @@ md = torch.from_numpy(masks.view(np.int32)).to(dev)
 sc, cl = torch.from_numpy(scores).to(dev), torch.from_numpy(cls).to(dev)
 rows.append(("mask_nms n=1000 800x1333 C=80", gpu_ms(lambda: nms.mask_nms(md, sc, cl, 0.5), 3),
              cpu_ms(lambda: rk.mask_nms(masks, scores, cls, 0.5))))
+# f4: the kp / ae heads of the decoder at inference (B=8, 16 channels, 1024x2048): 64 B/px read + 20 B/px written
+from isg_b200.utils.heads import InferenceHeads
+kc, ac = torch.nn.Conv2d(16, 1, 1), torch.nn.Conv2d(16, 4, 1)
+heads = InferenceHeads(kc, ac)
+xf = torch.randn((8, 16, 1024, 2048), device=dev)
+g_ms = gpu_ms(lambda: heads(xf), 10)
+xc = xf[:1].cpu()
+c_ms = cpu_ms(lambda: (torch.nn.functional.conv2d(xc, kc.weight, kc.bias), torch.nn.functional.conv2d(xc, ac.weight, ac.bias),
+                       torch.nn.functional.conv2d(xc, torch.zeros(2, 16, 1, 1), None))) * 8
+rows.append(("decoder heads kp+ae B=8 16ch 1024x2048 (%.0f GB/s)" % (84 * 8 * 1024 * 2048 / g_ms / 1e6), g_ms, c_ms))
+del xf
 for name, g, c in rows:
-    print("%-48s device %9.3f ms   cpu oracle %10.2f ms" % (name, g, c), flush=True)
+    print("%-58s device %9.3f ms   cpu %10.2f ms" % (name, g, c), flush=True)

@@ -335,6 +335,29 @@ def test_anchors_golden(mods, golden):
         Anchors()(torch.empty((1, 3, 128, 256)))                       # no CPU path
 
 
+def test_inference_heads_golden(mods, golden):
+    """f4: the kp / ae heads of the reference's EfficientDecoder (1x1 convolutions, models/efficient.py:508-510,536-541) in
+    one pass, `tan` dropped; against the reference module's own outputs (fp32, summation order differs: rtol 1e-5)"""
+    from isg_b200.utils.heads import InferenceHeads
+    g = golden("heads")
+    kp_conv = torch.nn.Conv2d(16, 1, 1); ae_conv = torch.nn.Conv2d(16, 4, 1)
+    with torch.no_grad():
+        kp_conv.weight.copy_(torch.from_numpy(g["w_kp"])); kp_conv.bias.copy_(torch.from_numpy(g["b_kp"]))
+        ae_conv.weight.copy_(torch.from_numpy(g["w_ae"])); ae_conv.bias.copy_(torch.from_numpy(g["b_ae"]))
+    heads = InferenceHeads(kp_conv, ae_conv)
+    kp, ae, tan = heads(torch.from_numpy(g["x"]).to(DEV))
+    assert tan is None and kp.shape == (2, 1, 24, 40) and ae.shape == (2, 4, 24, 40)
+    np.testing.assert_allclose(kp.cpu().numpy(), g["kp"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ae.cpu().numpy(), g["ae"], rtol=1e-5, atol=1e-6)
+    # the outputs feed the decode directly: full-size planes, same layout as the model's
+    x = torch.randn((1, 16, 256, 512), device=DEV)
+    kp, ae, _ = heads(x)
+    want = torch.nn.functional.conv2d(x.cpu(), torch.from_numpy(g["w_ae"]), torch.from_numpy(g["b_ae"]))
+    np.testing.assert_allclose(ae.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        heads(torch.zeros(1, 16, 8, 8))
+
+
 def test_bbox_transform_and_clip_vs_oracle(mods, oracle, golden):
     rd, _ = oracle
     g = golden("decode_boxes")
