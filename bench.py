@@ -62,9 +62,6 @@ def parse_args():
     ap.add_argument("--inputs", default="default", choices=["default", "wide"],
                     help="wide: embedding offsets ae[0:2] ~ N(0,1) off the outlines (unbounded logits: the tanh of the dense "
                          "kernel takes its exp/divide branch instead of the |x| < 0.55 polynomial)")
-    ap.add_argument("--assign", default="onepass", choices=["onepass", "dense"],
-                    help="onepass: the dense kernel collects the top-k candidates while it streams kp (kp read once per step); "
-                         "dense: exact threshold first (sample -> filter -> select), then the dense kernel applies it.  Same results")
     ap.add_argument("--ring", type=int, default=4, help="independent pipelines used round-robin (1 = every step on its own)")
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling: decode this many images per step in total, sharded over the ranks (config 3: 64)")
@@ -451,7 +448,7 @@ def run_ours(args, wl, rank, world, local_rank):
 
     def submit(timed_kernel=False):
         return ring.submit(d["kp"], d["ae"], d["anchors"], d["regression"], d["classification"], CLS_TH, IOU_TH,
-                           obj_pixel_th=OBJ_PIXEL_TH, assign=args.assign, time_main=timed_kernel)
+                           obj_pixel_th=OBJ_PIXEL_TH, assign="dense", time_main=timed_kernel)
 
     # warm-up; the kept / candidate / keep-pixel counts of the batch for the config block
     for _ in range(max(args.warmup, 3)):
@@ -525,15 +522,14 @@ def run_ours(args, wl, rank, world, local_rank):
     p0.dplan.events = []
     for _ in range(KERNEL_TIMING_LAUNCHES):
         p0.run_native(d["kp"], d["ae"], d["anchors"], d["regression"], d["classification"], CLS_TH, IOU_TH, obj_pixel_th=OBJ_PIXEL_TH,
-                      assign=args.assign, time_main=True)
+                      assign="dense", time_main=True)
         torch.cuda.synchronize(dev)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in p0.dplan.events]))
     iso0, iso1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_iso = 50
     iso0.record()
     for _ in range(n_iso):
-        p0.run_native(d["kp"], d["ae"], d["anchors"], d["regression"], d["classification"], CLS_TH, IOU_TH, obj_pixel_th=OBJ_PIXEL_TH,
-                      assign=args.assign)
+        p0.run_native(d["kp"], d["ae"], d["anchors"], d["regression"], d["classification"], CLS_TH, IOU_TH, obj_pixel_th=OBJ_PIXEL_TH)
     iso1.record()
     torch.cuda.synchronize(dev)
     iso_ms = iso0.elapsed_time(iso1) / n_iso
@@ -615,11 +611,9 @@ def run_ours(args, wl, rank, world, local_rank):
             cpu["port_value"] = n_img * H * W / (time.perf_counter() - t0) / 1e6
     config = {"workload": args.workload, "inputs": args.inputs, "B_per_gpu": B, "H": H, "W": W, "seeds_per_image": [int(v) for v in n_keep[:8]],
               "candidates_per_image": [int(v) for v in n_cand[:8]], "keep_pixels_per_image": [int(v) for v in counts[:8]],
-              "anchors": A, "classes": C, "kp_th": wl["kp_th"], "mode": "dense", "assign": args.assign,
+              "anchors": A, "classes": C, "kp_th": wl["kp_th"], "mode": "dense",
               "l2": "inputs are %.0f MB per step (> 126 MB L2); no flush" % (sum(v.numel() * 4 for v in d.values()) / 1e6),
-              "step": ("box head + NMS + seeds + top-k sample + tile lists + fused assign (collects the top-k candidates) + exact threshold / peak test on the candidates"
-                       if args.assign == "onepass" else "box head + NMS + seeds + top-k (sample, filter, select) + tile lists + fused assign")
-                      + " + per-instance polygons (point sets, internal point, angular sort, centre test)"
+              "step": "box head + NMS + seeds + top-k + tile lists + fused assign + per-instance polygons (point sets, internal point, angular sort, centre test)"
                       + (" + k-means refinement of every image" if use_kmeans else ""),
               "pipelining": "steps go round-robin through %d independent pipelines (own plans / streams, one isg_decode_step call each); "
                             "neighbouring steps overlap, every step runs all of its kernels" % len(ring.pipes),

@@ -144,26 +144,6 @@ int isg_assign_sparse(const float* ae, int64_t img_stride, int64_t plane_stride,
                       const uint32_t* seeds, const float* ghost, const int32_t* n_seeds, int B, int Nmax,
                       int H, int W, const float* ys, const float* xs,
                       int32_t* label, float* score, uint8_t* flag, int32_t* stats, isg_stream_t stream);
-/* ONE-PASS selection + assignment (kp is read from HBM once per step instead of twice):
- *   isg_topk_sample          a conservative lower bound of the k-th largest kp value from a strided sample -> topk ws
- *                            (ISG_EUNSUPPORTED for H*W < 65536 or 4k > H*W: use isg_topk_threshold + isg_assign_dense);
- *   isg_assign_dense_onepass assigns every pixel like isg_assign_dense and appends every pixel >= that bound
- *                            (key, position) to the workspace's candidate list while it streams kp;
- *   isg_topk_finish          exact k-th largest key among the candidates -> thr_key[B]; the 3x3 peak test of select_points
- *                            (utils/decode.py:84-85) for the selected candidates only -> keepbits (zeroed by the call).
- *                            Images whose candidate list cannot contain the answer (fewer than k candidates, capacity
- *                            exceeded: plateaus, adversarial orderings) get the whole-image select + the ordinary keep pass,
- *                            so the result is always that of isg_topk_threshold + isg_keep_points.
- * ws: isg_topk_workspace_bytes(B, H, W, k) bytes, 256-byte aligned, shared by the three calls of a step. */
-int isg_topk_sample(const float* kp, int B, int H, int W, int64_t img_stride, int k, void* ws, size_t ws_bytes,
-                    isg_stream_t stream);
-int isg_assign_dense_onepass(const float* kp, int64_t kp_img_stride, const float* ae, int64_t ae_img_stride,
-                             int64_t ae_plane_stride, void* topk_ws, size_t topk_ws_bytes, int k,
-                             const uint32_t* seeds, const float* ghost, const int32_t* n_seeds, int B, int Nmax,
-                             int H, int W, const float* ys, const float* xs, int32_t* label_map, void* workspace,
-                             size_t workspace_bytes, int lists_prebuilt, isg_stream_t stream);
-int isg_topk_finish(const float* kp, int B, int H, int W, int64_t img_stride, int k, void* ws, size_t ws_bytes,
-                    uint32_t* thr_key, uint32_t* keepbits, isg_stream_t stream);
 /* label_map[b, idx[b,m]] = label[b,m] for the compacted keep pixels (m < min(count[b], cap)); every other element of
  * label_map is left untouched.  Lets the consumers of the dense label map (isg_instance_polygons, which looks labels up
  * at keep pixels only) run behind isg_assign_sparse. */
@@ -339,7 +319,6 @@ int isg_decode_heads(const float* x, int B, int Cin, int H, int W, const float* 
  * joined back into `main` with the two caller-owned events; then the assignment and (polygons != 0)
  * isg_instance_polygons on `main`.  Every pointer has the meaning documented at the entry point that consumes it.
  *   ISG_ASSIGN_DENSE : isg_assign_dense (label for every pixel; needs label_map, keepbits, dense_ws).
- *   ISG_ASSIGN_DENSE_ONEPASS: the same results with kp read once (falls back to ISG_ASSIGN_DENSE where unsupported).
  *   ISG_ASSIGN_SPARSE: isg_assign_sparse + isg_scatter_labels (keep pixels only; needs idx, count, label too).  In this
  *                      mode `ae` and `regression` may be DEVICE ADDRESSES OF MAPPED HOST MEMORY (isg_host_device_pointer):
  *                      they are only read at the keep pixels / candidate anchors, so the planes never cross PCIe.
@@ -348,7 +327,6 @@ int isg_decode_heads(const float* x, int B, int Cin, int H, int W, const float* 
  * ------------------------------------------------------------------------------------------ */
 #define ISG_ASSIGN_DENSE  0
 #define ISG_ASSIGN_SPARSE 1
-#define ISG_ASSIGN_DENSE_ONEPASS 2   /* isg_topk_sample (side) -> isg_assign_dense_onepass -> isg_topk_finish (main) */
 typedef struct isg_decode_step {
   int struct_bytes;
   int assign, polygons;

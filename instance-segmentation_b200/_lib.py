@@ -38,7 +38,7 @@ class DecodeStep(C.Structure):
     ]
 
 
-ISG_ASSIGN_DENSE, ISG_ASSIGN_SPARSE, ISG_ASSIGN_DENSE_ONEPASS = 0, 1, 2
+ISG_ASSIGN_DENSE, ISG_ASSIGN_SPARSE = 0, 1
 
 # name -> (restype, argtypes); mirrors include/isg.h one to one
 PROTOTYPES = {
@@ -57,9 +57,6 @@ PROTOTYPES = {
     "isg_stats_init": (I, [P, I, I, P]),
     "isg_gather_build_seeds": (I, [P, P, P, P, P, I, I, I, P, P, I, I, F, F, P, P, P, P, P, P, P, P, P]),
     "isg_assign_sparse": (I, [P, I64, I64, P, P, I, P, P, P, I, I, I, I, P, P, P, P, P, P, P]),
-    "isg_topk_sample": (I, [P, I, I, I, I64, I, P, SZ, P]),
-    "isg_assign_dense_onepass": (I, [P, I64, P, I64, I64, P, SZ, I, P, P, P, I, I, I, I, P, P, P, P, SZ, I, P]),
-    "isg_topk_finish": (I, [P, I, I, I, I64, I, P, SZ, P, P, P]),
     "isg_scatter_labels": (I, [P, P, I, P, I, I, I, P, P]),
     "isg_gather_embeddings": (I, [P, I64, I64, P, P, I, I, I, I, P, P, P, P]),
     "isg_host_device_pointer": (I, [P, P]),
@@ -143,8 +140,7 @@ launch_count = 0
 _LAUNCHES = {
     "isg_topk_threshold": 3, "isg_keep_points": 1, "isg_select_points": 4, "isg_nms_hm": 1,
     "isg_compact_points": 1, "isg_build_seeds": 1, "isg_stats_init": 1, "isg_assign_sparse": 1,
-    "isg_gather_build_seeds": 1, "isg_scatter_labels": 1, "isg_gather_embeddings": 1, "isg_topk_sample": 1, "isg_assign_dense_onepass": lambda a: 1 if a[20] else 2,
-    "isg_topk_finish": 3, "isg_build_tile_lists": 1, "isg_assign_dense": lambda a: 1 if a[21] else 2, "isg_gather_labels": 1, "isg_instance_polygons": lambda a: 1 if a[21] else 2, "isg_decode_boxes": 1,
+    "isg_gather_build_seeds": 1, "isg_scatter_labels": 1, "isg_gather_embeddings": 1, "isg_build_tile_lists": 1, "isg_assign_dense": lambda a: 1 if a[21] else 2, "isg_gather_labels": 1, "isg_instance_polygons": lambda a: 1 if a[21] else 2, "isg_decode_boxes": 1,
     "isg_gather_kept": 1, "isg_mask_nms": 5, "isg_mask_pair_counts": 1, "isg_pairwise": 1,
     "isg_bbox_transform": 1, "isg_clip_boxes": 1, "isg_generate_anchors": 1, "isg_decode_heads": 1, "isg_pack_masks": 1, "isg_fill_polygons": 1,
     # (idx,label,flag,count,cap,n_seeds,B,Nmax,...): one multisplit kernel unless the seed table is huge

@@ -759,31 +759,6 @@ scatter_labels_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict
 }
 }  // namespace isg
 
-// One-pass variant of isg_assign_dense: the selection threshold is not known yet.  The kernel assigns every pixel exactly
-// as isg_assign_dense does and, instead of applying the top-k threshold and the 3x3 test itself, appends every pixel at or
-// above the sample bound left in `topk_ws` by isg_topk_sample to that workspace's candidate list; isg_topk_finish then
-// selects the exact threshold among the candidates and evaluates the peak test for them alone.  kp is read from HBM
-// ONCE per step instead of twice (filter pass + dense pass).
-extern "C" int isg_assign_dense_onepass(const float* kp, int64_t kp_img_stride, const float* ae, int64_t ae_img_stride,
-                                        int64_t ae_plane_stride, void* topk_ws, size_t topk_ws_bytes, int k,
-                                        const uint32_t* seeds, const float* ghost, const int32_t* n_seeds, int B, int Nmax,
-                                        int H, int W, const float* ys, const float* xs, int32_t* label_map, void* workspace,
-                                        size_t workspace_bytes, int lists_prebuilt, isg_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (!kp || !ae || !topk_ws || !seeds || !ghost || !n_seeds || !ys || !xs || !label_map) return ISG_EINVAL;
-  if (B <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || B > 65535 || k <= 0) return ISG_EINVAL;
-  if (kp_img_stride < (int64_t)H * W || ae_plane_stride < (int64_t)H * W) return ISG_EINVAL;
-  if (!aligned16(seeds) || !aligned16(ghost) || ((uintptr_t)topk_ws & 255)) return ISG_EINVAL;
-  if (topk_ws_bytes < isg_topk_workspace_bytes(B, H, W, k)) return ISG_EWORKSPACE;
-  if (!workspace || workspace_bytes < dense_workspace_bytes(B, Nmax, H, W) || !aligned16(workspace)) return ISG_EINVAL;
-  const bool vec = (W % 4 == 0) && (kp_img_stride % 4 == 0) && (ae_img_stride % 4 == 0) && (ae_plane_stride % 4 == 0) &&
-                   aligned16(kp) && aligned16(ae) && aligned16(label_map);
-  if (!vec || tuning().dense_v1) return ISG_EUNSUPPORTED;      // the caller uses isg_topk_threshold + isg_assign_dense
-  return launch_dense_v4(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, nullptr, seeds, ghost, n_seeds, B, Nmax, H, W,
-                         ys, xs, label_map, nullptr, nullptr, nullptr, workspace, workspace_bytes, lists_prebuilt ? 2 : 0, stream,
-                         topk_ws, k);
-}
-
 namespace isg {
 __global__ void __launch_bounds__(256)
 gather_embeddings_kernel(const float* __restrict__ ae, int64_t img_stride, int64_t plane_stride, const int32_t* __restrict__ idx,

@@ -31,7 +31,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include "keep.cuh"
-#include "topk_ws.cuh"
 
 // sigma = exp(ae[2:4]) of the dense kernel: the compensated form (<= 2 ulp) unless ISG_D4_BARE_SIGMA is defined
 #ifdef ISG_D4_BARE_SIGMA
@@ -281,8 +280,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
                 int Wwords, int tilesX, int tilesY, int nstages, int cap, const unsigned char* __restrict__ lists,
                 const uint16_t* __restrict__ ovf, const float* __restrict__ ys, const float* __restrict__ xs,
                 int32_t* __restrict__ label_map, float* __restrict__ score_map, uint32_t* __restrict__ keepbits,
-                int32_t* __restrict__ stats, unsigned int* __restrict__ sched, int dyn_tail, int dbg_flags, int skip_ae,
-                void* __restrict__ cand_ws, int cand_k) {
+                int32_t* __restrict__ stats, unsigned int* __restrict__ sched, int dyn_tail, int dbg_flags, int skip_ae) {
   static_assert(RW % 2 == 0, "rows are processed in pairs");
   using Geo = D4Geom<RW, WG>;
   constexpr int kConsumers = WG * G;
@@ -341,8 +339,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
       // the slot must have been released by the consumers of its previous tile
       if (round >= 1) d4_wait_parked(&empty[slot], (uint32_t)((round - 1) & 1));
       unsigned char* st = smem + L.stage + (size_t)slot * Geo::kStage;
-      // selection threshold of the image; one-pass mode: the sample's lower bound of the candidates (topk workspace)
-      s_thr[slot] = cand_ws ? *topk_ws_view(cand_ws, b, H * W, cand_k).lower : __ldg(thr_key + b);   // released by the arrive below
+      s_thr[slot] = __ldg(thr_key + b);          // ordinary store: released to the consumers by the arrive below
       const bool with_ae = nh > 0 || skip_ae == 0;
       mbar_expect_tx(&full[slot], (with_ae ? Geo::kTx : (uint32_t)Geo::kKpBytes) + list_bytes);
       bulk_g2s(smem + L.list + (size_t)slot * L.list_stride, lists + (size_t)t * list_bytes, list_bytes, &full[slot]);
@@ -405,56 +402,18 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
       uint32_t* kbrow = keepbits + ((size_t)b * H + ybeg) * Wwords + (x0 >> 5);
       const bool kbwriter = ((lane & 7) == 0) && colvalid;
 
-      const bool cand_mode = cand_ws != nullptr;
-      RowK up, mid;
-      if (!cand_mode) { up = d4_prep(krow, lane, halo_off, thr); mid = d4_prep(krow + kD4KpW, lane, halo_off, thr); }
+      RowK up = d4_prep(krow, lane, halo_off, thr);
+      RowK mid = d4_prep(krow + kD4KpW, lane, halo_off, thr);
 #pragma unroll
       for (int rp = 0; rp < RW; rp += 2) {
         const int y = ybeg + rp;
         if (y >= H) break;                                                  // warp-uniform
         const bool row1 = y + 1 < H;
-        uint32_t nib0 = 0, nib1 = 0;
-        if (cand_mode) {
-          // --- one-pass selection: every pixel >= the sample bound is appended (key, position) to the image's candidate
-          // list; the exact k-th largest key and the 3x3 peak test follow on the candidates alone (isg_topk_finish) ---
-          const float4 r0 = *reinterpret_cast<const float4*>(krow + (rp + 1) * kD4KpW + 4 + lane * 4);
-          const float4 r1 = *reinterpret_cast<const float4*>(krow + (rp + 2) * kD4KpW + 4 + lane * 4);
-          const float m8 = fmaxf(fmaxf(fmaxf(r0.x, r0.y), fmaxf(r0.z, r0.w)), row1 ? fmaxf(fmaxf(r1.x, r1.y), fmaxf(r1.z, r1.w)) : r0.x);
-          const bool any = colvalid && !(m8 < thr.f);                        // float pre-test; exact key test below
-          if (__any_sync(0xffffffffu, any)) {
-            const float xv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-            const uint32_t lower = s_thr[slot];
-            uint32_t hit = 0;
-            if (any) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const uint32_t kk = float_key(xv[i]);
-                if ((i < 4 || row1) && kk >= lower && kk != 0xffffffffu) hit |= 1u << i;
-              }
-            }
-            const int c = __popc(hit);
-            int inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-            const TopkWs cw = topk_ws_view(cand_ws, b, H * W, cand_k);
-            uint32_t base = 0;
-            if (lane == 31 && inc > 0) base = atomicAdd(cw.ncand, (uint32_t)inc);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            uint32_t o2 = base + (uint32_t)(inc - c);
-            const uint32_t capc = (uint32_t)topk_cand_cap(H * W, cand_k);
-            while (hit) {
-              const int i = __ffs(hit) - 1;
-              hit &= hit - 1;
-              if (o2 < capc) { cw.cand[o2] = float_key(xv[i]); cw.pos[o2] = (uint32_t)((y + (i >> 2)) * W + x0 + (i & 3)); }
-              ++o2;
-            }
-          }
-        } else {
         // --- keep bits of rows y, y+1 ---
         const RowK dn0 = d4_prep(krow + (rp + 2) * kD4KpW, lane, halo_off, thr);
         const RowK dn1 = d4_prep(krow + (rp + 3) * kD4KpW, lane, halo_off, thr);
-        nib0 = d4_keep(up, mid, dn0);
-        nib1 = d4_keep(mid, dn0, dn1);
+        uint32_t nib0 = d4_keep(up, mid, dn0);
+        uint32_t nib1 = d4_keep(mid, dn0, dn1);
         up = dn0; mid = dn1;
         if (!colvalid) { nib0 = 0; nib1 = 0; }
         if (!row1) nib1 = 0;
@@ -464,7 +423,6 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
             kbrow[(size_t)rp * Wwords] = w0;
             if (row1) kbrow[(size_t)(rp + 1) * Wwords] = w1;
           }
-        }
         }
 
         float bq[2][4];
@@ -674,10 +632,7 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
                                int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds, const float* ghost,
                                const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys, const float* xs,
                                int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats, void* workspace,
-                               size_t workspace_bytes, int max_stages, int mode, cudaStream_t stream, void* cand_ws = nullptr,
-                               int cand_k = 0) {
-  // cand_ws != null: one-pass selection (the kernel appends the candidate pixels to the top-k workspace instead of
-  // applying an exact threshold; keepbits is not written)
+                               size_t workspace_bytes, int max_stages, int mode, cudaStream_t stream) {
   // mode 0: tile lists + dense kernel; 1: tile lists only (isg_build_tile_lists); 2: dense kernel only (lists prebuilt)
   using Geo = D4Geom<RW, WG>;
   static_assert(Geo::TH >= kD4MinTileRows, "workspace is sized for tiles of at least kD4MinTileRows rows");
@@ -755,12 +710,12 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
     ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, true>, tm_kp, tm_ae, thr_key, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
                                 tilesY, nstages, cap, clists, covf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail,
-                                dbg_flags, skip_ae, cand_ws, cand_k));
+                                dbg_flags, skip_ae));
   } else {
     ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, false>, tm_kp, tm_ae, thr_key, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
                                 tilesY, nstages, cap, clists, covf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail,
-                                dbg_flags, skip_ae, cand_ws, cand_k));
+                                dbg_flags, skip_ae));
   }
   ISG_LAUNCH_CHECK();
   return ISG_OK;
@@ -771,13 +726,13 @@ inline int launch_dense_v4(const float* kp, int64_t kp_img_stride, const float* 
                            int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds, const float* ghost,
                            const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys, const float* xs,
                            int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats, void* workspace,
-                           size_t workspace_bytes, int mode, cudaStream_t stream, void* cand_ws = nullptr, int cand_k = 0) {
+                           size_t workspace_bytes, int mode, cudaStream_t stream) {
   const Tuning& tn = tuning();
   const int rw = tn.dense_rw, wg = tn.dense_wg, g = tn.dense_g, st = tn.dense_stages > 0 ? tn.dense_stages : kD4MaxStages;
 #define ISG_V4_CASE(RW_, WG_, G_)                                                                                      \
   if (rw == RW_ && wg == WG_ && g == G_)                                                                               \
     return launch_dense_v4_cfg<RW_, WG_, G_>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, \
-                                             n_seeds, B, Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, workspace, workspace_bytes, st, mode, stream, cand_ws, cand_k);
+                                             n_seeds, B, Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, workspace, workspace_bytes, st, mode, stream);
   ISG_V4_CASE(2, 8, 2)
   ISG_V4_CASE(4, 4, 3)
   ISG_V4_CASE(4, 4, 4)

@@ -5,12 +5,12 @@
 #include <cstdlib>
 #include <algorithm>
 #include "keep.cuh"
-#include "topk_ws.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace isg {
 
+constexpr int kHistBins = 2048;          // 11-bit digits (11 + 11 + 10 = 32)
 constexpr int kHistThreads = 256;
 constexpr int kHistPxPerBlock = 16384;   // 16 float4 per thread
 
@@ -157,6 +157,29 @@ constexpr int kSelThreads = 1024;
 constexpr int kSampleMax = 32768;        // sample keys kept in shared memory (128 KB)
 constexpr int kFilterThreads = 256;
 constexpr int kFilterPxPerBlock = 8192;  // 8 float4 per thread; the block's candidates always fit in smem
+
+struct TopkWs {            // per-image views
+  uint32_t* hist;          // [3][2048]   (legacy multi-CTA path)
+  uint32_t* lower;         // [1]
+  uint32_t* ncand;         // [1]
+  uint32_t* cand;          // [cap_c]
+};
+__host__ __device__ inline size_t topk_cand_cap(int npx, int k) {
+  size_t c = (size_t)8 * (size_t)k + 8192;
+  return c < (size_t)npx ? c : (size_t)npx;
+}
+__host__ __device__ inline size_t topk_ws_per_image(int npx, int k) {
+  size_t s = 3 * kHistBins * sizeof(uint32_t) + 64 + topk_cand_cap(npx, k) * sizeof(uint32_t);
+  return (s + 255) & ~(size_t)255;
+}
+__host__ __device__ inline TopkWs topk_ws_view(void* ws, int b, int npx, int k) {
+  char* p = (char*)ws + (size_t)b * topk_ws_per_image(npx, k);
+  TopkWs v;
+  v.hist = (uint32_t*)p; p += 3 * kHistBins * sizeof(uint32_t);
+  v.lower = (uint32_t*)p; v.ncand = (uint32_t*)(p + 32); p += 64;
+  v.cand = (uint32_t*)p;
+  return v;
+}
 
 // ---- alternative fast path (ISG_TOPK_PATH=radix): two-level radix select with a 15-bit first digit ---------------
 // (1) topk_hist15_kernel: ONE pass over the batch builds, per image, the histogram of the top 15 key bits (sign,
@@ -564,7 +587,7 @@ topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   const uint32_t nc = *v.ncand;
   const bool bin_mode = v.lower[3] != 0u;
   const uint32_t rank = bin_mode ? v.lower[2] : (uint32_t)k;      // rank of the answer among the candidates
-  const bool use_cand = topk_cand_usable(nc, rank, npx, k);
+  const bool use_cand = nc >= rank && rank >= 1u && (size_t)nc <= topk_cand_cap(npx, k);
   uint32_t key;
   if (use_cand && nc <= (uint32_t)kSmallSel) {   // cluster-uniform: one CTA sorts the few candidates in shared memory
     if (cluster.block_rank() != 0) return;
@@ -606,12 +629,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(32 * kKeepWarps)
 keep_kernel(const float* __restrict__ kp, int64_t img_stride, int H, int W, int Wwords,
             const uint32_t* __restrict__ thr_key, uint32_t* __restrict__ keepbits,
-            uint8_t* __restrict__ mask_u8, void* topk_ws, int k) {
+            uint8_t* __restrict__ mask_u8) {
   const int b = blockIdx.z;
-  if (topk_ws) {   // one-pass mode: this full pass only serves the images whose candidate list was not usable
-    const TopkWs v = topk_ws_view(topk_ws, b, H * W, k);
-    if (topk_cand_usable(*v.ncand, (uint32_t)k, H * W, k)) return;
-  }
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int x0 = (blockIdx.x * 32 + lane) * 4;
   const int ybeg = (blockIdx.y * kKeepWarps + warp) * kKeepRowsPerWarp;
@@ -637,41 +656,6 @@ keep_kernel(const float* __restrict__ kp, int64_t img_stride, int H, int W, int 
         if (x0 + i < W) mrow[x0 + i] = (nib >> i) & 1u;
     }
     up = mid; mid = dn;
-  }
-}
-
-// ---- one-pass mode: keep bits from the candidate list -----------------------------------------------------------
-// The dense kernel appended every pixel >= the sample bound (key, position) while it streamed kp; once the exact k-th
-// largest key is known only those candidates can be selected, so the 3x3 peak test (select_points, utils/decode.py:84-85)
-// is evaluated for them alone - 8 neighbour reads per selected candidate instead of a second pass over the heat map.
-__global__ void __launch_bounds__(256)
-keep_fixup_kernel(const float* __restrict__ kp, int64_t img_stride, int H, int W, int Wwords, int k, void* ws,
-                  const uint32_t* __restrict__ thr_key, uint32_t* __restrict__ keepbits) {
-  const int b = blockIdx.y;
-  const int npx = H * W;
-  const TopkWs v = topk_ws_view(ws, b, npx, k);
-  const uint32_t nc = *v.ncand;
-  if (!topk_cand_usable(nc, (uint32_t)k, npx, k)) return;      // the full keep pass serves this image
-  const uint32_t thr = thr_key[b];
-  const float* img = kp + (int64_t)b * img_stride;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
-    if (v.cand[i] < thr) continue;                              // not among the k largest
-    const int p = (int)v.pos[i];
-    const int y = p / W, x = p - y * W;
-    const float c = __ldg(img + p);
-    bool keep = true;
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int yy = y + dy;
-      if (yy < 0 || yy >= H) continue;                          // -inf padding (:45-47)
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = x + dx;
-        if ((dy == 0 && dx == 0) || xx < 0 || xx >= W) continue;
-        const float q = __ldg(img + (int64_t)yy * W + xx);
-        const float vq = float_key(q) >= thr ? q : 0.0f;        // mat * mask (:84): unselected neighbours count as 0
-        if (vq > c) keep = false;                               // NaN neighbours never win, like fmax in the row form
-      }
-    }
-    if (keep) atomicOr(keepbits + ((size_t)b * H + y) * Wwords + (x >> 5), 1u << (x & 31));
   }
 }
 
@@ -918,50 +902,6 @@ extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t 
   return ISG_OK;
 }
 
-// ---- one-pass selection: sample -> [dense kernel appends the candidates] -> select + keep fix-up --------------------
-static bool onepass_supported(int64_t npx64, int k) { return k > 0 && npx64 >= 65536 && (int64_t)4 * k <= npx64; }
-
-extern "C" int isg_topk_sample(const float* kp, int B, int H, int W, int64_t img_stride, int k, void* ws, size_t ws_bytes,
-                               isg_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (!kp || B <= 0 || H <= 0 || W <= 0 || k < 0 || B > 65535) return ISG_EINVAL;
-  const int64_t npx64 = (int64_t)H * W;
-  if (npx64 > (int64_t)1 << 30 || img_stride < npx64 || (int64_t)k > npx64) return ISG_EINVAL;
-  if (!onepass_supported(npx64, k)) return ISG_EUNSUPPORTED;
-  if (!ws || ws_bytes < isg_topk_workspace_bytes(B, H, W, k) || ((uintptr_t)ws & 255)) return ISG_EWORKSPACE;
-  const int npx = (int)npx64;
-  int stride = 64;
-  while (npx / stride > kSample1Max) stride *= 2;
-  topk_sample1_kernel<<<B, kSelThreads, 0, stream>>>(kp, img_stride, npx, k, stride, ws);
-  ISG_LAUNCH_CHECK();
-  return ISG_OK;
-}
-
-extern "C" int isg_topk_finish(const float* kp, int B, int H, int W, int64_t img_stride, int k, void* ws, size_t ws_bytes,
-                               uint32_t* thr_key, uint32_t* keepbits, isg_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (!kp || !thr_key || !keepbits || B <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
-  const int64_t npx64 = (int64_t)H * W;
-  if (npx64 > (int64_t)1 << 30 || img_stride < npx64 || !onepass_supported(npx64, k)) return ISG_EINVAL;
-  if (!ws || ws_bytes < isg_topk_workspace_bytes(B, H, W, k) || ((uintptr_t)ws & 255)) return ISG_EWORKSPACE;
-  const int npx = (int)npx64;
-  const int Wwords = cdiv(W, 32);
-  ISG_CUDA(cudaMemsetAsync(keepbits, 0, (size_t)B * H * Wwords * sizeof(uint32_t), stream));
-  // exact k-th largest among the candidates (whole-image select when the list is not usable)
-  topk_select_kernel<<<dim3(kSelCluster, B), dim3(kSelThreads), 0, stream>>>(kp, img_stride, npx, k, ws, thr_key);
-  const size_t capc = topk_cand_cap(npx, k);
-  keep_fixup_kernel<<<dim3((unsigned)std::min<size_t>(cdiv64((int64_t)capc, 256), 64), B), 256, 0, stream>>>(
-      kp, img_stride, H, W, Wwords, k, ws, thr_key, keepbits);
-  // images whose candidate list overflowed or fell short (plateaus, adversarial orderings): the ordinary full keep pass
-  const bool vec = (W % 4 == 0) && (img_stride % 4 == 0) && (((uintptr_t)kp & 15) == 0);
-  dim3 block(32, kKeepWarps);
-  dim3 grid(cdiv(W, 128), cdiv(H, kKeepWarps * kKeepRowsPerWarp), B);
-  if (vec) keep_kernel<true><<<grid, block, 0, stream>>>(kp, img_stride, H, W, Wwords, thr_key, keepbits, nullptr, ws, k);
-  else keep_kernel<false><<<grid, block, 0, stream>>>(kp, img_stride, H, W, Wwords, thr_key, keepbits, nullptr, ws, k);
-  ISG_LAUNCH_CHECK();
-  return ISG_OK;
-}
-
 extern "C" int isg_keep_points(const float* kp, int B, int H, int W, int64_t img_stride,
                                const uint32_t* thr_key, uint32_t* keepbits, uint8_t* mask_u8,
                                isg_stream_t stream_) {
@@ -972,8 +912,8 @@ extern "C" int isg_keep_points(const float* kp, int B, int H, int W, int64_t img
   const bool vec = (W % 4 == 0) && (img_stride % 4 == 0) && (((uintptr_t)kp & 15) == 0);
   dim3 block(32, kKeepWarps);
   dim3 grid(cdiv(W, 128), cdiv(H, kKeepWarps * kKeepRowsPerWarp), B);
-  if (vec) keep_kernel<true><<<grid, block, 0, stream>>>(kp, img_stride, H, W, Wwords, thr_key, keepbits, mask_u8, nullptr, 0);
-  else keep_kernel<false><<<grid, block, 0, stream>>>(kp, img_stride, H, W, Wwords, thr_key, keepbits, mask_u8, nullptr, 0);
+  if (vec) keep_kernel<true><<<grid, block, 0, stream>>>(kp, img_stride, H, W, Wwords, thr_key, keepbits, mask_u8);
+  else keep_kernel<false><<<grid, block, 0, stream>>>(kp, img_stride, H, W, Wwords, thr_key, keepbits, mask_u8);
   ISG_LAUNCH_CHECK();
   return ISG_OK;
 }

@@ -23,7 +23,7 @@ extern "C" int isg_decode_step(const isg_decode_step_t* s) {
   if (!s || s->struct_bytes != (int)sizeof(isg_decode_step_t)) return ISG_EINVAL;
   // `main` may be the default stream (a null handle); `side` must be a different stream
   if (!s->side || !s->fork_event || !s->join_event || s->main == s->side) return ISG_EINVAL;
-  if (s->assign != ISG_ASSIGN_DENSE && s->assign != ISG_ASSIGN_SPARSE && s->assign != ISG_ASSIGN_DENSE_ONEPASS) return ISG_EINVAL;
+  if (s->assign != ISG_ASSIGN_DENSE && s->assign != ISG_ASSIGN_SPARSE) return ISG_EINVAL;
   cudaStream_t main = (cudaStream_t)s->main, side = (cudaStream_t)s->side;
   cudaEvent_t fork = (cudaEvent_t)s->fork_event, join = (cudaEvent_t)s->join_event;
   const int B = s->B, H = s->H, W = s->W, N = s->Nmax;
@@ -31,15 +31,8 @@ extern "C" int isg_decode_step(const isg_decode_step_t* s) {
   // top-k threshold on the side stream, behind everything enqueued on `main` so far
   STEP_CUDA(cudaEventRecord(fork, main));
   STEP_CUDA(cudaStreamWaitEvent(side, fork, 0));
-  int assign = s->assign;
-  if (assign == ISG_ASSIGN_DENSE_ONEPASS) {     // only the sample bound is needed before the dense kernel
-    const int rc = isg_topk_sample(s->kp, B, H, W, s->kp_img_stride, s->kp_th, s->topk_ws, s->topk_ws_bytes, side);
-    if (rc == ISG_EUNSUPPORTED) assign = ISG_ASSIGN_DENSE;       // small image / large k: the two-pass form
-    else if (rc != ISG_OK) return rc;
-  }
-  if (assign != ISG_ASSIGN_DENSE_ONEPASS)
-    STEP_TRY(isg_topk_threshold(s->kp, B, H, W, s->kp_img_stride, s->kp_th, s->thr_key, s->topk_ws, s->topk_ws_bytes, side));
-  if (assign == ISG_ASSIGN_SPARSE) {   // keep bits + compaction only need kp and the threshold: stay on the side stream
+  STEP_TRY(isg_topk_threshold(s->kp, B, H, W, s->kp_img_stride, s->kp_th, s->thr_key, s->topk_ws, s->topk_ws_bytes, side));
+  if (s->assign == ISG_ASSIGN_SPARSE) {   // keep bits + compaction only need kp and the threshold: stay on the side stream
     STEP_TRY(isg_keep_points(s->kp, B, H, W, s->kp_img_stride, s->thr_key, s->keepbits, nullptr, side));
     STEP_TRY(isg_compact_points(s->keepbits, B, H, W, s->cap, s->idx, s->count, side));
   }
@@ -53,27 +46,12 @@ extern "C" int isg_decode_step(const isg_decode_step_t* s) {
   STEP_TRY(isg_gather_build_seeds(s->cand_boxes, s->cand_scores, s->cand_cls, s->keep, s->n_keep, B, s->cand_cap, N, s->ys,
                                   s->xs, H, W, s->ghost_k, s->scale, s->rois, s->scores, s->cls, s->n_seeds, s->seeds,
                                   s->ghost, s->stats, s->img_total, main));
-  if (assign != ISG_ASSIGN_SPARSE)
+  if (s->assign == ISG_ASSIGN_DENSE)
     STEP_TRY(isg_build_tile_lists(s->seeds, s->n_seeds, B, N, H, W, s->dense_ws, s->dense_ws_bytes, main));
   STEP_CUDA(cudaStreamWaitEvent(main, join, 0));
 
   if (s->time_begin) STEP_CUDA(cudaEventRecord((cudaEvent_t)s->time_begin, main));
-  if (assign == ISG_ASSIGN_DENSE_ONEPASS) {
-    int rc = isg_assign_dense_onepass(s->kp, s->kp_img_stride, s->ae, s->ae_img_stride, s->ae_plane_stride, s->topk_ws,
-                                      s->topk_ws_bytes, s->kp_th, s->seeds, s->ghost, s->n_seeds, B, N, H, W, s->ys, s->xs,
-                                      s->label_map, s->dense_ws, s->dense_ws_bytes, 1, main);
-    if (rc == ISG_EUNSUPPORTED) {    // layout the tensor-map kernel cannot take: exact threshold + the two-pass kernel on main
-      STEP_TRY(isg_topk_threshold(s->kp, B, H, W, s->kp_img_stride, s->kp_th, s->thr_key, s->topk_ws, s->topk_ws_bytes, main));
-      STEP_TRY(isg_assign_dense(s->kp, s->kp_img_stride, s->ae, s->ae_img_stride, s->ae_plane_stride, s->thr_key, s->seeds,
-                                s->ghost, s->n_seeds, B, N, H, W, s->ys, s->xs, s->label_map, nullptr, s->keepbits, nullptr,
-                                s->dense_ws, s->dense_ws_bytes, 1, main));
-      if (s->time_end) STEP_CUDA(cudaEventRecord((cudaEvent_t)s->time_end, main));
-    } else {
-      if (rc != ISG_OK) return rc;
-      if (s->time_end) STEP_CUDA(cudaEventRecord((cudaEvent_t)s->time_end, main));
-      STEP_TRY(isg_topk_finish(s->kp, B, H, W, s->kp_img_stride, s->kp_th, s->topk_ws, s->topk_ws_bytes, s->thr_key, s->keepbits, main));
-    }
-  } else if (assign == ISG_ASSIGN_DENSE) {
+  if (s->assign == ISG_ASSIGN_DENSE) {
     STEP_TRY(isg_assign_dense(s->kp, s->kp_img_stride, s->ae, s->ae_img_stride, s->ae_plane_stride, s->thr_key, s->seeds,
                               s->ghost, s->n_seeds, B, N, H, W, s->ys, s->xs, s->label_map, nullptr, s->keepbits, nullptr,
                               s->dense_ws, s->dense_ws_bytes, 1, main));
@@ -83,7 +61,7 @@ extern "C" int isg_decode_step(const isg_decode_step_t* s) {
                                s->n_seeds, B, N, H, W, s->ys, s->xs, s->label, nullptr, nullptr, nullptr, main));
     STEP_TRY(isg_scatter_labels(s->idx, s->count, s->cap, s->label, B, H, W, s->label_map, main));
   }
-  if (s->time_end && assign != ISG_ASSIGN_DENSE_ONEPASS) STEP_CUDA(cudaEventRecord((cudaEvent_t)s->time_end, main));
+  if (s->time_end) STEP_CUDA(cudaEventRecord((cudaEvent_t)s->time_end, main));
   if (s->polygons)
     STEP_TRY(isg_instance_polygons(s->keepbits, s->label_map, s->rois, ISG_BOX_XYXY, s->ghost, s->n_seeds, B, N, H, W, s->cap,
                                    s->obj_pixel_th, s->poly_points, s->inst_start, s->inst_count, s->inst_flags,

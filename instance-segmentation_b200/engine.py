@@ -436,7 +436,6 @@ class DecodePipeline:
     def run_native(self, kp, ae, anchors, regression, classification, cls_th, iou_th, obj_pixel_th: int = 0,
                    assign: str = "dense", polygons: bool = True, time_main: bool = False) -> None:
         """One whole step through isg_decode_step (a single host call) on the current stream + the side stream.
-        assign "onepass": the dense kernel appends the selection candidates itself (kp is read once per step; same results);
         assign "sparse": only the keep pixels are assigned (isg_assign_sparse + isg_scatter_labels); `ae` and `regression`
         may then be PINNED HOST tensors - they are gathered over PCIe at the keep pixels / candidate anchors instead of
         being uploaded.  Results as for run(tail="polygons")."""
@@ -449,12 +448,10 @@ class DecodePipeline:
         assert ae.shape == (B, 4, H, W) and ae.dtype == torch.float32 and _rows_contiguous(ae)
         assert regression.shape == (B, bp.A, 4) and classification.shape == (B, bp.A, bp.C) and anchors.numel() == bp.A * 4
         assert regression.is_contiguous() and classification.is_contiguous() and anchors.is_contiguous() and classification.is_cuda
-        if assign not in ("dense", "sparse", "onepass"):
-            raise ValueError("assign must be 'dense', 'onepass' or 'sparse'")
         sparse = assign == "sparse"
         if not sparse and not (ae.is_cuda and regression.is_cuda):
             raise ValueError("host-resident ae / regression need assign='sparse'")
-        st.assign = {"dense": _lib.ISG_ASSIGN_DENSE, "sparse": _lib.ISG_ASSIGN_SPARSE, "onepass": _lib.ISG_ASSIGN_DENSE_ONEPASS}[assign]
+        st.assign = _lib.ISG_ASSIGN_SPARSE if sparse else _lib.ISG_ASSIGN_DENSE
         st.polygons, st.obj_pixel_th = 1 if polygons else 0, int(obj_pixel_th)
         st.cls_th, st.iou_th = float(np.float32(cls_th)), float(iou_th)
         st.kp, st.kp_img_stride = ptr(kp), kp.stride(0) if B > 1 else H * W
@@ -469,9 +466,7 @@ class DecodePipeline:
         rc = _lib.lib().isg_decode_step(ctypes.byref(st))
         if rc != 0:
             raise _lib.IsgError(rc, "isg_decode_step")
-        # kernels enqueued: top-k 3 (one-pass: sample 1 + select / fix-up / guarded keep 3), box head + NMS + seeds 3, tile lists +
-        # dense 2 (sparse: keep + compact + assign + scatter 4), polygons 1
-        _lib.launch_count += {"dense": 8, "onepass": 9, "sparse": 10}[assign] + (1 if polygons else 0)
+        _lib.launch_count += (8 if sparse else 8) + (1 if polygons else 0) + (2 if sparse else 0)
         if time_main:
             ev = (self._t0, self._t1)
             self._t0, self._t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -36,9 +36,6 @@ draw_flag = False     # set by evaluate.py:41 (the code reads decode_cfg.draw_fl
 # "dense": fused label map for every pixel (isg_assign_dense); "sparse": only the selected pixels, the
 # reference's own amount of work (isg_assign_sparse).  Both give identical detections.
 decode_mode = os.environ.get("ISG_DECODE_MODE", "dense")
-# dense mode on the device fast path: "onepass" = the dense kernel collects the selection candidates while it streams kp
-# (kp is read once per step), "dense" = exact top-k threshold first, then the dense kernel applies it; identical results
-dense_assign = os.environ.get("ISG_DENSE_ASSIGN", "onepass")
 # dense mode, identity val-transform, no drawing: run the per-instance polygon stage on the device
 # (isg_instance_polygons); False keeps it on the host (cv2/numpy, the reference's own calls)
 device_polygon_stage = os.environ.get("ISG_DEVICE_POLYGONS", "1") != "0"
@@ -806,7 +803,7 @@ def _decode_output_batch(inputs, outs, infos, transforms, decode_cfg, device):
             ring = _get_ring(1, B, A, C, H, W, height, width, int(decode_cfg.kp_th), dev, cap, max_keep, min_cap,
                              float(decode_cfg.wh_delta), float(compute_scale(None)))
             slot = ring.submit(kp, ae, anc, reg, cls_t, decode_cfg.cls_th, decode_cfg.iou_th,
-                               obj_pixel_th=int(decode_cfg.obj_pixel_th), assign=dense_assign, fetch=True)
+                               obj_pixel_th=int(decode_cfg.obj_pixel_th), assign="dense", fetch=True)
             pipe = ring.pipes[slot]
             last_timing["d2h_bytes"] = pipe.bplan.arena.wait()
             over = _plan_overflow(pipe)

@@ -114,66 +114,6 @@ def test_topk_threshold_paths(mods, shape, k, kind, path, monkeypatch):
     assert f == np.float32(kth)
 
 
-@pytest.mark.parametrize("shape,k,kind", [((1024, 2048), 20000, "normal"), ((512, 1024), 20000, "normal"), ((256, 512), 3000, "negative"),
-                                          ((512, 1024), 20000, "flat"), ((512, 1024), 5000, "sorted"), ((256, 256), 1, "normal"),
-                                          ((300, 500), 37000, "normal"), ((128, 256), 500, "normal"), ((256, 260), 4000, "normal")])
-def test_onepass_selection_equals_two_pass(mods, shape, k, kind):
-    """isg_topk_sample -> isg_assign_dense_onepass (candidate append) -> isg_topk_finish against isg_topk_threshold +
-    isg_keep_points: the same threshold key and the same keep bits, incl. the fall-backs (flat / sorted images defeat the
-    sample bound or overflow the candidate list; small images and widths without a tensor map are refused up front)"""
-    lib, eng = mods["lib"], mods["engine"]
-    H, W = shape
-    B = 2
-    g = torch.Generator(device="cpu").manual_seed(H * 7 + k)
-    if kind == "normal":
-        kp = torch.randn((B, H, W), generator=g)
-    elif kind == "negative":      # every value negative: selected pixels next to unselected (0) neighbours are dropped (:84-85)
-        kp = -torch.rand((B, H, W), generator=g) - 0.5
-    elif kind == "flat":
-        kp = (torch.rand((B, H, W), generator=g) < 0.01).float() * 3.0 - 1.0
-    else:
-        kp = torch.arange(B * H * W, dtype=torch.float32).view(B, H, W) * 1e-3
-    dev = torch.device(DEV)
-    kp = kp.to(dev)
-    ae = torch.zeros((B, 4, H, W), device=dev)
-    Ww = (W + 31) // 32
-    ws_bytes = int(lib.lib().isg_topk_workspace_bytes(B, H, W, k))
-    ws, ws_ptr = eng.aligned_workspace(ws_bytes, dev)
-    thr_a = torch.empty(B, dtype=torch.int32, device=dev); thr_b = torch.empty_like(thr_a)
-    kb_a = torch.empty((B, H, Ww), dtype=torch.int32, device=dev); kb_b = torch.full_like(kb_a, -1)
-    s = eng.stream_ptr(dev)
-    lib.call("isg_topk_threshold", kp.data_ptr(), B, H, W, H * W, k, thr_a.data_ptr(), ws_ptr, ws_bytes, s)
-    lib.call("isg_keep_points", kp.data_ptr(), B, H, W, H * W, thr_a.data_ptr(), kb_a.data_ptr(), 0, s)
-    rc = lib.lib().isg_topk_sample(kp.data_ptr(), B, H, W, H * W, k, ws_ptr, ws_bytes, s)
-    if H * W < 65536 or 4 * k > H * W:
-        assert rc == -3                                   # ISG_EUNSUPPORTED: the step uses the two-pass form
-        return
-    assert rc == 0
-    plan = eng.DecodePlan(B, H, W, 4, k, dev, "dense", want_score=False)
-    rois = torch.tensor([[[10.5, 10.5, 60.5, 50.5]] * 4] * B, device=dev)
-    n = torch.full((B,), 1, dtype=torch.int32, device=dev)
-    lib.call("isg_build_seeds", rois.data_ptr(), 0, n.data_ptr(), B, 4, plan.ys.data_ptr(), plan.xs.data_ptr(), H, W, plan.ghost_k, 1.0,
-             plan.seeds.data_ptr(), plan.ghost.data_ptr(), s)
-    rc = lib.lib().isg_assign_dense_onepass(kp.data_ptr(), H * W, ae.data_ptr(), 4 * H * W, H * W, ws_ptr, ws_bytes, k, plan.seeds.data_ptr(),
-                                            plan.ghost.data_ptr(), n.data_ptr(), B, 4, H, W, plan.ys.data_ptr(), plan.xs.data_ptr(),
-                                            plan.label_map.data_ptr(), plan.dense_ws.data_ptr(), plan.dense_ws_bytes, 0, s)
-    if W % 4:
-        assert rc == -3
-        return
-    assert rc == 0
-    lib.call("isg_topk_finish", kp.data_ptr(), B, H, W, H * W, k, ws_ptr, ws_bytes, thr_b.data_ptr(), kb_b.data_ptr(), s)
-    torch.cuda.synchronize()
-    assert torch.equal(thr_a, thr_b)
-    assert torch.equal(kb_a, kb_b), int((kb_a != kb_b).sum())
-    # the labels do not depend on the selection: same map as the two-pass kernel
-    lm = plan.label_map.clone()
-    lib.call("isg_assign_dense", kp.data_ptr(), H * W, ae.data_ptr(), 4 * H * W, H * W, thr_a.data_ptr(), plan.seeds.data_ptr(), plan.ghost.data_ptr(),
-             n.data_ptr(), B, 4, H, W, plan.ys.data_ptr(), plan.xs.data_ptr(), plan.label_map.data_ptr(), 0, plan.keepbits.data_ptr(), 0,
-             plan.dense_ws.data_ptr(), plan.dense_ws_bytes, 0, s)
-    torch.cuda.synchronize()
-    assert torch.equal(lm, plan.label_map) and torch.equal(plan.keepbits, kb_a)
-
-
 def test_nms_hm_golden(mods, golden):
     g = golden("select_points")
     heat = torch.from_numpy(g["heat"]).to(DEV)
@@ -880,7 +820,7 @@ def test_decode_ring_overlapped_steps_equal_isolated_steps(mods):
         st, ct, fl, pts = dp.inst_start.cpu().numpy(), dp.inst_count.cpu().numpy(), dp.inst_flags.cpu().numpy(), dp.poly_points.cpu().numpy()
         want.append((n, bp.rois.cpu().numpy(), {(b, i): (int(fl[b, i]), pts[b, st[b, i]:st[b, i] + ct[b, i]].copy())
                                                 for b in range(B) for i in range(int(n[b]))}))
-    for assign in ("dense", "onepass", "sparse"):
+    for assign in ("dense", "sparse"):
         ring = engine.DecodeRing(make, 3)
         for seq in ([0, 1, 2], [2, 2, 0, 1, 1, 0, 2, 1, 0]):
             slots = []
