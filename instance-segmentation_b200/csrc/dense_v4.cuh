@@ -402,19 +402,29 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
       uint32_t* kbrow = keepbits + ((size_t)b * H + ybeg) * Wwords + (x0 >> 5);
       const bool kbwriter = ((lane & 7) == 0) && colvalid;
 
-      RowK up = d4_prep(krow, lane, halo_off, thr);
-      RowK mid = d4_prep(krow + kD4KpW, lane, halo_off, thr);
 #pragma unroll
       for (int rp = 0; rp < RW; rp += 2) {
         const int y = ybeg + rp;
         if (y >= H) break;                                                  // warp-uniform
         const bool row1 = y + 1 < H;
         // --- keep bits of rows y, y+1 ---
-        const RowK dn0 = d4_prep(krow + (rp + 2) * kD4KpW, lane, halo_off, thr);
-        const RowK dn1 = d4_prep(krow + (rp + 3) * kD4KpW, lane, halo_off, thr);
-        uint32_t nib0 = d4_keep(up, mid, dn0);
-        uint32_t nib1 = d4_keep(mid, dn0, dn1);
-        up = dn0; mid = dn1;
+        // A row segment without a selected pixel cannot hold a keep pixel, and ~1 % of the pixels are selected: test the
+        // maximum of the lane's four raw values first (3 FMNMX + 1 compare per row) and run the thresholded 3x3 window
+        // only for the rows of this warp that do hold a selected pixel.  (+-0 / NaN thresholds order by key: always run.)
+        uint32_t nib0 = 0, nib1 = 0;
+        bool a0 = true, a1 = true;
+        if (!thr.use_int) {
+          const float4 q0 = *reinterpret_cast<const float4*>(krow + (rp + 1) * kD4KpW + 4 + lane * 4);
+          const float4 q1 = *reinterpret_cast<const float4*>(krow + (rp + 2) * kD4KpW + 4 + lane * 4);
+          a0 = __any_sync(0xffffffffu, fmaxf(fmaxf(q0.x, q0.y), fmaxf(q0.z, q0.w)) >= thr.f);
+          a1 = __any_sync(0xffffffffu, fmaxf(fmaxf(q1.x, q1.y), fmaxf(q1.z, q1.w)) >= thr.f);
+        }
+        if (a0 || a1) {                                                      // warp-uniform
+          const RowK r1 = d4_prep(krow + (rp + 1) * kD4KpW, lane, halo_off, thr);
+          const RowK r2 = d4_prep(krow + (rp + 2) * kD4KpW, lane, halo_off, thr);
+          if (a0) nib0 = d4_keep(d4_prep(krow + rp * kD4KpW, lane, halo_off, thr), r1, r2);
+          if (a1) nib1 = d4_keep(r1, r2, d4_prep(krow + (rp + 3) * kD4KpW, lane, halo_off, thr));
+        }
         if (!colvalid) { nib0 = 0; nib1 = 0; }
         if (!row1) nib1 = 0;
         {
