@@ -155,8 +155,15 @@ __global__ void fill_u32_kernel(uint32_t* p, int n, uint32_t v) {
 // is always exact.
 constexpr int kSelThreads = 1024;
 constexpr int kSampleMax = 32768;        // sample keys kept in shared memory (128 KB)
-constexpr int kFilterThreads = 256;
-constexpr int kFilterPxPerBlock = 8192;  // 8 float4 per thread; the block's candidates always fit in smem
+#ifndef ISG_FILTER_THREADS
+#define ISG_FILTER_THREADS 256
+#endif
+#ifndef ISG_FILTER_UNROLL
+#define ISG_FILTER_UNROLL 4
+#endif
+constexpr int kFilterThreads = ISG_FILTER_THREADS;
+constexpr int kFilterUnroll = ISG_FILTER_UNROLL;                         // independent 128-bit loads in flight per thread
+constexpr int kFilterPxPerBlock = kFilterThreads * 4 * kFilterUnroll;    // the block's candidates always fit in shared memory
 
 struct TopkWs {            // per-image views
   uint32_t* hist;          // [3][2048]   (legacy multi-CTA path)
@@ -521,7 +528,7 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   // NOTE: 0xffffffff marks "not a candidate"; a real key of 0xffffffff (a NaN payload) is dropped, NaNs are
   // outside the contract.
   if (vec) {
-    constexpr int kUnroll = 8;                                  // independent 128-bit loads in flight per thread (the block in one go)
+    constexpr int kUnroll = kFilterUnroll;                      // the block's pixels in one go
     for (int p0 = base; p0 < end; p0 += kFilterThreads * 4 * kUnroll) {   // warp-uniform trip count
       float4 q[kUnroll];
       bool in[kUnroll];
