@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--inputs", default="default", choices=["default", "wide"],
                     help="wide: embedding offsets ae[0:2] ~ N(0,1) off the outlines (unbounded logits: the tanh of the dense "
                          "kernel takes its exp/divide branch instead of the |x| < 0.55 polynomial)")
-    ap.add_argument("--ring", type=int, default=4, help="independent pipelines used round-robin (1 = every step on its own)")
+    ap.add_argument("--ring", type=int, default=6, help="independent pipelines used round-robin (1 = every step on its own)")
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling: decode this many images per step in total, sharded over the ranks (config 3: 64)")
     ap.add_argument("--min-seconds", type=float, default=0.0, help="repeat the timed region until it lasted this long (sustained line)")
