@@ -14,6 +14,8 @@ namespace isg {
 // ---------------------------------------------------------------------------------------------
 constexpr int kFrontThreads = 256;
 
+constexpr int kFrontPer = 2;          // anchors per thread (their score rows are loaded before either is examined)
+
 __global__ void __launch_bounds__(kFrontThreads)
 decode_boxes_kernel(const float* __restrict__ anchors, const float* __restrict__ regression,
                     const float* __restrict__ classification, int A, int C, float xmax_clip, float ymax_clip,
@@ -22,53 +24,84 @@ decode_boxes_kernel(const float* __restrict__ anchors, const float* __restrict__
                     int32_t* __restrict__ cand_count, bool vec) {
   pdl_trigger();      // the NMS kernel behind this one may be scheduled early; it waits for this grid (common.cuh)
   const int b = blockIdx.y;
-  const int a = blockIdx.x * kFrontThreads + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  float best = -INFINITY;
-  int cls = 0;
-  if (a < A) {
-    const float* p = classification + ((size_t)b * A + a) * C;
-    if (vec) {
-      for (int c = 0; c < C; c += 4) {
-        const float4 v = ldg_stream4(p + c);
-        if (v.x > best) { best = v.x; cls = c; }
-        if (v.y > best) { best = v.y; cls = c + 1; }
-        if (v.z > best) { best = v.z; cls = c + 2; }
-        if (v.w > best) { best = v.w; cls = c + 3; }
+  float best[kFrontPer];
+  int cls[kFrontPer];
+  if (vec && C == 8) {
+    // the common head (8 classes): both 128-bit halves of every anchor's score row in flight before any compare
+    float4 v[kFrontPer][2];
+#pragma unroll
+    for (int u = 0; u < kFrontPer; ++u) {
+      const int a = (blockIdx.x * kFrontPer + u) * kFrontThreads + threadIdx.x;
+      const float* p = classification + ((size_t)b * A + min(a, A - 1)) * 8;
+      v[u][0] = ldg_stream4(p); v[u][1] = ldg_stream4(p + 4);
+    }
+#pragma unroll
+    for (int u = 0; u < kFrontPer; ++u) {
+      best[u] = -INFINITY; cls[u] = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 q = v[u][h];
+        if (q.x > best[u]) { best[u] = q.x; cls[u] = 4 * h; }
+        if (q.y > best[u]) { best[u] = q.y; cls[u] = 4 * h + 1; }
+        if (q.z > best[u]) { best[u] = q.z; cls[u] = 4 * h + 2; }
+        if (q.w > best[u]) { best[u] = q.w; cls[u] = 4 * h + 3; }
       }
-    } else {
-      for (int c = 0; c < C; ++c) {
-        const float v = ldg_stream1(p + c);
-        if (v > best) { best = v; cls = c; }
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < kFrontPer; ++u) {
+      const int a = (blockIdx.x * kFrontPer + u) * kFrontThreads + threadIdx.x;
+      best[u] = -INFINITY; cls[u] = 0;
+      if (a < A) {
+        const float* p = classification + ((size_t)b * A + a) * C;
+        if (vec) {
+          for (int c = 0; c < C; c += 4) {
+            const float4 q = ldg_stream4(p + c);
+            if (q.x > best[u]) { best[u] = q.x; cls[u] = c; }
+            if (q.y > best[u]) { best[u] = q.y; cls[u] = c + 1; }
+            if (q.z > best[u]) { best[u] = q.z; cls[u] = c + 2; }
+            if (q.w > best[u]) { best[u] = q.w; cls[u] = c + 3; }
+          }
+        } else {
+          for (int c = 0; c < C; ++c) {
+            const float q = ldg_stream1(p + c);
+            if (q > best[u]) { best[u] = q; cls[u] = c; }
+          }
+        }
       }
     }
   }
-  const bool hit = (a < A) && (best > thr);                  // scores > threshold (utils/decode.py:384)
-  const unsigned bal = __ballot_sync(0xffffffffu, hit);
-  if (bal == 0) return;
-  int base = 0;
-  if (lane == __ffs(bal) - 1) base = atomicAdd(cand_count + b, __popc(bal));
-  base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-  if (!hit) return;
-  const int pos = base + __popc(bal & ((1u << lane) - 1u));
-  if (pos >= cap) return;
-  // BBoxTransform (utils/utils.py:331-346); anchors (y1,x1,y2,x2), regression (dy,dx,dh,dw)
-  const float4 an = __ldg(reinterpret_cast<const float4*>(anchors) + a);
-  const float4 rg = __ldg(reinterpret_cast<const float4*>(regression) + (size_t)b * A + a);
-  const float yca = __fmul_rn(__fadd_rn(an.x, an.z), 0.5f), xca = __fmul_rn(__fadd_rn(an.y, an.w), 0.5f);
-  const float ha = __fsub_rn(an.z, an.x), wa = __fsub_rn(an.w, an.y);
-  const float w = __fmul_rn(expf(rg.w), wa), h = __fmul_rn(expf(rg.z), ha);
-  const float yc = __fadd_rn(__fmul_rn(rg.x, ha), yca), xc = __fadd_rn(__fmul_rn(rg.y, wa), xca);
-  float ymin = __fsub_rn(yc, __fmul_rn(h, 0.5f)), xmin = __fsub_rn(xc, __fmul_rn(w, 0.5f));
-  float ymax = __fadd_rn(yc, __fmul_rn(h, 0.5f)), xmax = __fadd_rn(xc, __fmul_rn(w, 0.5f));
-  // ClipBoxes (utils/utils.py:357-361)
-  xmin = fmaxf(xmin, 0.0f); ymin = fmaxf(ymin, 0.0f);
-  xmax = fminf(xmax, xmax_clip); ymax = fminf(ymax, ymax_clip);
-  const size_t o = (size_t)b * cap + pos;
-  cand_boxes[o] = make_float4(xmin, ymin, xmax, ymax);
-  cand_scores[o] = best;
-  cand_cls[o] = cls;
-  cand_anchor[o] = a;
+#pragma unroll
+  for (int u = 0; u < kFrontPer; ++u) {
+    const int a = (blockIdx.x * kFrontPer + u) * kFrontThreads + threadIdx.x;
+    const bool hit = (a < A) && (best[u] > thr);                  // scores > threshold (utils/decode.py:384)
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (bal == 0) continue;
+    int base = 0;
+    if (lane == __ffs(bal) - 1) base = atomicAdd(cand_count + b, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+    if (!hit) continue;
+    const int pos = base + __popc(bal & ((1u << lane) - 1u));
+    if (pos >= cap) continue;
+    // BBoxTransform (utils/utils.py:331-346); anchors (y1,x1,y2,x2), regression (dy,dx,dh,dw)
+    const float4 an = __ldg(reinterpret_cast<const float4*>(anchors) + a);
+    const float4 rg = __ldg(reinterpret_cast<const float4*>(regression) + (size_t)b * A + a);
+    const float yca = __fmul_rn(__fadd_rn(an.x, an.z), 0.5f), xca = __fmul_rn(__fadd_rn(an.y, an.w), 0.5f);
+    const float ha = __fsub_rn(an.z, an.x), wa = __fsub_rn(an.w, an.y);
+    const float w = __fmul_rn(expf(rg.w), wa), h = __fmul_rn(expf(rg.z), ha);
+    const float yc = __fadd_rn(__fmul_rn(rg.x, ha), yca), xc = __fadd_rn(__fmul_rn(rg.y, wa), xca);
+    float ymin = __fsub_rn(yc, __fmul_rn(h, 0.5f)), xmin = __fsub_rn(xc, __fmul_rn(w, 0.5f));
+    float ymax = __fadd_rn(yc, __fmul_rn(h, 0.5f)), xmax = __fadd_rn(xc, __fmul_rn(w, 0.5f));
+    // ClipBoxes (utils/utils.py:357-361)
+    xmin = fmaxf(xmin, 0.0f); ymin = fmaxf(ymin, 0.0f);
+    xmax = fminf(xmax, xmax_clip); ymax = fminf(ymax, ymax_clip);
+    const size_t o = (size_t)b * cap + pos;
+    cand_boxes[o] = make_float4(xmin, ymin, xmax, ymax);
+    cand_scores[o] = best[u];
+    cand_cls[o] = cls[u];
+    cand_anchor[o] = a;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -759,7 +792,7 @@ extern "C" int isg_decode_boxes(const float* anchors, const float* regression, c
   if (!aligned16(anchors) || !aligned16(regression) || !aligned16(cand_boxes)) return ISG_EINVAL;
   const bool vec = (C % 4 == 0) && aligned16(classification);
   ISG_CUDA(cudaMemsetAsync(cand_count, 0, (size_t)B * sizeof(int32_t), stream));
-  dim3 grid(cdiv(A, kFrontThreads), B);
+  dim3 grid(cdiv(A, kFrontThreads * kFrontPer), B);
   decode_boxes_kernel<<<grid, kFrontThreads, 0, stream>>>(anchors, regression, classification, A, C, (float)(W - 1),
                                                           (float)(H - 1), thr, cap, reinterpret_cast<float4*>(cand_boxes),
                                                           cand_scores, cand_cls, cand_anchor, cand_count, vec);
