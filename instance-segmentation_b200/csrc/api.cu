@@ -22,6 +22,7 @@ static Tuning read_tuning() {
   if (const char* e = getenv("ISG_DENSE_SPARE")) t.dense_spare = atoi(e) > 0 ? atoi(e) : 0;
   if (const char* e = getenv("ISG_DENSE_SKIP_AE")) t.dense_skip_ae = e[0] != '0';
   if (const char* e = getenv("ISG_TOPK_PATH")) t.topk_radix = e[0] == 'r';
+  if (const char* e = getenv("ISG_NMS_ROUNDS")) t.nms_rounds = atoi(e) > 0 ? atoi(e) : 0;
   if (const char* e = getenv("ISG_TOPK_SAMPLE")) t.topk_cluster_sample = e[0] == 'c';
   return t;
 }

@@ -252,49 +252,138 @@ nms_mask_kernel(const int32_t* __restrict__ count, int cap, double thr, int conv
 }
 
 // ---------------------------------------------------------------------------------------------
-// NMS step 3: greedy scan.  One CTA per image; 64-box chunks are resolved in order.  The
-// within-chunk dependency (64 sequential steps on one 64-bit word) runs in one thread on shared
-// memory; the cross-chunk propagation (OR of the kept rows into later words) is parallel.
+// Parallel suppression scan (shared by the fused small kernel and the staged scan).
+// The greedy keep set is the unique solution of  keep[i] = !OR_{j<i} (keep[j] & S[j][i])  (S = the strictly upper
+// triangular suppression matrix in rank order).  One ROUND computes  K <- ~OR_{j in K} row[j]  from K = all ones: a
+// fully parallel OR-reduction over the rows that are currently kept.  After r rounds the first r ranks are final
+// (induction over the rank), so a round that changes nothing has reached the greedy result; the number of rounds is
+// the depth of the longest suppression chain + 2 - a handful for detections - instead of one dependent step per
+// candidate.  A pathological chain (every box suppressing only its successor) would need ~n/2 rounds: after
+// `max_rounds` the function gives up and the caller runs the sequential scan.
+// rows: [n][rstride] 64-bit words in shared memory, word w of row j valid for w >= j/64.  K: [nw] keep words (result),
+// R32: [2*nw] scratch.  Lane layout: a lane owns ONE word column (conflict-free 8-byte shared loads) and a share of
+// the rows, ORs its kept rows in a register and meets the other lanes once per round.  Called by the whole CTA.
 // ---------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 256;   // >= nw for cap <= 16384
+__device__ __forceinline__ unsigned long long nms_valid_word(int w, int n) {
+  const int left = n - w * 64;
+  return left >= 64 ? ~0ull : (left <= 0 ? 0ull : ((1ull << left) - 1ull));
+}
+__device__ bool nms_parallel_scan(const unsigned long long* rows, int rstride, int n, int nw, unsigned long long* K,
+                                  uint32_t* R32, int max_rounds) {
+  const int t = threadIdx.x, T = blockDim.x, lane = t & 31, warp = t >> 5, nwarps = T >> 5;
+  int G = 1;
+  while (G < nw && G < 32) G <<= 1;             // lanes per row (word columns handled at once)
+  const int rpw = 32 / G;                        // rows per warp and sweep
+  const int wl = lane & (G - 1), rsub = lane / G;
+  for (int w = t; w < nw; w += T) K[w] = nms_valid_word(w, n);
+  for (int w = t; w < 2 * nw; w += T) R32[w] = 0u;
+  __syncthreads();
+  for (int round = 0; round < max_rounds; ++round) {
+    for (int wb = 0; wb < nw; wb += 32) {        // word columns wb .. wb+31 (one pass unless nw > 32)
+      const int w = wb + wl;
+      unsigned long long acc = 0ull;
+      for (int j = warp * rpw + rsub; j < n; j += nwarps * rpw) {
+        const int wj = j >> 6;
+        if (w >= wj && w < nw && ((K[wj] >> (j & 63)) & 1ull)) acc |= rows[(size_t)j * rstride + w];
+      }
+      for (int o = G; o < 32; o <<= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, o);
+      if (rsub == 0 && w < nw) {
+        const uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32);
+        if (lo) atomicOr(&R32[2 * w], lo);
+        if (hi) atomicOr(&R32[2 * w + 1], hi);
+      }
+    }
+    __syncthreads();
+    int changed = 0;
+    for (int w = t; w < nw; w += T) {
+      const unsigned long long nk = ~((unsigned long long)R32[2 * w] | ((unsigned long long)R32[2 * w + 1] << 32)) & nms_valid_word(w, n);
+      changed |= nk != K[w];
+      K[w] = nk; R32[2 * w] = 0u; R32[2 * w + 1] = 0u;
+    }
+    if (!__syncthreads_or(changed)) return true;
+  }
+  return false;
+}
+// keep list of a converged scan: the kept ranks in rank order.  pre: [nw + 1] scratch.  Called by the whole CTA.
+template <typename IdOf>
+__device__ void nms_emit_kept(const unsigned long long* K, int n, int nw, int* pre, int32_t* out, int32_t* n_keep_b, IdOf id_of) {
+  const int t = threadIdx.x, T = blockDim.x;
+  for (int w = t; w <= nw; w += T) {
+    int s = 0;
+    for (int u = 0; u < w; ++u) s += __popcll(K[u]);
+    pre[w] = s;
+  }
+  __syncthreads();
+  for (int j = t; j < n; j += T) {
+    const unsigned long long kw = K[j >> 6];
+    if ((kw >> (j & 63)) & 1ull) out[pre[j >> 6] + __popcll(kw & ((1ull << (j & 63)) - 1ull))] = id_of(j);
+  }
+  if (t == 0) *n_keep_b = pre[nw];
+}
 
-// Shared-memory staging of the suppression rows (dynamic shared memory), chosen by the launcher:
-//   staged 2: the WHOLE matrix [n][nw] is loaded once (fits for up to ~1400 candidates) - no global round trip inside
-//             the chunk loop at all;
-//   staged 1: the rows of the current chunk, words c .. nchunk-1 only, are loaded by all threads before the chunk is
-//             resolved;
-//   staged 0: rows are read from global memory (very large candidate sets).
-// The 64 dependent steps of a chunk run in one thread on registers (fully unrolled: test bit q, OR row q's diagonal
-// word); the propagation of the kept rows into the later words is one independent load per row and thread.
+// ---------------------------------------------------------------------------------------------
+// NMS step 3: suppression scan.  One CTA per image.
+//   * whole matrix staged (n * ceil(n/64) words fit in the dynamic shared memory - up to ~1400 candidates whatever the
+//     row capacity, the rows are staged compactly): parallel rounds (nms_parallel_scan), no dependent chain at all;
+//   * otherwise, or when the rounds do not converge: the sequential scan - 64-box chunks are resolved in order, the
+//     within-chunk dependency (64 steps on one 64-bit word) runs in one thread on registers (fully unrolled: test bit
+//     q, OR row q's diagonal word), the propagation of the kept rows into the later words is one independent load per
+//     row and thread.  The rows of the current chunk (words c .. nchunk-1) are staged in shared memory when they fit,
+//     else read from global memory (very large candidate sets).
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanMaxWords = ISG_NMS_MAX_BOXES / 64;   // 256 suppression words a row at most
+
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const int32_t* __restrict__ count, int cap, void* ws, int32_t* __restrict__ keep,
-                int32_t* __restrict__ n_keep, int staged) {
+                int32_t* __restrict__ n_keep, int smem_words, int max_rounds) {
   extern __shared__ __align__(16) unsigned long long scan_rows[];
   const int b = blockIdx.x, t = threadIdx.x;
   const int n = min(max(count[b], 0), cap);
   const NmsWs v = nms_ws_view(ws, b, cap);
   const int nw = (cap + 63) / 64;
   const int nchunk = (n + 63) / 64;
-  __shared__ unsigned long long remv[kScanThreads];
-  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long remv[kScanMaxWords];
   __shared__ unsigned long long s_kept;
-  remv[t] = 0ull;
+  if (t < kScanMaxWords) remv[t] = 0ull;
   int nk = 0;
   int32_t* out = keep + (size_t)b * cap;
+  // staging mode (block-uniform): 2 = whole matrix, compact rows [n][nchunk]; 1 = the current chunk; 0 = none
+  const int staged = (long long)n * nchunk <= smem_words ? 2 : (64 * nchunk <= smem_words ? 1 : 0);
   if (staged == 2) {
-    const uint4* src = reinterpret_cast<const uint4*>(v.mask);          // rows are 8-byte words; n * nw of them
-    const int n2 = (n * nw) >> 1;
-    for (int e = t; e < n2; e += kScanThreads) reinterpret_cast<uint4*>(scan_rows)[e] = src[e];
-    if (t == 0 && ((n * nw) & 1)) scan_rows[n * nw - 1] = v.mask[(size_t)n * nw - 1];
+    // words below a row's diagonal block are never read (and never written by nms_mask_kernel): skip them
+    const int total = n * nchunk;
+    for (int e0 = t; e0 < total; e0 += 4 * kScanThreads) {
+      unsigned long long q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kScanThreads;
+        const int j = e / nchunk, w = e - j * nchunk;
+        q[u] = (e < total && w >= (j >> 6)) ? v.mask[(size_t)j * nw + w] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (e0 + u * kScanThreads < total) scan_rows[e0 + u * kScanThreads] = q[u];
+    }
   }
   __syncthreads();
+  if (staged == 2 && max_rounds > 0) {
+    __shared__ unsigned long long Kw[kScanMaxWords];
+    __shared__ uint32_t R32[2 * kScanMaxWords];
+    __shared__ int pre[kScanMaxWords + 1];
+    if (nms_parallel_scan(scan_rows, nchunk, n, nchunk, Kw, R32, max_rounds)) {   // block-uniform
+      const int32_t* order = v.order;
+      nms_emit_kept(Kw, n, nchunk, pre, out, n_keep + b, [&](int j) { return order[j]; });
+      return;
+    }
+    __syncthreads();
+  }
   for (int c = 0; c < nchunk; ++c) {
     const int base = c * 64;
     const int m = min(64, n - base);
     const int nwc = nchunk - c;                 // staged 1: words c .. nchunk-1 of each row
     const unsigned long long* rows;
     int rstride, woff;
-    if (staged == 2) { rows = scan_rows + (size_t)base * nw; rstride = nw; woff = 0; }
+    if (staged == 2) { rows = scan_rows + (size_t)base * nchunk; rstride = nchunk; woff = 0; }
     else if (staged == 1) {
       for (int e = t; e < m * nwc; e += kScanThreads) {
         const int q = e / nwc, w = e - q * nwc;
@@ -335,18 +424,16 @@ nms_scan_kernel(const int32_t* __restrict__ count, int cap, void* ws, int32_t* _
   if (t == 0) n_keep[b] = nk;
 }
 
-// launch helper: picks the staging mode by what fits in shared memory
+// launch helper: the kernel picks its staging mode from the candidate count; the dynamic shared memory is sized for the
+// whole matrix when the row capacity allows it at all, else for one 64-row chunk
 static inline cudaError_t launch_nms_scan(const int32_t* count, int B, int cap, void* ws, int32_t* keep, int32_t* n_keep,
                                           cudaStream_t stream) {
   const size_t nw = (size_t)(cap + 63) / 64;
-  const size_t all = (size_t)cap * nw * sizeof(unsigned long long), chunk = 64 * nw * sizeof(unsigned long long);
-  const int staged = all <= 200 * 1024 ? 2 : (chunk <= 160 * 1024 ? 1 : 0);
-  const size_t smem = staged == 2 ? all : (staged == 1 ? chunk : 0);
-  if (staged) {
-    const cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  nms_scan_kernel<<<B, kScanThreads, smem, stream>>>(count, cap, ws, keep, n_keep, staged);
+  const size_t all = (size_t)cap * nw * 8, budget = 200 * 1024;
+  const size_t smem = std::min(all, budget);
+  const cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  nms_scan_kernel<<<B, kScanThreads, smem, stream>>>(count, cap, ws, keep, n_keep, (int)(smem / 8), tuning().nms_rounds);
   return cudaGetLastError();
 }
 
@@ -360,7 +447,7 @@ constexpr int kRankSortMax = 512;   // up to this many candidates: rank sort ins
 __global__ void __launch_bounds__(kSortThreads)
 nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int32_t* __restrict__ cls,
                  const int32_t* __restrict__ tiebreak, const int32_t* __restrict__ count, int cap, int P,
-                 double thr, int convention, int32_t* __restrict__ keep, int32_t* __restrict__ n_keep) {
+                 double thr, int convention, int32_t* __restrict__ keep, int32_t* __restrict__ n_keep, int max_rounds) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nwP = P / 64 > 0 ? P / 64 : 1;
   float4* sbox = reinterpret_cast<float4*>(smem_raw);                               // [P]
@@ -507,6 +594,17 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
     }
   }
   __syncthreads();
+  // parallel suppression scan (nms_parallel_scan); the sequential scan below only runs when it did not converge
+  if (max_rounds > 0) {
+    __shared__ unsigned long long Kw[kSmallMax / 64];
+    __shared__ uint32_t R32[2 * kSmallMax / 64];
+    __shared__ int pre[kSmallMax / 64 + 1];
+    if (nms_parallel_scan(mask, nwP, n, nw, Kw, R32, max_rounds)) {               // block-uniform
+      nms_emit_kept(Kw, n, nw, pre, keep + (size_t)b * cap, n_keep + b, [&](int j) { return (int32_t)val[j]; });
+      return;
+    }
+    __syncthreads();
+  }
   // greedy scan by warp 0, 64-box chunks, no block barriers.  The 64 dependent steps of a chunk run in ONE lane on
   // registers (fully unrolled: test bit q of the running word, OR row q's diagonal word): ~12 cycles a step whether the
   // box is kept or not, instead of a shuffle round trip (~180 cycles) per kept box.  The kept rows are then OR-ed into
@@ -1020,7 +1118,7 @@ extern "C" int isg_box_nms(const float* boxes, const float* scores, const int32_
     const size_t smem = (size_t)P * (16 + 8 + 4 + 4) + (size_t)P * nwP * 8;
     ISG_CUDA(cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ISG_CUDA(launch_pdl(nms_small_kernel, dim3(B), dim3(kSortThreads), smem, stream, reinterpret_cast<const float4*>(boxes), scores,
-                        cls, tiebreak, count, cap, P, thr, convention, keep, n_keep));
+                        cls, tiebreak, count, cap, P, thr, convention, keep, n_keep, tuning().nms_rounds));
     ISG_LAUNCH_CHECK();
     return ISG_OK;
   }

@@ -387,6 +387,37 @@ def test_py_cpu_nms_vs_oracle(mods, oracle, n, thr):
     assert np.array_equal(np.asarray(mods["nms"].py_cpu_nms(dets, thr)), np.asarray(rk.py_cpu_nms(dets, thr)))
 
 
+@pytest.mark.parametrize("n", [300, 1200])
+def test_nms_suppression_chain_falls_back_to_sequential_scan(mods, oracle, n):
+    """every box suppresses only its successor: the parallel suppression scan (one round per level of the chain) gives up
+    after its round limit and the sequential scan finishes - small fused kernel (n <= 1024) and staged scan"""
+    _, rk = oracle
+    x = 30.0 * np.arange(n, dtype=np.float32)
+    dets = np.stack([x, np.zeros_like(x), x + 100.0, np.full_like(x, 50.0), np.linspace(0.99, 0.01, n).astype(np.float32)], axis=1)
+    want = rk.py_cpu_nms(dets, 0.5)
+    assert list(want) == list(range(0, n, 2))
+    assert np.array_equal(np.asarray(mods["nms"].py_cpu_nms(dets, 0.5)), np.asarray(want))
+
+
+@pytest.mark.parametrize("rounds", ["0", "2"])
+@pytest.mark.parametrize("n", [700, 1250])
+def test_nms_parallel_and_sequential_scans_agree(mods, oracle, n, rounds, monkeypatch):
+    """ISG_NMS_ROUNDS=0 disables the parallel scan, 2 makes it give up on most inputs: same keep list either way"""
+    _, rk = oracle
+    lib = mods["lib"]
+    dets = mods["synth"].make_nms_boxes(n + 1, n, extent=900.0, thr=0.4, plus1=True)
+    want = np.asarray(rk.py_cpu_nms(dets, 0.4))
+    assert np.array_equal(np.asarray(mods["nms"].py_cpu_nms(dets, 0.4)), want)
+    monkeypatch.setenv("ISG_NMS_ROUNDS", rounds)
+    lib.lib().isg_debug_reload_tuning()
+    try:
+        got = np.asarray(mods["nms"].py_cpu_nms(dets, 0.4))
+    finally:
+        monkeypatch.delenv("ISG_NMS_ROUNDS")
+        lib.lib().isg_debug_reload_tuning()
+    assert np.array_equal(got, want)
+
+
 def test_boxes_nms_intended_semantics(mods, oracle):
     _, rk = oracle
     dets = mods["synth"].make_nms_boxes(9, 400, extent=500.0, thr=0.4, plus1=True)
