@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ISG_ABI_VERSION 4
+#define ISG_ABI_VERSION 5
 
 #define ISG_OK            0
 #define ISG_EINVAL       (-1)  /* bad argument (null pointer, negative extent, k > H*W ...) */
@@ -48,7 +48,12 @@ typedef void* isg_stream_t;    /* cudaStream_t */
 
 /* NMS conventions */
 #define ISG_NMS_PLUS1_LE 0  /* utils/nms.py:19,31-36: areas and overlaps use +1, survivor iff IoU <= thr (fp32 thr) */
-#define ISG_NMS_TV_GT    1  /* torchvision batched_nms as called at utils/decode.py:400: no +1, suppress iff IoU > thr, class aware */
+#define ISG_NMS_TV_GT    1  /* torchvision nms per class on the ORIGINAL coordinates (_batched_nms_vanilla): no +1, suppress iff IoU > thr */
+#define ISG_NMS_TV_TRICK 2  /* torchvision _batched_nms_coordinate_trick: before the IoU every box is shifted by
+                             * class * (largest coordinate of the image's candidates + 1), all in fp32 - what
+                             * batched_nms at utils/decode.py:400 does in torchvision 0.5.0 (the reference's pin) */
+#define ISG_NMS_TV_BATCHED 3 /* batched_nms of current torchvision on CPU tensors: the coordinate trick for up to 1000
+                             * candidates (boxes.numel() <= 4000), per-class NMS on the original coordinates above */
 #define ISG_NMS_MAX_BOXES 16384
 
 /* k-means metrics (utils/kmeans.py:34-39) */
@@ -206,8 +211,11 @@ int isg_decode_boxes(const float* anchors, const float* regression, const float*
  * torchvision.ops.batched_nms as called at utils/decode.py:400 (ISG_NMS_TV_GT).
  * boxes [B,cap,4] (x1,y1,x2,y2), scores [B,cap], cls [B,cap] int32 (nullable = class agnostic),
  * tiebreak [B,cap] int32 (nullable: candidate index is used; on equal scores the LARGER tiebreak
- * value is visited first for PLUS1_LE and the SMALLER first for TV_GT), count [B] device int32
- * (clamped to cap).  cap <= ISG_NMS_MAX_BOXES.
+ * value is visited first for PLUS1_LE and the SMALLER first for the TV_* conventions), count [B] device int32
+ * (clamped to cap).  cap <= ISG_NMS_MAX_BOXES.  The three TV_* conventions differ only in the coordinates the IoU is
+ * evaluated on (the shifted fp32 coordinates of the trick lose low-order bits, so a pair whose IoU is within ~1e-4 of
+ * thr can resolve differently); boxes of different classes never suppress each other in any of them (with negative
+ * coordinates torchvision's trick could let neighbouring classes overlap - not reproduced).
  * keep [B,cap] int32: candidate indices in pick order; n_keep [B].
  * ------------------------------------------------------------------------------------------ */
 size_t isg_box_nms_workspace_bytes(int B, int cap);
@@ -331,6 +339,7 @@ typedef struct isg_decode_step {
   int struct_bytes;
   int assign, polygons;
   int B, H, W, img_h, img_w, A, C, Nmax, cand_cap, cap, kp_th, obj_pixel_th;
+  int nms_convention;          /* ISG_NMS_TV_GT / ISG_NMS_TV_TRICK / ISG_NMS_TV_BATCHED (utils/decode.py:400) */
   float cls_th, ghost_k, scale;
   double iou_th;
   /* model outputs */

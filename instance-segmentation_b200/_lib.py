@@ -21,7 +21,7 @@ class DecodeStep(C.Structure):
     _fields_ = [
         ("struct_bytes", I), ("assign", I), ("polygons", I),
         ("B", I), ("H", I), ("W", I), ("img_h", I), ("img_w", I), ("A", I), ("C", I), ("Nmax", I), ("cand_cap", I), ("cap", I),
-        ("kp_th", I), ("obj_pixel_th", I),
+        ("kp_th", I), ("obj_pixel_th", I), ("nms_convention", I),
         ("cls_th", F), ("ghost_k", F), ("scale", F), ("iou_th", D),
         ("kp", P), ("kp_img_stride", I64), ("ae", P), ("ae_img_stride", I64), ("ae_plane_stride", I64),
         ("anchors", P), ("regression", P), ("classification", P), ("ys", P), ("xs", P),
@@ -93,6 +93,8 @@ PROTOTYPES = {
 
 ISG_NMS_PLUS1_LE = 0
 ISG_NMS_TV_GT = 1
+ISG_NMS_TV_TRICK = 2
+ISG_NMS_TV_BATCHED = 3
 ISG_NMS_MAX_BOXES = 16384
 ISG_KMEANS_EUCLIDEAN = 0
 ISG_KMEANS_COSINE = 1

@@ -135,6 +135,33 @@ __host__ __device__ inline NmsWs nms_ws_view(void* ws, int b, int cap) {
   return v;
 }
 
+// torchvision's coordinate trick (_batched_nms_coordinate_trick): offset = float(class) * (max coordinate + 1), added
+// to all four coordinates in fp32.  Used for ISG_NMS_TV_TRICK always and for ISG_NMS_TV_BATCHED while the candidate
+// set has at most 1000 boxes (boxes.numel() <= 4000, batched_nms's CPU dispatch rule).
+__device__ __forceinline__ bool nms_uses_trick(int convention, int n) {
+  return convention == ISG_NMS_TV_TRICK || (convention == ISG_NMS_TV_BATCHED && n <= 1000);
+}
+__device__ __forceinline__ float4 nms_shift_box(float4 b, int cls, float max_plus_1) {
+  const float off = __fmul_rn((float)cls, max_plus_1);
+  return make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
+}
+// largest coordinate of the image's n candidate boxes (boxes.max()), + 1; every thread of the CTA gets the result
+__device__ float nms_block_max_plus_1(const float4* __restrict__ boxes_b, int n, float* red /* [32] shared */) {
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float4 q = boxes_b[i];
+    m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  float r = -INFINITY;
+  for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) r = fmaxf(r, red[w]);
+  return __fadd_rn(r, 1.0f);
+}
+
 __global__ void __launch_bounds__(kSortThreads)
 nms_sort_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int32_t* __restrict__ cls,
                 const int32_t* __restrict__ tiebreak, const int32_t* __restrict__ count, int cap, int P,
@@ -175,12 +202,16 @@ nms_sort_kernel(const float4* __restrict__ boxes, const float* __restrict__ scor
     }
   }
   NmsWs v = nms_ws_view(ws, b, cap);
+  __shared__ float red[32];
+  const bool trick = cls && nms_uses_trick(convention, n);                 // block-uniform
+  const float mp1 = trick ? nms_block_max_plus_1(boxes + (size_t)b * cap, n, red) : 0.0f;
   for (int r = t; r < n; r += kSortThreads) {
     const int i = (int)val[r];
     const size_t o = (size_t)b * cap + i;
+    const int c = cls ? cls[o] : 0;
     v.order[r] = i;
-    v.sbox[r] = boxes[o];
-    v.scls[r] = cls ? cls[o] : 0;
+    v.sbox[r] = trick ? nms_shift_box(boxes[o], c, mp1) : boxes[o];        // sbox only feeds the IoU tests
+    v.scls[r] = c;
   }
 }
 
@@ -244,7 +275,7 @@ nms_mask_kernel(const int32_t* __restrict__ count, int cap, double thr, int conv
     unsigned long long bits = 0ull;
     for (int c = (rb == cb ? t + 1 : 0); c < ncol; ++c) {
       if (ccls[c] != ac) continue;   // class aware (batched_nms); class-agnostic callers pass cls = NULL -> all 0
-      const bool s = (convention == ISG_NMS_TV_GT) ? suppresses_tv(a, cbox[c], thr) : suppresses_plus1(a, cbox[c], thr_f);
+      const bool s = (convention != ISG_NMS_PLUS1_LE) ? suppresses_tv(a, cbox[c], thr) : suppresses_plus1(a, cbox[c], thr_f);
       if (s) bits |= 1ull << c;
     }
     v.mask[(size_t)i * nw + cb] = bits;
@@ -269,13 +300,14 @@ __device__ __forceinline__ unsigned long long nms_valid_word(int w, int n) {
   return left >= 64 ? ~0ull : (left <= 0 ? 0ull : ((1ull << left) - 1ull));
 }
 __device__ bool nms_parallel_scan(const unsigned long long* rows, int rstride, int n, int nw, unsigned long long* K,
-                                  uint32_t* R32, int max_rounds) {
+                                  uint32_t* R32, int max_rounds, const unsigned long long* alive = nullptr) {
   const int t = threadIdx.x, T = blockDim.x, lane = t & 31, warp = t >> 5, nwarps = T >> 5;
   int G = 1;
   while (G < nw && G < 32) G <<= 1;             // lanes per row (word columns handled at once)
   const int rpw = 32 / G;                        // rows per warp and sweep
   const int wl = lane & (G - 1), rsub = lane / G;
-  for (int w = t; w < nw; w += T) K[w] = nms_valid_word(w, n);
+  // `alive` (nullable, [nw] words): candidates already suppressed from outside never count (tiled large-set path)
+  for (int w = t; w < nw; w += T) K[w] = nms_valid_word(w, n) & (alive ? alive[w] : ~0ull);
   for (int w = t; w < 2 * nw; w += T) R32[w] = 0u;
   __syncthreads();
   for (int round = 0; round < max_rounds; ++round) {
@@ -296,7 +328,8 @@ __device__ bool nms_parallel_scan(const unsigned long long* rows, int rstride, i
     __syncthreads();
     int changed = 0;
     for (int w = t; w < nw; w += T) {
-      const unsigned long long nk = ~((unsigned long long)R32[2 * w] | ((unsigned long long)R32[2 * w + 1] << 32)) & nms_valid_word(w, n);
+      const unsigned long long nk = ~((unsigned long long)R32[2 * w] | ((unsigned long long)R32[2 * w + 1] << 32)) & nms_valid_word(w, n) &
+                                    (alive ? alive[w] : ~0ull);
       changed |= nk != K[w];
       K[w] = nk; R32[2 * w] = 0u; R32[2 * w + 1] = 0u;
     }
@@ -501,10 +534,16 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
       }
     }
   }
-  for (int r = t; r < n; r += kSortThreads) {
-    const size_t o = (size_t)b * cap + val[r];
-    sbox[r] = boxes[o];
-    scls[r] = cls ? cls[o] : 0;
+  {
+    __shared__ float red[32];
+    const bool trick = cls && nms_uses_trick(convention, n);               // block-uniform
+    const float mp1 = trick ? nms_block_max_plus_1(boxes + (size_t)b * cap, n, red) : 0.0f;
+    for (int r = t; r < n; r += kSortThreads) {
+      const size_t o = (size_t)b * cap + val[r];
+      const int c = cls ? cls[o] : 0;
+      sbox[r] = trick ? nms_shift_box(boxes[o], c, mp1) : boxes[o];        // sbox only feeds the IoU tests
+      scls[r] = c;
+    }
   }
   if (t < kSmallMax / 64) remv[t] = 0ull;
   __syncthreads();
@@ -558,7 +597,7 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
       for (int q = posof[i] + 1 + sub; q < qend; q += 4) {
         const int c = memb[q];                                  // rank > i, ascending
         if (scls[c] != ac) continue;                            // another class hashed into the same bucket
-        const bool sup = (convention == ISG_NMS_TV_GT) ? suppresses_tv(a, sbox[c], thr) : suppresses_plus1(a, sbox[c], thr_f);
+        const bool sup = (convention != ISG_NMS_PLUS1_LE) ? suppresses_tv(a, sbox[c], thr) : suppresses_plus1(a, sbox[c], thr_f);
         if (!sup) continue;
         const unsigned long long bit = 1ull << (c & 63);
         const int w = c >> 6;
@@ -584,7 +623,7 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
       for (int q = posof[i] + 1 + sub; q < qend; q += R) {
         const int c = memb[q];                                  // rank > i, ascending
         if (scls[c] != ac) continue;                            // another class hashed into the same bucket
-        const bool sup = (convention == ISG_NMS_TV_GT) ? suppresses_tv(a, sbox[c], thr) : suppresses_plus1(a, sbox[c], thr_f);
+        const bool sup = (convention != ISG_NMS_PLUS1_LE) ? suppresses_tv(a, sbox[c], thr) : suppresses_plus1(a, sbox[c], thr_f);
         if (!sup) continue;
         const int w = c >> 6;
         if (w != cur_w) { if (cur_w >= 0) atomicOr(&mask[(size_t)i * nwP + cur_w], bits); cur_w = w; bits = 0ull; }
@@ -646,6 +685,249 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
     __syncwarp();
   }
   if (t == 0) n_keep[b] = nk;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NMS, large candidate sets (cap > ISG_NMS_MAX_BOXES, e.g. an untrained head that fires on every anchor): no
+// suppression matrix (it would be cap^2 / 8 bytes).  (1) one CTA per image sorts the candidates by (score desc,
+// tie-break) with a stable LSD radix sort in global memory; (2) the ranks are resolved tile by tile (1024 ranks):
+// nms_tile_resolve_kernel decides the tile's still-alive members among themselves (1024 x 1024 bit matrix in shared
+// memory + the parallel suppression scan) and appends the kept ones to the keep list, nms_tile_suppress_kernel then
+// clears the alive bit of every later candidate one of them suppresses.  Work is O(n * kept) like the reference's
+// torchvision call; the path exists for completeness, not for speed.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLargeTile = 1024;
+constexpr int kLargeTileWords = kLargeTile / 64;
+
+struct NmsLargeWs {
+  unsigned long long* key[2];   // [cap] x 2 (ping-pong)
+  uint32_t* val[2];             // [cap] x 2
+  int32_t* order;               // [cap] candidate index of rank r
+  float4* sbox;                 // [cap] boxes in rank order (shifted for the coordinate trick)
+  int32_t* scls;                // [cap]
+  uint32_t* alive;              // [ceil(cap/32)]
+  float4* tbox;                 // [kLargeTile] kept boxes of the current tile
+  int32_t* tcls;                // [kLargeTile]
+  int32_t* tcount;              // [4]
+};
+__host__ __device__ inline size_t nms_large_ws_per_image(int cap) {
+  const size_t c = ((size_t)cap + 63) & ~(size_t)63;
+  return c * (8 * 2 + 4 * 2 + 4 + 16 + 4) + c / 8 + 128 + (size_t)kLargeTile * 20 + 256;
+}
+__host__ __device__ inline NmsLargeWs nms_large_ws_view(void* ws, int b, int cap) {
+  const size_t c = ((size_t)cap + 63) & ~(size_t)63;
+  char* p = (char*)ws + (size_t)b * ((nms_large_ws_per_image(cap) + 255) & ~(size_t)255);
+  NmsLargeWs v;
+  v.key[0] = (unsigned long long*)p; p += c * 8;
+  v.key[1] = (unsigned long long*)p; p += c * 8;
+  v.sbox = (float4*)p; p += c * 16;
+  v.val[0] = (uint32_t*)p; p += c * 4;
+  v.val[1] = (uint32_t*)p; p += c * 4;
+  v.order = (int32_t*)p; p += c * 4;
+  v.scls = (int32_t*)p; p += c * 4;
+  v.alive = (uint32_t*)p; p += c / 8 + 128;          // one tile of slack: the last tile reads 32 whole words
+  v.tbox = (float4*)p; p += (size_t)kLargeTile * 16;
+  v.tcls = (int32_t*)p; p += (size_t)kLargeTile * 4;
+  v.tcount = (int32_t*)p;
+  return v;
+}
+
+// stable LSD radix sort (8 passes of 8 bits over the inverted 64-bit key = descending order), one CTA per image
+__global__ void __launch_bounds__(1024)
+nms_large_sort_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int32_t* __restrict__ cls,
+                      const int32_t* __restrict__ tiebreak, const int32_t* __restrict__ count, int cap, int convention,
+                      void* ws, int32_t* __restrict__ n_keep) {
+  __shared__ uint32_t hist[256], base[256];
+  __shared__ uint32_t wcnt[32][257];
+  __shared__ float red[32];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n = min(max(count[b], 0), cap);
+  NmsLargeWs v = nms_large_ws_view(ws, b, cap);
+  for (int i = t; i < n; i += 1024) {
+    const size_t o = (size_t)b * cap + i;
+    const uint32_t tb = tiebreak ? (uint32_t)tiebreak[o] : (uint32_t)i;
+    const uint32_t low = (convention == ISG_NMS_PLUS1_LE) ? tb : (0xffffffffu - tb);
+    v.key[0][i] = ~(((unsigned long long)float_key(scores[o]) << 32) | low);     // ascending on the inverted key
+    v.val[0][i] = (uint32_t)i;
+  }
+  for (int w = t; w < (cap + 63) / 64 * 2 + 32; w += 1024) {
+    const int left = n - w * 32;
+    v.alive[w] = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+  }
+  if (t == 0) { n_keep[b] = 0; v.tcount[0] = 0; }
+  __syncthreads();
+  int cur = 0;
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 8 * pass;
+    const unsigned long long* kin = v.key[cur]; const uint32_t* vin = v.val[cur];
+    unsigned long long* kout = v.key[cur ^ 1]; uint32_t* vout = v.val[cur ^ 1];
+    if (t < 256) hist[t] = 0u;
+    __syncthreads();
+    for (int i = t; i < n; i += 1024) atomicAdd(&hist[(uint32_t)(kin[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    if (t == 0) { uint32_t run = 0; for (int d = 0; d < 256; ++d) { base[d] = run; run += hist[d]; } }
+    __syncthreads();
+    for (int t0 = 0; t0 < n; t0 += 1024) {
+      for (int e = t; e < 32 * 257; e += 1024) (&wcnt[0][0])[e] = 0u;
+      __syncthreads();
+      const int i = t0 + t;
+      const bool valid = i < n;
+      unsigned long long k = 0ull; uint32_t vv = 0u; uint32_t d = 256u;
+      if (valid) { k = kin[i]; vv = vin[i]; d = (uint32_t)(k >> shift) & 255u; }
+      const unsigned same = __match_any_sync(0xffffffffu, d);
+      const int rank_in_warp = __popc(same & ((1u << lane) - 1u));
+      if (valid && rank_in_warp == 0) wcnt[warp][d] = (uint32_t)__popc(same);
+      __syncthreads();
+      if (t < 256) {                                   // per digit: offsets of the warps in warp order, advance the base
+        uint32_t run = base[t];
+        for (int w = 0; w < 32; ++w) { const uint32_t c = wcnt[w][t]; wcnt[w][t] = run; run += c; }
+        base[t] = run;
+      }
+      __syncthreads();
+      if (valid) { const uint32_t pos = wcnt[warp][d] + (uint32_t)rank_in_warp; kout[pos] = k; vout[pos] = vv; }
+      __syncthreads();
+    }
+    cur ^= 1;
+  }
+  const uint32_t* val = v.val[cur];
+  const bool trick = cls && nms_uses_trick(convention, n);                 // block-uniform
+  const float mp1 = trick ? nms_block_max_plus_1(boxes + (size_t)b * cap, n, red) : 0.0f;
+  for (int r = t; r < n; r += 1024) {
+    const int i = (int)val[r];
+    const size_t o = (size_t)b * cap + i;
+    const int c = cls ? cls[o] : 0;
+    v.order[r] = i;
+    v.sbox[r] = trick ? nms_shift_box(boxes[o], c, mp1) : boxes[o];
+    v.scls[r] = c;
+  }
+}
+
+// tile `tile` (ranks tile*1024 ..): the alive members decide among themselves; kept ones go to the keep list (rank
+// order) and, with their boxes, to the tile table nms_tile_suppress_kernel reads
+__global__ void __launch_bounds__(1024)
+nms_tile_resolve_kernel(const int32_t* __restrict__ count, int cap, int tile, double thr, int convention, void* ws,
+                        int32_t* __restrict__ keep, int32_t* __restrict__ n_keep, int max_rounds) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  float4* sb = reinterpret_cast<float4*>(tile_smem);                                   // [1024]
+  unsigned long long* rows = reinterpret_cast<unsigned long long*>(sb + kLargeTile);     // [1024][16]
+  int* sc = reinterpret_cast<int*>(rows + (size_t)kLargeTile * kLargeTileWords);         // [1024]
+  __shared__ unsigned long long alive[kLargeTileWords], Kw[kLargeTileWords];
+  __shared__ uint32_t R32[2 * kLargeTileWords];
+  __shared__ int pre[kLargeTileWords + 1];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int n = min(max(count[b], 0), cap);
+  const int base = tile * kLargeTile;
+  NmsLargeWs v = nms_large_ws_view(ws, b, cap);
+  if (base >= n) { if (t == 0) v.tcount[0] = 0; return; }
+  const int m = min(kLargeTile, n - base);
+  if (t < kLargeTileWords) {
+    const uint32_t lo = v.alive[(base >> 5) + 2 * t], hi = v.alive[(base >> 5) + 2 * t + 1];
+    alive[t] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+  }
+  if (t < m) { sb[t] = v.sbox[base + t]; sc[t] = v.scls[base + t]; }
+  __syncthreads();
+  {
+    const float thr_f = (float)thr;
+    const bool me = t < m && ((alive[t >> 6] >> (t & 63)) & 1ull);
+    const float4 a = me ? sb[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ac = me ? sc[t] : 0;
+    unsigned long long bits = 0ull;
+    int cw = t >> 6;
+    for (int w = 0; w < (t >> 6); ++w) rows[(size_t)t * kLargeTileWords + w] = 0ull;
+    for (int c = (t & ~63); c < ((m + 63) & ~63); ++c) {                                  // words from the diagonal one on
+      if ((c >> 6) != cw) { rows[(size_t)t * kLargeTileWords + cw] = bits; bits = 0ull; cw = c >> 6; }
+      if (!me || c <= t || c >= m || sc[c] != ac || !((alive[c >> 6] >> (c & 63)) & 1ull)) continue;
+      const bool sup = (convention != ISG_NMS_PLUS1_LE) ? suppresses_tv(a, sb[c], thr) : suppresses_plus1(a, sb[c], thr_f);
+      if (sup) bits |= 1ull << (c & 63);
+    }
+    rows[(size_t)t * kLargeTileWords + cw] = bits;
+    for (int w = cw + 1; w < kLargeTileWords; ++w) rows[(size_t)t * kLargeTileWords + w] = 0ull;
+  }
+  __syncthreads();
+  const int nw = (m + 63) >> 6;
+  if (!nms_parallel_scan(rows, kLargeTileWords, m, nw, Kw, R32, max_rounds, alive)) {    // block-uniform
+    // did not converge (a suppression chain): sequential scan by warp 0
+    __syncthreads();
+    if (t < 32) {
+      unsigned long long rem = 0ull, kept = 0ull;      // lane w < 16 owns removed / kept word w
+      for (int i = 0; i < m; ++i) {
+        const int wi = i >> 6;
+        const unsigned long long rw = __shfl_sync(0xffffffffu, rem, wi), aw = alive[wi];
+        const bool take = ((aw >> (i & 63)) & 1ull) && !((rw >> (i & 63)) & 1ull);     // warp-uniform
+        if (take) {
+          if (t == wi) kept |= 1ull << (i & 63);
+          if (t < kLargeTileWords) rem |= rows[(size_t)i * kLargeTileWords + t];
+        }
+      }
+      if (t < kLargeTileWords) Kw[t] = kept;
+    }
+    __syncthreads();
+  }
+  const int nk0 = n_keep[b];
+  const int32_t* order = v.order;
+  __shared__ int tile_kept;
+  nms_emit_kept(Kw, m, nw, pre, keep + (size_t)b * cap + nk0, &tile_kept, [&](int j) { return order[base + j]; });
+  __syncthreads();
+  if (t < m && ((Kw[t >> 6] >> (t & 63)) & 1ull)) {
+    const int pos = pre[t >> 6] + __popcll(Kw[t >> 6] & ((1ull << (t & 63)) - 1ull));
+    v.tbox[pos] = sb[t]; v.tcls[pos] = sc[t];
+  }
+  if (t == 0) { v.tcount[0] = tile_kept; n_keep[b] = nk0 + tile_kept; }
+}
+
+// every still-alive candidate behind the tile against the tile's kept boxes; a warp owns one word of the alive mask
+__global__ void __launch_bounds__(256)
+nms_tile_suppress_kernel(const int32_t* __restrict__ count, int cap, int tile, double thr, int convention, void* ws) {
+  __shared__ float4 kb[kLargeTile];
+  __shared__ int kc[kLargeTile];
+  const int b = blockIdx.y, t = threadIdx.x, lane = t & 31;
+  const int n = min(max(count[b], 0), cap);
+  NmsLargeWs v = nms_large_ws_view(ws, b, cap);
+  const int first = (tile + 1) * kLargeTile;
+  if (first >= n) return;
+  const int nkept = v.tcount[0];
+  if (nkept == 0) return;
+  for (int i = t; i < nkept; i += 256) { kb[i] = v.tbox[i]; kc[i] = v.tcls[i]; }
+  __syncthreads();
+  const float thr_f = (float)thr;
+  for (long long j0 = (long long)first + ((long long)blockIdx.x * 256 + (t - lane)); j0 < n; j0 += (long long)gridDim.x * 256) {
+    const int j = (int)j0 + lane;
+    const uint32_t word = v.alive[j0 >> 5];
+    bool live = j < n && ((word >> lane) & 1u);
+    if (live) {
+      const float4 c = v.sbox[j];
+      const int cc = v.scls[j];
+      for (int i = 0; i < nkept; ++i) {
+        if (kc[i] != cc) continue;
+        const bool sup = (convention != ISG_NMS_PLUS1_LE) ? suppresses_tv(kb[i], c, thr) : suppresses_plus1(kb[i], c, thr_f);
+        if (sup) { live = false; break; }
+      }
+    }
+    const uint32_t still = __ballot_sync(0xffffffffu, live);
+    if (lane == 0 && still != word) v.alive[j0 >> 5] = still;
+  }
+}
+
+static int run_nms_large(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
+                         const int32_t* count, int B, int cap, double thr, int convention, int32_t* keep,
+                         int32_t* n_keep, void* ws, cudaStream_t stream) {
+  nms_large_sort_kernel<<<B, 1024, 0, stream>>>(reinterpret_cast<const float4*>(boxes), scores, cls, tiebreak, count, cap,
+                                                convention, ws, n_keep);
+  ISG_LAUNCH_CHECK();
+  const size_t smem = (size_t)kLargeTile * (16 + 8 * kLargeTileWords + 4);
+  ISG_CUDA(cudaFuncSetAttribute(nms_tile_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = cdiv(cap, kLargeTile);
+  const int rounds = tuning().nms_rounds;
+  for (int tile = 0; tile < tiles; ++tile) {
+    nms_tile_resolve_kernel<<<B, 1024, smem, stream>>>(count, cap, tile, thr, convention, ws, keep, n_keep, rounds);
+    const int later = cap - (tile + 1) * kLargeTile;
+    if (later > 0) {
+      dim3 grid((unsigned)std::min(cdiv(later, 256), 148 * 8), (unsigned)B);
+      nms_tile_suppress_kernel<<<grid, 256, 0, stream>>>(count, cap, tile, thr, convention, ws);
+    }
+  }
+  ISG_LAUNCH_CHECK();
+  return ISG_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1084,6 +1366,7 @@ extern "C" int isg_pack_masks(const uint8_t* dense, int n, int H, int W, uint32_
 
 extern "C" size_t isg_box_nms_workspace_bytes(int B, int cap) {
   if (B <= 0 || cap <= 0) return 0;
+  if (cap > ISG_NMS_MAX_BOXES) return (size_t)B * ((nms_large_ws_per_image(cap) + 255) & ~(size_t)255);
   return (size_t)B * nms_ws_per_image(cap);
 }
 
@@ -1109,9 +1392,15 @@ extern "C" int isg_box_nms(const float* boxes, const float* scores, const int32_
                            int32_t* n_keep, void* ws, size_t ws_bytes, isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!boxes || !scores || !count || !keep || !n_keep || B <= 0 || cap <= 0 || B > 65535) return ISG_EINVAL;
-  if (convention != ISG_NMS_PLUS1_LE && convention != ISG_NMS_TV_GT) return ISG_EINVAL;
-  if (cap > ISG_NMS_MAX_BOXES) return ISG_EUNSUPPORTED;
+  if (convention != ISG_NMS_PLUS1_LE && convention != ISG_NMS_TV_GT && convention != ISG_NMS_TV_TRICK &&
+      convention != ISG_NMS_TV_BATCHED)
+    return ISG_EINVAL;
+  if (cap > (1 << 24)) return ISG_EUNSUPPORTED;
   if (!aligned16(boxes)) return ISG_EINVAL;
+  if (cap > ISG_NMS_MAX_BOXES) {   // no suppression matrix: sort + tile-by-tile resolution
+    if (!ws || ws_bytes < isg_box_nms_workspace_bytes(B, cap) || ((uintptr_t)ws & 255)) return ISG_EWORKSPACE;
+    return run_nms_large(boxes, scores, cls, tiebreak, count, B, cap, thr, convention, keep, n_keep, ws, stream);
+  }
   if (cap <= kSmallMax) {   // fused single-CTA path, no workspace needed
     const int P = next_pow2(cap);
     const int nwP = P / 64 > 0 ? P / 64 : 1;

@@ -24,6 +24,8 @@ extern "C" int isg_decode_step(const isg_decode_step_t* s) {
   // `main` may be the default stream (a null handle); `side` must be a different stream
   if (!s->side || !s->fork_event || !s->join_event || s->main == s->side) return ISG_EINVAL;
   if (s->assign != ISG_ASSIGN_DENSE && s->assign != ISG_ASSIGN_SPARSE) return ISG_EINVAL;
+  if (s->nms_convention != ISG_NMS_TV_GT && s->nms_convention != ISG_NMS_TV_TRICK && s->nms_convention != ISG_NMS_TV_BATCHED)
+    return ISG_EINVAL;
   cudaStream_t main = (cudaStream_t)s->main, side = (cudaStream_t)s->side;
   cudaEvent_t fork = (cudaEvent_t)s->fork_event, join = (cudaEvent_t)s->join_event;
   const int B = s->B, H = s->H, W = s->W, N = s->Nmax;
@@ -42,7 +44,7 @@ extern "C" int isg_decode_step(const isg_decode_step_t* s) {
   STEP_TRY(isg_decode_boxes(s->anchors, s->regression, s->classification, B, s->A, s->C, s->img_h, s->img_w, s->cls_th,
                             s->cand_cap, s->cand_boxes, s->cand_scores, s->cand_cls, s->cand_anchor, s->cand_count, main));
   STEP_TRY(isg_box_nms(s->cand_boxes, s->cand_scores, s->cand_cls, s->cand_anchor, s->cand_count, B, s->cand_cap, s->iou_th,
-                       ISG_NMS_TV_GT, s->keep, s->n_keep, s->nms_ws, s->nms_ws_bytes, main));
+                       s->nms_convention, s->keep, s->n_keep, s->nms_ws, s->nms_ws_bytes, main));
   STEP_TRY(isg_gather_build_seeds(s->cand_boxes, s->cand_scores, s->cand_cls, s->keep, s->n_keep, B, s->cand_cap, N, s->ys,
                                   s->xs, H, W, s->ghost_k, s->scale, s->rois, s->scores, s->cls, s->n_seeds, s->seeds,
                                   s->ghost, s->stats, s->img_total, main));

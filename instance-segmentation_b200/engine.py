@@ -97,6 +97,12 @@ def popcount_rows(bits: torch.Tensor):
     return np.unpackbits(a.reshape(a.shape[0], -1).view(np.uint8), axis=1).sum(axis=1)
 
 
+# Box NMS of the decode (torchvision.ops.batched_nms at utils/decode.py:400).  ISG_NMS_TV_BATCHED reproduces the batched_nms
+# of current torchvision on CPU tensors (coordinate trick for <= 1000 candidates, per-class NMS above) - what the reference
+# computes in this image; ISG_NMS_TV_TRICK is torchvision 0.5.0 (the reference's pin); ISG_NMS_TV_GT never shifts the boxes.
+BOX_NMS_CONVENTION = _lib.ISG_NMS_TV_BATCHED
+
+
 def aligned_workspace(nbytes: int, device: torch.device):
     """(tensor, 256-byte aligned device pointer) of at least `nbytes`"""
     t = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
@@ -315,7 +321,7 @@ class BoxPlan:
         self.device = require_cuda(device)
         check_device(self.device)
         self.B, self.A, self.C, self.H, self.W = int(B), int(A), int(C), int(H), int(W)
-        self.cap = int(min(cap, _lib.ISG_NMS_MAX_BOXES, A))
+        self.cap = int(min(cap, A))
         self.N = int(min(max_keep, self.cap))
         d, i32, f32 = self.device, torch.int32, torch.float32
         B, cap, N = self.B, self.cap, self.N
@@ -353,7 +359,7 @@ class BoxPlan:
              float(np.float32(cls_th)), self.cap, ptr(self.cand_boxes), ptr(self.cand_scores), ptr(self.cand_cls),
              ptr(self.cand_anchor), ptr(self.cand_count), s)
         call("isg_box_nms", ptr(self.cand_boxes), ptr(self.cand_scores), ptr(self.cand_cls), ptr(self.cand_anchor),
-             ptr(self.cand_count), B, self.cap, float(iou_th), _lib.ISG_NMS_TV_GT, ptr(self.keep), ptr(self.n_keep),
+             ptr(self.cand_count), B, self.cap, float(iou_th), BOX_NMS_CONVENTION, ptr(self.keep), ptr(self.n_keep),
              self.ws_ptr, self.ws_bytes, s)
         if gather:
             call("isg_gather_kept", ptr(self.cand_boxes), ptr(self.cand_scores), ptr(self.cand_cls), ptr(self.keep),
@@ -453,6 +459,7 @@ class DecodePipeline:
             raise ValueError("host-resident ae / regression need assign='sparse'")
         st.assign = _lib.ISG_ASSIGN_SPARSE if sparse else _lib.ISG_ASSIGN_DENSE
         st.polygons, st.obj_pixel_th = 1 if polygons else 0, int(obj_pixel_th)
+        st.nms_convention = BOX_NMS_CONVENTION
         st.cls_th, st.iou_th = float(np.float32(cls_th)), float(iou_th)
         st.kp, st.kp_img_stride = ptr(kp), kp.stride(0) if B > 1 else H * W
         st.ae, st.ae_img_stride, st.ae_plane_stride = device_address(ae), ae.stride(0) if B > 1 else 4 * H * W, ae.stride(1)
@@ -578,7 +585,7 @@ def make_pipeline(B, A, C, H, W, img_h, img_w, kp_th, device, cand_cap=1024, max
                   scale=1.0) -> "DecodePipeline":
     """box plan + dense-mode decode plan + pipeline sharing one read-back arena"""
     device = require_cuda(device)
-    N = int(min(max_keep, min(cand_cap, _lib.ISG_NMS_MAX_BOXES, A)))
+    N = int(min(max_keep, min(cand_cap, A)))
     cap = min(max(min(int(kp_th), H * W), int(min_cap), 1), H * W)
     arena = Arena(Arena.bytes_for(B, N, cap), device)
     bplan = BoxPlan(B, A, C, img_h, img_w, device, cand_cap, max_keep, arena=arena)

@@ -236,6 +236,31 @@ def make_nms_boxes(seed: int, n: int, extent: float = 1000.0, thr: float = 0.5, 
     return np.concatenate([b, s[:, None]], axis=1).astype(np.float32)
 
 
+def make_near_threshold_boxes(seed: int, n_pairs: int, thr: float, ncls: int = 8, extent: float = 2000.0):
+    """Adversarial NMS input: pairs of same-class boxes whose IoU sits within a few fp32 ulps of `thr` (bisection on a
+    horizontal shift in fp64), so that the low-order bits of the coordinates the IoU is evaluated on decide the
+    outcome - torchvision's coordinate trick and its per-class NMS resolve a few percent of the pairs differently.
+    Returns boxes [2n,4] (x1,y1,x2,y2) float32, scores [2n] float32 (distinct), classes [2n] int64."""
+    rs = np.random.RandomState(seed)
+    out_b, out_c = [], []
+    for _ in range(n_pairs):
+        w, h = rs.uniform(30, 200, 2)
+        x, y = rs.uniform(0, extent - 2 * w), rs.uniform(0, extent - h)
+        lo, hi = 0.0, w
+        for _ in range(60):                 # IoU of two equal boxes shifted by d in x: (w - d) / (w + d)
+            mid = 0.5 * (lo + hi)
+            if (w - mid) / (w + mid) > thr:
+                lo = mid
+            else:
+                hi = mid
+        d = lo + rs.uniform(-3e-5, 3e-5) * w
+        c = rs.randint(0, ncls)
+        out_b += [[x, y, x + w, y + h], [x + d, y, x + d + w, y + h]]
+        out_c += [c, c]
+    s = _distinct_float32(rs.uniform(0.1, 1.0, size=2 * n_pairs).astype(np.float32))
+    return np.asarray(out_b, np.float32), s, np.asarray(out_c, np.int64)
+
+
 def make_masks(seed: int, n: int, H: int, W: int, C: int = 80):
     """n ellipse masks bit-packed to uint32 [n,H,ceil(W/32)], boxes int32 [n,4] (x0,y0,x1,y1), scores, classes."""
     rs = np.random.RandomState(seed)

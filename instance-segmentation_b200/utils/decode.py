@@ -491,11 +491,8 @@ def decode_boxes(x, anchors, regression, classification, threshold, iou_threshol
                                     cap, max_keep)
         n_cand = plan.cand_count.cpu().numpy()
         n_keep = plan.n_keep.cpu().numpy()
-        if n_cand.max(initial=0) > plan.cap and plan.cap < min(_lib.ISG_NMS_MAX_BOXES, plan.A):
-            cap = min(cap * 4, _lib.ISG_NMS_MAX_BOXES); continue
-        if n_cand.max(initial=0) > plan.cap:
-            raise RuntimeError("decode_boxes: %d candidates above cls_th exceed the supported %d per image"
-                               % (int(n_cand.max()), plan.cap))
+        if n_cand.max(initial=0) > plan.cap:          # plan.cap < A here: every anchor can be a candidate at most
+            cap = max(cap * 4, int(n_cand.max())); continue
         if n_keep.max(initial=0) > plan.N:
             max_keep = min(max_keep * 4, plan.cap); continue
         break
@@ -642,9 +639,7 @@ def _plan_overflow(pipe, sparse=False):
         tot = max(tot, int(dp.host["count"].max()))
     if n_cand <= bp.cap and n_keep <= bp.N and tot <= dp.cap:
         return None
-    if n_cand > bp.cap and bp.cap >= min(_lib.ISG_NMS_MAX_BOXES, bp.A):
-        raise RuntimeError("decode_output: %d candidates above cls_th exceed the supported %d per image" % (n_cand, bp.cap))
-    cand_cap = min(max(bp.cap * 4, n_cand), _lib.ISG_NMS_MAX_BOXES) if n_cand > bp.cap else bp.cap
+    cand_cap = min(max(bp.cap * 4, n_cand), bp.A) if n_cand > bp.cap else bp.cap
     return cand_cap, (min(max(bp.N * 4, n_keep), cand_cap) if n_keep > bp.N else bp.N), (tot if tot > dp.cap else 0)
 
 
@@ -827,11 +822,8 @@ def _decode_output_batch(inputs, outs, infos, transforms, decode_cfg, device):
         last_timing["d2h_bytes"] = 0
         n_cand = _host(bplan.cand_count)
         n_keep = _host(bplan.n_keep)
-        if n_cand.max(initial=0) > bplan.cap:
-            if bplan.cap >= min(_lib.ISG_NMS_MAX_BOXES, bplan.A):
-                raise RuntimeError("decode_output: %d candidates above cls_th exceed the supported %d per image"
-                                   % (int(n_cand.max()), bplan.cap))
-            cap = min(cap * 4, _lib.ISG_NMS_MAX_BOXES); continue
+        if n_cand.max(initial=0) > bplan.cap:         # bplan.cap < A here
+            cap = max(cap * 4, int(n_cand.max())); continue
         if n_keep.max(initial=0) > bplan.N:
             max_keep = min(max(max_keep * 4, int(n_keep.max())), bplan.cap); continue
         need = int(_host(plan.count).max(initial=0))

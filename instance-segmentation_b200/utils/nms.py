@@ -23,9 +23,7 @@ def _dev(t=None) -> torch.device:
 
 
 def _run_box_nms(boxes, scores, cls, thr, convention, dev):
-    n = boxes.shape[0]
-    if n > _lib.ISG_NMS_MAX_BOXES:
-        raise RuntimeError("box NMS supports at most %d boxes per call (got %d)" % (_lib.ISG_NMS_MAX_BOXES, n))
+    n = boxes.shape[0]       # more than ISG_NMS_MAX_BOXES: the library's tiled large-set path (no suppression matrix)
     lib = _lib.lib()
     count = torch.tensor([n], dtype=torch.int32, device=dev)
     keep = torch.empty(n, dtype=torch.int32, device=dev)

@@ -347,6 +347,17 @@ def batched_nms_numpy(boxes: np.ndarray, scores: np.ndarray, classes: np.ndarray
     return keep[np.argsort(-scores[keep], kind="stable")]
 
 
+def batched_nms_trick_numpy(boxes: np.ndarray, scores: np.ndarray, classes: np.ndarray, thr: float) -> np.ndarray:
+    """torchvision.ops.boxes._batched_nms_coordinate_trick restated (the only form of batched_nms in torchvision 0.5.0,
+    the reference's pin, and the CPU path of current torchvision for up to 1000 boxes): every box is shifted by
+    float32(class) * (boxes.max() + 1) in fp32 and ONE class-agnostic NMS runs on the shifted coordinates."""
+    if len(boxes) == 0:
+        return np.zeros(0, dtype=np.int64)
+    b = boxes.astype(np.float32)
+    off = classes.astype(np.float32) * (b.max() + np.float32(1))
+    return nms_torchvision_numpy(b + off[:, None], scores, thr)
+
+
 def decode_boxes(height, width, anchors, regression, classification, threshold, iou_threshold, use_torchvision=True):
     """utils/decode.py:377-419; x is only used for its H, W."""
     from torchvision.ops.boxes import batched_nms

@@ -451,6 +451,120 @@ def test_tv_nms_vs_torchvision(mods):
     assert np.array_equal(got, want)
 
 
+def _box_nms(mods, boxes, scores, cls, thr, convention):
+    lib, eng = mods["lib"], mods["engine"]
+    d = torch.device(DEV)
+    n = len(boxes)
+    bt = torch.from_numpy(boxes.copy()).to(d).contiguous(); st = torch.from_numpy(scores.copy()).to(d)
+    ct = torch.from_numpy(cls.astype(np.int32)).to(d); count = torch.tensor([n], dtype=torch.int32, device=d)
+    keep = torch.empty(n, dtype=torch.int32, device=d); nk = torch.empty(1, dtype=torch.int32, device=d)
+    wsb = int(lib.lib().isg_box_nms_workspace_bytes(1, n))
+    ws, ws_ptr = eng.aligned_workspace(max(wsb, 256), d)
+    lib.call("isg_box_nms", bt.data_ptr(), st.data_ptr(), ct.data_ptr(), 0, count.data_ptr(), 1, n, thr, convention,
+             keep.data_ptr(), nk.data_ptr(), ws_ptr, wsb, eng.stream_ptr(d))
+    return keep[:int(nk.item())].cpu().numpy()
+
+
+@pytest.mark.parametrize("n_pairs", [300, 600])        # 600 / 1200 boxes: fused small kernel / staged path
+def test_box_nms_conventions_follow_torchvision_on_near_threshold_pairs(mods, n_pairs):
+    """IoUs within a few fp32 ulps of the threshold: the coordinate trick (shifted fp32 coordinates) and the per-class
+    NMS resolve some pairs differently; each convention of isg_box_nms must reproduce its torchvision function bit for
+    bit, and ISG_NMS_TV_BATCHED the dispatch of batched_nms itself (trick up to 1000 boxes, per-class above)"""
+    tvb = pytest.importorskip("torchvision.ops.boxes")
+    lib = mods["lib"]
+    differ = 0
+    for seed in (11, 12):
+        b, s, c = mods["synth"].make_near_threshold_boxes(seed, n_pairs, 0.5)
+        tb, ts, tc = torch.from_numpy(b), torch.from_numpy(s), torch.from_numpy(c)
+        trick = tvb._batched_nms_coordinate_trick(tb, ts, tc, 0.5).numpy()
+        vanilla = tvb._batched_nms_vanilla(tb, ts, tc, 0.5).numpy()
+        assert np.array_equal(_box_nms(mods, b, s, c, 0.5, lib.ISG_NMS_TV_TRICK), trick)
+        assert np.array_equal(_box_nms(mods, b, s, c, 0.5, lib.ISG_NMS_TV_GT), vanilla)
+        assert np.array_equal(_box_nms(mods, b, s, c, 0.5, lib.ISG_NMS_TV_BATCHED), tvb.batched_nms(tb, ts, tc, 0.5).numpy())
+        differ += len(set(trick.tolist()) ^ set(vanilla.tolist()))
+    assert differ > 0
+
+
+def _random_boxes(seed, n, extent, ncls):
+    rs = np.random.RandomState(seed)
+    ctr = rs.uniform(0, extent, size=(n, 2)); wh = rs.uniform(20, 200, size=(n, 2))
+    b = np.concatenate([ctr - wh / 2, ctr + wh / 2], axis=1).astype(np.float32)
+    s = rs.permutation(n).astype(np.float32) / np.float32(n) + np.float32(0.001)          # distinct scores
+    return b, s, rs.randint(0, ncls, size=n).astype(np.int64)
+
+
+@pytest.mark.parametrize("rounds", [None, "0"])
+def test_box_nms_beyond_the_matrix_limit_follows_torchvision(mods, rounds, monkeypatch):
+    """more candidates than ISG_NMS_MAX_BOXES (an untrained head fires on every anchor): the tiled large-set path (radix
+    sort + tile-by-tile resolution, no suppression matrix) gives torchvision's keep list; rounds=0 forces the sequential
+    scan inside every tile"""
+    tvb = pytest.importorskip("torchvision.ops.boxes")
+    lib = mods["lib"]
+    n = 40000
+    assert n > lib.ISG_NMS_MAX_BOXES
+    b, s, c = _random_boxes(5, n, 3000.0, 8)
+    tb, ts, tc = torch.from_numpy(b), torch.from_numpy(s), torch.from_numpy(c)
+    if rounds is not None:
+        monkeypatch.setenv("ISG_NMS_ROUNDS", rounds)
+        lib.lib().isg_debug_reload_tuning()
+    try:
+        got_gt = _box_nms(mods, b, s, c, 0.5, lib.ISG_NMS_TV_GT)
+        got_batched = _box_nms(mods, b, s, c, 0.5, lib.ISG_NMS_TV_BATCHED)
+        got_trick = _box_nms(mods, b, s, c, 0.5, lib.ISG_NMS_TV_TRICK)
+    finally:
+        if rounds is not None:
+            monkeypatch.delenv("ISG_NMS_ROUNDS")
+            lib.lib().isg_debug_reload_tuning()
+    vanilla = tvb._batched_nms_vanilla(tb, ts, tc, 0.5).numpy()
+    assert np.array_equal(got_gt, vanilla)
+    assert np.array_equal(got_batched, tvb.batched_nms(tb, ts, tc, 0.5).numpy())
+    assert np.array_equal(got_trick, tvb._batched_nms_coordinate_trick(tb, ts, tc, 0.5).numpy())
+
+
+def test_py_cpu_nms_beyond_the_matrix_limit(mods, oracle):
+    _, rk = oracle
+    b, s, _ = _random_boxes(6, 20000, 2500.0, 1)
+    dets = np.concatenate([b, s[:, None]], axis=1).astype(np.float32)
+    assert np.array_equal(np.asarray(mods["nms"].py_cpu_nms(dets, 0.5)), np.asarray(rk.py_cpu_nms(dets, 0.5)))
+
+
+def test_decode_boxes_every_anchor_fires(mods, oracle):
+    """all of ~24.5 k anchors above cls_th (what an untrained classification head produces): the reference runs
+    batched_nms on all of them (utils/decode.py:395-400); the drop-in re-plans past ISG_NMS_MAX_BOXES instead of raising"""
+    rd, _ = oracle
+    H, W = 256, 512
+    anchors = mods["utils"].Anchors()(torch.zeros((1, 3, H, W), device=DEV)).cpu()
+    A, C = anchors.shape[1], 4
+    assert A > mods["lib"].ISG_NMS_MAX_BOXES
+    g = torch.Generator().manual_seed(3)
+    regression = torch.randn((1, A, 4), generator=g) * 0.2
+    regression[..., 2:] = 0.0            # exp(0) is exact on both sides: the decoded boxes are bit-identical
+    classification = torch.rand((1, A, C), generator=g) * 0.5 + 0.3
+    want = rd.decode_boxes(H, W, anchors, regression, classification, 0.25, 0.4)[0]
+    got = mods["decode"].decode_boxes(torch.zeros((1, 3, H, W)), anchors.to(DEV), regression.to(DEV), classification.to(DEV), 0.25, 0.4)[0]
+    assert len(want["scores"]) > 100
+    assert np.array_equal(got["class_ids"], want["class_ids"])
+    assert np.array_equal(got["scores"], want["scores"])
+    np.testing.assert_allclose(got["rois"], want["rois"], rtol=1e-6, atol=1e-4)
+
+
+def test_decode_boxes_near_threshold_pairs_follow_the_reference(mods, oracle):
+    """decode_boxes on anchors that form near-threshold pairs (regression 0, so the decoded boxes are the anchors): the
+    kept set must be the one torchvision.ops.batched_nms gives the reference (utils/decode.py:400), bit for bit"""
+    rd, _ = oracle
+    b, s, c = mods["synth"].make_near_threshold_boxes(21, 350, 0.5, extent=1000.0)
+    A, C, H, W = len(b), 8, 1024, 2048
+    anchors = torch.from_numpy(np.ascontiguousarray(b[:, [1, 0, 3, 2]]))[None]          # y1,x1,y2,x2
+    regression = torch.zeros((1, A, 4))
+    classification = torch.zeros((1, A, C))
+    classification[0, torch.arange(A), torch.from_numpy(c)] = torch.from_numpy(s)
+    want = rd.decode_boxes(H, W, anchors, regression, classification, 0.05, 0.5)[0]
+    got = mods["decode"].decode_boxes(torch.zeros((1, 3, H, W)), anchors.to(DEV), regression.to(DEV), classification.to(DEV), 0.05, 0.5)[0]
+    assert np.array_equal(got["class_ids"], want["class_ids"])
+    assert np.array_equal(got["scores"], want["scores"])
+    assert np.array_equal(got["rois"], want["rois"])
+
+
 # ---------------------------------------------------------------------------------------------- full decode
 @pytest.mark.parametrize("mode", ["sparse", "dense", "dense-host-polygons"])
 def test_decode_output_vs_oracle(mods, oracle, mode):

@@ -174,3 +174,23 @@ def test_anchor_restatement_matches_reference(golden):
         assert a.shape[1] == int(g["count_%dx%d" % (h, w)])
         assert np.array_equal(np.frombuffer(hashlib.sha256(a.tobytes()).digest(), dtype=np.uint8), g["sha_%dx%d" % (h, w)])
         assert np.array_equal(a[0, g["rows_%dx%d" % (h, w)]], g["vals_%dx%d" % (h, w)])
+
+
+def test_batched_nms_restatements_vs_torchvision_near_threshold():
+    """pairs whose IoU sits within a few fp32 ulps of the threshold: the coordinate trick and the per-class NMS of
+    torchvision disagree on some of them; each restatement must follow its own library function exactly"""
+    import isg_b200  # noqa: F401
+    from isg_b200 import synth
+    from oracle import ref_decode as rd
+    tvb = pytest.importorskip("torchvision.ops.boxes")
+    differ = 0
+    for seed in range(3):
+        b, s, c = synth.make_near_threshold_boxes(seed, 300, 0.5)
+        tb, ts, tc = torch.from_numpy(b), torch.from_numpy(s), torch.from_numpy(c)
+        trick = tvb._batched_nms_coordinate_trick(tb, ts, tc, 0.5).numpy()
+        vanilla = tvb._batched_nms_vanilla(tb, ts, tc, 0.5).numpy()
+        assert np.array_equal(rd.batched_nms_trick_numpy(b, s, c, 0.5), trick)
+        assert np.array_equal(rd.batched_nms_numpy(b, s, c, 0.5), vanilla)
+        assert np.array_equal(tvb.batched_nms(tb, ts, tc, 0.5).numpy(), trick)      # 600 boxes: numel <= 4000
+        differ += len(set(trick.tolist()) ^ set(vanilla.tolist()))
+    assert differ > 0      # the inputs do separate the two conventions
