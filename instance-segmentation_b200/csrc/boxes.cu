@@ -712,7 +712,7 @@ struct NmsLargeWs {
 };
 __host__ __device__ inline size_t nms_large_ws_per_image(int cap) {
   const size_t c = ((size_t)cap + 63) & ~(size_t)63;
-  return c * (8 * 2 + 4 * 2 + 4 + 16 + 4) + c / 8 + 128 + (size_t)kLargeTile * 20 + 256;
+  return c * (8 * 2 + 4 * 2 + 4 + 16 + 4) + ((c / 8 + 128 + 15) & ~(size_t)15) + (size_t)kLargeTile * 20 + 256;
 }
 __host__ __device__ inline NmsLargeWs nms_large_ws_view(void* ws, int b, int cap) {
   const size_t c = ((size_t)cap + 63) & ~(size_t)63;
@@ -725,7 +725,7 @@ __host__ __device__ inline NmsLargeWs nms_large_ws_view(void* ws, int b, int cap
   v.val[1] = (uint32_t*)p; p += c * 4;
   v.order = (int32_t*)p; p += c * 4;
   v.scls = (int32_t*)p; p += c * 4;
-  v.alive = (uint32_t*)p; p += c / 8 + 128;          // one tile of slack: the last tile reads 32 whole words
+  v.alive = (uint32_t*)p; p += (c / 8 + 128 + 15) & ~(size_t)15;          // one tile of slack: the last tile reads 32 whole words
   v.tbox = (float4*)p; p += (size_t)kLargeTile * 16;
   v.tcls = (int32_t*)p; p += (size_t)kLargeTile * 4;
   v.tcount = (int32_t*)p;

@@ -539,7 +539,9 @@ def test_decode_boxes_every_anchor_fires(mods, oracle):
     g = torch.Generator().manual_seed(3)
     regression = torch.randn((1, A, 4), generator=g) * 0.2
     regression[..., 2:] = 0.0            # exp(0) is exact on both sides: the decoded boxes are bit-identical
-    classification = torch.rand((1, A, C), generator=g) * 0.5 + 0.3
+    classification = torch.full((1, A, C), 0.26)                 # distinct maxima: the order of equal scores is unspecified
+    top = torch.randperm(A, generator=g).float() / A * 0.5 + 0.3
+    classification[0, torch.arange(A), torch.randint(0, C, (A,), generator=g)] = top
     want = rd.decode_boxes(H, W, anchors, regression, classification, 0.25, 0.4)[0]
     got = mods["decode"].decode_boxes(torch.zeros((1, 3, H, W)), anchors.to(DEV), regression.to(DEV), classification.to(DEV), 0.25, 0.4)[0]
     assert len(want["scores"]) > 100
