@@ -539,8 +539,45 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
         q[u] = in[u] ? ldg_stream4(img + p) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       // Candidates are a few percent of the pixels: reject in the float domain first (x < lower_f as floats implies
-      // key(x) < lower; -0 / NaN / a NaN bound fail the strict compare and take the exact key test), and let the rare
-      // survivors append themselves one by one (the candidate list is an unordered set).
+      // key(x) < lower; -0 / NaN / a NaN bound fail the strict compare and take the exact key test).
+#ifndef ISG_FILTER_INLINE_APPEND
+      // Main loop without any divergence: one test per 128-bit group (its maximum below the bound rejects all four
+      // pixels: 3 FMNMX + 1 compare; fmaxf drops NaN operands, and NaNs are outside the contract) sets a flag bit.  Nearly
+      // every warp holds a group with a candidate, but only a lane or two of it: the flagged groups are handled AFTER the
+      // loop, where the warp runs the append code once per flagged group of its busiest lane (1-2 times) instead of once
+      // per pixel position of every group (the append is ~20 instructions: exact key test, one shared-memory atomic for
+      // the group's candidates, up to four stores).
+      uint32_t hit = 0u;
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const float m4 = fmaxf(fmaxf(q[u].x, q[u].y), fmaxf(q[u].z, q[u].w));
+        hit |= (in[u] && !(m4 < lower_f)) ? (1u << u) : 0u;
+      }
+      while (hit) {
+        const int u = __ffs(hit) - 1;
+        hit &= hit - 1u;
+        float4 g = q[0];                                    // register select (a dynamic index would go to local memory)
+#pragma unroll
+        for (int w = 1; w < kUnroll; ++w) if (u == w) g = q[w];
+        const float x4[4] = {g.x, g.y, g.z, g.w};
+        uint32_t kk[4];
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          kk[i] = float_key(x4[i]);
+          const bool ok = !(x4[i] < lower_f) && kk[i] >= lower && kk[i] <= upper && kk[i] != 0xffffffffu;
+          if (!ok) kk[i] = 0xffffffffu;
+          c += ok ? 1 : 0;
+        }
+        if (c) {
+          uint32_t o2 = atomicAdd(&s_count, (uint32_t)c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (kk[i] != 0xffffffffu) buf[o2++] = kk[i];
+        }
+      }
+#else
+      // variant kept for A/B measurements: the survivors append themselves inside the loop, one by one
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         // one test per 128-bit group first: its maximum below the bound rejects all four pixels (3 FMNMX + 1 compare
@@ -556,6 +593,7 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
           }
         }
       }
+#endif
     }
   } else {
     for (int p0 = base; p0 < end; p0 += kFilterThreads * 4) {   // warp-uniform trip count

@@ -597,6 +597,33 @@ def test_decode_output_vs_oracle(mods, oracle, mode):
             assert_polygon_equivalent(dec, p1, p2, ctr2)
 
 
+def test_decode_output_replans_past_the_nms_matrix_limit(mods):
+    """every anchor above cls_th: decode_output grows its candidate / seed plans past ISG_NMS_MAX_BOXES (tiled large-set NMS)
+    instead of raising, and every detection it returns is one of decode_boxes' boxes"""
+    synth, dec = mods["synth"], mods["decode"]
+    H, W, C = 256, 512, 4
+    anchors = synth.make_anchors(H, W)
+    img = synth.make_scene(77, H, W, 10, C, anchors)[0]
+    A = anchors.shape[1] if anchors.ndim == 3 else anchors.shape[0]
+    assert A > mods["lib"].ISG_NMS_MAX_BOXES
+    g = torch.Generator().manual_seed(4)
+    reg = torch.randn((1, A, 4), generator=g) * 0.2
+    reg[..., 2:] = 0.0
+    cls = torch.full((1, A, C), 0.26)
+    cls[0, torch.arange(A), torch.randint(0, C, (A,), generator=g)] = torch.randperm(A, generator=g).float() / A * 0.5 + 0.3
+    anc = torch.from_numpy(anchors).reshape(1, A, 4)
+    kp, ae = torch.from_numpy(img.kp)[None], torch.from_numpy(img.ae)[None]
+    boxes = dec.decode_boxes(torch.zeros((1, 3, H, W)), anc.to(DEV), reg.to(DEV), cls.to(DEV), 0.25, 0.1)[0]
+    cfg = DecodeCfg(kp_th=3000)
+    cfg.cls_th, cfg.iou_th = 0.25, 0.1
+    got = dec.decode_output(torch.zeros((1, 3, H, W)), ((kp.to(DEV), ae.to(DEV), None), reg.to(DEV), cls.to(DEV), anc.to(DEV)),
+                            [TransInfo("/nonexistent.png", (H, W))], IdentityTransforms(), cfg, torch.device(DEV))
+    assert len(got) == 1 and len(boxes["scores"]) > 64
+    known = {(int(c), np.float32(f).item()) for c, f in zip(boxes["class_ids"], boxes["scores"])}
+    for c, f, ctr, poly in got[0]:
+        assert (int(c), np.float32(f).item()) in known and len(poly) >= 1
+
+
 @pytest.mark.parametrize("mode", ["sparse", "dense", "dense-host-polygons"])
 def test_decode_output_plateau_overflow_is_not_silent(mods, mode):
     """A plateau at the k-th value: every tied pixel is selected, so an image keeps more pixels than k.  The drop-in must
