@@ -169,6 +169,7 @@ nms_sort_kernel(const float4* __restrict__ boxes, const float* __restrict__ scor
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);   // [P]
   uint32_t* val = reinterpret_cast<uint32_t*>(key + P);                        // [P]
+  pdl_trigger();      // isg_mask_nms runs its mask-area pass (independent of the order) alongside this single-CTA sort
   const int b = blockIdx.x, t = threadIdx.x;
   const int n = min(max(count[b], 0), cap);
   int Pn = 1;
@@ -1009,6 +1010,9 @@ mask_area_kernel(const uint32_t* __restrict__ masks, int H, int Wwords, const in
     area[i] = a;
     bbox[i] = make_int4(bx0, by0, bx1, by1);
   }
+  // launched with programmatic stream serialisation behind the (independent) rank sort: this grid only completes once
+  // the sort has, so that everything later in the stream sees both results (a no-op for an ordinary launch)
+  pdl_wait();
 }
 
 // One warp per (row ri, block of 32 later ranks rj): the lanes test class equality and bounding-box overlap of their
@@ -1436,12 +1440,13 @@ extern "C" int isg_mask_nms(const uint32_t* masks, int n, int H, int Wwords, con
   NmsWs v = nms_ws_view(ws, 0, n);
   const int nw = cdiv(n, 64);
   set_int_kernel<<<1, 1, 0, stream>>>(cnt, n);
-  mask_area_kernel<<<n, 256, 0, stream>>>(masks, H, Wwords, reinterpret_cast<const int4*>(bboxes), area, bbox);
   // rank order by (score desc, larger index first on ties) — the greedy loop of utils/nms.py:20-37.
   // sbox is not needed: boxes pointer is only dereferenced for sbox, so hand the sort a dummy view.
   int rc = run_nms_stages(reinterpret_cast<const float*>(bbox), scores, cls, nullptr, cnt, 1, n, thr, ISG_NMS_PLUS1_LE,
                           keep, n_keep, ws, stream, false);
   if (rc) return rc;
+  // the HBM-bound area / bounding-box pass does not depend on the order: it starts while the single-CTA sort runs
+  ISG_CUDA(launch_pdl(mask_area_kernel, dim3(n), dim3(256), 0, stream, masks, H, Wwords, reinterpret_cast<const int4*>(bboxes), area, bbox));
   ISG_CUDA(cudaMemsetAsync(v.mask, 0, (size_t)n * nw * 8, stream));
   const long long items = (long long)n * cdiv(n, 32);            // (row, block of 32 later ranks) per warp
   const int blocks = (int)std::min<long long>((items * 32 + 255) / 256, 148LL * 16);
