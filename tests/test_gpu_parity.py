@@ -529,25 +529,27 @@ def test_py_cpu_nms_beyond_the_matrix_limit(mods, oracle):
 
 
 def test_decode_boxes_every_anchor_fires(mods, oracle):
-    """all of ~24.5 k anchors above cls_th (what an untrained classification head produces): the reference runs
-    batched_nms on all of them (utils/decode.py:395-400); the drop-in re-plans past ISG_NMS_MAX_BOXES instead of raising"""
+    """all of ~24.5 k anchors above cls_th (what an untrained classification head produces), two images: the reference
+    runs batched_nms on all of them (utils/decode.py:395-400); the drop-in re-plans past ISG_NMS_MAX_BOXES instead of raising"""
     rd, _ = oracle
-    H, W = 256, 512
+    H, W, B = 256, 512, 2
     anchors = mods["utils"].Anchors()(torch.zeros((1, 3, H, W), device=DEV)).cpu()
     A, C = anchors.shape[1], 4
     assert A > mods["lib"].ISG_NMS_MAX_BOXES
     g = torch.Generator().manual_seed(3)
-    regression = torch.randn((1, A, 4), generator=g) * 0.2
+    regression = torch.randn((B, A, 4), generator=g) * 0.2
     regression[..., 2:] = 0.0            # exp(0) is exact on both sides: the decoded boxes are bit-identical
-    classification = torch.full((1, A, C), 0.26)                 # distinct maxima: the order of equal scores is unspecified
-    top = torch.randperm(A, generator=g).float() / A * 0.5 + 0.3
-    classification[0, torch.arange(A), torch.randint(0, C, (A,), generator=g)] = top
-    want = rd.decode_boxes(H, W, anchors, regression, classification, 0.25, 0.4)[0]
-    got = mods["decode"].decode_boxes(torch.zeros((1, 3, H, W)), anchors.to(DEV), regression.to(DEV), classification.to(DEV), 0.25, 0.4)[0]
-    assert len(want["scores"]) > 100
-    assert np.array_equal(got["class_ids"], want["class_ids"])
-    assert np.array_equal(got["scores"], want["scores"])
-    np.testing.assert_allclose(got["rois"], want["rois"], rtol=1e-6, atol=1e-4)
+    classification = torch.full((B, A, C), 0.26)                 # distinct maxima: the order of equal scores is unspecified
+    for b in range(B):
+        top = torch.randperm(A, generator=g).float() / A * 0.5 + 0.3
+        classification[b, torch.arange(A), torch.randint(0, C, (A,), generator=g)] = top
+    want = rd.decode_boxes(H, W, anchors, regression, classification, 0.25, 0.4)
+    got = mods["decode"].decode_boxes(torch.zeros((B, 3, H, W)), anchors.to(DEV), regression.to(DEV), classification.to(DEV), 0.25, 0.4)
+    for b in range(B):
+        assert len(want[b]["scores"]) > 100
+        assert np.array_equal(got[b]["class_ids"], want[b]["class_ids"])
+        assert np.array_equal(got[b]["scores"], want[b]["scores"])
+        np.testing.assert_allclose(got[b]["rois"], want[b]["rois"], rtol=1e-6, atol=1e-4)
 
 
 def test_decode_boxes_near_threshold_pairs_follow_the_reference(mods, oracle):
