@@ -52,6 +52,37 @@ ALGO_BYTES_PER_PIXEL = 24   # dense kernel: kp + 4 ae planes read (20 B) + int32
 KERNEL_TIMING_LAUNCHES = 24
 
 
+def l2_note(in_bytes, out_bytes):
+    tot = (in_bytes + out_bytes) / 1e6
+    return ("a step reads %.0f MB of inputs and writes a %.0f MB label map: %.0f MB %s the 126 MB L2; no flush%s"
+            % (in_bytes / 1e6, out_bytes / 1e6, tot, ">" if tot > 126 else "<", "" if tot > 126 else " (CI-sized workload, not a bench line)"))
+
+
+def workload_config(args, wl):
+    """The `config` block of a bench line: static facts of the workload only, so that the repo arm and the reference arm
+    (--impl reference) print the SAME dictionary for the same command line.  Measured facts of the batch (seeds, candidates,
+    keep pixels per image, ...) go to `workload_stats`."""
+    if wl.get("kind") == "mask_nms":
+        H, W, n = wl["H"], wl["W"], wl["N"]
+        return {"workload": args.workload, "masks": n, "H": H, "W": W, "classes": wl["C"], "iou_thr": wl["thr"],
+                "step": "mask-IoU NMS of %d bit-packed masks: per-mask popcount + tight bbox, score sort, same-class pair IoU on the bbox "
+                        "intersection, greedy scan" % n,
+                "l2": "masks are %.0f MB per step (> 126 MB L2); no flush" % (n * H * ((W + 31) // 32) * 4 / 1e6)}
+    H, W = wl["H"], wl["W"]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    B = -(-args.global_batch // world) if args.global_batch > 0 else wl["B"]      # rank 0's shard (dist.shard_range)
+    A, C = 9 * sum((H // s) * (W // s) for s in (8, 16, 32, 64, 128)), wl["C"]     # utils/utils.py:419-443
+    cfg = {"workload": args.workload, "inputs": args.inputs, "B_per_gpu": B, "H": H, "W": W, "seeds_nominal": wl["N"], "anchors": A,
+           "classes": C, "kp_th": wl["kp_th"], "cls_th": CLS_TH, "iou_th": IOU_TH, "wh_delta": WH_DELTA, "obj_pixel_th": OBJ_PIXEL_TH,
+           "l2": l2_note(B * (5 * H * W + A * (4 + C)) * 4 + A * 16, B * H * W * 4),
+           "step": "decode_output of one batch: box head + NMS + seeds + top-k + 3x3 peaks + embedding / membership / assignment + "
+                   "per-instance polygons (point sets, internal point, angular sort, centre test)"
+                   + (" + k-means refinement of every image" if wl.get("kmeans") else "")}
+    if args.global_batch > 0:
+        cfg["global_batch"] = args.global_batch
+    return cfg
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -294,7 +325,7 @@ def run_reference(args, wl, rank, world):
     line = {"impl": "reference", "metric": "decoded Mpix/s", "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": 1, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "inputs": args.inputs, **{k: wl[k] for k in ("B", "H", "W", "N", "C", "kp_th")}},
+            "config": workload_config(args, wl),
             "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
                              "split_ms_per_image": split},
             "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -326,7 +357,7 @@ def run_reference_mask_nms(args, wl):
               "utils/image.py:188-191 on bit-packed masks (the reference has no mask NMS function; pair count grows with n^2)" % (n, wl["N"]))
     line = {"impl": "reference", "metric": "decoded Mpix/s", "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": 1,
             "warmup": 0, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-            "data": "synthetic", "config": {"workload": args.workload, **{k: wl[k] for k in ("B", "H", "W", "N", "C")}},
+            "data": "synthetic", "config": workload_config(args, wl),
             "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -402,9 +433,7 @@ def run_mask_nms(args, wl, rank, world, local_rank):
     line = {"metric": "decoded Mpix/s", "value": world * n * H * W * steps / (t_max * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
             "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": t_max / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": args.workload, "masks": n, "H": H, "W": W, "classes": wl["C"], "iou_thr": wl["thr"], "kept": kept,
-                       "step": "isg_mask_nms on %d bit-packed masks: per-mask popcount + tight bbox, score sort, same-class pair IoU on the bbox intersection, greedy scan" % n,
-                       "l2": "masks are %.0f MB per step (> 126 MB L2); no flush" % (algo / 1e6)},
+            "config": workload_config(args, wl), "workload_stats": {"kept": kept},
             "roofline": {"bound": "hbm", "kernel": "isg_mask_nms (mask_area_kernel + nms_sort + mask_pair_kernel + nms_scan); algorithmic bytes = one read of every mask word",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "peak_source": peak_src, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo,
@@ -609,21 +638,16 @@ def run_ours(args, wl, rank, world, local_rank):
             t0 = time.perf_counter()
             rd.decode_output(H, W, outs, kp_th=wl["kp_th"], cls_th=CLS_TH, iou_th=IOU_TH, wh_delta=WH_DELTA)
             cpu["port_value"] = n_img * H * W / (time.perf_counter() - t0) / 1e6
-    config = {"workload": args.workload, "inputs": args.inputs, "B_per_gpu": B, "H": H, "W": W, "seeds_per_image": [int(v) for v in n_keep[:8]],
-              "candidates_per_image": [int(v) for v in n_cand[:8]], "keep_pixels_per_image": [int(v) for v in counts[:8]],
-              "anchors": A, "classes": C, "kp_th": wl["kp_th"], "mode": "dense",
-              "l2": "inputs are %.0f MB per step (> 126 MB L2); no flush" % (sum(v.numel() * 4 for v in d.values()) / 1e6),
-              "step": "box head + NMS + seeds + top-k + tile lists + fused assign + per-instance polygons (point sets, internal point, angular sort, centre test)"
-                      + (" + k-means refinement of every image" if use_kmeans else ""),
-              "pipelining": "steps go round-robin through %d independent pipelines (own plans / streams, one isg_decode_step call each); "
-                            "neighbouring steps overlap, every step runs all of its kernels" % len(ring.pipes),
-              "isolated_step_ms": iso_ms, "timed_region_s": t_max * 1e-3}
-    if strong:
-        config["global_batch"] = args.global_batch
+    config = workload_config(args, wl)
+    stats = {"seeds_per_image": [int(v) for v in n_keep[:8]], "candidates_per_image": [int(v) for v in n_cand[:8]],
+             "keep_pixels_per_image": [int(v) for v in counts[:8]], "mode": "dense",
+             "pipelining": "steps go round-robin through %d independent pipelines (own plans / streams, one isg_decode_step call each); "
+                           "neighbouring steps overlap, every step runs all of its kernels" % len(ring.pipes),
+             "isolated_step_ms": iso_ms, "timed_region_s": t_max * 1e-3}
     line = {"metric": "decoded Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": total_steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t_max / total_steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary()}
+            "workload_stats": stats, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary()}
     if use_kmeans:
         line["kmeans"] = {"iterations_per_image": float(np.mean(km_state["iters"])), "calls": len(km_state["iters"]),
                           "points_per_image": [int(v) for v in counts], "clusters_per_image": [int(v) for v in n_keep]}
