@@ -23,6 +23,11 @@
 //     tile a warp owns RW consecutive rows and walks down them with a rolling window of the separable 3x3 maximum; a
 //     lane owns 4 consecutive pixels of each row;
 //   * consumers are stateless with respect to images: everything they need is in the stage (header + list);
+//   * EARLY RELEASE: a warp hands its stage slot back as soon as the kp window and the ae values of its rows are in
+//     registers, before the membership loop; the tile lists live in their own ring, G slots deeper than the stage ring
+//     (D4Smem), so they stay valid until the group has finished the tile.  Measured: 3 / 4 / 5 stages 76.7 / 71.6 / 70.4 us
+//     with release at the end of the tile, 71.7 / 70.2 / 70.4 us with early release - at 5 stages the ring depth is not
+//     the bound, the early release makes the kernel insensitive to it (ISG_DENSE_DEBUG bit 2 restores the late release);
 //   * the membership loop tracks the SMALLEST exponent q instead of the largest exp(-q): exp is monotone, so the
 //     winner is the same seed whenever two memberships differ as fp32 numbers, and the transcendental per
 //     (pixel, seed) pair disappears.  q >= ln(2^150) is where exp(-q) rounds to 0 in fp32 (label stays 0).
@@ -200,12 +205,15 @@ __device__ __forceinline__ void d4_tma_4d(void* dst, const CUtensorMap* tm, int 
 template <int RW, int WG>
 struct D4Smem {
   int stage, list, list_stride, bars, thr, total;
-  __host__ __device__ D4Smem(int cap, int nstages) {
+  // The list ring is G slots deeper than the stage ring: consumers hand a stage back as soon as its pixels are in
+  // registers (early release) but keep reading the tile's list; the list slot of tile s is reused by tile s + nstages + G,
+  // which the producer issues only after the same group released tile s + G - i.e. after it finished tile s.
+  __host__ __device__ D4Smem(int cap, int nstages, int G) {
     using Geo = D4Geom<RW, WG>;
     int o = 0;
     stage = o; o += nstages * Geo::kStage;
     list_stride = (int)sizeof(TileHdr) + cap * (int)sizeof(SeedRec);
-    list = o;  o += nstages * list_stride;
+    list = o;  o += (nstages + G) * list_stride;
     bars = o;  o += 2 * kD4MaxStages * 8;
     thr = o;   o += kD4MaxStages * 4;           // selection threshold key of the tile in each slot (written by the producer)
     total = o;
@@ -284,8 +292,9 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
   static_assert(RW % 2 == 0, "rows are processed in pairs");
   using Geo = D4Geom<RW, WG>;
   constexpr int kConsumers = WG * G;
+  const bool early_release = !(dbg_flags & 4);        // measurement aid: bit 2 = release stages only at the end of a tile
   extern __shared__ __align__(1024) unsigned char smem[];
-  const D4Smem<RW, WG> L(cap, nstages);
+  const D4Smem<RW, WG> L(cap, nstages, G);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);           // [kD4MaxStages]
   uint64_t* empty = full + kD4MaxStages;                                 // [kD4MaxStages]
   uint32_t* s_thr = reinterpret_cast<uint32_t*>(smem + L.thr);           // [kD4MaxStages]
@@ -306,7 +315,8 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
     const int tiles_per_img = tilesX * tilesY;
     const unsigned T = (unsigned)B * (unsigned)tiles_per_img;
     const uint32_t list_bytes = (uint32_t)L.list_stride;
-    int slot = 0, round = 0;
+    const int lslots = nstages + G;
+    int slot = 0, round = 0, ls = 0;                       // ls: slot of the list ring (tile sequence number mod lslots)
     // Tile order: the first n_static tiles of a CTA are c, c + P, c + 2P, ... (P = grid size; neighbouring CTAs work
     // on neighbouring tiles, no scheduling traffic); the last `dyn_tail` tiles per CTA (and the remainder of T / P)
     // come from a global counter (zeroed by the host before the launch) so that CTAs that finish early take over work
@@ -342,7 +352,8 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
       s_thr[slot] = __ldg(thr_key + b);          // ordinary store: released to the consumers by the arrive below
       const bool with_ae = nh > 0 || skip_ae == 0;
       mbar_expect_tx(&full[slot], (with_ae ? Geo::kTx : (uint32_t)Geo::kKpBytes) + list_bytes);
-      bulk_g2s(smem + L.list + (size_t)slot * L.list_stride, lists + (size_t)t * list_bytes, list_bytes, &full[slot]);
+      bulk_g2s(smem + L.list + (size_t)ls * L.list_stride, lists + (size_t)t * list_bytes, list_bytes, &full[slot]);
+      if (++ls == lslots) ls = 0;
       d4_tma_3d(st, &tm_kp, x0t - 4, y0t - 1, b, &full[slot]);
       if (with_ae) d4_tma_4d(st + Geo::kKpStage, &tm_ae, x0t, y0t, 0, b, &full[slot]);
       if (++slot == nstages) { slot = 0; ++round; }
@@ -357,7 +368,8 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
     // one end marker per consumer group (the next G stages cover every group once)
     for (int g = 0; g < G; ++g) {
       if (round >= 1) d4_wait_parked(&empty[slot], (uint32_t)((round - 1) & 1));
-      reinterpret_cast<TileHdr*>(smem + L.list + (size_t)slot * L.list_stride)->nhit = -1;
+      reinterpret_cast<TileHdr*>(smem + L.list + (size_t)ls * L.list_stride)->nhit = -1;
+      if (++ls == lslots) ls = 0;
       mbar_arrive_plain(&full[slot]);
       if (++slot == nstages) { slot = 0; ++round; }
     }
@@ -372,15 +384,17 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
   // ========================================= consumers =========================================
   const int grp = warp / WG, wl = warp % WG;
   const int halo_off = (lane == 31) ? (4 + kD4TileW) : 3;
-  int slot = grp, rnd = 0;
+  const int lslots = nstages + G;
+  int slot = grp, rnd = 0, ls = grp;
   while (true) {
+    bool released = false;                                                  // warp-uniform: stage already handed back
     // Slots are shared between groups over time and TMA completions are not ordered, so the previous fill of this
     // slot (another group's tile) may not have landed when this group gets here; a parity wait only tells "this
     // phase" from "the one before".  The previous occupant's RELEASE (empty phase rnd-1) implies its fill completed,
     // and it cannot be more than one phase away (the release of fill rnd is ours): wait for it first.
     if (rnd > 0) d4_wait(&empty[slot], (uint32_t)((rnd - 1) & 1), 0, 6, slot, rnd);
     d4_wait(&full[slot], (uint32_t)(rnd & 1), 0, 5, slot, rnd);
-    const unsigned char* lst = smem + L.list + (size_t)slot * L.list_stride;
+    const unsigned char* lst = smem + L.list + (size_t)ls * L.list_stride;
     const int4 h0 = *reinterpret_cast<const int4*>(lst);                    // b, y0, x0, nhit
     const int nhit = h0.w;
     if (nhit < 0) break;
@@ -456,6 +470,13 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
             const float4 a3 = *reinterpret_cast<const float4*>(ar + 3 * Geo::kAePlane);
             sy[r][0] = exp_fast_ftz2(pack2(a2.x, a2.y)); sy[r][1] = exp_fast_ftz2(pack2(a2.z, a2.w));
             sx[r][0] = exp_fast_ftz2(pack2(a3.x, a3.y)); sx[r][1] = exp_fast_ftz2(pack2(a3.z, a3.w));
+          }
+          // Early release: with the last row pair in registers nothing of the stage is read again (the list lives in
+          // its own, deeper ring), so the producer can refill the slot while this warp computes.
+          if (rp + 2 >= RW && early_release) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+            released = true;
           }
           float amax = 0.0f;
 #pragma unroll
@@ -615,11 +636,15 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
         }
       }
     }
-    // every read of the stage and of its list is done: hand the slot back to the producer
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[slot]);
+    // every read of the stage and of its list is done: hand the slot back to the producer (unless already done)
+    if (!released) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);
+    }
     slot += G;
     if (slot >= nstages) { slot -= nstages; ++rnd; }
+    ls += G;
+    if (ls >= lslots) ls -= lslots;
   }
 }
 
@@ -649,7 +674,7 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   if (Nmax > 65535) return ISG_EUNSUPPORTED;
   const int cap = dense_list_cap(Nmax);
   int nstages = std::min(max_stages, kD4MaxStages);
-  while (nstages > 1 && D4Smem<RW, WG>(cap, nstages).total > 227 * 1024) --nstages;
+  while (nstages > 1 && D4Smem<RW, WG>(cap, nstages, G).total > 227 * 1024) --nstages;
   if (nstages < G + 1) return ISG_EUNSUPPORTED;
   const int tilesX = cdiv(W, kD4TileW), tilesY = cdiv(H, Geo::TH);
   const long long T = (long long)B * tilesX * tilesY;
@@ -700,7 +725,7 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   const Tuning& tn = tuning();
   // one CTA per SM; `dense_spare` SMs stay free for the small kernels of neighbouring pipeline steps (engine.py)
   const int grid = (int)std::min<long long>(T, std::max(1, sms - tn.dense_spare));
-  const size_t smem = (size_t)D4Smem<RW, WG>(cap, nstages).total;
+  const size_t smem = (size_t)D4Smem<RW, WG>(cap, nstages, G).total;
   const int Wwords = cdiv(W, 32);
   const int threads = 32 * (WG * G + 1);
   const int dyn_tail = tn.dense_tail;                 // tiles per CTA left to the dynamic scheduler

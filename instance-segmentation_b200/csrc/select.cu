@@ -370,9 +370,11 @@ topk_sample1_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, i
   TopkWs v = topk_ws_view(ws, b, npx, k);
   uint32_t lower = 0u;                  // 0: every pixel is a candidate (the select step then falls back if needed)
   if (rk < (long long)S) {              // block-uniform
+    // Two radix passes (22 of the 32 key bits): the bound only has to be conservative, and the start of the 10-bit bin that
+    // holds the sample's rk-th key is - it admits at most the few extra candidates of that bin.
     uint32_t prefix = 0, pmask = 0, krem = (uint32_t)rk;
 #pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
+    for (int pass = 0; pass < 2; ++pass) {
       for (int i = t; i < kHistBins; i += kSelThreads) sh_hist[i] = 0;
       __syncthreads();
       for (int i0 = 0; i0 < S; i0 += kSelThreads) {          // warp-uniform trip count
@@ -388,8 +390,7 @@ topk_sample1_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, i
       resolve_digit(sh_hist, krem, &d, &k2);
       krem = k2;
       if (pass == 0) { prefix = d << 21; pmask = 0xffe00000u; }
-      else if (pass == 1) { prefix |= d << 10; pmask = 0xfffffc00u; }
-      else prefix |= d;
+      else prefix |= d << 10;
     }
     lower = prefix;
   }
