@@ -612,9 +612,11 @@ def run_ours(args, wl, rank, world, local_rank):
     if rank != 0:
         return
     peak, peak_src = measured_peak()
-    algo = ALGO_BYTES_PER_PIXEL * B * H * W
+    # ISG_SPLIT_KEEP=1 (labels-only dense kernel, keep bits from the top-k candidates): kp is not read by this kernel
+    algo = (ALGO_BYTES_PER_PIXEL - 4 if engine.SPLIT_KEEP else ALGO_BYTES_PER_PIXEL) * B * H * W
     achieved = algo / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "dense_v4_kernel (isg_assign_dense; its tile lists are prebuilt on the box branch)",
+    roofline = {"bound": "hbm", "kernel": ("dense_v4_kernel, labels-only form (isg_assign_labels, 20 B/pixel; keep bits from isg_topk_keep)" if engine.SPLIT_KEEP else
+                           "dense_v4_kernel (isg_assign_dense; its tile lists are prebuilt on the box branch)"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload + ("" if args.inputs == "default" else ":" + args.inputs)),
                 "peak_source": peak_src, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ISG_ABI_VERSION 5
+#define ISG_ABI_VERSION 6
 
 #define ISG_OK            0
 #define ISG_EINVAL       (-1)  /* bad argument (null pointer, negative extent, k > H*W ...) */
@@ -179,6 +179,23 @@ int isg_assign_dense(const float* kp, int64_t kp_img_stride,
                      int H, int W, const float* ys, const float* xs,
                      int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats,
                      void* workspace, size_t workspace_bytes, int lists_prebuilt, isg_stream_t stream);
+/* Split form of the dense step (kp is read from HBM once per step instead of twice):
+ *   isg_topk_keep - isg_topk_threshold that also writes the keep bits (select_points, utils/decode.py:71-85: selected AND
+ *     3x3 maximum of the thresholded map): the kernel that finds the exact threshold evaluates the peak test at the ~k
+ *     selected pixels of its candidate list right away, instead of a second pass over the map (it walks the whole image by
+ *     itself when the list is not complete).  keepbits [B,H,ceil(W/32)] is zeroed by the call unless keepbits_zeroed != 0
+ *     (the caller zeroed it on this stream).  Same workspace as isg_topk_threshold.
+ *   isg_assign_labels - isg_assign_dense without kp / thr_key / keepbits / stats: reads the 4 ae planes once, writes
+ *     label_map (and score_map).  20 B/pixel.  Same workspace, tile lists and lists_prebuilt meaning as isg_assign_dense.
+ *     Returns ISG_EUNSUPPORTED for layouts the tensor-map kernel cannot take (W % 4 != 0, unaligned planes): call
+ *     isg_assign_dense instead.
+ * Together they produce bit-identical label_map / keepbits to isg_assign_dense. */
+int isg_topk_keep(const float* kp, int B, int H, int W, int64_t img_stride, int k, uint32_t* thr_key,
+                  uint32_t* keepbits, int keepbits_zeroed, void* workspace, size_t workspace_bytes, isg_stream_t stream);
+int isg_assign_labels(const float* ae, int64_t ae_img_stride, int64_t ae_plane_stride,
+                      const uint32_t* seeds, const float* ghost, const int32_t* n_seeds, int B, int Nmax,
+                      int H, int W, const float* ys, const float* xs, int32_t* label_map, float* score_map,
+                      void* workspace, size_t workspace_bytes, int lists_prebuilt, isg_stream_t stream);
 /* dense mode: labels / scores / ghost flags of the compacted keep pixels read back from the maps.
  * score_map nullable (then score is not written).  stats (nullable, pre-initialised by isg_stats_init): count /
  * bbox of the flagged pixels per instance - the same numbers isg_assign_dense accumulates when it is given a stats
@@ -326,7 +343,8 @@ int isg_decode_heads(const float* x, int B, int Cin, int H, int W, const float* 
  * on `main`; isg_topk_threshold (ISG_ASSIGN_SPARSE: + isg_keep_points + isg_compact_points) on `side`, forked from and
  * joined back into `main` with the two caller-owned events; then the assignment and (polygons != 0)
  * isg_instance_polygons on `main`.  Every pointer has the meaning documented at the entry point that consumes it.
- *   ISG_ASSIGN_DENSE : isg_assign_dense (label for every pixel; needs label_map, keepbits, dense_ws).
+ *   ISG_ASSIGN_DENSE : isg_assign_dense (label for every pixel; needs label_map, keepbits, dense_ws); with
+ *                      split_keep != 0: isg_topk_keep on `side` instead of isg_topk_threshold + isg_assign_labels.
  *   ISG_ASSIGN_SPARSE: isg_assign_sparse + isg_scatter_labels (keep pixels only; needs idx, count, label too).  In this
  *                      mode `ae` and `regression` may be DEVICE ADDRESSES OF MAPPED HOST MEMORY (isg_host_device_pointer):
  *                      they are only read at the keep pixels / candidate anchors, so the planes never cross PCIe.
@@ -361,6 +379,7 @@ typedef struct isg_decode_step {
   int32_t* img_total; void* poly_ws; size_t poly_ws_bytes;
   /* streams (cudaStream_t) and events (cudaEvent_t) */
   isg_stream_t main; isg_stream_t side; void* fork_event; void* join_event; void* time_begin; void* time_end;
+  int split_keep;              /* ISG_ASSIGN_DENSE: keep bits from the top-k candidates, labels-only dense kernel */
 } isg_decode_step_t;
 int isg_decode_step(const isg_decode_step_t* step);
 size_t isg_decode_step_bytes(void);   /* host query: sizeof(isg_decode_step_t) as compiled into the library */

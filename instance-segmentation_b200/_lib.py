@@ -35,6 +35,7 @@ class DecodeStep(C.Structure):
         ("poly_points", P), ("inst_start", P), ("inst_count", P), ("inst_flags", P), ("inst_internal", P),
         ("img_total", P), ("poly_ws", P), ("poly_ws_bytes", SZ),
         ("main", P), ("side", P), ("fork_event", P), ("join_event", P), ("time_begin", P), ("time_end", P),
+        ("split_keep", I),
     ]
 
 
@@ -63,6 +64,8 @@ PROTOTYPES = {
     "isg_assign_dense_workspace_bytes": (SZ, [I, I, I, I]),
     "isg_build_tile_lists": (I, [P, P, I, I, I, I, P, SZ, P]),
     "isg_assign_dense": (I, [P, I64, P, I64, I64, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P, SZ, I, P]),
+    "isg_topk_keep": (I, [P, I, I, I, I64, I, P, P, I, P, SZ, P]),
+    "isg_assign_labels": (I, [P, I64, I64, P, P, P, I, I, I, I, P, P, P, P, P, SZ, I, P]),
     "isg_gather_labels": (I, [P, P, P, P, I, P, I, I, I, I, P, P, P, P, P]),
     "isg_group_points": (I, [P, P, P, P, I, P, I, I, P, P, P]),
     "isg_decode_boxes": (I, [P, P, P, I, I, I, I, I, F, I, P, P, P, P, P, P]),

@@ -711,6 +711,25 @@ extern "C" int isg_build_tile_lists(const uint32_t* seeds, const int32_t* n_seed
   return rc == ISG_EUNSUPPORTED ? ISG_OK : rc;   // unsupported geometry: isg_assign_dense falls back and needs no lists
 }
 
+extern "C" int isg_assign_labels(const float* ae, int64_t ae_img_stride, int64_t ae_plane_stride, const uint32_t* seeds,
+                                 const float* ghost, const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys,
+                                 const float* xs, int32_t* label_map, float* score_map, void* workspace,
+                                 size_t workspace_bytes, int lists_prebuilt, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!ae || !seeds || !ghost || !n_seeds || !ys || !xs || !label_map) return ISG_EINVAL;
+  if (B <= 0 || Nmax <= 0 || H <= 0 || W <= 0 || B > 65535) return ISG_EINVAL;
+  if (ae_plane_stride < (int64_t)H * W) return ISG_EINVAL;
+  if (!aligned16(seeds) || !aligned16(ghost)) return ISG_EINVAL;
+  if (!workspace || workspace_bytes < dense_workspace_bytes(B, Nmax, H, W) || !aligned16(workspace)) return ISG_EINVAL;
+  if ((size_t)Nmax * sizeof(SeedRec) * 2 > 200 * 1024) return ISG_EUNSUPPORTED;
+  const bool vec = (W % 4 == 0) && (ae_img_stride % 4 == 0) && (ae_plane_stride % 4 == 0) && aligned16(ae) &&
+                   aligned16(label_map) && (!score_map || aligned16(score_map));
+  if (!vec || tuning().dense_v1) return ISG_EUNSUPPORTED;
+  return launch_dense_v4(nullptr, 0, ae, ae_img_stride, ae_plane_stride, nullptr, seeds, ghost, n_seeds, B, Nmax, H, W, ys, xs,
+                         label_map, score_map, nullptr, nullptr, workspace, workspace_bytes, lists_prebuilt ? 2 : 0, stream,
+                         /*with_kp=*/false);
+}
+
 extern "C" int isg_assign_dense(const float* kp, int64_t kp_img_stride, const float* ae, int64_t ae_img_stride,
                                 int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds,
                                 const float* ghost, const int32_t* n_seeds, int B, int Nmax, int H, int W,

@@ -67,11 +67,13 @@ inline isg_encode_tiled_fn get_encode_tiled() {
   return reinterpret_cast<isg_encode_tiled_fn>(fn);
 }
 
-template <int RW, int WG>
+// KP = false: the labels-only form (isg_assign_labels) - no kp box in the stage, the keep bits come from
+// isg_keep_from_candidates
+template <int RW, int WG, bool KP = true>
 struct D4Geom {
   static constexpr int TH = RW * WG;                                  // tile rows
   static constexpr int kKpRows = TH + 2;
-  static constexpr int kKpBytes = kD4KpW * kKpRows * 4;
+  static constexpr int kKpBytes = KP ? kD4KpW * kKpRows * 4 : 0;
   static constexpr int kKpStage = (kKpBytes + 127) / 128 * 128;
   static constexpr int kAePlane = kD4TileW * TH;                      // floats
   static constexpr int kAeBytes = kAePlane * 16;
@@ -202,14 +204,14 @@ __device__ __forceinline__ void d4_tma_4d(void* dst, const CUtensorMap* tm, int 
 }
 
 // shared-memory layout (byte offsets from the dynamic shared base)
-template <int RW, int WG>
+template <int RW, int WG, bool KP = true>
 struct D4Smem {
   int stage, list, list_stride, bars, thr, total;
   // The list ring is G slots deeper than the stage ring: consumers hand a stage back as soon as its pixels are in
   // registers (early release) but keep reading the tile's list; the list slot of tile s is reused by tile s + nstages + G,
   // which the producer issues only after the same group released tile s + G - i.e. after it finished tile s.
   __host__ __device__ D4Smem(int cap, int nstages, int G) {
-    using Geo = D4Geom<RW, WG>;
+    using Geo = D4Geom<RW, WG, KP>;
     int o = 0;
     stage = o; o += nstages * Geo::kStage;
     list_stride = (int)sizeof(TileHdr) + cap * (int)sizeof(SeedRec);
@@ -280,7 +282,7 @@ tile_lists_kernel(const SeedRec* __restrict__ seeds, const int32_t* __restrict__
   }
 }
 
-template <int RW, int WG, int G, bool SCORE>
+template <int RW, int WG, int G, bool SCORE, bool KP>
 __global__ void __launch_bounds__(32 * (WG * G + 1), 1)
 dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant__ CUtensorMap tm_ae,
                 const uint32_t* __restrict__ thr_key, const SeedRec* __restrict__ seeds, const float4* __restrict__ ghost,
@@ -290,11 +292,11 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
                 int32_t* __restrict__ label_map, float* __restrict__ score_map, uint32_t* __restrict__ keepbits,
                 int32_t* __restrict__ stats, unsigned int* __restrict__ sched, int dyn_tail, int dbg_flags, int skip_ae) {
   static_assert(RW % 2 == 0, "rows are processed in pairs");
-  using Geo = D4Geom<RW, WG>;
+  using Geo = D4Geom<RW, WG, KP>;
   constexpr int kConsumers = WG * G;
   const bool early_release = !(dbg_flags & 4);        // measurement aid: bit 2 = release stages only at the end of a tile
   extern __shared__ __align__(1024) unsigned char smem[];
-  const D4Smem<RW, WG> L(cap, nstages, G);
+  const D4Smem<RW, WG, KP> L(cap, nstages, G);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);           // [kD4MaxStages]
   uint64_t* empty = full + kD4MaxStages;                                 // [kD4MaxStages]
   uint32_t* s_thr = reinterpret_cast<uint32_t*>(smem + L.thr);           // [kD4MaxStages]
@@ -349,12 +351,12 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
       // the slot must have been released by the consumers of its previous tile
       if (round >= 1) d4_wait_parked(&empty[slot], (uint32_t)((round - 1) & 1));
       unsigned char* st = smem + L.stage + (size_t)slot * Geo::kStage;
-      s_thr[slot] = __ldg(thr_key + b);          // ordinary store: released to the consumers by the arrive below
+      if (KP) s_thr[slot] = __ldg(thr_key + b);  // ordinary store: released to the consumers by the arrive below
       const bool with_ae = nh > 0 || skip_ae == 0;
       mbar_expect_tx(&full[slot], (with_ae ? Geo::kTx : (uint32_t)Geo::kKpBytes) + list_bytes);
       bulk_g2s(smem + L.list + (size_t)ls * L.list_stride, lists + (size_t)t * list_bytes, list_bytes, &full[slot]);
       if (++ls == lslots) ls = 0;
-      d4_tma_3d(st, &tm_kp, x0t - 4, y0t - 1, b, &full[slot]);
+      if (KP) d4_tma_3d(st, &tm_kp, x0t - 4, y0t - 1, b, &full[slot]);
       if (with_ae) d4_tma_4d(st + Geo::kKpStage, &tm_ae, x0t, y0t, 0, b, &full[slot]);
       if (++slot == nstages) { slot = 0; ++round; }
       if (i_static < n_static) {
@@ -402,7 +404,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
     const int ybeg = h0.y + wl * RW;
     if (ybeg < H && !(dbg_flags & 1)) {                                     // warp-uniform (ragged bottom)
       const int4 h1 = *reinterpret_cast<const int4*>(lst + 16);             // -, n_seeds, tile, pad
-      const Thr thr = make_thr(s_thr[slot]);
+      const Thr thr = make_thr(KP ? s_thr[slot] : 0xffffffffu);
       const int x0 = h0.z + lane * 4;
       const bool colvalid = x0 < W;                                         // W % 4 == 0: a lane is all in or all out
       float xs4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -426,6 +428,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
         // maximum of the lane's four raw values first (3 FMNMX + 1 compare per row) and run the thresholded 3x3 window
         // only for the rows of this warp that do hold a selected pixel.  (+-0 / NaN thresholds order by key: always run.)
         uint32_t nib0 = 0, nib1 = 0;
+        if (KP) {
         bool a0 = true, a1 = true;
         if (!thr.use_int) {
           const float4 q0 = *reinterpret_cast<const float4*>(krow + (rp + 1) * kD4KpW + 4 + lane * 4);
@@ -448,6 +451,7 @@ dense_v4_kernel(const __grid_constant__ CUtensorMap tm_kp, const __grid_constant
             if (row1) kbrow[(size_t)(rp + 1) * Wwords] = w1;
           }
         }
+        }   // KP
 
         float bq[2][4];
         int lab[2][4];
@@ -662,19 +666,19 @@ inline size_t dense_workspace_bytes(int B, int Nmax, int H, int W) {
   return kDenseSchedBytes + dense_lists_bytes(T, Nmax) + (((size_t)T * Nmax * 2 + 255) & ~(size_t)255);
 }
 
-template <int RW, int WG, int G>
+template <int RW, int WG, int G, bool KP>
 inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const float* ae, int64_t ae_img_stride,
                                int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds, const float* ghost,
                                const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys, const float* xs,
                                int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats, void* workspace,
                                size_t workspace_bytes, int max_stages, int mode, cudaStream_t stream) {
   // mode 0: tile lists + dense kernel; 1: tile lists only (isg_build_tile_lists); 2: dense kernel only (lists prebuilt)
-  using Geo = D4Geom<RW, WG>;
+  using Geo = D4Geom<RW, WG, KP>;
   static_assert(Geo::TH >= kD4MinTileRows, "workspace is sized for tiles of at least kD4MinTileRows rows");
   if (Nmax > 65535) return ISG_EUNSUPPORTED;
   const int cap = dense_list_cap(Nmax);
   int nstages = std::min(max_stages, kD4MaxStages);
-  while (nstages > 1 && D4Smem<RW, WG>(cap, nstages, G).total > 227 * 1024) --nstages;
+  while (nstages > 1 && D4Smem<RW, WG, KP>(cap, nstages, G).total > 227 * 1024) --nstages;
   if (nstages < G + 1) return ISG_EUNSUPPORTED;
   const int tilesX = cdiv(W, kD4TileW), tilesY = cdiv(H, Geo::TH);
   const long long T = (long long)B * tilesX * tilesY;
@@ -700,7 +704,7 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   static isg_encode_tiled_fn encode = get_encode_tiled();
   if (!encode) return ISG_EUNSUPPORTED;
   CUtensorMap tm_kp, tm_ae;
-  {
+  if (KP) {
     const cuuint64_t dim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t str[2] = {(cuuint64_t)W * 4, (cuuint64_t)kp_img_stride * 4};
     const cuuint32_t box[3] = {kD4KpW, (cuuint32_t)Geo::kKpRows, 1};
@@ -719,13 +723,14 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return ISG_EUNSUPPORTED;
   }
+  if (!KP) tm_kp = tm_ae;                               // never dereferenced by the labels-only kernel
   int dev = 0, sms = kSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const Tuning& tn = tuning();
   // one CTA per SM; `dense_spare` SMs stay free for the small kernels of neighbouring pipeline steps (engine.py)
   const int grid = (int)std::min<long long>(T, std::max(1, sms - tn.dense_spare));
-  const size_t smem = (size_t)D4Smem<RW, WG>(cap, nstages, G).total;
+  const size_t smem = (size_t)D4Smem<RW, WG, KP>(cap, nstages, G).total;
   const int Wwords = cdiv(W, 32);
   const int threads = 32 * (WG * G + 1);
   const int dyn_tail = tn.dense_tail;                 // tiles per CTA left to the dynamic scheduler
@@ -742,13 +747,13 @@ inline int launch_dense_v4_cfg(const float* kp, int64_t kp_img_stride, const flo
   const unsigned char* clists = lists;
   const uint16_t* covf = ovf;
   if (score_map) {
-    ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, true>, tm_kp, tm_ae, thr_key, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
+    ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, true, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, true, KP>, tm_kp, tm_ae, thr_key, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
                                 tilesY, nstages, cap, clists, covf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail,
                                 dbg_flags, skip_ae));
   } else {
-    ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, false>, tm_kp, tm_ae, thr_key, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
+    ISG_CUDA(cudaFuncSetAttribute(dense_v4_kernel<RW, WG, G, false, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ISG_CUDA(cudaLaunchKernelEx(&cfg, dense_v4_kernel<RW, WG, G, false, KP>, tm_kp, tm_ae, thr_key, srec, ghost4, Nmax, B, H, W, Wwords, tilesX,
                                 tilesY, nstages, cap, clists, covf, ys, xs, label_map, score_map, keepbits, stats, sched, dyn_tail,
                                 dbg_flags, skip_ae));
   }
@@ -761,12 +766,14 @@ inline int launch_dense_v4(const float* kp, int64_t kp_img_stride, const float* 
                            int64_t ae_plane_stride, const uint32_t* thr_key, const uint32_t* seeds, const float* ghost,
                            const int32_t* n_seeds, int B, int Nmax, int H, int W, const float* ys, const float* xs,
                            int32_t* label_map, float* score_map, uint32_t* keepbits, int32_t* stats, void* workspace,
-                           size_t workspace_bytes, int mode, cudaStream_t stream) {
+                           size_t workspace_bytes, int mode, cudaStream_t stream, bool with_kp = true) {
   const Tuning& tn = tuning();
   const int rw = tn.dense_rw, wg = tn.dense_wg, g = tn.dense_g, st = tn.dense_stages > 0 ? tn.dense_stages : kD4MaxStages;
 #define ISG_V4_CASE(RW_, WG_, G_)                                                                                      \
   if (rw == RW_ && wg == WG_ && g == G_)                                                                               \
-    return launch_dense_v4_cfg<RW_, WG_, G_>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, \
+    return with_kp ? launch_dense_v4_cfg<RW_, WG_, G_, true>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, \
+                                             n_seeds, B, Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, workspace, workspace_bytes, st, mode, stream) \
+                   : launch_dense_v4_cfg<RW_, WG_, G_, false>(kp, kp_img_stride, ae, ae_img_stride, ae_plane_stride, thr_key, seeds, ghost, \
                                              n_seeds, B, Nmax, H, W, ys, xs, label_map, score_map, keepbits, stats, workspace, workspace_bytes, st, mode, stream);
   ISG_V4_CASE(2, 8, 2)
   ISG_V4_CASE(4, 4, 3)

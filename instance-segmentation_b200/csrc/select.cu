@@ -167,16 +167,18 @@ constexpr int kFilterPxPerBlock = kFilterThreads * 4 * kFilterUnroll;    // the 
 
 struct TopkWs {            // per-image views
   uint32_t* hist;          // [3][2048]   (legacy multi-CTA path)
-  uint32_t* lower;         // [1]
+  uint32_t* lower;         // [8]: 0 lower bound, 2 rank inside the bin / 3 bin-mode flag (two-level radix select),
+                           //      4 "the candidate list holds every selected pixel" (written by topk_select_kernel)
   uint32_t* ncand;         // [1]
-  uint32_t* cand;          // [cap_c]
+  uint32_t* cand;          // [cap_c] candidate keys
+  uint32_t* cand_pos;      // [cap_c] their pixel indices (y * W + x): isg_keep_from_candidates
 };
 __host__ __device__ inline size_t topk_cand_cap(int npx, int k) {
   size_t c = (size_t)8 * (size_t)k + 8192;
   return c < (size_t)npx ? c : (size_t)npx;
 }
 __host__ __device__ inline size_t topk_ws_per_image(int npx, int k) {
-  size_t s = 3 * kHistBins * sizeof(uint32_t) + 64 + topk_cand_cap(npx, k) * sizeof(uint32_t);
+  size_t s = 3 * kHistBins * sizeof(uint32_t) + 64 + 2 * topk_cand_cap(npx, k) * sizeof(uint32_t);
   return (s + 255) & ~(size_t)255;
 }
 __host__ __device__ inline TopkWs topk_ws_view(void* ws, int b, int npx, int k) {
@@ -185,6 +187,7 @@ __host__ __device__ inline TopkWs topk_ws_view(void* ws, int b, int npx, int k) 
   v.hist = (uint32_t*)p; p += 3 * kHistBins * sizeof(uint32_t);
   v.lower = (uint32_t*)p; v.ncand = (uint32_t*)(p + 32); p += 64;
   v.cand = (uint32_t*)p;
+  v.cand_pos = v.cand + topk_cand_cap(npx, k);
   return v;
 }
 
@@ -491,9 +494,13 @@ topk_pick15_kernel(const uint32_t* __restrict__ hist15, int npx, int k, void* ws
   }
 }
 
+// POS: also record the candidates' pixel indices (isg_topk_keep evaluates the peak test at them)
+template <bool POS>
 __global__ void __launch_bounds__(kFilterThreads)
 topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, void* ws, bool vec) {
   __shared__ uint32_t buf[kFilterPxPerBlock];
+  __shared__ uint16_t bufp[POS ? kFilterPxPerBlock : 1];     // pixel index of buf[i] relative to the block's first pixel
+  static_assert(kFilterPxPerBlock <= 65536, "block-relative pixel offsets are 16-bit");
   __shared__ uint32_t s_count, s_base;
   pdl_trigger();
   pdl_wait();                          // `lower` / `ncand` come from the kernel launched just before
@@ -509,7 +516,7 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   const int base = blockIdx.x * kFilterPxPerBlock;
   const int end = min(base + kFilterPxPerBlock, npx);
   // candidate keys of one 4-pixel group -> this block's shared-memory list (warp-aggregated append)
-  auto append4 = [&](uint32_t (&key)[4], int c) {
+  auto append4 = [&](uint32_t (&key)[4], int c, int pfirst, int pstep) {
     if (__any_sync(0xffffffffu, c > 0)) {
       int inc = c;
 #pragma unroll
@@ -523,7 +530,7 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
       uint32_t o2 = wbase + inc - c;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        if (key[i] != 0xffffffffu) buf[o2++] = key[i];
+        if (key[i] != 0xffffffffu) { buf[o2] = key[i]; if (POS) bufp[o2] = (uint16_t)(pfirst + i * pstep - base); ++o2; }
     }
   };
   // NOTE: 0xffffffff marks "not a candidate"; a real key of 0xffffffff (a NaN payload) is dropped, NaNs are
@@ -572,9 +579,10 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
         }
         if (c) {
           uint32_t o2 = atomicAdd(&s_count, (uint32_t)c);
+          const uint32_t pg = (uint32_t)(p0 - base + u * kFilterThreads * 4 + t * 4);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (kk[i] != 0xffffffffu) buf[o2++] = kk[i];
+            if (kk[i] != 0xffffffffu) { buf[o2] = kk[i]; if (POS) bufp[o2] = (uint16_t)(pg + i); ++o2; }
         }
       }
 #else
@@ -590,7 +598,10 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
         for (int i = 0; i < 4; ++i) {
           if (!(x4[i] < lower_f)) {
             const uint32_t kk = float_key(x4[i]);
-            if (kk >= lower && kk <= upper && kk != 0xffffffffu) buf[atomicAdd(&s_count, 1u)] = kk;
+            if (kk >= lower && kk <= upper && kk != 0xffffffffu) {
+              const uint32_t o2 = atomicAdd(&s_count, 1u);
+              buf[o2] = kk; if (POS) bufp[o2] = (uint16_t)(p0 - base + u * kFilterThreads * 4 + t * 4 + i);
+            }
           }
         }
       }
@@ -606,7 +617,7 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
         key[i] = 0xffffffffu;
         if (p < end) { const uint32_t kk = float_key(__ldg(img + p)); if (kk >= lower && kk <= upper) { key[i] = kk; ++c; } }
       }
-      append4(key, c);
+      append4(key, c, p0 + t, kFilterThreads);
     }
   }
   __syncthreads();
@@ -617,14 +628,44 @@ topk_filter_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   const size_t capc = topk_cand_cap(npx, k);
   const uint32_t g = s_base;
   for (uint32_t i = t; i < n; i += kFilterThreads)
-    if ((size_t)g + i < capc) v.cand[g + i] = buf[i];
+    if ((size_t)g + i < capc) { v.cand[g + i] = buf[i]; if (POS) v.cand_pos[g + i] = (uint32_t)base + bufp[i]; }
+}
+
+// ---- keep bits from the top-k candidate list -------------------------------------------------
+// The filter pass of the top-k threshold already visited every pixel; its candidate list (keys >= a lower bound, with
+// their pixel indices) holds every selected pixel whenever the select step could use it.  The 3x3 peak test (keep.cuh)
+// then only has to be evaluated at the ~k selected candidates instead of streaming the whole map a second time: eight
+// scattered neighbour loads per selected pixel, one atomicOr per keep pixel into the zeroed bit plane.  The select kernel
+// does this itself as soon as it knows the threshold (isg_topk_keep); when the list is not complete (overflow, fall-back
+// select, bin mode) it walks the whole image instead.
+__device__ __forceinline__ void keep_test_and_set(const float* __restrict__ img, int p, float c, int H, int W, int Wwords,
+                                                  uint32_t thr, uint32_t* __restrict__ kb) {
+  const int y = p / W, x = p - y * W;
+  float m = c;                                   // v(c) = c: the pixel is selected
+  float nb[8];
+  bool in[8];
+  int q = 0;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      if (dy == 0 && dx == 0) continue;
+      const int yy = y + dy, xx = x + dx;
+      in[q] = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      nb[q] = in[q] ? __ldg(img + (int64_t)yy * W + xx) : 0.0f;
+      ++q;
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)                    // unselected neighbours count as 0, pixels outside the image not at all
+    if (in[i]) m = fmaxf(m, float_key(nb[i]) >= thr ? nb[i] : 0.0f);
+  if (c >= m) atomicOr(kb + (size_t)y * Wwords + (x >> 5), 1u << (x & 31));
 }
 
 constexpr int kSmallSel = 4096;   // candidates sorted by one CTA in shared memory
 
 __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
 topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, void* ws,
-                   uint32_t* __restrict__ thr_key) {
+                   uint32_t* __restrict__ thr_key, int H, int W, uint32_t* __restrict__ keepbits) {
   __shared__ uint32_t sh_hist[2 * kHistBins];
   cg::cluster_group cluster = cg::this_cluster();
   pdl_wait();                          // the candidate list comes from the filter kernel
@@ -634,6 +675,68 @@ topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   const bool bin_mode = v.lower[3] != 0u;
   const uint32_t rank = bin_mode ? v.lower[2] : (uint32_t)k;      // rank of the answer among the candidates
   const bool use_cand = nc >= rank && rank >= 1u && (size_t)nc <= topk_cand_cap(npx, k);
+  // the candidates are all keys >= lower and the answer is one of them: every selected pixel is in the list
+  const bool complete = use_cand && !bin_mode;
+  if (cluster.block_rank() == 0 && threadIdx.x == 0) v.lower[4] = complete ? 1u : 0u;
+  // keep bits (isg_topk_keep; keepbits zeroed by the caller): the 3x3 peak test at the selected pixels, by `nthr` threads
+  // of which this one is number `me`
+  auto set_keep_bits = [&](uint32_t thr, int me, int nthr) {
+    const float* img = kp + (int64_t)b * img_stride;
+    const int Wwords = (W + 31) / 32;
+    uint32_t* kb = keepbits + (size_t)b * H * Wwords;
+    if (complete) {
+      // two candidates per thread and round: their list entries, then all their neighbour loads, are in flight together
+      // (the loop is a chain of dependent DRAM / L2 round trips otherwise)
+      constexpr int kBatch = 2;
+      for (int i0 = me; i0 < (int)nc; i0 += nthr * kBatch) {
+        uint32_t ck[kBatch];
+        int p[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int i = i0 + u * nthr;
+          ck[u] = i < (int)nc ? v.cand[i] : 0u;
+          p[u] = i < (int)nc ? (int)v.cand_pos[i] : 0;
+        }
+        float nb[kBatch][8];
+        uint32_t inm[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          inm[u] = 0u;
+          const bool act = i0 + u * nthr < (int)nc && ck[u] >= thr;
+          const int y = p[u] / W, x = p[u] - y * W;
+          int q = 0;
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              if (dy == 0 && dx == 0) continue;
+              const int yy = y + dy, xx = x + dx;
+              const bool in = act && yy >= 0 && yy < H && xx >= 0 && xx < W;
+              nb[u][q] = in ? __ldg(img + (int64_t)yy * W + xx) : 0.0f;
+              inm[u] |= in ? (1u << q) : 0u;
+              ++q;
+            }
+          if (act) inm[u] |= 0x100u;
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          if (!(inm[u] & 0x100u)) continue;
+          const float c = float_from_ukey(ck[u]);
+          float m = c;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (inm[u] & (1u << q)) m = fmaxf(m, float_key(nb[u][q]) >= thr ? nb[u][q] : 0.0f);
+          const int y = p[u] / W, x = p[u] - y * W;
+          if (c >= m) atomicOr(kb + (size_t)y * Wwords + (x >> 5), 1u << (x & 31));
+        }
+      }
+    } else {
+      for (int p = me; p < npx; p += nthr) {
+        const float c = __ldg(img + p);
+        if (float_key(c) >= thr) keep_test_and_set(img, p, c, H, W, Wwords, thr, kb);
+      }
+    }
+  };
   uint32_t key;
   if (use_cand && nc <= (uint32_t)kSmallSel) {   // cluster-uniform: one CTA sorts the few candidates in shared memory
     if (cluster.block_rank() != 0) return;
@@ -654,7 +757,9 @@ topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
         __syncthreads();
       }
     }
-    if (t == 0) thr_key[b] = sk[rank - 1];
+    const uint32_t thr = sk[rank - 1];
+    if (t == 0) thr_key[b] = thr;
+    if (keepbits) set_keep_bits(thr, t, kSelThreads);
     return;
   }
   if (use_cand) {   // cluster-uniform
@@ -665,6 +770,7 @@ topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
     key = cluster_radix_select(cluster, sh_hist, npx, (uint32_t)k, [&](int i) { return float_key(__ldg(img + i)); });
   }
   if (cluster.block_rank() == 0 && threadIdx.x == 0) thr_key[b] = key;
+  if (keepbits) set_keep_bits(key, (int)cluster.block_rank() * kSelThreads + (int)threadIdx.x, kSelCluster * kSelThreads);
 }
 
 // ---- stand-alone keep kernel ---------------------------------------------------------------
@@ -879,9 +985,11 @@ extern "C" size_t isg_topk_workspace_bytes(int B, int H, int W, int k) {
   return (size_t)B * topk_ws_per_image(H * W, k) + topk_hist15_bytes(B);
 }
 
-extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t img_stride, int k,
-                                  uint32_t* thr_key, void* ws, size_t ws_bytes, isg_stream_t stream_) {
+// keepbits != nullptr: isg_topk_keep - the keep bits are produced together with the threshold
+static int topk_threshold_impl(const float* kp, int B, int H, int W, int64_t img_stride, int k, uint32_t* thr_key, void* ws,
+                               size_t ws_bytes, uint32_t* keepbits, bool* keep_done, isg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (keep_done) *keep_done = false;
   if (!kp || !thr_key || B <= 0 || H <= 0 || W <= 0 || k < 0 || B > 65535) return ISG_EINVAL;
   const int64_t npx64 = (int64_t)H * W;
   if (npx64 > (int64_t)1 << 30 || img_stride < npx64) return ISG_EINVAL;
@@ -936,16 +1044,39 @@ extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t 
       topk_pick15_kernel<<<B, 1024, 0, stream>>>(hist15, npx, k, ws);
     }
     dim3 grid(cdiv(npx, kFilterPxPerBlock), B);
-    ISG_CUDA(launch_pdl(topk_filter_kernel, grid, dim3(kFilterThreads), 0, stream, kp, img_stride, npx, k, ws, vec));
+    if (keepbits) ISG_CUDA(launch_pdl(topk_filter_kernel<true>, grid, dim3(kFilterThreads), 0, stream, kp, img_stride, npx, k, ws, vec));
+    else ISG_CUDA(launch_pdl(topk_filter_kernel<false>, grid, dim3(kFilterThreads), 0, stream, kp, img_stride, npx, k, ws, vec));
   } else {
     // small image: one CTA per image selects over all pixels directly (ncand = 0 -> full-image mode)
     const size_t per = topk_ws_per_image(npx, k);
     for (int b = 0; b < B; ++b)
       ISG_CUDA(cudaMemsetAsync((char*)ws + (size_t)b * per + 3 * kHistBins * sizeof(uint32_t), 0, 64, stream));
   }
-  ISG_CUDA(launch_pdl(topk_select_kernel, dim3(kSelCluster, B), dim3(kSelThreads), 0, stream, kp, img_stride, npx, k, ws, thr_key));
+  ISG_CUDA(launch_pdl(topk_select_kernel, dim3(kSelCluster, B), dim3(kSelThreads), 0, stream, kp, img_stride, npx, k, ws, thr_key,
+                      H, W, keepbits));
   ISG_LAUNCH_CHECK();
+  if (keep_done) *keep_done = keepbits != nullptr;
   return ISG_OK;
+}
+
+extern "C" int isg_topk_threshold(const float* kp, int B, int H, int W, int64_t img_stride, int k,
+                                  uint32_t* thr_key, void* ws, size_t ws_bytes, isg_stream_t stream_) {
+  return topk_threshold_impl(kp, B, H, W, img_stride, k, thr_key, ws, ws_bytes, nullptr, nullptr, stream_);
+}
+
+extern "C" int isg_keep_points(const float* kp, int B, int H, int W, int64_t img_stride, const uint32_t* thr_key,
+                               uint32_t* keepbits, uint8_t* mask_u8, isg_stream_t stream_);
+
+extern "C" int isg_topk_keep(const float* kp, int B, int H, int W, int64_t img_stride, int k, uint32_t* thr_key,
+                             uint32_t* keepbits, int keepbits_zeroed, void* ws, size_t ws_bytes, isg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!keepbits || B <= 0 || H <= 0 || W <= 0) return ISG_EINVAL;
+  if (!keepbits_zeroed) ISG_CUDA(cudaMemsetAsync(keepbits, 0, (size_t)B * H * cdiv(W, 32) * sizeof(uint32_t), stream));
+  bool done = false;
+  const int rc = topk_threshold_impl(kp, B, H, W, img_stride, k, thr_key, ws, ws_bytes, keepbits, &done, stream_);
+  if (rc != ISG_OK || done) return rc;
+  // the threshold paths without a select kernel (k = 0, large k): the streaming keep kernel
+  return isg_keep_points(kp, B, H, W, img_stride, thr_key, keepbits, nullptr, stream_);
 }
 
 extern "C" int isg_keep_points(const float* kp, int B, int H, int W, int64_t img_stride,

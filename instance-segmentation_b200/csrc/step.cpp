@@ -1,6 +1,7 @@
 // isg_decode_step — one whole decode step (utils/decode.py:444-461: decode_boxes + per-image decode_single) enqueued by
 // ONE host call: box head -> class-aware NMS -> detection tables + seeds -> tile lists on `main`, the top-k threshold
-// on `side` (it does not depend on the boxes), then the assignment and the per-instance polygon stage on `main`.
+// on `side` (it does not depend on the boxes; split_keep: together with the keep bits, from its candidate list), then the
+// assignment and the per-instance polygon stage on `main`.
 // Pure host code over the entry points of include/isg.h: what engine.DecodePipeline did with a dozen Python calls per
 // step, which bounded the step rate once neighbouring steps were overlapped.
 #include <cuda_runtime.h>
@@ -33,7 +34,13 @@ extern "C" int isg_decode_step(const isg_decode_step_t* s) {
   // top-k threshold on the side stream, behind everything enqueued on `main` so far
   STEP_CUDA(cudaEventRecord(fork, main));
   STEP_CUDA(cudaStreamWaitEvent(side, fork, 0));
-  STEP_TRY(isg_topk_threshold(s->kp, B, H, W, s->kp_img_stride, s->kp_th, s->thr_key, s->topk_ws, s->topk_ws_bytes, side));
+  const bool split = s->assign == ISG_ASSIGN_DENSE && s->split_keep != 0;
+  if (split) {    // threshold + keep bits from its candidate list in one go (the bit plane is zeroed first)
+    STEP_CUDA(cudaMemsetAsync(s->keepbits, 0, (size_t)B * H * ((W + 31) / 32) * sizeof(uint32_t), side));
+    STEP_TRY(isg_topk_keep(s->kp, B, H, W, s->kp_img_stride, s->kp_th, s->thr_key, s->keepbits, 1, s->topk_ws, s->topk_ws_bytes, side));
+  } else {
+    STEP_TRY(isg_topk_threshold(s->kp, B, H, W, s->kp_img_stride, s->kp_th, s->thr_key, s->topk_ws, s->topk_ws_bytes, side));
+  }
   if (s->assign == ISG_ASSIGN_SPARSE) {   // keep bits + compaction only need kp and the threshold: stay on the side stream
     STEP_TRY(isg_keep_points(s->kp, B, H, W, s->kp_img_stride, s->thr_key, s->keepbits, nullptr, side));
     STEP_TRY(isg_compact_points(s->keepbits, B, H, W, s->cap, s->idx, s->count, side));
@@ -54,9 +61,15 @@ extern "C" int isg_decode_step(const isg_decode_step_t* s) {
 
   if (s->time_begin) STEP_CUDA(cudaEventRecord((cudaEvent_t)s->time_begin, main));
   if (s->assign == ISG_ASSIGN_DENSE) {
-    STEP_TRY(isg_assign_dense(s->kp, s->kp_img_stride, s->ae, s->ae_img_stride, s->ae_plane_stride, s->thr_key, s->seeds,
-                              s->ghost, s->n_seeds, B, N, H, W, s->ys, s->xs, s->label_map, nullptr, s->keepbits, nullptr,
-                              s->dense_ws, s->dense_ws_bytes, 1, main));
+    int rc = ISG_EUNSUPPORTED;
+    if (split)
+      rc = isg_assign_labels(s->ae, s->ae_img_stride, s->ae_plane_stride, s->seeds, s->ghost, s->n_seeds, B, N, H, W, s->ys,
+                             s->xs, s->label_map, nullptr, s->dense_ws, s->dense_ws_bytes, 1, main);
+    if (rc == ISG_EUNSUPPORTED)     // not split, or a layout only the fused form takes (it rewrites the same keep bits)
+      rc = isg_assign_dense(s->kp, s->kp_img_stride, s->ae, s->ae_img_stride, s->ae_plane_stride, s->thr_key, s->seeds,
+                            s->ghost, s->n_seeds, B, N, H, W, s->ys, s->xs, s->label_map, nullptr, s->keepbits, nullptr,
+                            s->dense_ws, s->dense_ws_bytes, 1, main);
+    STEP_TRY(rc);
   } else {
     // only the keep pixels: `ae` may live in mapped host memory (16 B per keep pixel cross PCIe instead of the planes)
     STEP_TRY(isg_assign_sparse(s->ae, s->ae_img_stride, s->ae_plane_stride, s->idx, s->count, s->cap, s->seeds, s->ghost,

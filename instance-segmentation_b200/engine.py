@@ -7,6 +7,8 @@ synchronises with the host; results are read back once per batch.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -101,6 +103,12 @@ def popcount_rows(bits: torch.Tensor):
 # of current torchvision on CPU tensors (coordinate trick for <= 1000 candidates, per-class NMS above) - what the reference
 # computes in this image; ISG_NMS_TV_TRICK is torchvision 0.5.0 (the reference's pin); ISG_NMS_TV_GT never shifts the boxes.
 BOX_NMS_CONVENTION = _lib.ISG_NMS_TV_BATCHED
+# Dense steps of isg_decode_step: threshold and keep bits from the top-k candidate list in one go (isg_topk_keep) + the labels-only dense
+# kernel (isg_assign_labels), so that kp is read from HBM once per step; False (default) = the fused form
+# (isg_assign_dense).  Both give bit-identical label maps and keep bits.  Measured: the labels-only kernel
+# takes 56.9 us instead of 67.6, but the scattered neighbour loads of the peak test at the ~20 k selected pixels per image
+# cost the select kernel the same 10 us - no net gain, so the fused form stays the default.
+SPLIT_KEEP = os.environ.get("ISG_SPLIT_KEEP", "0") == "1"
 
 
 def aligned_workspace(nbytes: int, device: torch.device):
@@ -460,6 +468,7 @@ class DecodePipeline:
         st.assign = _lib.ISG_ASSIGN_SPARSE if sparse else _lib.ISG_ASSIGN_DENSE
         st.polygons, st.obj_pixel_th = 1 if polygons else 0, int(obj_pixel_th)
         st.nms_convention = BOX_NMS_CONVENTION
+        st.split_keep = 1 if (SPLIT_KEEP and not sparse) else 0
         st.cls_th, st.iou_th = float(np.float32(cls_th)), float(iou_th)
         st.kp, st.kp_img_stride = ptr(kp), kp.stride(0) if B > 1 else H * W
         st.ae, st.ae_img_stride, st.ae_plane_stride = device_address(ae), ae.stride(0) if B > 1 else 4 * H * W, ae.stride(1)
@@ -473,7 +482,7 @@ class DecodePipeline:
         rc = _lib.lib().isg_decode_step(ctypes.byref(st))
         if rc != 0:
             raise _lib.IsgError(rc, "isg_decode_step")
-        _lib.launch_count += (8 if sparse else 8) + (1 if polygons else 0) + (2 if sparse else 0)
+        _lib.launch_count += 8 + (1 if polygons else 0) + (2 if sparse else 0)
         if time_main:
             ev = (self._t0, self._t1)
             self._t0, self._t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

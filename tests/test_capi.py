@@ -37,7 +37,7 @@ def test_library_exports_every_header_symbol(built):
 def test_binding_table_matches_header(built):
     assert sorted(built.PROTOTYPES) == header_symbols()
     lib = built.lib()
-    assert lib.isg_abi_version() == 5
+    assert lib.isg_abi_version() == 6
     assert lib.isg_strerror(0) == b"ok" and lib.isg_strerror(-1) == b"invalid argument"
 
 

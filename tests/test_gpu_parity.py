@@ -1093,3 +1093,106 @@ def test_pipelined_steps_equal_isolated_steps(mods):
     run(batches[1], False)
     n, got = snapshot()
     assert np.array_equal(n, want[1][0]) and all(np.array_equal(got[k][1], want[1][1][k][1]) for k in got)
+
+
+# ---------------------------------------------------------------------------------------------- split dense step
+def _split_vs_fused(mods, kp, ae, rois, n_seeds, kp_th, N):
+    """label map + keep bits of isg_assign_dense (fused) and of isg_topk_keep + isg_assign_labels (split), through the C ABI"""
+    lib, engine = mods["lib"], mods["engine"]
+    call, ptr, sp = lib.call, engine.ptr, engine.stream_ptr
+    B, _, H, W = ae.shape
+    dev = torch.device(DEV)
+    plan = engine.DecodePlan(B, H, W, N, kp_th, dev, "dense", want_score=False)
+    kp_d, ae_d = kp.to(dev).contiguous(), ae.to(dev).contiguous()
+    rois_d, ns_d = rois.to(dev).contiguous(), n_seeds.to(dev)
+    plan.run(kp_d, ae_d, rois_d, ns_d)                                   # fused: thr_key, seeds, label_map, keepbits
+    torch.cuda.synchronize()
+    fused = plan.label_map.clone(), plan.keepbits.clone()
+    thr_f = plan.thr_key.clone()
+    kb = torch.full_like(plan.keepbits, -1)                              # garbage: the call must zero the plane itself
+    lab = torch.full_like(plan.label_map, -7)
+    s = sp(dev)
+    k2 = kp_d[:, 0] if kp_d.dim() == 4 else kp_d
+    plan.thr_key.fill_(0)
+    call("isg_topk_keep", ptr(k2), B, H, W, k2.stride(0) if B > 1 else H * W, kp_th, ptr(plan.thr_key), ptr(kb), 0, plan.ws_ptr,
+         plan.ws_bytes, s)
+    torch.cuda.synchronize()
+    assert torch.equal(plan.thr_key, thr_f)
+    rc = lib.lib().isg_assign_labels(ptr(ae_d), ae_d.stride(0) if B > 1 else 4 * H * W, ae_d.stride(1), ptr(plan.seeds),
+                                     ptr(plan.ghost), ptr(ns_d), B, N, H, W, ptr(plan.ys), ptr(plan.xs), ptr(lab), None,
+                                     ptr(plan.dense_ws), plan.dense_ws_bytes, 0, s)
+    torch.cuda.synchronize()
+    return fused, (lab, kb), rc
+
+
+@pytest.mark.parametrize("shape,N,kp_th,kind", [
+    ((512, 1024), 40, 20000, "scene"),       # sample -> filter -> select: complete candidate list
+    ((384, 640), 20, 3000, "scene"),         # ragged tiles (H % 16, W % 128 != 0)
+    ((128, 256), 6, 500, "scene"),           # small image: no candidate list (whole-image select) -> full pass inside the kernel
+    ((256, 512), 6, 100000, "scene"),        # large k: multi-CTA radix select, no candidate list -> streaming keep kernel
+    ((256, 512), 6, 100, "flat"),            # plateau: every pixel ties at the threshold, the candidate list overflows
+    ((256, 512), 6, 5000, "negative"),       # selected negative values next to unselected (0) neighbours are dropped
+])
+def test_split_dense_step_equals_fused(mods, shape, N, kp_th, kind):
+    synth = mods["synth"]
+    H, W = shape
+    B = 2
+    imgs = [synth.make_image(900 + b, H, W, N) for b in range(B)]
+    kp = torch.from_numpy(np.stack([im.kp for im in imgs]))
+    if kind == "flat":
+        kp = torch.zeros_like(kp); kp[1] = 0.5
+    elif kind == "negative":
+        kp = -kp.abs() - 0.25
+    ae = torch.from_numpy(np.stack([im.ae for im in imgs]))
+    rois = torch.from_numpy(np.stack([im.rois for im in imgs]))
+    n_seeds = torch.tensor([N] * B, dtype=torch.int32)
+    (lab_f, kb_f), (lab_s, kb_s), rc = _split_vs_fused(mods, kp, ae, rois, n_seeds, kp_th, N)
+    assert rc == 0
+    assert torch.equal(kb_s, kb_f), "keep bits differ"
+    assert torch.equal(lab_s, lab_f), "label maps differ"
+    if kind == "scene":
+        assert int(unpack_bits(kb_f.cpu().numpy(), W).sum()) > 0
+
+
+def test_assign_labels_refuses_widths_the_tensor_map_cannot_take(mods):
+    """W % 4 != 0: isg_assign_labels answers ISG_EUNSUPPORTED (the step then runs the fused form, which serves any width)"""
+    synth = mods["synth"]
+    H, W, N = 96, 258, 4
+    im = synth.make_image(950, H, W, N)
+    (_, _), (_, _), rc = _split_vs_fused(mods, torch.from_numpy(im.kp)[None], torch.from_numpy(im.ae)[None],
+                                         torch.from_numpy(im.rois)[None], torch.tensor([N], dtype=torch.int32), 300, N)
+    assert rc == -3          # ISG_EUNSUPPORTED
+
+
+def test_decode_ring_split_keep_equals_fused_steps(mods):
+    """whole steps through isg_decode_step: split (keep bits from the top-k candidates + labels-only dense kernel) against
+    the fused dense kernel - identical polygon tables"""
+    synth, engine = mods["synth"], mods["engine"]
+    H, W, B, N = 256, 512, 2, 10
+    dev = torch.device(DEV)
+    anchors = synth.make_anchors(H, W)
+    scenes = [synth.make_scene(960 + b, H, W, N, 8, anchors) for b in range(B)]
+    kp = torch.from_numpy(np.stack([s[0].kp for s in scenes])).to(dev)
+    ae = torch.from_numpy(np.stack([s[0].ae for s in scenes])).to(dev)
+    reg = torch.from_numpy(np.stack([s[1] for s in scenes])).to(dev); cls = torch.from_numpy(np.stack([s[2] for s in scenes])).to(dev)
+    anc = torch.from_numpy(anchors).to(dev)
+    res = {}
+    saved = engine.SPLIT_KEEP
+    try:
+        for split in (False, True):
+            engine.SPLIT_KEEP = split
+            pipe = engine.make_pipeline(B, anchors.shape[1], 8, H, W, H, W, 3000, dev, cand_cap=512, max_keep=64)
+            pipe.run_native(kp, ae, anc, reg, cls, 0.3, 0.2, obj_pixel_th=2)
+            torch.cuda.synchronize()
+            dp = pipe.dplan
+            res[split] = [t.clone() for t in (dp.label_map, dp.keepbits, dp.img_total, dp.inst_count, dp.inst_flags)]
+            st, ct, pts = dp.inst_start.cpu().numpy(), dp.inst_count.cpu().numpy(), dp.poly_points.cpu().numpy()
+            # an instance's slot in poly_points depends on the order the CTAs finish in: compare instance by instance
+            res[split].append([[pts[b, st[b, i]:st[b, i] + ct[b, i]].copy() for i in range(dp.N)] for b in range(B)])
+    finally:
+        engine.SPLIT_KEEP = saved
+    assert int(res[True][2].sum().item()) > 0
+    for a, b in zip(res[False][:5], res[True][:5]):
+        assert torch.equal(a, b)
+    for pa, pb in zip(res[False][5], res[True][5]):
+        assert len(pa) == len(pb) and all(np.array_equal(x, y) for x, y in zip(pa, pb))

@@ -15,6 +15,8 @@ run coco --workload coco_800x1333_c80_n1000
 run wide --inputs wide --no-cpu
 run sustained --min-seconds 2.5 --no-e2e --no-cpu
 run ring1 --ring 1 --no-e2e --no-cpu
+ISG_SPLIT_KEEP=1 run split --no-e2e --no-cpu
+ISG_SPLIT_KEEP=1 run split_ring1 --ring 1 --no-e2e --no-cpu
 run ref_default --impl reference --steps 3
 run ref_half --impl reference --steps 3 --workload half_512x1024_b8_n50
 run ref_crowd --impl reference --steps 2 --workload crowd_1024x2048_b4_n500
@@ -30,11 +32,18 @@ full topk_filter topk_filter 4 python bench.py --steps 4 --warmup 3 --no-e2e --n
 full nms_small nms_small 4 python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --ring 1
 full polygons instance_polygons 4 python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --ring 1
 full decode_boxes decode_boxes_kernel 4 python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --ring 1
+ISG_SPLIT_KEEP=1 full dense_split dense_v4 4 python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --ring 1
+ISG_SPLIT_KEEP=1 full topk_select_split topk_select 4 python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --ring 1
+ISG_SPLIT_KEEP=1 $NCU --metrics gpu__time_duration.sum -c 150 --csv --log-file $O/r2ev_launches_split.csv python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --ring 1 > $O/r2ev_ncu4.log 2>&1
 full kmeans kmeans_loop 2 python bench.py --workload crowd_1024x2048_b4_n500_kmeans --steps 2 --warmup 3 --no-e2e --no-cpu --ring 1
+if [ -z "${EV_QUICK:-}" ]; then
 full mask_area mask_area 2 python bench.py --workload coco_800x1333_c80_n1000 --steps 2 --warmup 3 --no-e2e --no-cpu
 full mask_pair mask_pair 2 python bench.py --workload coco_800x1333_c80_n1000 --steps 2 --warmup 3 --no-e2e --no-cpu
+fi
 full nms_scan nms_scan 2 python bench.py --workload coco_800x1333_c80_n1000 --steps 2 --warmup 3 --no-e2e --no-cpu
+if [ -z "${EV_QUICK:-}" ]; then
 full fill_polygons fill_polygons 1 python tools/bench_fill.py
-python tools/bench_fill.py > $O/r2ev_fill_polygons.txt 2>&1
 python tools/overlap_experiment.py > $O/r2ev_overlap.txt 2>&1
+fi
+python tools/bench_fill.py > $O/r2ev_fill_polygons.txt 2>&1
 ls -la $O/r2ev_*.ncu-rep

@@ -25,7 +25,8 @@ with open(os.path.join(P, "r2_launch_summary.txt"), "w") as out:
     out.write("# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py ... (tools/collect_evidence.sh)\n"
               "# per-launch times are cold-cache and serialised: they give each kernel's SHARE of a step, not bench values\n")
     for name, what in (("default", "cityscapes_1024x2048_b8_n100, --ring 1 (one pipeline, steps not overlapped)"),
-                       ("coco", "coco_800x1333_c80_n1000 (isg_mask_nms)"), ("kmeans", "crowd_1024x2048_b4_n500_kmeans, --ring 1")):
+                       ("coco", "coco_800x1333_c80_n1000 (isg_mask_nms)"), ("kmeans", "crowd_1024x2048_b4_n500_kmeans, --ring 1"),
+                       ("split", "cityscapes_1024x2048_b8_n100, --ring 1, ISG_SPLIT_KEEP=1 (isg_topk_keep + labels-only dense kernel)")):
         path = os.path.join(G, "%s_launches_%s.csv" % (PREFIX, name))
         if not os.path.exists(path):
             continue
