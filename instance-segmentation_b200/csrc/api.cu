@@ -24,6 +24,7 @@ static Tuning read_tuning() {
   if (const char* e = getenv("ISG_TOPK_PATH")) t.topk_radix = e[0] == 'r';
   if (const char* e = getenv("ISG_NMS_ROUNDS")) t.nms_rounds = atoi(e) > 0 ? atoi(e) : 0;
   if (const char* e = getenv("ISG_TOPK_SAMPLE")) t.topk_cluster_sample = e[0] == 'c';
+  if (const char* e = getenv("ISG_TOPK_SELECT")) t.topk_cluster_select = e[0] == 'c';
   return t;
 }
 static std::mutex g_tuning_mutex;

@@ -228,6 +228,7 @@ struct Tuning {
   int dense_skip_ae = 1;     // ISG_DENSE_SKIP_AE=0: load the ae planes of tiles no seed box overlaps too (A/B measurements)
   int topk_radix = 0;        // ISG_TOPK_PATH=radix: sampling-free two-level radix select
   int topk_cluster_sample = 0;   // ISG_TOPK_SAMPLE=cluster
+  int topk_cluster_select = 0;   // ISG_TOPK_SELECT=cluster: the 8-CTA cluster form of the select step (64 CTAs per batch of 8)
   int nms_rounds = 32;       // ISG_NMS_ROUNDS: rounds of the parallel suppression scan before the sequential fall-back (0 = sequential only)
 };
 const Tuning& tuning();      // api.cu

@@ -773,6 +773,83 @@ topk_select_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, in
   if (keepbits) set_keep_bits(key, (int)cluster.block_rank() * kSelThreads + (int)threadIdx.x, kSelCluster * kSelThreads);
 }
 
+// Single-CTA form of the select step (default).  The cluster form above spreads ~25 k candidates per image over 8 CTAs of
+// 1024 threads: 64 CTAs, each of which needs a whole SM's register file - in a ring of overlapped steps they cannot share
+// an SM with the persistent dense kernel of a neighbouring step, which then starts 64 of its 148 CTAs late.  One CTA per
+// image does the three radix passes with block barriers only (no DSMEM histogram sums): about the same latency, an eighth
+// of the SMs.  Candidates are re-read from global memory in every pass (100 KB per image, L2-resident).  The whole-image
+// fall-back (incomplete candidate list) runs the same code over all pixels: slow, and only for degenerate inputs.
+template <typename KeyAt>
+__device__ uint32_t block_radix_select(uint32_t* sh_hist, int n, uint32_t rank, KeyAt key_at) {
+  const int t = threadIdx.x, lane = t & 31;
+  uint32_t prefix = 0, pmask = 0, krem = rank;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int i = t; i < kHistBins; i += kSelThreads) sh_hist[i] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += kSelThreads * 8) {     // warp-uniform trip count, 8 independent loads in flight
+      uint32_t key[8];
+      bool in[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int i = i0 + u * kSelThreads + t; in[u] = i < n; key[u] = in[u] ? key_at(i) : 0u; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool ok = in[u] && (key[u] & pmask) == prefix;
+        if (pass == 0) hist_add_match(sh_hist, digit_of(key[u], pass), ok, lane);
+        else if (ok) atomicAdd(&sh_hist[digit_of(key[u], pass)], 1u);
+      }
+    }
+    __syncthreads();
+    uint32_t d, k2;
+    resolve_digit(sh_hist, krem, &d, &k2);
+    krem = k2;
+    if (pass == 0) { prefix = d << 21; pmask = 0xffe00000u; }
+    else if (pass == 1) { prefix |= d << 10; pmask = 0xfffffc00u; }
+    else prefix |= d;
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+topk_select1_kernel(const float* __restrict__ kp, int64_t img_stride, int npx, int k, void* ws,
+                    uint32_t* __restrict__ thr_key, int H, int W, uint32_t* __restrict__ keepbits) {
+  __shared__ uint32_t sh_hist[kHistBins];
+  pdl_wait();                          // the candidate list comes from the filter kernel
+  const int b = blockIdx.x, t = threadIdx.x;
+  const TopkWs v = topk_ws_view(ws, b, npx, k);
+  const uint32_t nc = *v.ncand;
+  const bool bin_mode = v.lower[3] != 0u;
+  const uint32_t rank = bin_mode ? v.lower[2] : (uint32_t)k;
+  const bool use_cand = nc >= rank && rank >= 1u && (size_t)nc <= topk_cand_cap(npx, k);
+  const bool complete = use_cand && !bin_mode;
+  if (t == 0) v.lower[4] = complete ? 1u : 0u;
+  const float* img = kp + (int64_t)b * img_stride;
+  uint32_t key;
+  if (use_cand) {                      // block-uniform
+    const uint32_t* cand = v.cand;
+    key = block_radix_select(sh_hist, (int)nc, rank, [&](int i) { return cand[i]; });
+  } else {
+    key = block_radix_select(sh_hist, npx, (uint32_t)k, [&](int i) { return float_key(__ldg(img + i)); });
+  }
+  if (t == 0) thr_key[b] = key;
+  if (!keepbits) return;
+  // keep bits (isg_topk_keep): the 3x3 peak test at the selected pixels
+  const int Wwords = (W + 31) / 32;
+  uint32_t* kb = keepbits + (size_t)b * H * Wwords;
+  if (complete) {
+    for (int i = t; i < (int)nc; i += kSelThreads) {
+      const uint32_t ck = v.cand[i];
+      const int p = (int)v.cand_pos[i];
+      if (ck >= key) keep_test_and_set(img, p, float_from_ukey(ck), H, W, Wwords, key, kb);
+    }
+  } else {
+    for (int p = t; p < npx; p += kSelThreads) {
+      const float c = __ldg(img + p);
+      if (float_key(c) >= key) keep_test_and_set(img, p, c, H, W, Wwords, key, kb);
+    }
+  }
+}
+
 // ---- stand-alone keep kernel ---------------------------------------------------------------
 constexpr int kKeepRowsPerWarp = 4;
 constexpr int kKeepWarps = 8;
@@ -1052,8 +1129,12 @@ static int topk_threshold_impl(const float* kp, int B, int H, int W, int64_t img
     for (int b = 0; b < B; ++b)
       ISG_CUDA(cudaMemsetAsync((char*)ws + (size_t)b * per + 3 * kHistBins * sizeof(uint32_t), 0, 64, stream));
   }
-  ISG_CUDA(launch_pdl(topk_select_kernel, dim3(kSelCluster, B), dim3(kSelThreads), 0, stream, kp, img_stride, npx, k, ws, thr_key,
-                      H, W, keepbits));
+  if (tuning().topk_cluster_select)
+    ISG_CUDA(launch_pdl(topk_select_kernel, dim3(kSelCluster, B), dim3(kSelThreads), 0, stream, kp, img_stride, npx, k, ws, thr_key,
+                        H, W, keepbits));
+  else
+    ISG_CUDA(launch_pdl(topk_select1_kernel, dim3(B), dim3(kSelThreads), 0, stream, kp, img_stride, npx, k, ws, thr_key, H, W,
+                        keepbits));
   ISG_LAUNCH_CHECK();
   if (keep_done) *keep_done = keepbits != nullptr;
   return ISG_OK;

@@ -85,13 +85,15 @@ def test_topk_count_property_full_size(mods):
 
 @pytest.mark.parametrize("shape,k,kind", [((1024, 2048), 1, "normal"), ((1024, 2048), 700000, "normal"), ((512, 1024), 20000, "flat"),
                                           ((512, 1024), 5000, "sorted"), ((300, 500), 149999, "normal"), ((256, 256), 65536, "flat")])
-@pytest.mark.parametrize("path", ["sample", "radix"])
+@pytest.mark.parametrize("path", ["sample", "radix", "sample+cluster-select"])
 def test_topk_threshold_paths(mods, shape, k, kind, path, monkeypatch):
     """every host-selected path (sample/filter/select, legacy multi-CTA, single-CTA) and the in-kernel
     fallback (flat / sorted images defeat the sample bound) return the exact k-th largest value"""
     lib, eng = mods["lib"], mods["engine"]
     # sample/filter/select or two-level radix; libisg reads its tuning variables once, the debug hook re-reads them
-    monkeypatch.setenv("ISG_TOPK_PATH", path)
+    monkeypatch.setenv("ISG_TOPK_PATH", path.split("+")[0])
+    if path.endswith("cluster-select"):       # the 8-CTA cluster form of the select step (default: one CTA per image)
+        monkeypatch.setenv("ISG_TOPK_SELECT", "cluster")
     lib.lib().isg_debug_reload_tuning()
     H, W = shape
     g = torch.Generator(device="cpu").manual_seed(H + k)
@@ -110,6 +112,7 @@ def test_topk_threshold_paths(mods, shape, k, kind, path, monkeypatch):
     u = np.array([thr[0].item()], dtype=np.int32).view(np.uint32)[0]
     f = np.array([u & 0x7FFFFFFF if u & 0x80000000 else ~u], dtype=np.uint32).view(np.float32)[0]
     monkeypatch.delenv("ISG_TOPK_PATH")
+    monkeypatch.delenv("ISG_TOPK_SELECT", raising=False)
     lib.lib().isg_debug_reload_tuning()
     assert f == np.float32(kth)
 
