@@ -249,3 +249,27 @@ def test_dets_json_round_trip(tmp_path):
     d2, i2 = eval_util.load_dets(str(tmp_path), 12)
     assert d2 == [[[3, 0.75, [4.0, 5.0], [[1.0, 2.0], [3.0, 4.0], [5.0, 1.0]]]], []]
     assert i2 == [["/a/b_leftImg8bit.png", [8, 16]], ["/a/c.png", [8, 16]]]
+
+
+def test_peak_test_threshold_free_form_equals_select_points():
+    """DESIGN.md 4.1 (split form, next step): for a SELECTED pixel every larger neighbour is selected too, so
+    keep(p) = selected(p) and p >= every in-image neighbour (raw values) and (p >= 0 or every in-image neighbour is
+    selected) - what a filter pass can evaluate per candidate before the exact threshold is known (raw local maximum +
+    smallest neighbour).  Checked against the oracle's select_points (utils/decode.py:71-85) on maps with positive,
+    negative and mixed selected values."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import ref_decode as rd
+    g = torch.Generator().manual_seed(5)
+    for H, W, k, shift in ((40, 56, 300, 0.0), (33, 47, 900, -3.0), (24, 24, 500, 0.4), (16, 64, 1024, -1.0), (31, 29, 1, 2.0)):
+        mat = torch.randn((H, W), generator=g) + shift
+        want = rd.select_points(mat, k).bool()
+        thr = torch.topk(mat.reshape(-1), k).values[-1]
+        sel = mat >= thr
+        ninf, pinf = float("-inf"), float("inf")
+        nb_max = F.max_pool2d(F.pad(mat[None, None], (1, 1, 1, 1), value=ninf), 3, stride=1)[0, 0]       # includes the centre
+        nb_min = -F.max_pool2d(F.pad(-mat[None, None], (1, 1, 1, 1), value=ninf), 3, stride=1)[0, 0]     # smallest value of the window
+        local_max = mat >= nb_max
+        all_selected = nb_min >= thr                                   # the centre is selected, so this is about the neighbours
+        got = sel & local_max & ((mat >= 0) | all_selected)
+        assert torch.equal(got, want), (H, W, k, shift)
